@@ -1,0 +1,193 @@
+/*
+ * srgp.h -- plain-C ABI of the B200-native sparseRGPs hot path (libsrgp.so).
+ *
+ * This is the drop-in boundary: every entry point takes plain pointers and sizes (no torch / Rcpp types) and
+ * is what the reference's `.Call` layer for this path binds to.  Each declaration cites the reference
+ * interface it replaces (paths relative to the reference repo).  INTEGRATION.md shows the R-side `.Call`
+ * shim and the ctypes binding.
+ *
+ * Conventions
+ *   - All matrices are R matrices: column-major IEEE doubles, no padding; x(i,c) = x[i + n*c].
+ *   - Pointers are HOST pointers unless the name ends in `_dev`; the library copies to/from the GPU inside
+ *     the call and never retains a caller pointer after returning.
+ *   - Every function returns an int status (SRGP_OK == 0) unless stated; srgp_last_error() gives the message
+ *     (thread-local).  There is NO CPU fallback: without a usable sm_100 GPU every compute entry point
+ *     returns SRGP_ERR_CUDA.
+ *   - `l` is the length-scale array: 1 entry for SRGP_SQEXP / SRGP_EXP, d entries (l1..ld) for SRGP_ARD.
+ *   - Derivatives are with respect to log(theta) (the reference's transform = TRUE).
+ */
+#ifndef SRGP_H
+#define SRGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRGP_VERSION 100
+
+enum srgp_status {
+    SRGP_OK = 0,
+    SRGP_ERR_ARG = 1,            /* bad argument (NULL pointer, negative size, d > SRGP_MAX_D ...) */
+    SRGP_ERR_UNKNOWN_KERNEL = 2, /* reference: message on Rcerr + 0x0 matrix, no R error
+                                    (src/covariance_functionsC.cpp:161-168) */
+    SRGP_ERR_UNKNOWN_PAR = 3,    /* reference: message + 0x0 matrix (src/covariance_function_derivativesC.cpp:418-422) */
+    SRGP_ERR_CUDA = 4,           /* CUDA runtime / launch failure, or no device */
+    SRGP_ERR_NOT_PD = 5,         /* an m x m Cholesky failed; the R shim must raise an R error (R's chol() does) */
+    SRGP_ERR_STATE = 6,          /* call order (e.g. obj_grad before set_data) */
+    SRGP_ERR_COMM = 7            /* NCCL failure / libnccl not loadable */
+};
+
+enum srgp_kernel { SRGP_SQEXP = 0, SRGP_EXP = 1, SRGP_ARD = 2 };          /* cov_fun = "sqexp" | "exp" | "ard" */
+enum srgp_par { SRGP_PAR_SIGMA = 0, SRGP_PAR_L = 1, SRGP_PAR_TAU = 2, SRGP_PAR_LC = 3 };
+enum srgp_model { SRGP_VI = 0, SRGP_FIC = 1 };
+enum srgp_family { SRGP_BERNOULLI = 0, SRGP_POISSON = 1 };
+
+#define SRGP_MAX_D 64           /* input dimension limit of the GPU kernels */
+#define SRGP_UNIQUE_ID_BYTES 128
+
+typedef struct srgp_ctx srgp_ctx;
+
+/* ---------------------------------------------------------------- library / context ---------- */
+int srgp_version(void);
+const char *srgp_last_error(void);
+/* One context per GPU (one process per GPU under torchrun; several contexts per process also work).
+   Holds streams, scratch, the resident data shard and the NCCL communicator. */
+int srgp_ctx_create(int device, srgp_ctx **out);
+void srgp_ctx_destroy(srgp_ctx *ctx);
+int srgp_ctx_sync(srgp_ctx *ctx);
+
+/* ---------------------------------------------------------------- K1: covariance assembly ---- */
+/* Replaces make_cov_matC (src/covariance_functionsC.cpp:72-169) and make_cov_mat_ardC (:191-252).
+   x is n1 x d.  x_pred == NULL is the reference's `matrix()` (1x1 NA) sentinel: the n1 x n1 self-covariance
+   with tau^2 + delta added where i == j.  Otherwise x_pred is n2 x d and out is the n1 x n2 cross-covariance. */
+int srgp_make_cov_mat(srgp_ctx *ctx, int kernel, const double *x, int64_t n1, const double *x_pred, int64_t n2,
+                      int d, double sigma, const double *l, double tau, double delta, double *out);
+
+/* ---------------------------------------------------------------- K2: d Sigma / d log theta -- */
+/* Replaces dsig_dthetaC (src/covariance_function_derivativesC.cpp:307-552) and dsig_dtheta_ardC (:555-722).
+   par = SRGP_PAR_SIGMA | SRGP_PAR_L (sqexp, exp) | SRGP_PAR_LC with comp0 = 0-based component (ard) | SRGP_PAR_TAU.
+   Reproduces: tau derivative = 2 tau^2 where all coordinates are bit-equal (cross matrices too);
+   kernel == SRGP_EXP with a cross matrix returns zeros for anything but sigma / l. */
+int srgp_dsig_dtheta(srgp_ctx *ctx, int kernel, int par, int comp0, const double *x, int64_t n1,
+                     const double *x_pred, int64_t n2, int d, double sigma, const double *l, double tau,
+                     double *out);
+
+/* Device-resident variants (inputs and output already in HBM; `stream-ordered`, call srgp_ctx_sync to wait).
+   Used by bench.py for kernel-only timing. */
+int srgp_make_cov_mat_dev(srgp_ctx *ctx, int kernel, const double *x_dev, int64_t n1, const double *x_pred_dev,
+                          int64_t n2, int d, double sigma, const double *l, double tau, double delta,
+                          double *out_dev);
+int srgp_dsig_dtheta_dev(srgp_ctx *ctx, int kernel, int par, int comp0, const double *x_dev, int64_t n1,
+                         const double *x_pred_dev, int64_t n2, int d, double sigma, const double *l, double tau,
+                         double *out_dev);
+
+/* ---------------------------------------------------------------- scalar Rcpp exports -------- */
+/* The remaining registered routines (src/RcppExports.cpp:285-304) are per-pair scalars with no R call sites;
+   they are host code.  x1, x2 are contiguous length-d vectors. */
+void srgp_real_to_pos(const double *x, int64_t n, double *out);                                   /* derivativesC.cpp:11 */
+void srgp_pos_to_real(const double *x, int64_t n, double *out);                                   /* :19 */
+void srgp_real_to_bounded(const double *x, const double *ub, const double *lb, int64_t n, double *out); /* :27 */
+double srgp_cov_fun_sqrd_exp(const double *x1, const double *x2, int d, double sigma, double l);   /* functionsC.cpp:5 */
+double srgp_cov_fun_sqrd_exp_ard(const double *x1, const double *x2, int d, double sigma, const double *l); /* :16 */
+double srgp_cov_fun_exp(const double *x1, const double *x2, int d, double sigma, double l);        /* :45 */
+double srgp_dsqexp_dsigma(const double *x1, const double *x2, int d, double sigma, double l);      /* derivativesC.cpp:35 */
+double srgp_dsqexp_dsigma_ard(const double *x1, const double *x2, int d, double sigma, const double *l); /* :55 */
+double srgp_dsqexp_dl(const double *x1, const double *x2, int d, double sigma, double l);          /* :86 */
+double srgp_dsqexp_dl_ard(const double *x1, const double *x2, int d, double sigma, const double *l, int comp0); /* :107 */
+double srgp_dsqexp_dtau(const double *x1, const double *x2, int d, double tau);                    /* :142 */
+double srgp_dexp_dsigma(const double *x1, const double *x2, int d, double sigma, double l);        /* :232 */
+double srgp_dexp_dl(const double *x1, const double *x2, int d, double sigma, double l);            /* :252 */
+double srgp_dexp_dtau(const double *x1, const double *x2, int d, double tau);                      /* :272 */
+void srgp_dsqexp_dx2(const double *x1, const double *x2, int d, double sigma, double l, const double *lb,
+                     const double *ub, double *deriv, double *trans_par);                          /* :176 */
+void srgp_dsqexp_dx2_ard(const double *x1, const double *x2, int d, double sigma, const double *l,
+                         const double *lb, const double *ub, double *deriv, double *trans_par);    /* :197 */
+
+/* ---------------------------------------------------------------- K5: trace terms ------------ */
+/* trace_term_fun(cov_par, Sigma12, Sigma22, delta)  (R/vi_functions.R:14-27) on materialised inputs:
+   -(1/(2 tau^2)) * sum_i (sigma^2 + delta - Sigma12[i,] Sigma22^-1 Sigma12[i,]^T).  Sigma12 is n x m. */
+int srgp_trace_term(srgp_ctx *ctx, double sigma, double tau, double delta, const double *Sigma12, int64_t n,
+                    int64_t m, const double *Sigma22, double *out);
+/* dtrace_term_dcov_par(cov_par, A_trace) (R/vi_functions.R:54-60): -(1/(2 tau^2)) * sum(A_trace). */
+int srgp_dtrace_term_dcov_par(srgp_ctx *ctx, double tau, const double *A_trace, int64_t n, double *out);
+/* dtrace_term_dtau(cov_par, trace_term) (R/vi_functions.R:38-44): -2 * trace_term. */
+double srgp_dtrace_term_dtau(double trace_term);
+/* sum_ij Omega_ij * dSigma12_ij/dlog(theta) for every theta at once, never materialising dSigma12:
+   the reduction every `dSigma12_dtheta` use in R/vi_functions.R:344-398 collapses to.
+   Omega is n x m (host).  out has p entries ordered sigma, l (or l1..ld), tau. */
+int srgp_omega_dk_reduce(srgp_ctx *ctx, int kernel, const double *x, int64_t n, const double *xu, int64_t m,
+                         int d, double sigma, const double *l, double tau, const double *Omega, double *out);
+
+/* ---------------------------------------------------------------- fused objective + gradient - */
+/* Resident data shard: xy (n x d), y (n), mu (n, NULL = 0).  Under multi-GPU each rank passes ITS rows. */
+int srgp_set_data(srgp_ctx *ctx, const double *xy, int64_t n, int d, const double *y, const double *mu);
+/* Device-side generation of the synthetic benchmark workload (BASELINE.json config 5 recipe):
+   not part of the reference API; lets bench.py time with inputs resident in HBM. */
+int srgp_set_data_dev(srgp_ctx *ctx, const double *xy_dev, int64_t n, int d, const double *y_dev,
+                      const double *mu_dev);
+
+/* One optimiser iteration's evaluation for the sparse Gaussian models with fixed knots:
+     model == SRGP_VI  : elbo_fun (R/vi_functions.R:64-121) + delbo_dcov_par (:126-420)
+     model == SRGP_FIC : obj_fun_norm (R/laplace_approx_obj_funs.R:6-52) + dlogp_dcov_par
+                         (R/laplace_approx_gradient.R:720-968)
+   xu is m x d.  grad (may be NULL) receives p = d + 2 (ard) or 3 (sqexp) entries ordered like the
+   reference's cov_par list: sigma, l / l1..ld, tau; all with respect to log(theta).
+   With a communicator attached the row sums are all-reduced (one fused allreduce per pass) and every rank
+   returns the global objective and gradient. */
+int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
+                        const double *l, double tau, double delta, double *obj, double *grad);
+/* Same, but uploads xy / y / mu first: the one-shot call with the reference's argument list. */
+int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, const double *xy, int64_t n, int d,
+                             const double *y, const double *mu, const double *xu, int64_t m, double sigma,
+                             const double *l, double tau, double delta, double *obj, double *grad);
+
+/* ---------------------------------------------------------------- sparse Laplace ------------- */
+/* newtrap_sparseGP (R/newtrap_sparseGP.R:6-186) on the resident shard.  ff (n) in: start values, out: mode.
+   obj_hist receives up to maxit objective values, *n_iter their count.  grad_psi (n), u_mean (m),
+   u_var (m x m) may be NULL.  pois_m is the Poisson offset `m` (ignored for Bernoulli). */
+int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, const double *muu,
+                        double sigma, const double *l, double tau, double delta, double pois_m, int maxit,
+                        double tol, double *ff, double *obj_hist, int *n_iter, double *grad_psi, double *u_mean,
+                        double *u_var);
+/* dlogq_dcov_par (R/laplace_approx_gradient.R:25-339) at the mode ff. */
+int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                      const double *l, double tau, double delta, double pois_m, const double *ff, double *grad);
+
+/* ---------------------------------------------------------------- multi-GPU ------------------ */
+/* Row sharding over ranks with NCCL sum-allreduce of the pass partials (m x m Gram, m-vectors, scalars,
+   gradient partials).  Rank 0 calls srgp_comm_unique_id and distributes the bytes out of band
+   (bench.py: torch.distributed broadcast); every rank then calls srgp_comm_init. */
+int srgp_comm_unique_id(char id[SRGP_UNIQUE_ID_BYTES]);
+int srgp_comm_init(srgp_ctx *ctx, int world, int rank, const char id[SRGP_UNIQUE_ID_BYTES]);
+int srgp_comm_destroy(srgp_ctx *ctx);
+
+/* ---------------------------------------------------------------- instrumentation ------------ */
+/* Device memory helpers for callers without a CUDA binding (bench.py, tests). */
+int srgp_dev_alloc(srgp_ctx *ctx, int64_t bytes, void **out_dev);
+int srgp_dev_free(srgp_ctx *ctx, void *dev);
+int srgp_memcpy_h2d(srgp_ctx *ctx, void *dst_dev, const void *src, int64_t bytes);
+int srgp_memcpy_d2h(srgp_ctx *ctx, void *dst, const void *src_dev, int64_t bytes);
+int srgp_fill_normal_dev(srgp_ctx *ctx, double *dst_dev, int64_t n, uint64_t seed, double mean, double sd);
+/* CUDA-event timers on the context's own stream (torch.cuda.Event would not see it). */
+int srgp_timer_start(srgp_ctx *ctx);
+int srgp_timer_stop_ms(srgp_ctx *ctx, double *ms);
+/* Per-kernel accounting: when enabled, every launch of a named hot kernel is bracketed by CUDA events;
+   srgp_prof_get returns launches and accumulated milliseconds since the last reset. */
+enum srgp_prof_id {
+    SRGP_PROF_ASSEMBLE = 0, SRGP_PROF_GEN = 1, SRGP_PROF_GRAM = 2, SRGP_PROF_KM = 3, SRGP_PROF_DENSE = 4,
+    SRGP_PROF_REDUCE = 5, SRGP_PROF_COMM = 6, SRGP_PROF_COUNT = 8
+};
+int srgp_prof_enable(srgp_ctx *ctx, int on);
+int srgp_prof_reset(srgp_ctx *ctx);
+int srgp_prof_get(srgp_ctx *ctx, int id, int64_t *launches, double *ms);
+/* Total kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t srgp_launch_count(srgp_ctx *ctx);
+/* Flush L2 by writing a scratch buffer larger than the 126 MB L2 (timing hygiene between iterations). */
+int srgp_flush_l2(srgp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRGP_H */

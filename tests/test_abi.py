@@ -1,0 +1,58 @@
+"""The C-ABI library loads and exports every symbol include/srgp.h declares (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "srgp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(srgp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from sparsergps_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), "libsrgp.so does not export " + n
+
+
+def test_python_signatures_cover_header():
+    from sparsergps_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    _lib.load()
+
+
+def test_version_and_no_device_error():
+    from sparsergps_b200 import _lib
+    lib = _lib.load()
+    assert lib.srgp_version() == 100
+    import torch
+    if not torch.cuda.is_available():
+        h = _lib.vp()
+        st = lib.srgp_ctx_create(0, ctypes.byref(h))
+        assert st == _lib.ERR_CUDA          # fails loudly: no CPU fallback
+        assert b"no CPU fallback" in lib.srgp_last_error()
+
+
+def test_scalar_exports_known_answers():
+    # analytic known answers; host code in the library, no GPU needed
+    import numpy as np
+    from sparsergps_b200 import rcpp_exports as R
+    assert R.cov_fun_sqrd_expC([0.0], [1.0], {"sigma": 1, "l": 1}) == pytest.approx(0.6065306597126334, rel=1e-15)
+    cp = {"sigma": 2, "l1": 1, "l2": 2}
+    assert R.cov_fun_sqrd_exp_ardC([1.0, 2.0], [0.0, 0.0], cp, ["l1", "l2"]) == pytest.approx(1.4715177646857693, rel=1e-15)
+    assert R.dsqexp_dsigmaC([0.3], [0.3], {"sigma": 2, "l": 1})["derivative"] == pytest.approx(8.0)
+    assert R.dsqexp_dtauC([0.3, 1], [0.3, 1], {"tau": 0.5})["derivative"] == pytest.approx(0.5)
+    assert R.dsqexp_dtauC([0.3, 1], [0.3, 2], {"tau": 0.5})["derivative"] == 0.0
+    assert R.real_to_bounded([0.0], [3.0], [1.0])[0] == pytest.approx(2.0)
+    np.testing.assert_allclose(R.real_to_pos(R.pos_to_real([0.7, 2.0])), [0.7, 2.0], rtol=1e-15)
+    # exp kernel: L1 distance in the covariance, L2 in the derivatives (quirk Q8)
+    assert R.cov_fun_expC([0.0, 0.0], [3.0, 4.0], {"sigma": 1, "l": 1}) == pytest.approx(np.exp(-7.0))
+    assert R.dexp_dsigmaC([0.0, 0.0], [3.0, 4.0], {"sigma": 1, "l": 1})["derivative"] == pytest.approx(2 * np.exp(-5.0))
