@@ -80,6 +80,13 @@ SIGNATURES = {
 }
 
 
+# test hooks (csrc/srgp_internal.h) -- not part of the drop-in ABI
+INTERNAL_SIGNATURES = {
+    "srgp_test_gemm": (ci, [vp, ci, ci, ci, ci, ci, cd, dp, ci, dp, ci, cd, dp, ci, ci, ci, dp]),
+    "srgp_test_chol_inverse": (ci, [vp, ci, dp, dp, dp, dp, C.POINTER(ci), ci, dp]),
+}
+
+
 class SrgpError(RuntimeError):
     def __init__(self, status, message):
         super().__init__("libsrgp status %d: %s" % (status, message))
@@ -102,10 +109,11 @@ def load():
                 "sparsergps_b200/libsrgp.so is missing: run `python -m sparsergps_b200.build` "
                 "(or __graft_entry__.build()).  There is no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            f = getattr(lib, name)
-            f.restype = res
-            f.argtypes = args
+        for table in (SIGNATURES, INTERNAL_SIGNATURES):
+            for name, (res, args) in table.items():
+                f = getattr(lib, name)
+                f.restype = res
+                f.argtypes = args
         _lib = lib
     return _lib
 

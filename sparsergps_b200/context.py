@@ -35,6 +35,67 @@ class Context:
     def __exit__(self, *exc):
         self.close()
 
+    # ---- resident shard + fused evaluations -------------------------------------------------
+    def set_data(self, xy, y, mu=None):
+        """Upload this rank's rows: xy (n x d), y (n), mu (n or None = 0).  include/srgp.h: srgp_set_data."""
+        xy = L.fmat(xy)
+        y = L.fvec(y)
+        n, d = xy.shape
+        assert y.size == n
+        mup = None
+        if mu is not None:
+            mu = L.fvec(np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (n,)))
+            mup = L.ptr(mu)
+        L.check(self._lib.srgp_set_data(self.handle, L.ptr(xy), n, d, L.ptr(y), mup))
+        self.n, self.d = n, d
+
+    def set_data_dev(self, xy_dev, n, d, y_dev, mu_dev=None):
+        L.check(self._lib.srgp_set_data_dev(self.handle, xy_dev, int(n), int(d), y_dev, mu_dev))
+        self.n, self.d = int(n), int(d)
+
+    def gauss_obj_grad(self, model, cov_fun, xu, sigma, l, tau, delta, want_grad=True):
+        """One objective (+ gradient wrt log theta) evaluation on the resident shard.
+        model: "vi" | "fic"; returns (obj, grad ndarray ordered sigma, l / l1..ld, tau)."""
+        xu = L.fmat(xu)
+        m, d = xu.shape
+        assert d == self.d, "knots and data disagree on the input dimension"
+        lv = L.fvec(l)
+        p = (d + 2) if cov_fun == "ard" else 3
+        obj = L.cd()
+        grad = np.zeros(p)
+        L.check(self._lib.srgp_gauss_obj_grad(self.handle, L.VI if model == "vi" else L.FIC, L.KERNELS[cov_fun],
+                                              L.ptr(xu), m, float(sigma), L.ptr(lv), float(tau), float(delta),
+                                              C.byref(obj), L.ptr(grad) if want_grad else None))
+        return obj.value, (grad if want_grad else None)
+
+    def gauss_obj_grad_host(self, model, cov_fun, xy, y, mu, xu, sigma, l, tau, delta, want_grad=True):
+        """One-shot call with the reference's argument list (uploads xy / y / mu inside the call)."""
+        xy, y, xu, lv = L.fmat(xy), L.fvec(y), L.fmat(xu), L.fvec(l)
+        n, d = xy.shape
+        mup = None
+        if mu is not None:
+            mu = L.fvec(np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (n,)))
+            mup = L.ptr(mu)
+        p = (d + 2) if cov_fun == "ard" else 3
+        obj = L.cd()
+        grad = np.zeros(p)
+        L.check(self._lib.srgp_gauss_obj_grad_host(self.handle, L.VI if model == "vi" else L.FIC,
+                                                   L.KERNELS[cov_fun], L.ptr(xy), n, d, L.ptr(y), mup, L.ptr(xu),
+                                                   xu.shape[0], float(sigma), L.ptr(lv), float(tau), float(delta),
+                                                   C.byref(obj), L.ptr(grad) if want_grad else None))
+        self.n, self.d = n, d
+        return obj.value, (grad if want_grad else None)
+
+    # ---- multi-GPU ---------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(L.UNIQUE_ID_BYTES)
+        L.check(L.load().srgp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        L.check(self._lib.srgp_comm_init(self.handle, int(world), int(rank), unique_id))
+
     # ---- instrumentation -------------------------------------------------------------------
     def sync(self):
         L.check(self._lib.srgp_ctx_sync(self.handle))

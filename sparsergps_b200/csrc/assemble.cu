@@ -8,7 +8,7 @@
 // threads write consecutive rows of a column => 256-byte coalesced streaming stores.  The kernel is bound by
 // the HBM write of 8*n1*n2 bytes (plus the FP64 pipe for exp); nothing is read twice.
 #include "common.cuh"
-#include "kmath.cuh"
+#include "gauss.cuh"
 
 namespace srgp {
 
@@ -30,7 +30,7 @@ constexpr int ASM_COLS = 32;
 template <int KT, int MODE, int DT>
 __global__ void __launch_bounds__(ASM_ROWS)
 assemble_kernel(const double *__restrict__ x, int64_t n1, const double *__restrict__ xb, int64_t n2, int d_rt,
-                AsmParams p, int self, double *__restrict__ out)
+                AsmParams p, int self, double *__restrict__ out, int64_t ldo)
 {
     extern __shared__ double su[];  // [ASM_COLS][d]
     const int d = DT > 0 ? DT : d_rt;
@@ -96,39 +96,39 @@ assemble_kernel(const double *__restrict__ x, int64_t n1, const double *__restri
             } else if (MODE == MODE_ZERO) {
                 v = 0.0;
             } else if (KT == SRGP_ARD) {
-                double k = p.sigma2 * exp_nonpos(-0.5 * acc);
+                double k = p.sigma2 * exp(-0.5 * acc);
                 v = (MODE == MODE_COV) ? k : (MODE == MODE_DSIGMA) ? 2.0 * k : k * dc2;
             } else if (KT == SRGP_SQEXP) {
-                double k = p.sigma2 * exp_nonpos(p.c_exp * acc);
+                double k = p.sigma2 * exp(p.c_exp * acc);
                 v = (MODE == MODE_COV) ? k : (MODE == MODE_DSIGMA) ? 2.0 * k : k * (acc * p.inv_l2);
             } else {  // SRGP_EXP: covariance uses the L1 distance, derivatives the L2 distance (quirk Q8)
                 if (MODE == MODE_COV) {
-                    v = p.sigma2 * exp_nonpos(p.c_exp * acc);
+                    v = p.sigma2 * exp(p.c_exp * acc);
                 } else {
                     double r = sqrt(acc);
-                    double k = p.sigma2 * exp_nonpos(p.c_exp * r);
+                    double k = p.sigma2 * exp(p.c_exp * r);
                     v = (MODE == MODE_DSIGMA) ? 2.0 * k : k * (r * p.inv_l2);
                 }
             }
             const int64_t j = j0 + jj;
             if (MODE == MODE_COV && self && i == j) v = v + p.tau2_delta;
-            __stcs(out + i + n1 * j, v);
+            __stcs(out + i + ldo * j, v);
         }
     }
 }
 
 template <int KT, int MODE>
-static int launch_d(srgp_ctx *ctx, const double *x, int64_t n1, const double *xb, int64_t n2, int d,
-                    const AsmParams &p, int self, double *out)
+static int launch_d(srgp_ctx *ctx, cudaStream_t st, const double *x, int64_t n1, const double *xb, int64_t n2,
+                    int d, const AsmParams &p, int self, double *out, int64_t ldo)
 {
     dim3 block(ASM_ROWS);
     int64_t col_tiles = ceil_div(n2, ASM_COLS);
     dim3 grid((unsigned)ceil_div(n1, ASM_ROWS), (unsigned)(col_tiles < 65535 ? col_tiles : 65535));
     size_t smem = sizeof(double) * ASM_COLS * d;
-    KernelScope ks(ctx, SRGP_PROF_ASSEMBLE, ctx->stream);
+    KernelScope ks(ctx, SRGP_PROF_ASSEMBLE, st);
 #define SRGP_ASM_CASE(D)                                                                                  \
     case D:                                                                                               \
-        assemble_kernel<KT, MODE, D><<<grid, block, smem, ctx->stream>>>(x, n1, xb, n2, d, p, self, out); \
+        assemble_kernel<KT, MODE, D><<<grid, block, smem, st>>>(x, n1, xb, n2, d, p, self, out, ldo);       \
         break;
     switch (d) {
         SRGP_ASM_CASE(1)
@@ -140,7 +140,7 @@ static int launch_d(srgp_ctx *ctx, const double *x, int64_t n1, const double *xb
         SRGP_ASM_CASE(7)
         SRGP_ASM_CASE(8)
     default:
-        assemble_kernel<KT, MODE, 0><<<grid, block, smem, ctx->stream>>>(x, n1, xb, n2, d, p, self, out);
+        assemble_kernel<KT, MODE, 0><<<grid, block, smem, st>>>(x, n1, xb, n2, d, p, self, out, ldo);
     }
 #undef SRGP_ASM_CASE
     SRGP_LAUNCH_CHECK();
@@ -148,16 +148,16 @@ static int launch_d(srgp_ctx *ctx, const double *x, int64_t n1, const double *xb
 }
 
 template <int KT>
-static int launch_mode(srgp_ctx *ctx, int mode, const double *x, int64_t n1, const double *xb, int64_t n2, int d,
-                       const AsmParams &p, int self, double *out)
+static int launch_mode(srgp_ctx *ctx, cudaStream_t st, int mode, const double *x, int64_t n1, const double *xb,
+                       int64_t n2, int d, const AsmParams &p, int self, double *out, int64_t ldo)
 {
     switch (mode) {
-    case MODE_COV: return launch_d<KT, MODE_COV>(ctx, x, n1, xb, n2, d, p, self, out);
-    case MODE_DSIGMA: return launch_d<KT, MODE_DSIGMA>(ctx, x, n1, xb, n2, d, p, self, out);
-    case MODE_DL: return launch_d<KT, MODE_DL>(ctx, x, n1, xb, n2, d, p, self, out);
-    case MODE_DLC: return launch_d<KT, MODE_DLC>(ctx, x, n1, xb, n2, d, p, self, out);
-    case MODE_DTAU: return launch_d<KT, MODE_DTAU>(ctx, x, n1, xb, n2, d, p, self, out);
-    default: return launch_d<KT, MODE_ZERO>(ctx, x, n1, xb, n2, d, p, self, out);
+    case MODE_COV: return launch_d<KT, MODE_COV>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
+    case MODE_DSIGMA: return launch_d<KT, MODE_DSIGMA>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
+    case MODE_DL: return launch_d<KT, MODE_DL>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
+    case MODE_DLC: return launch_d<KT, MODE_DLC>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
+    case MODE_DTAU: return launch_d<KT, MODE_DTAU>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
+    default: return launch_d<KT, MODE_ZERO>(ctx, st, x, n1, xb, n2, d, p, self, out, ldo);
     }
 }
 
@@ -209,9 +209,25 @@ int assemble_dev(srgp_ctx *ctx, int kernel, int mode, int comp0, const double *x
     const int self = (xp_dev == nullptr);
     const double *xb = self ? x_dev : xp_dev;
     const int64_t nb = self ? n1 : n2;
-    if (kernel == SRGP_SQEXP) return launch_mode<SRGP_SQEXP>(ctx, mode, x_dev, n1, xb, nb, d, p, self, out_dev);
-    if (kernel == SRGP_EXP) return launch_mode<SRGP_EXP>(ctx, mode, x_dev, n1, xb, nb, d, p, self, out_dev);
-    return launch_mode<SRGP_ARD>(ctx, mode, x_dev, n1, xb, nb, d, p, self, out_dev);
+    if (kernel == SRGP_SQEXP)
+        return launch_mode<SRGP_SQEXP>(ctx, ctx->stream, mode, x_dev, n1, xb, nb, d, p, self, out_dev, n1);
+    if (kernel == SRGP_EXP)
+        return launch_mode<SRGP_EXP>(ctx, ctx->stream, mode, x_dev, n1, xb, nb, d, p, self, out_dev, n1);
+    return launch_mode<SRGP_ARD>(ctx, ctx->stream, mode, x_dev, n1, xb, nb, d, p, self, out_dev, n1);
+}
+
+// Self-covariance K(x, x) + nugget * I with an explicit output leading dimension (the m x m stage keeps its
+// matrices padded to ld = round_up(m, 128)).
+int assemble_dev_ld(srgp_ctx *ctx, cudaStream_t st, int kernel, const double *x_dev, int64_t n1, int d, double sigma,
+                    const double *l, double nugget, double *out_dev, int64_t ldo)
+{
+    AsmParams p;
+    fill_params(p, kernel, d, sigma, l, 0.0, nugget, 0);
+    if (kernel == SRGP_SQEXP)
+        return launch_mode<SRGP_SQEXP>(ctx, st, MODE_COV, x_dev, n1, x_dev, n1, d, p, 1, out_dev, ldo);
+    if (kernel == SRGP_EXP)
+        return launch_mode<SRGP_EXP>(ctx, st, MODE_COV, x_dev, n1, x_dev, n1, d, p, 1, out_dev, ldo);
+    return launch_mode<SRGP_ARD>(ctx, st, MODE_COV, x_dev, n1, x_dev, n1, d, p, 1, out_dev, ldo);
 }
 
 // par -> kernel mode, with the reference's dispatch rules.

@@ -1,0 +1,558 @@
+// dense.cu -- replicated m x m stage (K6): what R's chol / solve / det / %*% do on m x m matrices in
+// R/vi_functions.R:96-118,227-246, R/laplace_approx_obj_funs.R:30-48, R/newtrap_sparseGP.R:244-289.
+#include "dense.cuh"
+#include "gemm.cuh"
+
+namespace srgp {
+namespace dense {
+
+using namespace gemm;
+
+// ------------------------------------------------------------------------------------------------
+// DMMA GEMM
+// ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+    const double *A, *B;
+    double *C;
+    int64_t lda, ldb, ldc, sA, sB, sC;
+    int ktiles;
+    double alpha, beta;
+    int lower_only;
+};
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tm = blockIdx.x, tn = blockIdx.y;
+    if (g.lower_only && tn > tm) return;
+    const double *A = g.A + blockIdx.z * g.sA + (A_KC ? (int64_t)tm * BM * g.lda : (int64_t)tm * BM);
+    const double *B = g.B + blockIdx.z * g.sB + (B_KC ? (int64_t)tn * BN * g.ldb : (int64_t)tn * BN);
+    pipeline_init(sm);
+    double acc[8][4][2];
+    zero_acc(acc);
+    uint32_t it = 0;
+    mainloop<A_KC, B_KC, false>(sm, A, g.lda, B, g.ldb, nullptr, g.ktiles, it, acc);
+    if (is_producer()) return;
+    double *C = g.C + blockIdx.z * g.sC + (int64_t)tm * BM + (int64_t)tn * BN * g.ldc;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+        const int r = frag_row(mi);
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int c = frag_col(ni);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double *p = C + r + (int64_t)(c + e) * g.ldc;
+                double v = g.alpha * acc[mi][ni][e];
+                if (g.beta != 0.0) v += g.beta * *p;
+                *p = v;
+            }
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+static int launch_gemm(srgp_ctx *ctx, cudaStream_t s, dim3 grid, const GemmArgs &g)
+{
+    static bool configured = false;   // per template instantiation
+    if (!configured) {
+        SRGP_CUDA(cudaFuncSetAttribute(gemm_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        configured = true;
+    }
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    gemm_kernel<A_KC, B_KC><<<grid, THREADS, sizeof(Smem), s>>>(g);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+int gemm(srgp_ctx *ctx, cudaStream_t s, char transA, char transB, int M, int N, int K, double alpha,
+         const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc,
+         BatchDesc bd, bool lower_only)
+{
+    if (M % BM || N % BN || K % BK || M <= 0 || N <= 0 || K < 0) {
+        set_error("gemm: extents %d x %d x %d are not tile multiples", M, N, K);
+        return SRGP_ERR_ARG;
+    }
+    GemmArgs g{A, B, C, lda, ldb, ldc, bd.strideA, bd.strideB, bd.strideC, K / BK, alpha, beta, lower_only ? 1 : 0};
+    dim3 grid(M / BM, N / BN, bd.batch);
+    const bool akc = (transA == 'T'), bkc = (transB == 'N');
+    if (!akc && !bkc) return launch_gemm<false, false>(ctx, s, grid, g);
+    if (!akc && bkc) return launch_gemm<false, true>(ctx, s, grid, g);
+    if (akc && !bkc) return launch_gemm<true, false>(ctx, s, grid, g);
+    return launch_gemm<true, true>(ctx, s, grid, g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky: diagonal block factor + inverse in shared memory (one CTA), panel / trailing updates by DMMA GEMM
+// ------------------------------------------------------------------------------------------------
+constexpr int DLD = NB + 1;   // 129: odd stride, column-major block in shared memory
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *__restrict__ dinv,
+                  int *__restrict__ info, double *__restrict__ logdet_part)
+{
+    extern __shared__ double sh[];
+    double *s = sh;                 // NB x DLD
+    double *colv = sh + NB * DLD;   // NB
+    double *psum = colv + NB;       // 2 * NB
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx % NB, j = idx / NB;
+        s[i + j * DLD] = (i >= j) ? A[i + (int64_t)j * ld] : 0.0;
+    }
+    __syncthreads();
+    const int ti = tid & 15, tk = tid >> 4;
+    double ld_acc = 0.0;
+    for (int j = 0; j < NB; j++) {
+        if (tid == 0) {
+            const double piv = s[j + j * DLD];
+            if (!(piv > 0.0) && *info == 0) *info = col0 + j + 1;
+            const double r = sqrt(piv);
+            s[j + j * DLD] = r;
+            if (col0 + j < m) ld_acc += log(r);
+        }
+        __syncthreads();
+        const double djj = s[j + j * DLD];
+        if (tid < NB && tid > j) s[tid + j * DLD] = s[tid + j * DLD] / djj;
+        __syncthreads();
+        for (int k = j + 1 + tk; k < NB; k += 16) {
+            const double lkj = s[k + j * DLD];
+            for (int i = j + 1 + ti; i < NB; i += 16)
+                if (i >= k) s[i + k * DLD] = fma(-s[i + j * DLD], lkj, s[i + k * DLD]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *logdet_part = 2.0 * ld_acc;
+    // L back to global (strict upper part of the diagonal block zeroed)
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx % NB, j = idx / NB;
+        A[i + (int64_t)j * ld] = (i >= j) ? s[i + j * DLD] : 0.0;
+    }
+    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2 order):
+    //   X[j,j] = 1 / L[j,j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j,j]
+    const int row = tid & (NB - 1), half = tid >> 7;
+    for (int j = NB - 1; j >= 0; j--) {
+        if (tid < NB) colv[tid] = (tid > j) ? s[tid + j * DLD] : 0.0;
+        __syncthreads();
+        double p = 0.0;
+        if (row > j) {
+            const int len = row - j;               // k = j+1 .. row
+            const int mid = j + 1 + (len + 1) / 2;
+            const int k0 = half ? mid : j + 1, k1 = half ? row + 1 : mid;
+            for (int k = k0; k < k1; k++) p = fma(s[row + k * DLD], colv[k], p);
+        }
+        psum[half * NB + row] = p;
+        __syncthreads();
+        if (tid < NB) {
+            const double xjj = 1.0 / s[j + j * DLD];
+            if (tid == j) s[j + j * DLD] = xjj;
+            else if (tid > j) s[tid + j * DLD] = -(psum[tid] + psum[NB + tid]) * xjj;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx % NB, j = idx / NB;
+        dinv[i + j * NB] = (i >= j) ? s[i + j * DLD] : 0.0;
+    }
+}
+
+__global__ void sum_parts_kernel(const double *parts, int n, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += parts[i];
+        *out = s;
+    }
+}
+
+int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, int *info, double *logdet)
+{
+    static bool configured = false;
+    const size_t smem = sizeof(double) * (NB * DLD + 3 * NB);
+    if (!configured) {
+        SRGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int nb = mp / NB;
+    // logdet partials live at the tail of dinv (caller allocates mp*NB + nb doubles)
+    double *parts = dinv + (size_t)mp * NB;
+    for (int kb = 0; kb < nb; kb++) {
+        double *Akk = A + (size_t)kb * NB * ((size_t)mp + 1);
+        double *Dk = dinv + (size_t)kb * NB * NB;
+        {
+            KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+            potrf_diag_kernel<<<1, 256, smem, s>>>(Akk, mp, kb * NB, m, Dk, info, parts + kb);
+            SRGP_LAUNCH_CHECK();
+        }
+        const int Mr = mp - (kb + 1) * NB;
+        if (Mr > 0) {
+            double *A21 = Akk + NB;
+            double *A22 = Akk + NB * ((size_t)mp + 1);
+            // L21 = A21 * L11^-T  (in place: a CTA reads its 128 rows completely before writing them)
+            SRGP_TRY(gemm(ctx, s, 'N', 'T', Mr, NB, NB, 1.0, A21, mp, Dk, NB, 0.0, A21, mp));
+            // A22 -= L21 L21^T on the lower block triangle
+            SRGP_TRY(gemm(ctx, s, 'N', 'T', Mr, Mr, NB, -1.0, A21, mp, A21, mp, 1.0, A22, mp, BatchDesc(), true));
+        }
+    }
+    {
+        KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+        sum_parts_kernel<<<1, 32, 0, s>>>(parts, nb, logdet);
+        SRGP_LAUNCH_CHECK();
+    }
+    return SRGP_OK;
+}
+
+__global__ void scatter_diag_blocks_kernel(const double *__restrict__ dinv, double *__restrict__ Linv, int mp)
+{
+    // one CTA per diagonal block
+    const int kb = blockIdx.x;
+    const double *src = dinv + (size_t)kb * NB * NB;
+    double *dst = Linv + (size_t)kb * NB * ((size_t)mp + 1);
+    for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+        const int i = idx % NB, j = idx / NB;
+        dst[i + (size_t)j * mp] = src[i + j * NB];
+    }
+}
+
+int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *dinv, double *Linv, double *tmp)
+{
+    const int nb = mp / NB;
+    SRGP_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)mp * mp, s));
+    {
+        KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+        scatter_diag_blocks_kernel<<<nb, 256, 0, s>>>(dinv, Linv, mp);
+        SRGP_LAUNCH_CHECK();
+    }
+    const int64_t ld = mp;
+    auto at = [&](const double *base, int rb, int cb) { return base + (size_t)rb * NB + (size_t)cb * NB * ld; };
+    // recursive doubling over blocks of s128 * 128:  X21 = -X22 * (L21 * X11)
+    for (int sblk = 1; sblk < nb; sblk *= 2) {
+        const int full = nb / (2 * sblk);
+        if (full > 0) {
+            BatchDesc bd;
+            bd.batch = full;
+            bd.strideA = bd.strideB = bd.strideC = (int64_t)2 * sblk * NB * (ld + 1);
+            const int S = sblk * NB;
+            SRGP_TRY(gemm(ctx, s, 'N', 'N', S, S, S, 1.0, at(L, sblk, 0), ld, at(Linv, 0, 0), ld, 0.0,
+                          const_cast<double *>(at(tmp, sblk, 0)), ld, bd));
+            SRGP_TRY(gemm(ctx, s, 'N', 'N', S, S, S, -1.0, at(Linv, sblk, sblk), ld, at(tmp, sblk, 0), ld, 0.0,
+                          const_cast<double *>(at(Linv, sblk, 0)), ld, bd));
+        }
+        const int b0 = full * 2 * sblk, rem = nb - b0;
+        if (rem > sblk) {   // partial pair: left block of sblk, right block of rem - sblk
+            const int S = sblk * NB, Mr = (rem - sblk) * NB;
+            SRGP_TRY(gemm(ctx, s, 'N', 'N', Mr, S, S, 1.0, at(L, b0 + sblk, b0), ld, at(Linv, b0, b0), ld, 0.0,
+                          const_cast<double *>(at(tmp, b0 + sblk, b0)), ld));
+            SRGP_TRY(gemm(ctx, s, 'N', 'N', Mr, S, Mr, -1.0, at(Linv, b0 + sblk, b0 + sblk), ld,
+                          at(tmp, b0 + sblk, b0), ld, 0.0, const_cast<double *>(at(Linv, b0 + sblk, b0)), ld));
+        }
+    }
+    return SRGP_OK;
+}
+
+int lauum(srgp_ctx *ctx, cudaStream_t s, const double *Linv, int mp, double *Ainv)
+{
+    return gemm(ctx, s, 'T', 'N', mp, mp, mp, 1.0, Linv, mp, Linv, mp, 0.0, Ainv, mp);
+}
+
+int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *tmp,
+                 double *Ainv, int *info, double *logdet)
+{
+    SRGP_TRY(potrf(ctx, s, A, mp, m, dinv, info, logdet));
+    SRGP_TRY(trtri(ctx, s, A, mp, dinv, Linv, tmp));
+    return lauum(ctx, s, Linv, mp, Ainv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_identity_kernel(double *A, int mp, int m, double v)
+{
+    const int64_t total = (int64_t)mp * mp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % mp), j = (int)(idx / mp);
+        if (i >= m || j >= m) A[idx] = (i == j) ? v : 0.0;
+    }
+}
+
+int pad_identity(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double v)
+{
+    if (mp == m) return SRGP_OK;
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    pad_identity_kernel<<<ctx->sm_count, 256, 0, s>>>(A, mp, m, v);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+__global__ void axpby_kernel(int mp, int m, double a, const double *__restrict__ A, double b,
+                             const double *__restrict__ B, double add_diag, double *__restrict__ C)
+{
+    const int64_t total = (int64_t)mp * mp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % mp), j = (int)(idx / mp);
+        double v = a * A[idx];
+        if (b != 0.0) v += b * B[idx];
+        if (i == j && i < m) v += add_diag;
+        C[idx] = v;
+    }
+}
+
+int axpby(srgp_ctx *ctx, cudaStream_t s, int mp, int m, double a, const double *A, double b, const double *B,
+          double add_diag, double *C)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    axpby_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(mp, m, a, A, b, B, add_diag, C);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+__global__ void ger_kernel(int mp, double a, const double *__restrict__ x, const double *__restrict__ y,
+                           double *__restrict__ C)
+{
+    const int64_t total = (int64_t)mp * mp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % mp), j = (int)(idx / mp);
+        C[idx] += a * x[i] * y[j];
+    }
+}
+
+int ger(srgp_ctx *ctx, cudaStream_t s, int mp, double a, const double *x, const double *y, double *C)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    ger_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(mp, a, x, y, C);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+constexpr int GEMV_SPLIT = GEMV_SCRATCH;
+
+__global__ void gemv_partial_kernel(int mp, const double *__restrict__ A, const double *__restrict__ x,
+                                    double *__restrict__ part)
+{
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    const int cols = mp / GEMV_SPLIT, c0 = blockIdx.y * cols;
+    double acc = 0.0;
+    for (int c = c0; c < c0 + cols; c++) acc = fma(A[row + (int64_t)c * mp], x[c], acc);
+    part[blockIdx.y * mp + row] = acc;
+}
+
+__global__ void gemv_finish_kernel(int mp, double alpha, const double *__restrict__ part, double beta,
+                                   const double *__restrict__ y0, double *__restrict__ y)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= mp) return;
+    double acc = 0.0;
+    for (int sidx = 0; sidx < GEMV_SPLIT; sidx++) acc += part[sidx * mp + row];
+    double v = alpha * acc;
+    if (beta != 0.0) v += beta * y0[row];
+    y[row] = v;
+}
+
+int gemv(srgp_ctx *ctx, cudaStream_t s, int mp, double alpha, const double *A, const double *x, double beta,
+         const double *y0, double *y, double *scratch)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s, 2);
+    gemv_partial_kernel<<<dim3(mp / 128, GEMV_SPLIT), 128, 0, s>>>(mp, A, x, scratch);
+    SRGP_LAUNCH_CHECK();
+    gemv_finish_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(mp, alpha, scratch, beta, y0, y);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+constexpr int DOT_BLOCKS = 128;
+
+__global__ void dot_mm_partial_kernel(int mp, int m, const double *__restrict__ A, const double *__restrict__ B,
+                                      double *__restrict__ part)
+{
+    double acc = 0.0;
+    const int64_t total = (int64_t)mp * m;   // columns j < m
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % mp);
+        if (i < m) acc = fma(A[idx], B[idx], acc);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void sum_small_kernel(const double *__restrict__ part, int n, double *__restrict__ out)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+int dot_mm(srgp_ctx *ctx, cudaStream_t s, int mp, int m, const double *A, const double *B, double *out,
+           double *scratch)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s, 2);
+    dot_mm_partial_kernel<<<DOT_BLOCKS, 256, 0, s>>>(mp, m, A, B, scratch);
+    SRGP_LAUNCH_CHECK();
+    sum_small_kernel<<<1, 128, 0, s>>>(scratch, DOT_BLOCKS, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+__global__ void dot_v_kernel(int m, const double *__restrict__ x, const double *__restrict__ y,
+                             double *__restrict__ out)
+{
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) acc = fma(x[i], y[i], acc);
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+int dot_v(srgp_ctx *ctx, cudaStream_t s, int m, const double *x, const double *y, double *out)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    dot_v_kernel<<<1, 256, 0, s>>>(m, x, y, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+}  // namespace dense
+}  // namespace srgp
+
+// ------------------------------------------------------------------------------------------------
+// test hooks (declared in srgp_internal.h; not part of the drop-in ABI)
+// ------------------------------------------------------------------------------------------------
+#include "srgp_internal.h"
+using namespace srgp;
+
+extern "C" int srgp_test_gemm(srgp_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha,
+                              const double *A, int lda, const double *B, int ldb, double beta, double *C, int ldc,
+                              int lower_only, int reps, double *ms_out)
+{
+    SRGP_TRY(use_device(ctx));
+    const size_t a_elems = (size_t)lda * (transA ? M : K), b_elems = (size_t)ldb * (transB ? K : N);
+    const size_t c_elems = (size_t)ldc * N;
+    DevBuf dA, dB, dC;
+    SRGP_TRY(dA.reserve(a_elems * 8));
+    SRGP_TRY(dB.reserve(b_elems * 8));
+    SRGP_TRY(dC.reserve(c_elems * 8));
+    // stream-ordered copies: ctx->stream is non-blocking, so legacy-stream cudaMemcpy would not order with it
+    SRGP_CUDA(cudaMemcpyAsync(dA.p, A, a_elems * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SRGP_CUDA(cudaMemcpyAsync(dB.p, B, b_elems * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SRGP_CUDA(cudaMemcpyAsync(dC.p, C, c_elems * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int st = dense::gemm(ctx, ctx->stream, transA ? 'T' : 'N', transB ? 'T' : 'N', M, N, K, alpha, dA.d(), lda,
+                         dB.d(), ldb, beta, dC.d(), ldc, dense::BatchDesc(), lower_only != 0);
+    if (st == SRGP_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("gemm failed: %s", cudaGetErrorString(e));
+            st = SRGP_ERR_CUDA;
+        }
+    }
+    if (st == SRGP_OK) {
+        SRGP_CUDA(cudaMemcpyAsync(C, dC.p, c_elems * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (st == SRGP_OK && reps > 0 && ms_out) {
+        // timing run (result discarded): beta = 0 so repeated launches are idempotent
+        SRGP_CUDA(cudaEventRecord(ctx->tim0, ctx->stream));
+        for (int r = 0; r < reps; r++)
+            dense::gemm(ctx, ctx->stream, transA ? 'T' : 'N', transB ? 'T' : 'N', M, N, K, alpha, dA.d(), lda, dB.d(),
+                        ldb, 0.0, dC.d(), ldc, dense::BatchDesc(), lower_only != 0);
+        SRGP_CUDA(cudaEventRecord(ctx->tim1, ctx->stream));
+        SRGP_CUDA(cudaEventSynchronize(ctx->tim1));
+        float f;
+        SRGP_CUDA(cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1));
+        *ms_out = f / reps;
+    }
+    dA.release();
+    dB.release();
+    dC.release();
+    return st;
+}
+
+extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, double *L_out, double *Ainv_out,
+                                      double *logdet_out, int *info_out, int reps, double *ms_out)
+{
+    SRGP_TRY(use_device(ctx));
+    const int mp = (int)round_up(m, dense::NB);
+    const size_t mm = (size_t)mp * mp;
+    DevBuf dA, dA0, dDinv, dLinv, dTmp, dAinv, dMisc;
+    SRGP_TRY(dA.reserve(mm * 8));
+    SRGP_TRY(dA0.reserve(mm * 8));
+    SRGP_TRY(dDinv.reserve(((size_t)mp * dense::NB + mp / dense::NB) * 8));
+    SRGP_TRY(dLinv.reserve(mm * 8));
+    SRGP_TRY(dTmp.reserve(mm * 8));
+    SRGP_TRY(dAinv.reserve(mm * 8));
+    SRGP_TRY(dMisc.reserve(64));
+    SRGP_CUDA(cudaMemsetAsync(dA0.p, 0, mm * 8, ctx->stream));
+    SRGP_CUDA(cudaMemcpy2DAsync(dA0.p, (size_t)mp * 8, A, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    int *info = reinterpret_cast<int *>(dMisc.d() + 1);
+    double *logdet = dMisc.d();
+    int st = SRGP_OK;
+    const int total = 1 + (reps > 0 ? reps : 0);
+    for (int r = 0; r < total && st == SRGP_OK; r++) {
+        if (r == 1) cudaEventRecord(ctx->tim0, ctx->stream);
+        cudaMemcpyAsync(dA.p, dA0.p, mm * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemsetAsync(dMisc.p, 0, 64, ctx->stream);
+        st = dense::pad_identity(ctx, ctx->stream, dA.d(), mp, m, 1.0);
+        if (st == SRGP_OK)
+            st = dense::chol_inverse(ctx, ctx->stream, dA.d(), mp, m, dDinv.d(), dLinv.d(), dTmp.d(), dAinv.d(), info,
+                                     logdet);
+    }
+    if (st == SRGP_OK && reps > 0) {
+        cudaEventRecord(ctx->tim1, ctx->stream);
+        cudaEventSynchronize(ctx->tim1);
+        float f = 0.f;
+        cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1);
+        if (ms_out) *ms_out = f / reps;
+    }
+    if (st == SRGP_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("chol_inverse failed: %s", cudaGetErrorString(e));
+            st = SRGP_ERR_CUDA;
+        }
+    }
+    if (st == SRGP_OK) {
+        if (L_out)
+            cudaMemcpy2DAsync(L_out, (size_t)m * 8, dA.p, (size_t)mp * 8, (size_t)m * 8, m, cudaMemcpyDeviceToHost,
+                              ctx->stream);
+        if (Ainv_out)
+            cudaMemcpy2DAsync(Ainv_out, (size_t)m * 8, dAinv.p, (size_t)mp * 8, (size_t)m * 8, m,
+                              cudaMemcpyDeviceToHost, ctx->stream);
+        double misc[8];
+        cudaMemcpyAsync(misc, dMisc.p, 64, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (logdet_out) *logdet_out = misc[0];
+        if (info_out) *info_out = *reinterpret_cast<int *>(&misc[1]);
+    }
+    DevBuf *bufs[] = {&dA, &dA0, &dDinv, &dLinv, &dTmp, &dAinv, &dMisc};
+    for (auto *b : bufs) b->release();
+    return st;
+}

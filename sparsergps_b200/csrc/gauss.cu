@@ -1,0 +1,953 @@
+// gauss.cu -- fused objective + gradient of the sparse Gaussian models on the resident row shard.
+//
+//   model VI  : elbo_fun (reference R/vi_functions.R:64-121) + delbo_dcov_par (:126-420)
+//   model FIC : obj_fun_norm (R/laplace_approx_obj_funs.R:6-52) + dlogp_dcov_par (R/laplace_approx_gradient.R:720-968)
+//
+// The reference materialises Sigma12 twice and d+2 derivative matrices per evaluation and runs ~13 n x m x m
+// products per parameter.  Here everything n-dependent is two streaming passes over the rows (DESIGN.md
+// section 3; algebra checked against the literal transcription in oracle/ by tests/test_oracle.py):
+//
+//   pass 1   G1 = K^T K (SYRK on DMMA), b1 = K^T r, s0 = r^T r                      -> one allreduce
+//   m x m    chol(S), S^-1, chol(S + G), C, v, beta, M, N, log-dets                  (replicated)
+//   pass 2   T = K Mop (DMMA), Omega = T + a beta^T, sum_ij Omega_ij dK_ij(theta)    -> one allreduce
+//
+// K is generated in row chunks that stay L2-resident between the generator and the DMMA kernel (the FP64
+// pipe is shared by DFMA and DMMA on sm_100 -- profiles/r01_microbench.json -- so each K entry is generated
+// exactly once per pass instead of once per output tile); K never exists as an n x m matrix.
+#include <math.h>
+
+#include "common.cuh"
+#include "dense.cuh"
+#include "gauss.cuh"
+#include "gemm.cuh"
+
+namespace srgp {
+
+using namespace gemm;
+
+// ------------------------------------------------------------------------------------------------
+// generators
+// ------------------------------------------------------------------------------------------------
+// Row-major chunk for pass 1: Kr[i][j] = k(x_{r0+i}, u_j), leading dimension mp (knots contiguous).
+// One thread per knot, rows streamed through shared memory; also accumulates b1_j += K_ij r_i into this
+// CTA's own slot of b1part (read-modify-write across the chunk launches of one pass, deterministic).
+constexpr int GEN_ROWS_TILE = 32;
+
+template <int DT>
+__global__ void __launch_bounds__(128)
+gen_rowmajor_kernel(const double *__restrict__ X, int64_t ldx, const double *__restrict__ r, int64_t r0,
+                    int rows_valid, int rows_padded, const double *__restrict__ U, int m, int mp, int d_rt,
+                    GenParams p, double *__restrict__ Kr, double *__restrict__ b1part, int first)
+{
+    extern __shared__ double sx[];   // [GEN_ROWS_TILE][d] scaled rows, then [GEN_ROWS_TILE] residuals
+    const int d = DT > 0 ? DT : d_rt;
+    double *sr = sx + GEN_ROWS_TILE * d;
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const bool jvalid = j < m;
+    double uj[DT > 0 ? DT : 1];
+    if (DT > 0) {
+#pragma unroll
+        for (int c = 0; c < DT; c++) uj[c] = jvalid ? U[j + (int64_t)m * c] * p.invl[c] : 0.0;
+    }
+    const int rows_per_group = (rows_padded + gridDim.y - 1) / gridDim.y;
+    const int i_begin = blockIdx.y * rows_per_group;
+    const int i_end = min(rows_padded, i_begin + rows_per_group);
+    double bacc = 0.0;
+    for (int it0 = i_begin; it0 < i_end; it0 += GEN_ROWS_TILE) {
+        const int nt = min(GEN_ROWS_TILE, i_end - it0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt * d; t += 128) {
+            const int ii = t / d, c = t - ii * d;
+            const int i = it0 + ii;
+            sx[t] = (i < rows_valid) ? X[r0 + i + ldx * c] * p.invl[c] : 0.0;
+        }
+        if (threadIdx.x < nt) {
+            const int i = it0 + threadIdx.x;
+            sr[threadIdx.x] = (i < rows_valid) ? r[r0 + i] : 0.0;
+        }
+        __syncthreads();
+        for (int ii = 0; ii < nt; ii++) {
+            const int i = it0 + ii;
+            double k = 0.0;
+            if (jvalid && i < rows_valid) {
+                double s = 0.0;
+                if (DT > 0) {
+#pragma unroll
+                    for (int c = 0; c < DT; c++) {
+                        const double t = sx[ii * DT + c] - uj[c];
+                        s = fma(t, t, s);
+                    }
+                } else {
+                    for (int c = 0; c < d; c++) {
+                        const double t = sx[ii * d + c] - U[j + (int64_t)m * c] * p.invl[c];
+                        s = fma(t, t, s);
+                    }
+                }
+                k = p.sigma2 * exp(-0.5 * s);
+                bacc = fma(k, sr[ii], bacc);
+            }
+            Kr[(int64_t)i * mp + j] = k;
+        }
+    }
+    double *slot = b1part + (int64_t)blockIdx.y * mp + j;
+    *slot = first ? bacc : (*slot + bacc);
+}
+
+// Column-major chunk for pass 2: Kc[i + j*ldc] (rows contiguous); one thread per row, knots via shared memory.
+constexpr int GENC_ROWS = 256;
+constexpr int GENC_COLS = 32;
+
+template <int DT>
+__global__ void __launch_bounds__(GENC_ROWS)
+gen_colmajor_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0, int rows_valid, int rows_padded,
+                    const double *__restrict__ U, int m, int mp, int d_rt, GenParams p, double *__restrict__ Kc,
+                    int64_t ldc)
+{
+    extern __shared__ double su[];   // [GENC_COLS][d] scaled knots
+    const int d = DT > 0 ? DT : d_rt;
+    const int i = blockIdx.x * GENC_ROWS + threadIdx.x;
+    const bool ivalid = i < rows_valid;
+    double xi[DT > 0 ? DT : 1];
+    if (DT > 0) {
+#pragma unroll
+        for (int c = 0; c < DT; c++) xi[c] = ivalid ? X[r0 + i + ldx * c] * p.invl[c] : 0.0;
+    }
+    const int col_tiles = mp / GENC_COLS;
+    for (int jt = blockIdx.y; jt < col_tiles; jt += gridDim.y) {
+        const int j0 = jt * GENC_COLS;
+        __syncthreads();
+        for (int t = threadIdx.x; t < GENC_COLS * d; t += GENC_ROWS) {
+            const int jj = t / d, c = t - jj * d;
+            su[t] = (j0 + jj < m) ? U[j0 + jj + (int64_t)m * c] * p.invl[c] : 0.0;
+        }
+        __syncthreads();
+        if (i >= rows_padded) continue;
+#pragma unroll 4
+        for (int jj = 0; jj < GENC_COLS; jj++) {
+            double k = 0.0;
+            if (ivalid && j0 + jj < m) {
+                double s = 0.0;
+                if (DT > 0) {
+#pragma unroll
+                    for (int c = 0; c < DT; c++) {
+                        const double t = xi[c] - su[jj * DT + c];
+                        s = fma(t, t, s);
+                    }
+                } else {
+                    for (int c = 0; c < d; c++) {
+                        const double t = X[r0 + i + ldx * c] * p.invl[c] - su[jj * d + c];
+                        s = fma(t, t, s);
+                    }
+                }
+                k = p.sigma2 * exp(-0.5 * s);
+            }
+            Kc[i + (int64_t)(j0 + jj) * ldc] = k;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: SYRK over a row-major chunk, lower block triangle, split over the chunk's rows
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_to_tiles(int pair, int &tm, int &tn)
+{
+    // pair = tm (tm + 1) / 2 + tn, tn <= tm
+    tm = (int)((sqrtf(8.0f * pair + 1.0f) - 1.0f) * 0.5f);
+    while ((tm + 1) * (tm + 2) / 2 <= pair) tm++;
+    while (tm * (tm + 1) / 2 > pair) tm--;
+    tn = pair - tm * (tm + 1) / 2;
+}
+
+template <bool WEIGHT>
+__global__ void __launch_bounds__(THREADS, 1)
+syrk_chunk_kernel(const double *__restrict__ Kr, int mp, const double *__restrict__ w, int ktiles_per_split,
+                  double *__restrict__ Gpart, int first)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    int tm, tn;
+    pair_to_tiles(blockIdx.x, tm, tn);
+    const int split = blockIdx.y;
+    const int64_t k0 = (int64_t)split * ktiles_per_split * BK;
+    const double *A = Kr + (int64_t)tm * BM + k0 * mp;
+    const double *B = Kr + (int64_t)tn * BN + k0 * mp;
+    pipeline_init(sm);
+    double acc[8][4][2];
+    zero_acc(acc);
+    uint32_t it = 0;
+    mainloop<false, false, WEIGHT>(sm, A, mp, B, mp, WEIGHT ? w + k0 : nullptr, ktiles_per_split, it, acc);
+    if (is_producer()) return;
+    // accumulate into this CTA's own slot, stored in fragment order (fully coalesced)
+    double *slot = Gpart + ((int64_t)blockIdx.x * gridDim.y + split) * (BM * BN);
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double *p = slot + ((mi * 4 + ni) * 2 + e) * CONSUMER_THREADS + threadIdx.x;
+                *p = first ? acc[mi][ni][e] : (*p + acc[mi][ni][e]);
+            }
+}
+
+// Sum the split slots and scatter to the full symmetric matrix (both triangles).
+__global__ void __launch_bounds__(CONSUMER_THREADS)
+syrk_finalize_kernel(const double *__restrict__ Gpart, int splits, int mp, double *__restrict__ G)
+{
+    int tm, tn;
+    pair_to_tiles(blockIdx.x, tm, tn);
+    const double *base = Gpart + (int64_t)blockIdx.x * splits * (BM * BN);
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int off = ((mi * 4 + ni) * 2 + e) * CONSUMER_THREADS + threadIdx.x;
+                double v = 0.0;
+                for (int s = 0; s < splits; s++) v += base[(int64_t)s * (BM * BN) + off];
+                const int r = tm * BM + frag_row(mi), c = tn * BN + frag_col(ni) + e;
+                G[r + (int64_t)c * mp] = v;
+                if (tm != tn) G[c + (int64_t)r * mp] = v;
+                else if (r != c) { /* diagonal tile: both (r,c) and (c,r) are produced by this tile itself */ }
+            }
+}
+
+__global__ void sum_rows_kernel(const double *__restrict__ part, int groups, int mp, double *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mp) return;
+    double s = 0.0;
+    for (int g = 0; g < groups; g++) s += part[(int64_t)g * mp + j];
+    out[j] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: T = K * Mop on DMMA, then the fused "never materialise dK" reduction
+//   Omega_ij = rs_i * T_ij + ra_i * beta_j ;  P_ij = Omega_ij * K_ij
+//   out[0] += sum P_ij                      (d/dlog sigma = 2 * this)
+//   out[1 + c] += sum P_ij * ((x_ic - u_jc) / l_c)^2      (d/dlog l_c)
+//   out[1 + d] += sum over bit-identical (x_i, u_j) pairs of Omega_ij   (quirk Q4 tau term; pairs are also
+//                 appended to coin_list so the caller can add the (K S^-1)_ij part)
+// Each CTA owns one slot of `part` ([gridDim.x * gridDim.y][PART_STRIDE]) accumulated across chunk launches.
+// ------------------------------------------------------------------------------------------------
+constexpr int PART_STRIDE = SRGP_MAX_D + 8;
+
+struct KmArgs {
+    const double *Kc;       // chunk, column-major, ld = ldc
+    int64_t ldc;
+    const double *Mop;      // mp x mp, element (n = j', k = j) at j' + j*mp
+    int mp, m, d;
+    const double *X;        // resident rows (column-major, ld = ldx), chunk starts at r0
+    int64_t ldx, r0;
+    int rows_valid;
+    const double *U;        // m x d
+    const double *rs;       // per global row scale of T (null = 1)
+    const double *ra;       // per global row coefficient of beta (null = 0)
+    const double *beta;     // mp
+    double invl[SRGP_MAX_D];
+    int col_blocks_per_cta;
+    double *part;
+    int first;
+    int *coin_count;        // device counter
+    int *coin_list;         // (i_global_lo, j) pairs, capacity coin_cap
+    double *coin_omega;
+    int coin_cap;
+};
+
+
+template <int DT>
+__global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    // only the first d rows of xs / us are used; the struct is sized for SRGP_MAX_D but allocated for d
+    double *xs = reinterpret_cast<double *>(smem_raw + sizeof(Smem));
+    double *us = xs + a.d * BM;
+    double *red = us + a.d * BN;
+    const int d = DT > 0 ? DT : a.d;
+    const int rb = blockIdx.x;
+    const int i0 = rb * BM;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    pipeline_init(sm);
+    // stage the scaled rows of this row block once
+    for (int t = tid; t < d * BM; t += THREADS) {
+        const int c = t / BM, ii = t - c * BM;
+        const int i = i0 + ii;
+        xs[c * BM + ii] = (i < a.rows_valid) ? a.X[a.r0 + i + a.ldx * c] * a.invl[c] : 0.0;
+    }
+    if (!is_producer())
+        for (int t = lane; t < PART_STRIDE; t += 32) red[warp * PART_STRIDE + t] = 0.0;
+    __syncthreads();
+
+    uint32_t it = 0;
+    const int cb0 = blockIdx.y * a.col_blocks_per_cta;
+    for (int cbi = 0; cbi < a.col_blocks_per_cta; cbi++) {
+        const int cb = cb0 + cbi;
+        const int j0 = cb * BN;
+        double acc[8][4][2];
+        zero_acc(acc);
+        mainloop<false, false, false>(sm, a.Kc + i0, a.ldc, a.Mop + j0, a.mp, nullptr, a.mp / BK, it, acc);
+        // stage this column block's knots (all 288 threads), consumers then run the epilogue
+        __syncthreads();
+        for (int t = tid; t < d * BN; t += THREADS) {
+            const int c = t / BN, jj = t - c * BN;
+            const int j = j0 + jj;
+            us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
+        }
+        __syncthreads();
+        if (!is_producer()) {
+            // P = Omega * K in place
+            unsigned long long eqmask = 0ull;
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                const int ii = frag_row(mi);
+                const int64_t ig = a.r0 + i0 + ii;
+                const bool iv = (i0 + ii) < a.rows_valid;
+                const double rsi = (a.rs && iv) ? a.rs[ig] : 1.0;
+                const double rai = (a.ra && iv) ? a.ra[ig] : 0.0;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    const int jj = frag_col(ni);
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int j = j0 + jj + e;
+                        const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                        const double om = fma(rsi, acc[mi][ni][e], rai * a.beta[j]);
+                        acc[mi][ni][e] = om * k;
+                        if (iv && j < a.m) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
+                    }
+                }
+            }
+            double s0 = 0.0;
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) s0 += acc[mi][ni][0] + acc[mi][ni][1];
+            // per-dimension weighted sums
+            for (int c = 0; c < d; c++) {
+                double xv[8], uv[4][2];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++) xv[mi] = xs[c * BM + frag_row(mi)];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    uv[ni][0] = us[c * BN + frag_col(ni)];
+                    uv[ni][1] = us[c * BN + frag_col(ni) + 1];
+                }
+                double sc = 0.0;
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const double t = xv[mi] - uv[ni][e];
+                            sc = fma(acc[mi][ni][e], t * t, sc);
+                            if (t != 0.0) eqmask &= ~(1ull << ((mi * 4 + ni) * 2 + e));
+                        }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+                if (lane == 0) red[warp * PART_STRIDE + 1 + c] += sc;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            if (lane == 0) red[warp * PART_STRIDE + 0] += s0;
+            // quirk Q4: bit-identical data row / knot pairs (rare): record them for the tau derivative
+            if (eqmask) {
+                for (int mi = 0; mi < 8; mi++)
+                    for (int ni = 0; ni < 4; ni++)
+                        for (int e = 0; e < 2; e++)
+                            if (eqmask & (1ull << ((mi * 4 + ni) * 2 + e))) {
+                                const int ii = frag_row(mi), j = j0 + frag_col(ni) + e;
+                                const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                                const double om = acc[mi][ni][e] / k;   // k = sigma^2 > 0 for identical points
+                                const int slot = atomicAdd(a.coin_count, 1);
+                                if (slot < a.coin_cap) {
+                                    a.coin_list[2 * slot] = (int)(a.r0 + i0 + ii);
+                                    a.coin_list[2 * slot + 1] = j;
+                                    a.coin_omega[slot] = om;
+                                }
+                            }
+            }
+        }
+    }
+    __syncthreads();
+    // CTA reduction over the 8 consumer warps -> this CTA's slot
+    if (tid < 1 + d) {
+        double v = 0.0;
+        for (int w = 0; w < CONSUMER_WARPS; w++) v += red[w * PART_STRIDE + tid];
+        double *slot = a.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * PART_STRIDE + tid;
+        *slot = a.first ? v : (*slot + v);
+    }
+}
+
+__global__ void sum_part_kernel(const double *__restrict__ part, int slots, int stride, int count,
+                                double *__restrict__ out)
+{
+    // one warp per output entry
+    const int e = blockIdx.x;
+    if (e >= count) return;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < slots; i += 32) s += part[(int64_t)i * stride + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[e] = s;
+}
+
+// sum_jk N_jk dS_jk(theta) over the m x m knot block, dS generated on the fly from S = K_uu + nugget I:
+//   out[0] = sum N * Kuu (d/dlog sigma = 2 x),  out[1 + c] = sum N * Kuu * ((u_jc - u_kc) / l_c)^2,
+//   out[1 + d] = sum over bit-identical knot pairs (incl. j == k) of N_jk   (tau term for the Laplace models)
+constexpr int NS_BLOCKS = 128;
+__global__ void __launch_bounds__(256)
+ns_reduce_kernel(const double *__restrict__ N, const double *__restrict__ S, int mp, int m, int d,
+                 const double *__restrict__ U, GenParams p, double nugget, double *__restrict__ part)
+{
+    __shared__ double red[8][PART_STRIDE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = lane; t < PART_STRIDE; t += 32) red[warp][t] = 0.0;
+    __syncwarp();
+    const int64_t total = (int64_t)m * m;
+    double s0 = 0.0, seq = 0.0;
+    // each warp walks 32 consecutive entries at a time; per-dimension sums are reduced per step
+    for (int64_t base = ((int64_t)blockIdx.x * 8 + warp) * 32; base < total; base += (int64_t)gridDim.x * 8 * 32) {
+        const int64_t idx = base + lane;
+        double nk = 0.0;
+        int j = 0, k = 0;
+        bool valid = idx < total;
+        if (valid) {
+            j = (int)(idx % m);
+            k = (int)(idx / m);
+            const double kuu = S[j + (int64_t)k * mp] - (j == k ? nugget : 0.0);
+            nk = N[j + (int64_t)k * mp] * kuu;
+        }
+        s0 += nk;
+        bool alleq = valid;
+        for (int c = 0; c < d; c++) {
+            double t = 0.0;
+            if (valid) {
+                const double a = U[j + (int64_t)m * c], b = U[k + (int64_t)m * c];
+                if (a != b) alleq = false;
+                t = (a - b) * p.invl[c];
+            }
+            double sc = nk * t * t;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            if (lane == 0) red[warp][1 + c] += sc;
+        }
+        if (alleq) seq += N[j + (int64_t)k * mp];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        seq += __shfl_xor_sync(0xffffffffu, seq, o);
+    }
+    if (lane == 0) {
+        red[warp][0] = s0;
+        red[warp][1 + d] = seq;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 + d) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+        part[(int64_t)blockIdx.x * PART_STRIDE + threadIdx.x] = v;
+    }
+}
+
+__global__ void residual_kernel(const double *__restrict__ y, const double *__restrict__ mu, int64_t n,
+                                double *__restrict__ r, double *__restrict__ part)
+{
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = y[i] - (mu ? mu[i] : 0.0);
+        r[i] = v;
+        acc = fma(v, v, acc);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) part[blockIdx.x] = acc;
+    }
+}
+
+__global__ void scale_vec_kernel(const double *__restrict__ x, int64_t n, double a, double *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = a * x[i];
+}
+
+// y = a * x + b * z (length n; z may be null)
+__global__ void axpby_vec_kernel(int n, double a, const double *__restrict__ x, double b,
+                                 const double *__restrict__ z, double *__restrict__ y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x[i] + (z ? b * z[i] : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+GaussWS *gauss_ws(srgp_ctx *ctx)
+{
+    if (!ctx->ws) {
+        ctx->ws = new GaussWS();
+        ctx->ws_free = [](void *p) {
+            GaussWS *w = static_cast<GaussWS *>(p);
+            w->release();
+            delete w;
+        };
+    }
+    return static_cast<GaussWS *>(ctx->ws);
+}
+
+void GaussWS::release()
+{
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin};
+    for (auto *b : bufs) b->release();
+    if (h_scal) cudaFreeHost(h_scal);
+    h_scal = nullptr;
+}
+
+int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
+{
+    const int mp = (int)round_up(m, BM);
+    if (w->mp == mp && w->m == m && w->d == d && w->planned) return SRGP_OK;
+    w->m = m;
+    w->mp = mp;
+    w->d = d;
+    w->nt = mp / BM;
+    w->pairs = w->nt * (w->nt + 1) / 2;
+    // pass 1: pairs x splits CTAs ~ one wave; chunk ~ 48 MB so it stays in the 126 MB L2 with the Gram slots
+    w->splits = std::max(1, ctx->sm_count / w->pairs);
+    if (w->splits > 64) w->splits = 64;
+    const int64_t target_bytes = int64_t(48) << 20;
+    int64_t rows = target_bytes / (8 * (int64_t)mp);
+    const int quantum = BK * w->splits;
+    rows = std::max<int64_t>(quantum, rows / quantum * quantum);
+    w->rows1 = (int)rows;
+    // pass 2: row blocks x column groups ~ one wave
+    int cg = 1;
+    for (int c : {8, 4, 2}) {
+        if (w->nt % c == 0 && (int64_t)(ctx->sm_count / c) * BM * mp * 8 >= (int64_t(16) << 20)) {
+            cg = c;
+            break;
+        }
+    }
+    if (w->nt % cg) cg = 1;
+    w->cgroups = cg;
+    w->rblocks = std::max(1, ctx->sm_count / cg);
+    w->rows2 = w->rblocks * BM;
+    const size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
+    SRGP_TRY(w->chunk.reserve(chunk_elems * 8));
+    SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));
+    w->gen_groups = std::max(1, std::min(64, (ctx->sm_count * 4) / w->nt));
+    SRGP_TRY(w->b1part.reserve((size_t)w->gen_groups * mp * 8));
+    SRGP_TRY(w->U.reserve((size_t)m * d * 8));
+    SRGP_TRY(w->red1.reserve(((size_t)mp * mp + mp + 16) * 8));
+    SRGP_TRY(w->mats.reserve((size_t)GaussWS::NMATS * mp * mp * 8 + ((size_t)2 * mp * dense::NB + 512) * 8));
+    SRGP_TRY(w->vecs.reserve((size_t)GaussWS::NVECS * mp * 8 + (size_t)dense::GEMV_SCRATCH * mp * 8));
+    SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
+    SRGP_TRY(w->part2.reserve((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE * 8));
+    SRGP_TRY(w->coin.reserve((size_t)GaussWS::COIN_CAP * (2 * sizeof(int) + sizeof(double)) + 64));
+    if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
+    w->planned = true;
+    return SRGP_OK;
+}
+
+void fill_gen(GenParams &p, int kernel, int d, double sigma, const double *l)
+{
+    p.sigma2 = sigma * sigma;
+    for (int c = 0; c < SRGP_MAX_D; c++) p.invl[c] = 0.0;
+    for (int c = 0; c < d; c++) p.invl[c] = 1.0 / (kernel == SRGP_ARD ? l[c] : l[0]);
+}
+
+template <int DT>
+static void launch_gen_rm(cudaStream_t s, dim3 grid, size_t smem, const double *X, int64_t ldx, const double *r,
+                          int64_t r0, int rows_valid, int rows_padded, const double *U, int m, int mp, int d,
+                          const GenParams &p, double *Kr, double *b1part, int first)
+{
+    gen_rowmajor_kernel<DT><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p, Kr, b1part,
+                                                   first);
+}
+
+template <int DT>
+static void launch_gen_cm(cudaStream_t s, dim3 grid, size_t smem, const double *X, int64_t ldx, int64_t r0,
+                          int rows_valid, int rows_padded, const double *U, int m, int mp, int d, const GenParams &p,
+                          double *Kc, int64_t ldc)
+{
+    gen_colmajor_kernel<DT><<<grid, GENC_ROWS, smem, s>>>(X, ldx, r0, rows_valid, rows_padded, U, m, mp, d, p, Kc, ldc);
+}
+
+#define SRGP_D_SWITCH(d, CALL)                       \
+    switch (d) {                                     \
+    case 1: CALL(1); break;                          \
+    case 2: CALL(2); break;                          \
+    case 3: CALL(3); break;                          \
+    case 4: CALL(4); break;                          \
+    case 5: CALL(5); break;                          \
+    case 6: CALL(6); break;                          \
+    case 7: CALL(7); break;                          \
+    case 8: CALL(8); break;                          \
+    default: CALL(0); break;                         \
+    }
+
+// ---- pass 1 ----------------------------------------------------------------------------------------
+// G (mp x mp, both triangles), b1 (mp) <- sums over this shard's rows.  w: optional per-row weight
+// (G = K^T diag(w) K, b1 = K^T (w .* rvec)); rvec: per-row vector multiplied into b1.
+int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
+                double *G, double *b1)
+{
+    cudaStream_t s = ctx->stream;
+    static bool configured = false;
+    if (!configured) {
+        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        configured = true;
+    }
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int quantum = BK * w->splits;
+    int first = 1;
+    if (ctx->n == 0) {
+        SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)w->pairs * w->splits * BM * BN * 8, s));
+        SRGP_CUDA(cudaMemsetAsync(w->b1part.p, 0, (size_t)w->gen_groups * mp * 8, s));
+    }
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
+        const int rows_padded = (int)round_up(rows_valid, quantum);
+        {
+            KernelScope ks(ctx, SRGP_PROF_GEN, s);
+            dim3 grid(mp / 128, w->gen_groups);
+            const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
+#define CALL(D) launch_gen_rm<D>(s, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->chunk.d(), w->b1part.d(), first)
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            SRGP_LAUNCH_CHECK();
+        }
+        {
+            KernelScope ks(ctx, SRGP_PROF_GRAM, s);
+            dim3 grid(w->pairs, w->splits);
+            const int ktiles = rows_padded / quantum;
+            if (rowweight)
+                syrk_chunk_kernel<true><<<grid, THREADS, sizeof(Smem), s>>>(w->chunk.d(), mp, rowweight + r0, ktiles,
+                                                                            w->Gpart.d(), first);
+            else
+                syrk_chunk_kernel<false><<<grid, THREADS, sizeof(Smem), s>>>(w->chunk.d(), mp, nullptr, ktiles,
+                                                                             w->Gpart.d(), first);
+            SRGP_LAUNCH_CHECK();
+        }
+        first = 0;
+    }
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+        syrk_finalize_kernel<<<w->pairs, CONSUMER_THREADS, 0, s>>>(w->Gpart.d(), w->splits, mp, G);
+        SRGP_LAUNCH_CHECK();
+        sum_rows_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->b1part.d(), w->gen_groups, mp, b1);
+        SRGP_LAUNCH_CHECK();
+    }
+    return SRGP_OK;
+}
+
+// ---- pass 2 ----------------------------------------------------------------------------------------
+// out[0 .. d+1] <- sum over this shard's rows (see km_reduce_kernel).
+int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
+                const double *ra, const double *beta, double *out, bool accumulate_slots)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
+    static size_t configured_smem = 0;
+    if (configured_smem < smem) {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        SRGP_D_SWITCH(d, CALL)
+#undef CALL
+        configured_smem = smem;
+    }
+    if (smem > 227 * 1024) {
+        set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
+        return SRGP_ERR_ARG;
+    }
+    const int slots = w->rblocks * w->cgroups;
+    int first = accumulate_slots ? 0 : 1;
+    if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
+        const int rows_padded = w->rows2;   // the K*M kernel always runs all row blocks of the chunk
+        {
+            KernelScope ks(ctx, SRGP_PROF_GEN, s);
+            dim3 grid(ceil_div(rows_padded, GENC_ROWS), std::min(mp / GENC_COLS, 8));
+            const size_t gs = sizeof(double) * GENC_COLS * d;
+#define CALL(D) launch_gen_cm<D>(s, grid, gs, ctx->Xp, ctx->n, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->chunk.d(), (int64_t)w->rows2)
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            SRGP_LAUNCH_CHECK();
+        }
+        {
+            KernelScope ks(ctx, SRGP_PROF_KM, s);
+            KmArgs a;
+            a.Kc = w->chunk.d();
+            a.ldc = w->rows2;
+            a.Mop = Mop;
+            a.mp = mp;
+            a.m = m;
+            a.d = d;
+            a.X = ctx->Xp;
+            a.ldx = ctx->n;
+            a.r0 = r0;
+            a.rows_valid = rows_valid;
+            a.U = w->U.d();
+            a.rs = rs;
+            a.ra = ra;
+            a.beta = beta;
+            for (int c = 0; c < SRGP_MAX_D; c++) a.invl[c] = gp.invl[c];
+            a.col_blocks_per_cta = w->nt / w->cgroups;
+            a.part = w->part2.d();
+            a.first = first;
+            a.coin_count = reinterpret_cast<int *>(w->coin.p);
+            a.coin_list = reinterpret_cast<int *>(w->coin.p) + 16;
+            a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
+                                                      (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
+            a.coin_cap = GaussWS::COIN_CAP;
+            dim3 grid(w->rblocks, w->cgroups);
+#define CALL(D) km_reduce_kernel<D><<<grid, THREADS, smem, s>>>(a)
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            SRGP_LAUNCH_CHECK();
+        }
+        first = 0;
+    }
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        sum_part_kernel<<<d + 1, 32, 0, s>>>(w->part2.d(), slots, PART_STRIDE, d + 1, out);
+        SRGP_LAUNCH_CHECK();
+    }
+    return SRGP_OK;
+}
+
+
+// ---- small launchers -----------------------------------------------------------------------------------
+int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
+              double *out)
+{
+    cudaStream_t s = ctx->stream;
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+    ns_reduce_kernel<<<NS_BLOCKS, 256, 0, s>>>(N, S, w->mp, w->m, w->d, w->U.d(), gp, nugget, w->part2.d());
+    SRGP_LAUNCH_CHECK();
+    sum_part_kernel<<<w->d + 2, 32, 0, s>>>(w->part2.d(), NS_BLOCKS, PART_STRIDE, w->d + 2, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+// one warp per recorded pair: val_p = omega_p - coef * sum_k K(x_i, u_k) Sinv[k, j]
+__global__ void __launch_bounds__(256)
+coin_fix_kernel(const int *__restrict__ count, const int *__restrict__ list, const double *__restrict__ omega, int cap,
+                const double *__restrict__ X, int64_t ldx, const double *__restrict__ U, int m, int mp, int d,
+                GenParams p, const double *__restrict__ Sinv, double coef, double *__restrict__ vals)
+{
+    const int lane = threadIdx.x & 31;
+    const int npairs = min(*count, cap);
+    for (int pr = blockIdx.x * 8 + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8) {
+        const int i = list[2 * pr], j = list[2 * pr + 1];
+        double acc = 0.0;
+        for (int k = lane; k < m; k += 32) {
+            double sq = 0.0;
+            for (int c = 0; c < d; c++) {
+                const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
+                sq = fma(t, t, sq);
+            }
+            acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) vals[pr] = omega[pr] - coef * acc;
+    }
+}
+
+__global__ void coin_sum_kernel(const int *__restrict__ count, int cap, const double *__restrict__ vals,
+                                double *__restrict__ out)
+{
+    __shared__ double red[8];
+    const int npairs = min(*count, cap);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < npairs; i += blockDim.x) acc += vals[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w];
+        *out = v;
+    }
+}
+
+int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out)
+{
+    cudaStream_t s = ctx->stream;
+    int *count = reinterpret_cast<int *>(w->coin.p);
+    int *list = count + 16;
+    double *omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
+                                               (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
+    // per-pair values overwrite the omega array in place
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+    coin_fix_kernel<<<64, 256, 0, s>>>(count, list, omega, GaussWS::COIN_CAP, ctx->Xp, ctx->n, w->U.d(), w->m, w->mp,
+                                       w->d, gp, Sinv, coef, omega);
+    SRGP_LAUNCH_CHECK();
+    coin_sum_kernel<<<1, 256, 0, s>>>(count, GaussWS::COIN_CAP, omega, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+int scale_vec(srgp_ctx *ctx, const double *x, int64_t n, double a, double *out)
+{
+    if (n == 0) return SRGP_OK;
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, ctx->stream);
+    scale_vec_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(x, n, a, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+int axpby_vec(srgp_ctx *ctx, int n, double a, const double *x, double b, const double *z, double *y)
+{
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, ctx->stream);
+    axpby_vec_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, a, x, b, z, y);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+__global__ void set_scalar_kernel(double *dst, double v) { *dst = v; }
+__global__ void copy_scalar_kernel(double *dst, const double *src, int count)
+{
+    if (threadIdx.x < count) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+int set_scalar(srgp_ctx *ctx, double *dst, double v)
+{
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, ctx->stream);
+    set_scalar_kernel<<<1, 1, 0, ctx->stream>>>(dst, v);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+int copy_scalar(srgp_ctx *ctx, double *dst, const double *src, int count)
+{
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, ctx->stream);
+    copy_scalar_kernel<<<1, 128, 0, ctx->stream>>>(dst, src, count);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+}  // namespace srgp
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+using namespace srgp;
+
+static int set_data_common(srgp_ctx *ctx, int64_t n, int d)
+{
+    if (!ctx || n < 0 || d <= 0 || d > SRGP_MAX_D) {
+        set_error("bad argument (n = %lld, d = %d, SRGP_MAX_D = %d)", (long long)n, d, SRGP_MAX_D);
+        return SRGP_ERR_ARG;
+    }
+    SRGP_TRY(use_device(ctx));
+    GaussWS *w = gauss_ws(ctx);
+    ctx->n = n;
+    ctx->d = d;
+    SRGP_TRY(w->r.reserve(std::max<size_t>(8, (size_t)n * 8)));
+    SRGP_TRY(w->rowa.reserve(std::max<size_t>(8, (size_t)n * 8 * GaussWS::NROWV)));
+    SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
+    SRGP_TRY(w->part2.reserve((size_t)256 * PART_STRIDE * 8));
+    // residual r = y - mu and s0 = r^T r: independent of theta, computed once per data upload
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, ctx->stream, 2);
+        residual_kernel<<<128, 256, 0, ctx->stream>>>(ctx->yp, ctx->mup, n, w->r.d(), w->part2.d());
+        SRGP_LAUNCH_CHECK();
+        sum_part_kernel<<<1, 32, 0, ctx->stream>>>(w->part2.d(), 128, 1, 1, w->scal.d() + GaussWS::S_S0);
+        SRGP_LAUNCH_CHECK();
+    }
+    ctx->have_data = true;
+    return SRGP_OK;
+}
+
+extern "C" int srgp_set_data(srgp_ctx *ctx, const double *xy, int64_t n, int d, const double *y, const double *mu)
+{
+    if (!ctx || (n > 0 && (!xy || !y))) {
+        set_error("null pointer");
+        return SRGP_ERR_ARG;
+    }
+    SRGP_TRY(use_device(ctx));
+    SRGP_TRY(ctx->X.reserve(std::max<size_t>(8, (size_t)n * d * 8)));
+    SRGP_TRY(ctx->y.reserve(std::max<size_t>(8, (size_t)n * 8)));
+    SRGP_CUDA(cudaMemcpyAsync(ctx->X.p, xy, (size_t)n * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SRGP_CUDA(cudaMemcpyAsync(ctx->y.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->Xp = ctx->X.d();
+    ctx->yp = ctx->y.d();
+    ctx->mup = nullptr;
+    if (mu) {
+        SRGP_TRY(ctx->mu.reserve(std::max<size_t>(8, (size_t)n * 8)));
+        SRGP_CUDA(cudaMemcpyAsync(ctx->mu.p, mu, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->mup = ctx->mu.d();
+    }
+    return set_data_common(ctx, n, d);
+}
+
+extern "C" int srgp_set_data_dev(srgp_ctx *ctx, const double *xy_dev, int64_t n, int d, const double *y_dev,
+                                 const double *mu_dev)
+{
+    if (!ctx || (n > 0 && (!xy_dev || !y_dev))) {
+        set_error("null pointer");
+        return SRGP_ERR_ARG;
+    }
+    ctx->Xp = xy_dev;
+    ctx->yp = y_dev;
+    ctx->mup = mu_dev;
+    return set_data_common(ctx, n, d);
+}
+
+extern "C" int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
+                                   const double *l, double tau, double delta, double *obj, double *grad)
+{
+    if (!ctx || !xu || !l || !obj || m <= 0) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (!ctx->have_data) {
+        set_error("srgp_gauss_obj_grad called before srgp_set_data");
+        return SRGP_ERR_STATE;
+    }
+    if (kernel != SRGP_SQEXP && kernel != SRGP_ARD) {
+        set_error("Error: invalid covariance function (the sparse Gaussian models take \"sqexp\" or \"ard\")");
+        return SRGP_ERR_UNKNOWN_KERNEL;
+    }
+    if (m > 32768) {
+        set_error("m = %lld knots exceeds the supported 32768", (long long)m);
+        return SRGP_ERR_ARG;
+    }
+    SRGP_TRY(use_device(ctx));
+    GaussWS *w = gauss_ws(ctx);
+    SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
+    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (model == SRGP_VI) return gauss_vi(ctx, w, kernel, sigma, l, tau, delta, obj, grad);
+    if (model == SRGP_FIC) return gauss_fic(ctx, w, kernel, sigma, l, tau, delta, obj, grad);
+    set_error("unknown model %d", model);
+    return SRGP_ERR_ARG;
+}
+
+extern "C" int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, const double *xy, int64_t n, int d,
+                                        const double *y, const double *mu, const double *xu, int64_t m,
+                                        double sigma, const double *l, double tau, double delta, double *obj,
+                                        double *grad)
+{
+    SRGP_TRY(srgp_set_data(ctx, xy, n, d, y, mu));
+    return srgp_gauss_obj_grad(ctx, model, kernel, xu, m, sigma, l, tau, delta, obj, grad);
+}

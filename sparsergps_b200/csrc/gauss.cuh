@@ -1,0 +1,87 @@
+// gauss.cuh -- workspace of the fused Gaussian (VI / FIC) and Laplace pipelines.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace srgp {
+
+struct GenParams {
+    double sigma2;                 // sigma^2
+    double invl[SRGP_MAX_D];       // 1 / l_c (sqexp: the same 1 / l in every dimension)
+};
+
+struct GaussWS {
+    // plan (depends on m, d and the SM count)
+    bool planned = false;
+    int m = 0, mp = 0, d = 0, nt = 0, pairs = 0;
+    int splits = 1, rows1 = 0, gen_groups = 1;    // pass 1: SYRK split-K over the chunk rows
+    int cgroups = 1, rblocks = 1, rows2 = 0;      // pass 2: row blocks x column groups
+
+    DevBuf U;        // knots, m x d column-major
+    DevBuf chunk;    // L2-resident K chunk (row-major in pass 1, column-major in pass 2)
+    DevBuf Gpart;    // pass-1 Gram slots [pairs][splits][128*128] in fragment order
+    DevBuf b1part;   // pass-1 K^T r slots [gen_groups][mp]
+    DevBuf red1;     // pass-1 allreduce buffer: [G1 mp*mp | b1 mp | 16 scalars]
+    DevBuf r;        // residual y - mu (n)
+    DevBuf rowa;     // per-row vectors (NROWV x n)
+    DevBuf mats;     // NMATS m x m matrices (ld = mp) + two diagonal-block-inverse areas
+    DevBuf vecs;     // NVECS m-vectors + gemv scratch
+    DevBuf scal;     // device scalars
+    DevBuf part2;    // pass-2 per-CTA partial sums
+    DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
+    double *h_scal = nullptr;   // pinned mirror of scal
+
+    enum { NMATS = 16, NVECS = 12, NROWV = 6, NSCAL = 256, COIN_CAP = 65536 };
+    enum Mat { M_S = 0, M_SINV, M_A, M_C, M_LINV, M_TMP, M_CG, M_CGS, M_SG, M_SGS, M_N, M_MOP, M_T1, M_T2, M_X1, M_X2 };
+    enum Vec { V_B = 0, V_V, V_GV, V_TMP, V_BETA, V_T1, V_T2, V_T3 };
+    enum Scal {
+        S_S0 = 0, S_LOGDET_S, S_LOGDET_A, S_SUMQ, S_TRCG1, S_BV, S_B1V, S_VGV, S_INFO, S_NTOT, S_S0TOT, S_Q4,
+        S_P2 = 32,      // pass-2 sums: 1 + d entries, + q4 at S_P2 + 1 + d  (allreduced together)
+        S_NS = 128,     // N o dS sums: 2 + d entries
+        S_X = 224       // model-specific extras
+    };
+
+    double *mat(int i) const { return mats.d() + (size_t)i * mp * mp; }
+    double *dinv(int which) const { return mats.d() + (size_t)NMATS * mp * mp + (size_t)which * ((size_t)mp * 128 + 256); }
+    double *vec(int i) const { return vecs.d() + (size_t)i * mp; }
+    double *gemv_scratch() const { return vecs.d() + (size_t)NVECS * mp; }
+    double *rowv(int i, int64_t n) const { return rowa.d() + (size_t)i * n; }
+    double *sc(int i) const { return scal.d() + i; }
+    int *info(int which) const { return reinterpret_cast<int *>(scal.d() + S_INFO) + which; }
+    void release();
+};
+
+GaussWS *gauss_ws(srgp_ctx *ctx);
+int plan(srgp_ctx *ctx, GaussWS *w, int m, int d);
+void fill_gen(GenParams &p, int kernel, int d, double sigma, const double *l);
+
+// pass 1 over the resident shard: G (mp x mp, both triangles) = K^T diag(rowweight) K, b1 = K^T (rvec)
+// (rowweight may be null = 1; when given, rvec must already contain the weight).
+int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
+                double *G, double *b1);
+// pass 2: out[0] = sum_ij P_ij, out[1 + c] = sum_ij P_ij ((x_ic - u_jc) / l_c)^2 with
+// P = (rs_i (K Mop^T)_ij + ra_i beta_j) K_ij; bit-identical (row, knot) pairs are appended to w->coin.
+// accumulate_slots: add to the per-CTA slots of a previous gauss_pass2 call instead of restarting them.
+int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
+                const double *ra, const double *beta, double *out, bool accumulate_slots);
+// out[0] = sum N o Kuu, out[1 + c] = sum N o Kuu o D_c, out[1 + d] = sum of N over bit-identical knot pairs
+int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
+              double *out);
+// quirk Q4: *out = sum over recorded pairs of (omega_p - coef * (K S^-1)_{i_p j_p})
+int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
+int scale_vec(srgp_ctx *ctx, const double *x, int64_t n, double a, double *out);
+int axpby_vec(srgp_ctx *ctx, int n, double a, const double *x, double b, const double *z, double *y);
+int set_scalar(srgp_ctx *ctx, double *dst, double v);
+int copy_scalar(srgp_ctx *ctx, double *dst, const double *src, int count);
+
+int comm_allreduce(srgp_ctx *ctx, double *buf, size_t count, cudaStream_t s);
+int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
+             double *obj, double *grad);
+int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
+              double *obj, double *grad);
+// K1 with an explicit output leading dimension (assemble.cu)
+int assemble_dev_ld(srgp_ctx *ctx, cudaStream_t s, int kernel, const double *x_dev, int64_t n1, int d, double sigma,
+                    const double *l, double nugget, double *out_dev, int64_t ldo);
+
+}  // namespace srgp

@@ -1,0 +1,148 @@
+// gauss_vi.cu -- Gaussian VI (Titsias) objective + gradient: the stage sequence behind srgp_gauss_obj_grad.
+//
+// Reference: elbo_fun (R/vi_functions.R:64-121), trace_term_fun (:14-27), delbo_dcov_par (:126-420).
+// Reduced form (checked against the literal transcription by tests/test_oracle.py):
+//   Z = tau^2 + delta, B = 1/Z, r = y - mu, S = K_uu + delta I, G1 = K^T K, b1 = K^T r, G = B G1
+//   C = (S + G)^-1, b = B b1, v = C b, beta = S^-1 (b - G v), sum_q = tr(S^-1 G1)
+//   tt  = -(n (sigma^2 + delta) - sum_q) / (2 tau^2)
+//   obj = -B s0/2 + b^T v/2 - (n log Z - log|S| + log|S + G|)/2 - n log(2 pi)/2 + tt
+//   M   = (1/tau^2 - B) S^-1 + B C G S^-1 ;  Omega = K (M - B v beta^T) + B r beta^T
+//   N   = S^-1 G S^-1/2 - S^-1 G C G S^-1/2 - beta beta^T/2 - S^-1 G1 S^-1/(2 tau^2)
+//   g_sigma = 2 sum Omega o K + 2 sum N o K_uu - sigma^2 n / tau^2
+//   g_l_c   = sum Omega o K o D_c + sum N o K_uu o D_c(u)
+//   g_tau   = tau^2 sum alpha^2 - tau^2 (n B - B^2 tr(C G1)) - 2 tt  [+ quirk Q4 pairs],
+//             sum alpha^2 = B^2 (s0 - 2 b1^T v + v^T G1 v)
+#include <math.h>
+
+#include "dense.cuh"
+#include "gauss.cuh"
+
+namespace srgp {
+
+using W = GaussWS;
+
+static int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
+{
+    SRGP_CUDA(cudaMemcpyAsync(w->h_scal, w->scal.p, W::NSCAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("device execution failed: %s", cudaGetErrorString(e));
+        return SRGP_ERR_CUDA;
+    }
+    const int *info = reinterpret_cast<const int *>(w->h_scal + W::S_INFO);
+    for (int k = 0; k < 4; k++)
+        if (info[k] != 0) {
+            set_error("the leading minor of order %d is not positive definite (Cholesky %d of the m x m stage)",
+                      info[k], k);
+            return SRGP_ERR_NOT_PD;
+        }
+    return SRGP_OK;
+}
+
+int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
+             double *obj, double *grad)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const size_t mm = (size_t)mp * mp;
+    GenParams gp;
+    fill_gen(gp, kernel, d, sigma, l);
+    const double Z = tau * tau + delta, B = 1.0 / Z, itau2 = 1.0 / (tau * tau);
+
+    double *G1 = w->red1.d(), *b1 = G1 + mm, *tail = b1 + mp;
+    SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
+    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+
+    // ---- pass 1 -------------------------------------------------------------------------------------
+    SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G1, b1));
+    SRGP_TRY(copy_scalar(ctx, tail, w->sc(W::S_S0), 1));
+    SRGP_TRY(set_scalar(ctx, tail + 1, (double)ctx->n));
+    SRGP_TRY(comm_allreduce(ctx, G1, mm + mp + 2, s));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_S0TOT), tail, 1));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_NTOT), tail + 1, 1));
+
+    // ---- replicated m x m stage -----------------------------------------------------------------------
+    double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
+    double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP), *CG = w->mat(W::M_CG), *CGS = w->mat(W::M_CGS);
+    double *SG = w->mat(W::M_SG), *SGS = w->mat(W::M_SGS), *N = w->mat(W::M_N), *Mop = w->mat(W::M_MOP);
+    double *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2);
+    double *bv = w->vec(W::V_B), *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP);
+    double *beta = w->vec(W::V_BETA), *gsc = w->gemv_scratch();
+
+    // S = K_uu + delta I (self-covariance minus tau^2 I: R/vi_functions.R:736-741), identity on the padding
+    SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
+    SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
+    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
+    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, tmp, Sinv, w->info(0), w->sc(W::S_LOGDET_S)));
+    // A = S + B G1 ; C = A^-1
+    SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, B, G1, 0.0, A));
+    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, tmp, C, w->info(1), w->sc(W::S_LOGDET_A)));
+    // b = B b1 ; v = C b ; gv = G1 v ; beta = S^-1 (b - B gv)
+    SRGP_TRY(axpby_vec(ctx, mp, B, b1, 0.0, nullptr, bv));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, C, bv, 0.0, nullptr, v, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv, gsc));
+    SRGP_TRY(axpby_vec(ctx, mp, 1.0, bv, -B, gv, tv));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Sinv, tv, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::dot_mm(ctx, s, mp, m, Sinv, G1, w->sc(W::S_SUMQ), w->part2.d()));
+    SRGP_TRY(dense::dot_mm(ctx, s, mp, m, C, G1, w->sc(W::S_TRCG1), w->part2.d()));
+    SRGP_TRY(dense::dot_v(ctx, s, m, bv, v, w->sc(W::S_BV)));
+    SRGP_TRY(dense::dot_v(ctx, s, m, b1, v, w->sc(W::S_B1V)));
+    SRGP_TRY(dense::dot_v(ctx, s, m, v, gv, w->sc(W::S_VGV)));
+    if (grad) {
+        // CG = C G1 ; CGS = C G1 S^-1 ; Mop = (1/tau^2 - B) S^-1 + B^2 CGS - B beta v^T
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, G1, mp, 0.0, CG, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, CGS, mp));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, itau2 - B, Sinv, B * B, CGS, 0.0, Mop));
+        SRGP_TRY(dense::ger(ctx, s, mp, -B, beta, v, Mop));
+
+        // ---- pass 2 ---------------------------------------------------------------------------------
+        double *ra = w->rowv(0, ctx->n);
+        SRGP_TRY(scale_vec(ctx, w->r.d(), ctx->n, B, ra));
+        double *p2 = w->sc(W::S_P2);
+        SRGP_TRY(gauss_pass2(ctx, w, gp, Mop, nullptr, ra, beta, p2, false));
+        // quirk Q4: d K_ij / d log tau = 2 tau^2 on bit-identical (row, knot) pairs; the tau-gradient picks up
+        // sum (Omega_ij - (K S^-1)_ij / tau^2) there (the trace-term part of Omega does not apply to tau)
+        SRGP_TRY(coin_fix(ctx, w, gp, Sinv, itau2, p2 + 1 + d));
+        SRGP_TRY(comm_allreduce(ctx, p2, d + 2, s));
+
+        // ---- N and sum N o dS -------------------------------------------------------------------------
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, G1, mp, 0.0, SG, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'N', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5 * B - 0.5 * itau2, SGS, -0.5 * B * B, T2, 0.0, N));
+        SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
+        SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS)));
+    }
+    SRGP_TRY(fetch_scalars(ctx, w));
+
+    // ---- host: a handful of scalars ---------------------------------------------------------------------
+    const double *h = w->h_scal;
+    const double n = h[W::S_NTOT], s0 = h[W::S_S0TOT];
+    const double tt = -(0.5 * itau2) * (n * (sigma * sigma + delta) - h[W::S_SUMQ]);
+    *obj = -0.5 * B * s0 + 0.5 * h[W::S_BV] - 0.5 * (n * log(Z) - h[W::S_LOGDET_S] + h[W::S_LOGDET_A]) -
+           0.5 * n * log(2.0 * M_PI) + tt;
+    if (grad) {
+        const double *p2 = h + W::S_P2, *ns = h + W::S_NS;
+        grad[0] = 2.0 * p2[0] + 2.0 * ns[0] - itau2 * sigma * sigma * n;
+        if (kernel == SRGP_ARD) {
+            for (int c = 0; c < d; c++) grad[1 + c] = p2[1 + c] + ns[1 + c];
+        } else {
+            double g = 0.0;
+            for (int c = 0; c < d; c++) g += p2[1 + c] + ns[1 + c];
+            grad[1] = g;
+        }
+        const int ti = (kernel == SRGP_ARD) ? 1 + d : 2;
+        const double sum_alpha2 = B * B * (s0 - 2.0 * h[W::S_B1V] + h[W::S_VGV]);
+        grad[ti] = tau * tau * sum_alpha2 - tau * tau * (n * B - B * B * h[W::S_TRCG1]) - 2.0 * tt +
+                   2.0 * tau * tau * p2[1 + d];
+    }
+    return SRGP_OK;
+}
+
+int gauss_fic(srgp_ctx *, GaussWS *, int, double, const double *, double, double, double *, double *)
+{
+    set_error("FIC model: not implemented yet");
+    return SRGP_ERR_STATE;
+}
+
+}  // namespace srgp

@@ -6,13 +6,6 @@ extern "C" {
 int srgp_trace_term(srgp_ctx *, double, double, double, const double *, int64_t, int64_t, const double *, double *) { SRGP_TODO("srgp_trace_term"); }
 int srgp_dtrace_term_dcov_par(srgp_ctx *, double, const double *, int64_t, double *) { SRGP_TODO("srgp_dtrace_term_dcov_par"); }
 int srgp_omega_dk_reduce(srgp_ctx *, int, const double *, int64_t, const double *, int64_t, int, double, const double *, double, const double *, double *) { SRGP_TODO("srgp_omega_dk_reduce"); }
-int srgp_set_data(srgp_ctx *, const double *, int64_t, int, const double *, const double *) { SRGP_TODO("srgp_set_data"); }
-int srgp_set_data_dev(srgp_ctx *, const double *, int64_t, int, const double *, const double *) { SRGP_TODO("srgp_set_data_dev"); }
-int srgp_gauss_obj_grad(srgp_ctx *, int, int, const double *, int64_t, double, const double *, double, double, double *, double *) { SRGP_TODO("srgp_gauss_obj_grad"); }
-int srgp_gauss_obj_grad_host(srgp_ctx *, int, int, const double *, int64_t, int, const double *, const double *, const double *, int64_t, double, const double *, double, double, double *, double *) { SRGP_TODO("srgp_gauss_obj_grad_host"); }
 int srgp_laplace_newton(srgp_ctx *, int, int, const double *, int64_t, const double *, double, const double *, double, double, double, int, double, double *, double *, int *, double *, double *, double *) { SRGP_TODO("srgp_laplace_newton"); }
 int srgp_laplace_grad(srgp_ctx *, int, int, const double *, int64_t, double, const double *, double, double, double, const double *, double *) { SRGP_TODO("srgp_laplace_grad"); }
-int srgp_comm_unique_id(char *) { SRGP_TODO("srgp_comm_unique_id"); }
-int srgp_comm_init(srgp_ctx *, int, int, const char *) { SRGP_TODO("srgp_comm_init"); }
-int srgp_comm_destroy(srgp_ctx *) { return SRGP_OK; }
 }

@@ -1,0 +1,100 @@
+"""Fused VI objective + gradient (CUDA, through the C ABI) against the literal oracle: rel <= 1e-8 (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import reduced_model as red
+from oracle import ref_model as rm
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8      # north_star: relative 1e-8 on the objective and each gradient component
+
+
+def _names(cp):
+    return list(cp.keys())
+
+
+def _run(ctx, c, model="vi"):
+    cp = c["cov_par"]
+    ctx.set_data(c["x"], c["y"], c["mu"])
+    l = cases.lvec(cp)
+    return ctx.gauss_obj_grad(model, c["cov_fun"], c["xu"], cp["sigma"], l, cp["tau"], c["delta"])
+
+
+def _check(obj, grad, obj_ref, g_ref, names):
+    assert obj == pytest.approx(obj_ref, rel=RTOL)
+    scale = max(abs(v) for v in g_ref.values())
+    for k, nm in enumerate(names):
+        assert grad[k] == pytest.approx(g_ref[nm], rel=RTOL, abs=RTOL * 1e-3 * scale), nm
+
+
+@pytest.mark.parametrize("case", ["config1", "config2", "config3", "config5"])
+def test_vi_matches_literal_oracle(ctx, case):
+    c = {"config1": lambda: cases.config1(), "config2": lambda: cases.config2(),
+         "config3": lambda: cases.config3(n=2000, m=200), "config5": lambda: cases.config5(n=3000, m=300)}[case]()
+    obj, grad = _run(ctx, c)
+    obj_ref, g_ref = rm.vi_obj_grad(c["cov_par"], c["cov_fun"], c["xu"], c["x"], c["y"], c["mu"], c["delta"])
+    _check(obj, grad, obj_ref, g_ref, _names(c["cov_par"]))
+
+
+def test_vi_nonzero_mean_and_objective_only(ctx):
+    c = cases.config2(n=900, m=40)
+    c["mu"] = 0.3 + 0.1 * c["x"][:, 0]
+    obj, grad = _run(ctx, c)
+    obj_ref, g_ref = rm.vi_obj_grad(c["cov_par"], c["cov_fun"], c["xu"], c["x"], c["y"], c["mu"], c["delta"])
+    _check(obj, grad, obj_ref, g_ref, _names(c["cov_par"]))
+    cp = c["cov_par"]
+    obj2, g2 = ctx.gauss_obj_grad("vi", "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"], want_grad=False)
+    assert g2 is None and obj2 == pytest.approx(obj_ref, rel=RTOL)
+
+
+def test_vi_one_shot_host_call_and_ragged_sizes(ctx):
+    # n, m not multiples of any tile; several chunks in both passes
+    c = cases.config5(n=11003, m=130, seed=77)
+    cp = c["cov_par"]
+    obj, grad = ctx.gauss_obj_grad_host("vi", "ard", c["x"], c["y"], None, c["xu"], cp["sigma"], cases.lvec(cp),
+                                        cp["tau"], c["delta"])
+    obj_ref, g_ref = rm.vi_obj_grad(cp, "ard", c["xu"], c["x"], c["y"], c["mu"], c["delta"])
+    _check(obj, grad, obj_ref, g_ref, _names(cp))
+
+
+def test_vi_headline_shape_against_reduced_oracle(ctx):
+    """m = 1024, d = 8 (the headline knot count) at an n the reduced NumPy form finishes in seconds."""
+    c = cases.config5(n=20000, m=1024)
+    cp = c["cov_par"]
+    obj, grad = _run(ctx, c)
+    obj_ref, g_ref = red.vi_obj_grad(c["x"], c["y"], c["mu"], c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+    _check(obj, grad, obj_ref, g_ref, _names(cp))
+
+
+def test_vi_not_positive_definite_raises(ctx):
+    from sparsergps_b200._lib import NotPositiveDefinite
+    c = cases.config2(n=300, m=16)
+    xu = np.vstack([c["xu"], c["xu"][:4]])      # duplicated knots, delta = 0 -> singular S
+    ctx.set_data(c["x"], c["y"], None)
+    cp = c["cov_par"]
+    with pytest.raises(NotPositiveDefinite):
+        ctx.gauss_obj_grad("vi", "ard", xu, cp["sigma"], cases.lvec(cp), cp["tau"], 0.0)
+
+
+def test_vi_finite_difference_at_scale(ctx):
+    """Size-independent property at a size the oracle cannot reach: gradient == central difference of the objective."""
+    c = cases.config5(n=200_000, m=512)
+    cp = c["cov_par"]
+    ctx.set_data(c["x"], c["y"], None)
+    l = np.array(cases.lvec(cp))
+    obj, grad = ctx.gauss_obj_grad("vi", "ard", c["xu"], cp["sigma"], l, cp["tau"], c["delta"])
+    h = 1e-5
+    for k, name in [(0, "sigma"), (3, "l3"), (9, "tau")]:
+        def f(sign):
+            s, ll, t = cp["sigma"], l.copy(), cp["tau"]
+            if name == "sigma":
+                s *= np.exp(sign * h)
+            elif name == "tau":
+                t *= np.exp(sign * h)
+            else:
+                ll[2] *= np.exp(sign * h)
+            return ctx.gauss_obj_grad("vi", "ard", c["xu"], s, ll, t, c["delta"], want_grad=False)[0]
+        fd = (f(+1) - f(-1)) / (2 * h)
+        assert grad[k] == pytest.approx(fd, rel=5e-6), name
