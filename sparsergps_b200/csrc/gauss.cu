@@ -665,16 +665,17 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
     const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
-    static size_t configured_smem = 0;
-    if (configured_smem < smem) {
-#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        SRGP_D_SWITCH(d, CALL)
-#undef CALL
-        configured_smem = smem;
-    }
     if (smem > 227 * 1024) {
         set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
         return SRGP_ERR_ARG;
+    }
+    static size_t configured_smem[9] = {0};   // per template instantiation (index 0 = runtime d)
+    const int slot_d = (d >= 1 && d <= 8) ? d : 0;
+    if (configured_smem[slot_d] < smem) {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        SRGP_D_SWITCH(d, CALL)
+#undef CALL
+        configured_smem[slot_d] = smem;
     }
     const int slots = w->rblocks * w->cgroups;
     int first = accumulate_slots ? 0 : 1;

@@ -36,7 +36,7 @@ struct GaussWS {
     enum Mat { M_S = 0, M_SINV, M_A, M_C, M_LINV, M_TMP, M_CG, M_CGS, M_SG, M_SGS, M_N, M_MOP, M_T1, M_T2, M_X1, M_X2 };
     enum Vec { V_B = 0, V_V, V_GV, V_TMP, V_BETA, V_T1, V_T2, V_T3 };
     enum Scal {
-        S_S0 = 0, S_LOGDET_S, S_LOGDET_A, S_SUMQ, S_TRCG1, S_BV, S_B1V, S_VGV, S_INFO, S_NTOT, S_S0TOT, S_Q4,
+        S_S0 = 0, S_LOGDET_S, S_LOGDET_A, S_SUMQ, S_TRCG1, S_BV, S_B1V, S_VGV, S_INFO, S_INFO_HI, S_NTOT, S_S0TOT, S_Q4,
         S_P2 = 32,      // pass-2 sums: 1 + d entries, + q4 at S_P2 + 1 + d  (allreduced together)
         S_NS = 128,     // N o dS sums: 2 + d entries
         S_X = 224       // model-specific extras
