@@ -18,6 +18,9 @@ struct GemmArgs {
     int ktiles;
     double alpha, beta;
     int lower_only;
+    double *Ct;          // optional: also store the transposed result, Ct[c + r*ldct]
+    int64_t ldct, sCt;
+    int kmode;           // zero-skipping for triangular operands, see dense.cuh
 };
 
 template <bool A_KC, bool B_KC>
@@ -29,13 +32,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g)
     if (g.lower_only && tn > tm) return;
     const double *A = g.A + blockIdx.z * g.sA + (A_KC ? (int64_t)tm * BM * g.lda : (int64_t)tm * BM);
     const double *B = g.B + blockIdx.z * g.sB + (B_KC ? (int64_t)tn * BN * g.ldb : (int64_t)tn * BN);
+    // k-range: skip k-tiles where a triangular operand is known to be zero
+    int kt0 = 0, kt1 = g.ktiles;
+    if (g.kmode == KMODE_A_UPPER) kt0 = tm * (BM / BK);
+    else if (g.kmode == KMODE_B_LOWER) kt1 = min(g.ktiles, (tn + 1) * (BN / BK));
+    else if (g.kmode == KMODE_AB_UPPER) kt0 = max(tm, tn) * (BM / BK);
+    A += A_KC ? (int64_t)kt0 * BK : (int64_t)kt0 * BK * g.lda;
+    B += B_KC ? (int64_t)kt0 * BK : (int64_t)kt0 * BK * g.ldb;
     pipeline_init(sm);
     double acc[8][4][2];
     zero_acc(acc);
     uint32_t it = 0;
-    mainloop<A_KC, B_KC, false>(sm, A, g.lda, B, g.ldb, nullptr, g.ktiles, it, acc);
+    mainloop<A_KC, B_KC, false>(sm, A, g.lda, B, g.ldb, nullptr, max(0, kt1 - kt0), it, acc);
     if (is_producer()) return;
     double *C = g.C + blockIdx.z * g.sC + (int64_t)tm * BM + (int64_t)tn * BN * g.ldc;
+    double *Ct = g.Ct ? g.Ct + blockIdx.z * g.sCt + (int64_t)tn * BN + (int64_t)tm * BM * g.ldct : nullptr;
 #pragma unroll
     for (int mi = 0; mi < 8; mi++) {
         const int r = frag_row(mi);
@@ -48,6 +59,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g)
                 double v = g.alpha * acc[mi][ni][e];
                 if (g.beta != 0.0) v += g.beta * *p;
                 *p = v;
+                if (Ct) Ct[(c + e) + (int64_t)r * g.ldct] = v;
             }
         }
     }
@@ -70,13 +82,14 @@ static int launch_gemm(srgp_ctx *ctx, cudaStream_t s, dim3 grid, const GemmArgs 
 
 int gemm(srgp_ctx *ctx, cudaStream_t s, char transA, char transB, int M, int N, int K, double alpha,
          const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc,
-         BatchDesc bd, bool lower_only)
+         BatchDesc bd, bool lower_only, int kmode, double *Ct, int64_t ldct)
 {
     if (M % BM || N % BN || K % BK || M <= 0 || N <= 0 || K < 0) {
         set_error("gemm: extents %d x %d x %d are not tile multiples", M, N, K);
         return SRGP_ERR_ARG;
     }
-    GemmArgs g{A, B, C, lda, ldb, ldc, bd.strideA, bd.strideB, bd.strideC, K / BK, alpha, beta, lower_only ? 1 : 0};
+    GemmArgs g{A, B, C, lda, ldb, ldc, bd.strideA, bd.strideB, bd.strideC, K / BK, alpha, beta, lower_only ? 1 : 0,
+               Ct, ldct, bd.strideCt, kmode};
     dim3 grid(M / BM, N / BN, bd.batch);
     const bool akc = (transA == 'T'), bkc = (transB == 'N');
     if (!akc && !bkc) return launch_gemm<false, false>(ctx, s, grid, g);
@@ -90,73 +103,146 @@ int gemm(srgp_ctx *ctx, cudaStream_t s, char transA, char transB, int M, int N, 
 // ------------------------------------------------------------------------------------------------
 constexpr int DLD = NB + 1;   // 129: odd stride, column-major block in shared memory
 
+// Factor one 128 x 128 diagonal block and invert its Cholesky factor, in ONE CTA of 256 threads.
+// Thread (ti, tk) = (tid & 15, tid >> 4) keeps the 8 x 8 sub-block {(ti + 16 ii, tk + 16 kk)} in registers;
+// per column j only the scaled column (Cholesky) or the scaled row of the running inverse travels through a
+// double-buffered shared vector, followed by 64 register FMAs -- one __syncthreads per column.  The column /
+// block loops are split as j = 16 jb + jt with jb unrolled so every register index is static.
+//   outputs: L (lower, strict upper zeroed) back into A; X = L^-1 into dinv (lower) and X^T into dinvT (upper).
 __global__ void __launch_bounds__(256, 1)
 potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *__restrict__ dinv,
-                  int *__restrict__ info, double *__restrict__ logdet_part)
+                  double *__restrict__ dinvT, int *__restrict__ info, double *__restrict__ logdet_part)
 {
     extern __shared__ double sh[];
-    double *s = sh;                 // NB x DLD
-    double *colv = sh + NB * DLD;   // NB
-    double *psum = colv + NB;       // 2 * NB
+    double *Ls = sh;                   // NB x DLD: the factor, for the inverse phase
+    double *vec = Ls + NB * DLD;       // 2 x NB double-buffered broadcast vector
+    double *diag = vec + 2 * NB;       // NB pivots
+    __shared__ double red[8];
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx % NB, j = idx / NB;
-        s[i + j * DLD] = (i >= j) ? A[i + (int64_t)j * ld] : 0.0;
+    const int ti = tid & 15, tk = tid >> 4;
+    const int lane = tid & 31;
+    double a[8][8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const int i = ti + 16 * ii, k = tk + 16 * kk;
+            a[ii][kk] = (i >= k) ? A[i + (int64_t)k * ld] : 0.0;
+        }
+    // ---- Cholesky (right-looking) ----
+#pragma unroll
+    for (int jb = 0; jb < 8; jb++) {
+        for (int jt = 0; jt < 16; jt++) {
+            const int j = jb * 16 + jt;
+            double *cv = vec + (j & 1) * NB;
+            // the 16 owners of column j sit in one half-warp (tk == jt); the pivot owner is its lane ti == jt
+            const double piv = __shfl_sync(0xffffffffu, a[jb][jb], (lane & 16) + jt);
+            if (tk == jt) {
+                const double dj = sqrt(piv);
+                if (ti == jt) {
+                    if (!(piv > 0.0) && *info == 0) *info = col0 + j + 1;
+                    diag[j] = dj;
+                }
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    const int i = ti + 16 * ii;
+                    double v = 0.0;
+                    if (ii > jb || (ii == jb && ti > jt)) v = a[ii][jb] / dj;
+                    else if (ii == jb && ti == jt) v = dj;
+                    if (ii >= jb) a[ii][jb] = v;
+                    cv[i] = (i > j) ? v : 0.0;
+                }
+            }
+            __syncthreads();
+            double li[8], lk[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                li[q] = cv[ti + 16 * q];
+                lk[q] = cv[tk + 16 * q];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+                if (kk < jb) continue;                           // columns of finished blocks
+                const bool kact = (kk > jb) || (tk > jt);        // k > j
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    if (ii < kk) continue;                       // strictly upper sub-blocks are never read
+                    if (kact) a[ii][kk] = fma(-li[ii], lk[kk], a[ii][kk]);
+                }
+            }
+        }
     }
     __syncthreads();
-    const int ti = tid & 15, tk = tid >> 4;
-    double ld_acc = 0.0;
-    for (int j = 0; j < NB; j++) {
-        if (tid == 0) {
-            const double piv = s[j + j * DLD];
-            if (!(piv > 0.0) && *info == 0) *info = col0 + j + 1;
-            const double r = sqrt(piv);
-            s[j + j * DLD] = r;
-            if (col0 + j < m) ld_acc += log(r);
-        }
-        __syncthreads();
-        const double djj = s[j + j * DLD];
-        if (tid < NB && tid > j) s[tid + j * DLD] = s[tid + j * DLD] / djj;
-        __syncthreads();
-        for (int k = j + 1 + tk; k < NB; k += 16) {
-            const double lkj = s[k + j * DLD];
-            for (int i = j + 1 + ti; i < NB; i += 16)
-                if (i >= k) s[i + k * DLD] = fma(-s[i + j * DLD], lkj, s[i + k * DLD]);
-        }
-        __syncthreads();
+    // ---- log-determinant part, L to global and to shared memory ----
+    {
+        double v = 0.0;
+        if (tid < NB && col0 + tid < m) v = log(diag[tid]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[tid >> 5] = v;
     }
-    if (tid == 0) *logdet_part = 2.0 * ld_acc;
-    // L back to global (strict upper part of the diagonal block zeroed)
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx % NB, j = idx / NB;
-        A[i + (int64_t)j * ld] = (i >= j) ? s[i + j * DLD] : 0.0;
-    }
-    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2 order):
-    //   X[j,j] = 1 / L[j,j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j,j]
-    const int row = tid & (NB - 1), half = tid >> 7;
-    for (int j = NB - 1; j >= 0; j--) {
-        if (tid < NB) colv[tid] = (tid > j) ? s[tid + j * DLD] : 0.0;
-        __syncthreads();
-        double p = 0.0;
-        if (row > j) {
-            const int len = row - j;               // k = j+1 .. row
-            const int mid = j + 1 + (len + 1) / 2;
-            const int k0 = half ? mid : j + 1, k1 = half ? row + 1 : mid;
-            for (int k = k0; k < k1; k++) p = fma(s[row + k * DLD], colv[k], p);
+#pragma unroll
+    for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const int i = ti + 16 * ii, k = tk + 16 * kk;
+            const double v = (i >= k) ? a[ii][kk] : 0.0;
+            A[i + (int64_t)k * ld] = v;
+            Ls[i + k * DLD] = v;
         }
-        psum[half * NB + row] = p;
-        __syncthreads();
-        if (tid < NB) {
-            const double xjj = 1.0 / s[j + j * DLD];
-            if (tid == j) s[j + j * DLD] = xjj;
-            else if (tid > j) s[tid + j * DLD] = -(psum[tid] + psum[NB + tid]) * xjj;
+    __syncthreads();
+    if (tid == 0) *logdet_part = 2.0 * (red[0] + red[1] + red[2] + red[3]);
+    // ---- X = L^-1 by forward substitution on the identity held in registers ----
+    //   row j of X: x_j = x_j / L_jj ;  rows i > j: x_i -= L_ij x_j
+#pragma unroll
+    for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) a[ii][kk] = (ii == kk && ti == tk) ? 1.0 : 0.0;
+#pragma unroll
+    for (int jb = 0; jb < 8; jb++) {
+        for (int jt = 0; jt < 16; jt++) {
+            const int j = jb * 16 + jt;
+            double *rv = vec + (j & 1) * NB;
+            if (ti == jt) {                                      // owners of row j (16 threads, one per tk)
+                const double inv = 1.0 / diag[j];
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    double v = 0.0;
+                    if (kk <= jb) {
+                        v = a[jb][kk] * inv;
+                        a[jb][kk] = v;
+                    }
+                    rv[tk + 16 * kk] = v;
+                }
+            }
+            __syncthreads();
+            double li[8], rk[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                li[q] = Ls[ti + 16 * q + j * DLD];
+                rk[q] = rv[tk + 16 * q];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+                if (ii < jb) continue;
+                const bool iact = (ii > jb) || (ti > jt);        // i > j
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    if (kk > jb) continue;                       // X is lower triangular: columns k <= j only
+                    if (iact) a[ii][kk] = fma(-li[ii], rk[kk], a[ii][kk]);
+                }
+            }
         }
-        __syncthreads();
     }
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx % NB, j = idx / NB;
-        dinv[i + j * NB] = (i >= j) ? s[i + j * DLD] : 0.0;
-    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const int i = ti + 16 * ii, k = tk + 16 * kk;
+            const double v = (i >= k) ? a[ii][kk] : 0.0;
+            dinv[i + k * NB] = v;
+            dinvT[k + i * NB] = v;
+        }
 }
 
 __global__ void sum_parts_kernel(const double *parts, int n, double *out)
@@ -171,20 +257,21 @@ __global__ void sum_parts_kernel(const double *parts, int n, double *out)
 int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, int *info, double *logdet)
 {
     static bool configured = false;
-    const size_t smem = sizeof(double) * (NB * DLD + 3 * NB);
+    const size_t smem = sizeof(double) * (NB * DLD + 3 * NB);   // factor + 2 broadcast vectors + pivots
     if (!configured) {
         SRGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int nb = mp / NB;
-    // logdet partials live at the tail of dinv (caller allocates mp*NB + nb doubles)
-    double *parts = dinv + (size_t)mp * NB;
+    // dinv area layout (caller allocates 2*mp*NB + nb doubles): [X_kk blocks | X_kk^T blocks | logdet partials]
+    double *dinvT = dinv + (size_t)mp * NB;
+    double *parts = dinv + (size_t)2 * mp * NB;
     for (int kb = 0; kb < nb; kb++) {
         double *Akk = A + (size_t)kb * NB * ((size_t)mp + 1);
         double *Dk = dinv + (size_t)kb * NB * NB;
         {
             KernelScope ks(ctx, SRGP_PROF_DENSE, s);
-            potrf_diag_kernel<<<1, 256, smem, s>>>(Akk, mp, kb * NB, m, Dk, info, parts + kb);
+            potrf_diag_kernel<<<1, 256, smem, s>>>(Akk, mp, kb * NB, m, Dk, dinvT + (size_t)kb * NB * NB, info, parts + kb);
             SRGP_LAUNCH_CHECK();
         }
         const int Mr = mp - (kb + 1) * NB;
@@ -205,65 +292,77 @@ int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv,
     return SRGP_OK;
 }
 
-__global__ void scatter_diag_blocks_kernel(const double *__restrict__ dinv, double *__restrict__ Linv, int mp)
+__global__ void scatter_diag_blocks_kernel(const double *__restrict__ dinv, double *__restrict__ M, int mp)
 {
     // one CTA per diagonal block
     const int kb = blockIdx.x;
     const double *src = dinv + (size_t)kb * NB * NB;
-    double *dst = Linv + (size_t)kb * NB * ((size_t)mp + 1);
+    double *dst = M + (size_t)kb * NB * ((size_t)mp + 1);
     for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
         const int i = idx % NB, j = idx / NB;
         dst[i + (size_t)j * mp] = src[i + j * NB];
     }
 }
 
-int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *dinv, double *Linv, double *tmp)
+// X = L^-1 (lower) and W = X^T (upper) by recursive doubling over the diagonal:
+//   W12 = -(W11 L21^T) X22^T ,  X21 = W12^T
+// Both products are "NT" GEMMs on MN-contiguous operands (the tile engine's fast path); the second one stores
+// its result a second time transposed, which is how X21 is obtained.  Zero k-tiles of the triangular
+// operands are skipped.
+int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *dinv, double *Linv, double *LinvT,
+          double *tmp)
 {
     const int nb = mp / NB;
+    const double *dinvT = dinv + (size_t)mp * NB;
     SRGP_CUDA(cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)mp * mp, s));
+    SRGP_CUDA(cudaMemsetAsync(LinvT, 0, sizeof(double) * (size_t)mp * mp, s));
     {
-        KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+        KernelScope ks(ctx, SRGP_PROF_DENSE, s, 2);
         scatter_diag_blocks_kernel<<<nb, 256, 0, s>>>(dinv, Linv, mp);
+        SRGP_LAUNCH_CHECK();
+        scatter_diag_blocks_kernel<<<nb, 256, 0, s>>>(dinvT, LinvT, mp);
         SRGP_LAUNCH_CHECK();
     }
     const int64_t ld = mp;
-    auto at = [&](const double *base, int rb, int cb) { return base + (size_t)rb * NB + (size_t)cb * NB * ld; };
-    // recursive doubling over blocks of s128 * 128:  X21 = -X22 * (L21 * X11)
+    auto at = [&](const double *base, int rb, int cb) {
+        return const_cast<double *>(base) + (size_t)rb * NB + (size_t)cb * NB * ld;
+    };
+    auto pair = [&](int b0, int sl, int sr, int batch) -> int {
+        // left block [b0, b0+sl), right block [b0+sl, b0+sl+sr) (in units of NB); `batch` pairs, stride 2*sl
+        BatchDesc bd;
+        bd.batch = batch;
+        bd.strideA = bd.strideB = bd.strideC = bd.strideCt = (int64_t)2 * sl * NB * (ld + 1);
+        const int S = sl * NB, Mr = sr * NB;
+        // T' = W11 * L21^T   (S x Mr, at tmp[b0, b0+sl])
+        SRGP_TRY(gemm(ctx, s, 'N', 'T', S, Mr, S, 1.0, at(LinvT, b0, b0), ld, at(L, b0 + sl, b0), ld, 0.0,
+                      at(tmp, b0, b0 + sl), ld, bd, false, KMODE_A_UPPER));
+        // W12 = -T' * X22^T  (S x Mr, at LinvT[b0, b0+sl]);  X21 = W12^T at Linv[b0+sl, b0]
+        SRGP_TRY(gemm(ctx, s, 'N', 'T', S, Mr, Mr, -1.0, at(tmp, b0, b0 + sl), ld, at(Linv, b0 + sl, b0 + sl), ld,
+                      0.0, at(LinvT, b0, b0 + sl), ld, bd, false, KMODE_B_LOWER, at(Linv, b0 + sl, b0), ld));
+        return SRGP_OK;
+    };
     for (int sblk = 1; sblk < nb; sblk *= 2) {
         const int full = nb / (2 * sblk);
-        if (full > 0) {
-            BatchDesc bd;
-            bd.batch = full;
-            bd.strideA = bd.strideB = bd.strideC = (int64_t)2 * sblk * NB * (ld + 1);
-            const int S = sblk * NB;
-            SRGP_TRY(gemm(ctx, s, 'N', 'N', S, S, S, 1.0, at(L, sblk, 0), ld, at(Linv, 0, 0), ld, 0.0,
-                          const_cast<double *>(at(tmp, sblk, 0)), ld, bd));
-            SRGP_TRY(gemm(ctx, s, 'N', 'N', S, S, S, -1.0, at(Linv, sblk, sblk), ld, at(tmp, sblk, 0), ld, 0.0,
-                          const_cast<double *>(at(Linv, sblk, 0)), ld, bd));
-        }
+        if (full > 0) SRGP_TRY(pair(0, sblk, sblk, full));
         const int b0 = full * 2 * sblk, rem = nb - b0;
-        if (rem > sblk) {   // partial pair: left block of sblk, right block of rem - sblk
-            const int S = sblk * NB, Mr = (rem - sblk) * NB;
-            SRGP_TRY(gemm(ctx, s, 'N', 'N', Mr, S, S, 1.0, at(L, b0 + sblk, b0), ld, at(Linv, b0, b0), ld, 0.0,
-                          const_cast<double *>(at(tmp, b0 + sblk, b0)), ld));
-            SRGP_TRY(gemm(ctx, s, 'N', 'N', Mr, S, Mr, -1.0, at(Linv, b0 + sblk, b0 + sblk), ld,
-                          at(tmp, b0 + sblk, b0), ld, 0.0, const_cast<double *>(at(Linv, b0 + sblk, b0)), ld));
-        }
+        if (rem > sblk) SRGP_TRY(pair(b0, sblk, rem - sblk, 1));
     }
     return SRGP_OK;
 }
 
-int lauum(srgp_ctx *ctx, cudaStream_t s, const double *Linv, int mp, double *Ainv)
+// Ainv = X^T X = W W^T (full symmetric); k >= max(i, j) because W is upper triangular.
+int lauum(srgp_ctx *ctx, cudaStream_t s, const double *LinvT, int mp, double *Ainv)
 {
-    return gemm(ctx, s, 'T', 'N', mp, mp, mp, 1.0, Linv, mp, Linv, mp, 0.0, Ainv, mp);
+    return gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, LinvT, mp, LinvT, mp, 0.0, Ainv, mp, BatchDesc(), false,
+                KMODE_AB_UPPER);
 }
 
-int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *tmp,
-                 double *Ainv, int *info, double *logdet)
+int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *LinvT,
+                 double *tmp, double *Ainv, int *info, double *logdet)
 {
     SRGP_TRY(potrf(ctx, s, A, mp, m, dinv, info, logdet));
-    SRGP_TRY(trtri(ctx, s, A, mp, dinv, Linv, tmp));
-    return lauum(ctx, s, Linv, mp, Ainv);
+    SRGP_TRY(trtri(ctx, s, A, mp, dinv, Linv, LinvT, tmp));
+    return lauum(ctx, s, LinvT, mp, Ainv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -501,10 +600,11 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
     SRGP_TRY(use_device(ctx));
     const int mp = (int)round_up(m, dense::NB);
     const size_t mm = (size_t)mp * mp;
-    DevBuf dA, dA0, dDinv, dLinv, dTmp, dAinv, dMisc;
+    DevBuf dA, dA0, dDinv, dLinv, dLinvT, dTmp, dAinv, dMisc;
     SRGP_TRY(dA.reserve(mm * 8));
     SRGP_TRY(dA0.reserve(mm * 8));
-    SRGP_TRY(dDinv.reserve(((size_t)mp * dense::NB + mp / dense::NB) * 8));
+    SRGP_TRY(dDinv.reserve(((size_t)2 * mp * dense::NB + mp / dense::NB) * 8));
+    SRGP_TRY(dLinvT.reserve(mm * 8));
     SRGP_TRY(dLinv.reserve(mm * 8));
     SRGP_TRY(dTmp.reserve(mm * 8));
     SRGP_TRY(dAinv.reserve(mm * 8));
@@ -522,8 +622,8 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
         cudaMemsetAsync(dMisc.p, 0, 64, ctx->stream);
         st = dense::pad_identity(ctx, ctx->stream, dA.d(), mp, m, 1.0);
         if (st == SRGP_OK)
-            st = dense::chol_inverse(ctx, ctx->stream, dA.d(), mp, m, dDinv.d(), dLinv.d(), dTmp.d(), dAinv.d(), info,
-                                     logdet);
+            st = dense::chol_inverse(ctx, ctx->stream, dA.d(), mp, m, dDinv.d(), dLinv.d(), dLinvT.d(), dTmp.d(),
+                                     dAinv.d(), info, logdet);
     }
     if (st == SRGP_OK && reps > 0) {
         cudaEventRecord(ctx->tim1, ctx->stream);
@@ -552,7 +652,7 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
         if (logdet_out) *logdet_out = misc[0];
         if (info_out) *info_out = *reinterpret_cast<int *>(&misc[1]);
     }
-    DevBuf *bufs[] = {&dA, &dA0, &dDinv, &dLinv, &dTmp, &dAinv, &dMisc};
+    DevBuf *bufs[] = {&dA, &dA0, &dDinv, &dLinv, &dLinvT, &dTmp, &dAinv, &dMisc};
     for (auto *b : bufs) b->release();
     return st;
 }

@@ -12,30 +12,39 @@ constexpr int GEMV_SCRATCH = 16;   // gemv scratch is GEMV_SCRATCH * mp doubles
 
 struct BatchDesc {
     int batch = 1;
-    int64_t strideA = 0, strideB = 0, strideC = 0;
+    int64_t strideA = 0, strideB = 0, strideC = 0, strideCt = 0;
 };
+
+// k-range restriction for triangular operands (zero k-tiles are skipped)
+enum { KMODE_FULL = 0,
+       KMODE_A_UPPER = 1,    // op(A)[i, k] = 0 for k < i      -> k starts at the row tile
+       KMODE_B_LOWER = 2,    // op(B)^T[n, k] = 0 for k > n    -> k ends after the column tile
+       KMODE_AB_UPPER = 3 }; // both of the above kind (W W^T) -> k starts at max(row tile, column tile)
 
 // C = alpha * op(A) * op(B) + beta * C,  op(A) is M x K, op(B) is K x N (BLAS semantics, column-major).
 // M, N multiples of 128, K multiple of 16.  lower_only: skip tiles strictly above the block diagonal.
 int gemm(srgp_ctx *ctx, cudaStream_t s, char transA, char transB, int M, int N, int K, double alpha,
          const double *A, int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc,
-         BatchDesc bd = BatchDesc(), bool lower_only = false);
+         BatchDesc bd = BatchDesc(), bool lower_only = false, int kmode = KMODE_FULL, double *Ct = nullptr,
+         int64_t ldct = 0);
 
 // In-place blocked Cholesky A = L L^T of the leading mp x mp matrix (lower triangle referenced; on exit the
-// lower triangle holds L, diagonal blocks have a zeroed strict upper part).  dinv (mp x 128) receives the
-// inverses of the diagonal blocks of L.  *info (device int) is set to 1 + column index on a non-positive
+// lower triangle holds L, diagonal blocks have a zeroed strict upper part).  dinv (2*mp*128 + mp/128 doubles)
+// receives the inverses of the diagonal blocks of L, their transposes, and the per-block log-det parts.  *info (device int) is set to 1 + column index on a non-positive
 // pivot (R's chol() error); logdet (device double) receives 2 * sum_{i<m} log L_ii.
 int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, int *info, double *logdet);
 
-// Linv (mp x mp, fully written) = L^-1 given L (lower, as left by potrf) and dinv.  tmp is mp x mp scratch.
-int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *dinv, double *Linv, double *tmp);
+// Linv = L^-1 (lower) and LinvT = L^-T (upper), both mp x mp and fully written, given L (lower, as left by
+// potrf) and dinv.  tmp is mp x mp scratch.
+int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *dinv, double *Linv, double *LinvT,
+          double *tmp);
 
-// Ainv = Linv^T * Linv (full symmetric).
-int lauum(srgp_ctx *ctx, cudaStream_t s, const double *Linv, int mp, double *Ainv);
+// Ainv = L^-T L^-1 (full symmetric) from LinvT.
+int lauum(srgp_ctx *ctx, cudaStream_t s, const double *LinvT, int mp, double *Ainv);
 
-// Convenience: A (mp x mp, destroyed -> L) ; Ainv, logdet as above.  Linv / tmp are mp x mp scratch.
-int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *tmp,
-                 double *Ainv, int *info, double *logdet);
+// Convenience: A (mp x mp, destroyed -> L) ; Ainv, logdet as above.  Linv / LinvT / tmp are mp x mp scratch.
+int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *LinvT,
+                 double *tmp, double *Ainv, int *info, double *logdet);
 
 // ---- small kernels ----------------------------------------------------------------------------------
 // Put `v` on the padding diagonal (i >= m) and zero the rest of the padding rows / columns.

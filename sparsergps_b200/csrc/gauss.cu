@@ -15,6 +15,7 @@
 // pipe is shared by DFMA and DMMA on sm_100 -- profiles/r01_microbench.json -- so each K entry is generated
 // exactly once per pass instead of once per output tile); K never exists as an n x m matrix.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dense.cuh"
@@ -66,27 +67,40 @@ gen_rowmajor_kernel(const double *__restrict__ X, int64_t ldx, const double *__r
             sr[threadIdx.x] = (i < rows_valid) ? r[r0 + i] : 0.0;
         }
         __syncthreads();
-        for (int ii = 0; ii < nt; ii++) {
-            const int i = it0 + ii;
-            double k = 0.0;
-            if (jvalid && i < rows_valid) {
-                double s = 0.0;
-                if (DT > 0) {
+        // 4 rows in flight per thread: independent distance / exp chains hide the FP64 latency
+        for (int ii = 0; ii < nt; ii += 4) {
+            double sq[4] = {0.0, 0.0, 0.0, 0.0};
+            if (DT > 0) {
 #pragma unroll
-                    for (int c = 0; c < DT; c++) {
-                        const double t = sx[ii * DT + c] - uj[c];
-                        s = fma(t, t, s);
-                    }
-                } else {
-                    for (int c = 0; c < d; c++) {
-                        const double t = sx[ii * d + c] - U[j + (int64_t)m * c] * p.invl[c];
-                        s = fma(t, t, s);
+                for (int c = 0; c < DT; c++) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double t = sx[min(ii + q, GEN_ROWS_TILE - 1) * DT + c] - uj[c];
+                        sq[q] = fma(t, t, sq[q]);
                     }
                 }
-                k = p.sigma2 * exp(-0.5 * s);
-                bacc = fma(k, sr[ii], bacc);
+            } else {
+                for (int c = 0; c < d; c++) {
+                    const double ujc = jvalid ? U[j + (int64_t)m * c] * p.invl[c] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double t = sx[min(ii + q, GEN_ROWS_TILE - 1) * d + c] - ujc;
+                        sq[q] = fma(t, t, sq[q]);
+                    }
+                }
             }
-            Kr[(int64_t)i * mp + j] = k;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = it0 + ii + q;
+                if (ii + q < nt) {
+                    double k = 0.0;
+                    if (jvalid && i < rows_valid) {
+                        k = p.sigma2 * exp(-0.5 * sq[q]);
+                        bacc = fma(k, sr[ii + q], bacc);
+                    }
+                    Kr[(int64_t)i * mp + j] = k;
+                }
+            }
         }
     }
     double *slot = b1part + (int64_t)blockIdx.y * mp + j;
@@ -256,6 +270,17 @@ struct KmArgs {
 };
 
 
+__device__ __noinline__ void record_coincident(const KmArgs &a, int i_local, int j, double p_ij)
+{
+    const double k = a.Kc[i_local + (int64_t)j * a.ldc];
+    const int slot = atomicAdd(a.coin_count, 1);
+    if (slot < a.coin_cap) {
+        a.coin_list[2 * slot] = (int)(a.r0 + i_local);
+        a.coin_list[2 * slot + 1] = j;
+        a.coin_omega[slot] = p_ij / k;   // Omega_ij; k = sigma^2 > 0 for identical points
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 {
@@ -354,22 +379,18 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             if (lane == 0) red[warp * PART_STRIDE + 0] += s0;
-            // quirk Q4: bit-identical data row / knot pairs (rare): record them for the tau derivative
+            // quirk Q4: bit-identical data row / knot pairs (rare): record them for the tau derivative.
+            // The selection is fully unrolled so that acc[][][] is never indexed dynamically (that would
+            // move the accumulators to local memory for the whole kernel).
             if (eqmask) {
+#pragma unroll
                 for (int mi = 0; mi < 8; mi++)
+#pragma unroll
                     for (int ni = 0; ni < 4; ni++)
+#pragma unroll
                         for (int e = 0; e < 2; e++)
-                            if (eqmask & (1ull << ((mi * 4 + ni) * 2 + e))) {
-                                const int ii = frag_row(mi), j = j0 + frag_col(ni) + e;
-                                const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
-                                const double om = acc[mi][ni][e] / k;   // k = sigma^2 > 0 for identical points
-                                const int slot = atomicAdd(a.coin_count, 1);
-                                if (slot < a.coin_cap) {
-                                    a.coin_list[2 * slot] = (int)(a.r0 + i0 + ii);
-                                    a.coin_list[2 * slot + 1] = j;
-                                    a.coin_omega[slot] = om;
-                                }
-                            }
+                            if ((eqmask >> ((mi * 4 + ni) * 2 + e)) & 1ull)
+                                record_coincident(a, i0 + frag_row(mi), j0 + frag_col(ni) + e, acc[mi][ni][e]);
             }
         }
     }
@@ -528,31 +549,38 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     // pass 1: pairs x splits CTAs ~ one wave; chunk ~ 48 MB so it stays in the 126 MB L2 with the Gram slots
     w->splits = std::max(1, ctx->sm_count / w->pairs);
     if (w->splits > 64) w->splits = 64;
-    const int64_t target_bytes = int64_t(48) << 20;
+    int64_t chunk_mb = 48;
+    if (const char *e = getenv("SRGP_CHUNK_MB")) chunk_mb = std::max(4, atoi(e));
+    const int64_t target_bytes = chunk_mb << 20;
     int64_t rows = target_bytes / (8 * (int64_t)mp);
     const int quantum = BK * w->splits;
     rows = std::max<int64_t>(quantum, rows / quantum * quantum);
     w->rows1 = (int)rows;
     // pass 2: row blocks x column groups ~ one wave
+    // column groups: each CTA owns nt / cg column blocks of one 128-row block; cg = 4 keeps the chunk
+    // (sm_count / cg row blocks) near 40 MB at m = 1024 and gives every CTA two tiles per launch
     int cg = 1;
-    for (int c : {8, 4, 2}) {
-        if (w->nt % c == 0 && (int64_t)(ctx->sm_count / c) * BM * mp * 8 >= (int64_t(16) << 20)) {
+    for (int c : {4, 2, 8}) {
+        if (w->nt % c == 0) {
             cg = c;
             break;
         }
     }
-    if (w->nt % cg) cg = 1;
+    if (const char *e = getenv("SRGP_PASS2_CG")) {
+        const int c = atoi(e);
+        if (c >= 1 && w->nt % c == 0) cg = c;
+    }
     w->cgroups = cg;
     w->rblocks = std::max(1, ctx->sm_count / cg);
     w->rows2 = w->rblocks * BM;
     const size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
     SRGP_TRY(w->chunk.reserve(chunk_elems * 8));
     SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));
-    w->gen_groups = std::max(1, std::min(64, (ctx->sm_count * 4) / w->nt));
+    w->gen_groups = std::max(1, std::min(192, (ctx->sm_count * 8) / w->nt));
     SRGP_TRY(w->b1part.reserve((size_t)w->gen_groups * mp * 8));
     SRGP_TRY(w->U.reserve((size_t)m * d * 8));
     SRGP_TRY(w->red1.reserve(((size_t)mp * mp + mp + 16) * 8));
-    SRGP_TRY(w->mats.reserve((size_t)GaussWS::NMATS * mp * mp * 8 + ((size_t)2 * mp * dense::NB + 512) * 8));
+    SRGP_TRY(w->mats.reserve((size_t)GaussWS::NMATS * mp * mp * 8 + ((size_t)4 * mp * dense::NB + 512) * 8));
     SRGP_TRY(w->vecs.reserve((size_t)GaussWS::NVECS * mp * 8 + (size_t)dense::GEMV_SCRATCH * mp * 8));
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
     SRGP_TRY(w->part2.reserve((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE * 8));
@@ -685,7 +713,7 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
         const int rows_padded = w->rows2;   // the K*M kernel always runs all row blocks of the chunk
         {
             KernelScope ks(ctx, SRGP_PROF_GEN, s);
-            dim3 grid(ceil_div(rows_padded, GENC_ROWS), std::min(mp / GENC_COLS, 8));
+            dim3 grid(ceil_div(rows_padded, GENC_ROWS), std::min(mp / GENC_COLS, 64));
             const size_t gs = sizeof(double) * GENC_COLS * d;
 #define CALL(D) launch_gen_cm<D>(s, grid, gs, ctx->Xp, ctx->n, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->chunk.d(), (int64_t)w->rows2)
             SRGP_D_SWITCH(d, CALL)

@@ -43,7 +43,7 @@ struct GaussWS {
     };
 
     double *mat(int i) const { return mats.d() + (size_t)i * mp * mp; }
-    double *dinv(int which) const { return mats.d() + (size_t)NMATS * mp * mp + (size_t)which * ((size_t)mp * 128 + 256); }
+    double *dinv(int which) const { return mats.d() + (size_t)NMATS * mp * mp + (size_t)which * ((size_t)2 * mp * 128 + 256); }
     double *vec(int i) const { return vecs.d() + (size_t)i * mp; }
     double *gemv_scratch() const { return vecs.d() + (size_t)NVECS * mp; }
     double *rowv(int i, int64_t n) const { return rowa.d() + (size_t)i * n; }

@@ -65,7 +65,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
     double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP), *CG = w->mat(W::M_CG), *CGS = w->mat(W::M_CGS);
     double *SG = w->mat(W::M_SG), *SGS = w->mat(W::M_SGS), *N = w->mat(W::M_N), *Mop = w->mat(W::M_MOP);
-    double *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2);
+    double *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2), *LinvT = w->mat(W::M_X1);
     double *bv = w->vec(W::V_B), *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP);
     double *beta = w->vec(W::V_BETA), *gsc = w->gemv_scratch();
 
@@ -73,10 +73,12 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
     SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
     SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
-    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, tmp, Sinv, w->info(0), w->sc(W::S_LOGDET_S)));
+    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, LinvT, tmp, Sinv, w->info(0),
+                                 w->sc(W::S_LOGDET_S)));
     // A = S + B G1 ; C = A^-1
     SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, B, G1, 0.0, A));
-    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, tmp, C, w->info(1), w->sc(W::S_LOGDET_A)));
+    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1),
+                                 w->sc(W::S_LOGDET_A)));
     // b = B b1 ; v = C b ; gv = G1 v ; beta = S^-1 (b - B gv)
     SRGP_TRY(axpby_vec(ctx, mp, B, b1, 0.0, nullptr, bv));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, C, bv, 0.0, nullptr, v, gsc));
@@ -108,7 +110,8 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
         // ---- N and sum N o dS -------------------------------------------------------------------------
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, G1, mp, 0.0, SG, mp));
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'N', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
+        // C G1 S^-1 is symmetric, so SG * CGS = SG * CGS^T: the tile engine's fast NT form
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
         SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5 * B - 0.5 * itau2, SGS, -0.5 * B * B, T2, 0.0, N));
         SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
         SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS)));
