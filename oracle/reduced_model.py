@@ -153,3 +153,84 @@ def shard_bounds(n, world):
         out.append((lo, hi))
         lo = hi
     return out
+
+
+# ====================================================================================================
+# Gaussian FIC: obj_fun_norm + dlogp_dcov_par in row-separable form
+# ====================================================================================================
+def fic_rows_q(x, u, sigma, l, Sinv):
+    """pass 1a (rows): q_i = K_i S^-1 K_i^T."""
+    K, _ = kernel_matrix(x, u, sigma, l)
+    return np.sum((K @ Sinv) * K, axis=1)
+
+
+def fic_pass1(x, r, u, sigma, l, Bv):
+    """pass 1b (rows): G_B = K^T diag(B) K, b = K^T (B r), s0 = sum B r^2, s1 = sum log Z."""
+    K, _ = kernel_matrix(x, u, sigma, l)
+    return {"GB": K.T @ (Bv[:, None] * K), "b": K.T @ (Bv * r), "s0": float(np.sum(Bv * r * r)),
+            "s1": float(np.sum(-np.log(Bv))), "n": float(len(r))}
+
+
+def fic_mid(p1, S, Sinv, logdetS):
+    m = S.shape[0]
+    LA = np.linalg.cholesky(S + p1["GB"])
+    Cm = sla.cho_solve((LA, True), np.eye(m))
+    logdetA = 2 * np.sum(np.log(np.diag(LA)))
+    v = Cm @ p1["b"]
+    beta = Sinv @ (p1["b"] - p1["GB"] @ v)
+    n = p1["n"]
+    obj = -0.5 * p1["s0"] + 0.5 * float(p1["b"] @ v) - 0.5 * (p1["s1"] - logdetS + logdetA) - (n / 2) * math.log(2 * math.pi)
+    M2 = Cm @ p1["GB"] @ Sinv
+    return dict(obj=obj, C=Cm, v=v, beta=beta, M2=M2, n=n)
+
+
+def fic_rows_rho(x, r, u, sigma, l, Bv, mid):
+    """pass 2a (rows): c_i = K_i C K_i^T, alpha_i = B_i (r_i - K_i v), rho_i = alpha_i^2/2 - (B_i - B_i^2 c_i)/2."""
+    K, _ = kernel_matrix(x, u, sigma, l)
+    c = np.sum((K @ mid["C"]) * K, axis=1)
+    alpha = Bv * (r - K @ mid["v"])
+    rho = 0.5 * alpha ** 2 - 0.5 * (Bv - Bv ** 2 * c)
+    return alpha, rho
+
+
+def fic_pass2(x, u, sigma, l, tau, Bv, alpha, rho, Sinv, mid):
+    """pass 2b (rows): sum Omega o dK for sigma / l_c, G_rho = K^T diag(rho) K, sum rho, Q4 pairs."""
+    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
+    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    K, D = kernel_matrix(x, u, sigma, l)
+    Omega = (-Bv - 2 * rho)[:, None] * (K @ Sinv) + Bv[:, None] * (K @ mid["M2"]) + np.outer(alpha, mid["beta"])
+    P = Omega * K
+    eq = _coincident(x, u)
+    return {"g_sigma": 2 * float(P.sum()), "g_l": np.einsum("ij,ijc->c", P, D), "Grho": K.T @ (rho[:, None] * K),
+            "sum_rho": float(rho.sum()), "g_tau_q4": 2 * tau ** 2 * float(Omega[eq].sum()) if eq.any() else 0.0}
+
+
+def fic_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
+    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
+    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    m, d = u.shape
+    r = np.asarray(y, dtype=np.float64).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (len(x),))
+    bounds = shard_bounds(len(x), shards)
+    Kuu, _ = kernel_matrix(u, u, sigma, l)
+    S = Kuu + delta * np.eye(m)
+    LS = np.linalg.cholesky(S)
+    Sinv = sla.cho_solve((LS, True), np.eye(m))
+    logdetS = 2 * np.sum(np.log(np.diag(LS)))
+    Bs = [1.0 / (sigma ** 2 + tau ** 2 + delta - fic_rows_q(x[a:b], u, sigma, l, Sinv)) for a, b in bounds]
+    p1 = add_partials([fic_pass1(x[a:b], r[a:b], u, sigma, l, Bs[k]) for k, (a, b) in enumerate(bounds)])
+    mid = fic_mid(p1, S, Sinv, logdetS)
+    ar = [fic_rows_rho(x[a:b], r[a:b], u, sigma, l, Bs[k], mid) for k, (a, b) in enumerate(bounds)]
+    p2 = add_partials([fic_pass2(x[a:b], u, sigma, l, tau, Bs[k], ar[k][0], ar[k][1], Sinv, mid)
+                       for k, (a, b) in enumerate(bounds)])
+    GB = p1["GB"]
+    N = 0.5 * Sinv @ GB @ Sinv - 0.5 * Sinv @ GB @ mid["M2"] - 0.5 * np.outer(mid["beta"], mid["beta"]) \
+        + Sinv @ p2["Grho"] @ Sinv
+    grad = {"sigma": p2["g_sigma"] + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "sigma"))) + 2 * sigma ** 2 * p2["sum_rho"]}
+    if cov_fun == "ard":
+        for c in range(d):
+            nm = "l%d" % (c + 1)
+            grad[nm] = float(p2["g_l"][c]) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, nm)))
+    else:
+        grad["l"] = float(np.sum(p2["g_l"])) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun)))
+    grad["tau"] = 2 * tau ** 2 * p2["sum_rho"] + p2["g_tau_q4"]
+    return mid["obj"], grad

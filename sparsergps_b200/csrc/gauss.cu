@@ -263,6 +263,9 @@ struct KmArgs {
     int col_blocks_per_cta;
     double *part;
     int first;
+    const double *vvec;     // MODE_ROWFORM: optional m-vector v, rowkv_i = sum_j K_ij v_j
+    double *rowq_part;      // MODE_ROWFORM: [gridDim.y][ldc] per-column-group row sums of (K Mop^T) o K
+    double *rowkv_part;     // MODE_ROWFORM: same for K v (null when vvec is null)
     int *coin_count;        // device counter
     int *coin_list;         // (i_global_lo, j) pairs, capacity coin_cap
     double *coin_omega;
@@ -281,7 +284,9 @@ __device__ __noinline__ void record_coincident(const KmArgs &a, int i_local, int
     }
 }
 
-template <int DT>
+enum { MODE_GRAD = 0, MODE_ROWFORM = 1 };
+
+template <int DT, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -309,6 +314,9 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 
     uint32_t it = 0;
     const int cb0 = blockIdx.y * a.col_blocks_per_cta;
+    double rq[8], rkv[8];
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) rq[mi] = rkv[mi] = 0.0;
     for (int cbi = 0; cbi < a.col_blocks_per_cta; cbi++) {
         const int cb = cb0 + cbi;
         const int j0 = cb * BN;
@@ -323,6 +331,26 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
             us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
         }
         __syncthreads();
+        if (MODE == MODE_ROWFORM) {
+            // per-row sums over this column block: (K Mop^T)_ij K_ij and K_ij v_j
+            if (!is_producer()) {
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++) {
+                    const int ii = frag_row(mi);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int j = j0 + frag_col(ni) + e;
+                            const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                            rq[mi] = fma(acc[mi][ni][e], k, rq[mi]);
+                            if (a.vvec) rkv[mi] = fma(k, a.vvec[j], rkv[mi]);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
         if (!is_producer()) {
             // P = Omega * K in place
             unsigned long long eqmask = 0ull;
@@ -395,6 +423,37 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         }
     }
     __syncthreads();
+    if (MODE == MODE_ROWFORM) {
+        // rows are shared by the 4 lanes of a quad and by the 4 warps of one warp row: quad shuffle, then
+        // shared memory (xs is free now: [4 warp columns][128 rows] x 2 <= d * 128 doubles needs d >= 8, so
+        // the operand stage buffers are reused instead -- every k-tile has been consumed by now)
+        double *rowbuf = reinterpret_cast<double *>(sm.a[0]);
+        if (!is_producer()) {
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                double q = rq[mi], kv = rkv[mi];
+                q += __shfl_xor_sync(0xffffffffu, q, 1);
+                q += __shfl_xor_sync(0xffffffffu, q, 2);
+                kv += __shfl_xor_sync(0xffffffffu, kv, 1);
+                kv += __shfl_xor_sync(0xffffffffu, kv, 2);
+                if ((lane & 3) == 0) {
+                    const int wn = warp >> 1;
+                    rowbuf[wn * BM + frag_row(mi)] = q;
+                    rowbuf[(4 + wn) * BM + frag_row(mi)] = kv;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < BM) {
+            const double q = rowbuf[tid] + rowbuf[BM + tid] + rowbuf[2 * BM + tid] + rowbuf[3 * BM + tid];
+            a.rowq_part[(int64_t)blockIdx.y * a.ldc + i0 + tid] = q;
+            if (a.rowkv_part) {
+                const double kv = rowbuf[4 * BM + tid] + rowbuf[5 * BM + tid] + rowbuf[6 * BM + tid] + rowbuf[7 * BM + tid];
+                a.rowkv_part[(int64_t)blockIdx.y * a.ldc + i0 + tid] = kv;
+            }
+        }
+        return;
+    }
     // CTA reduction over the 8 consumer warps -> this CTA's slot
     if (tid < 1 + d) {
         double v = 0.0;
@@ -531,7 +590,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -585,6 +644,7 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
     SRGP_TRY(w->part2.reserve((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE * 8));
     SRGP_TRY(w->coin.reserve((size_t)GaussWS::COIN_CAP * (2 * sizeof(int) + sizeof(double)) + 64));
+    SRGP_TRY(w->rowpart.reserve((size_t)2 * w->cgroups * w->rows2 * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
     w->planned = true;
     return SRGP_OK;
@@ -685,10 +745,21 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
     return SRGP_OK;
 }
 
-// ---- pass 2 ----------------------------------------------------------------------------------------
-// out[0 .. d+1] <- sum over this shard's rows (see km_reduce_kernel).
-int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
-                const double *ra, const double *beta, double *out, bool accumulate_slots)
+// ---- pass 2 / row-form passes -------------------------------------------------------------------------
+// combine the per-column-group row sums of one chunk: out[r0 + i] = sum_g part[g][i]
+__global__ void combine_rows_kernel(const double *__restrict__ part, int groups, int64_t ld, int rows,
+                                    double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    double s = 0.0;
+    for (int g = 0; g < groups; g++) s += part[(int64_t)g * ld + i];
+    out[i] = s;
+}
+
+static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, const double *Mop, const double *rs,
+                   const double *ra, const double *beta, const double *vvec, double *out, bool accumulate_slots,
+                   double *rowq, double *rowkv)
 {
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
@@ -697,17 +768,25 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
         set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
         return SRGP_ERR_ARG;
     }
-    static size_t configured_smem[9] = {0};   // per template instantiation (index 0 = runtime d)
+    static size_t configured_smem[2][9] = {{0}};   // per template instantiation (index 0 = runtime d)
     const int slot_d = (d >= 1 && d <= 8) ? d : 0;
-    if (configured_smem[slot_d] < smem) {
-#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-        SRGP_D_SWITCH(d, CALL)
+    if (configured_smem[mode][slot_d] < smem) {
+        if (mode == MODE_GRAD) {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            SRGP_D_SWITCH(d, CALL)
 #undef CALL
-        configured_smem[slot_d] = smem;
+        } else {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_ROWFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
+        }
+        configured_smem[mode][slot_d] = smem;
     }
     const int slots = w->rblocks * w->cgroups;
     int first = accumulate_slots ? 0 : 1;
-    if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
+    if (mode == MODE_GRAD && ctx->n == 0 && first)
+        SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
+    double *rowpart = w->rowpart.d();
     for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2) {
         const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
         const int rows_padded = w->rows2;   // the K*M kernel always runs all row blocks of the chunk
@@ -741,20 +820,40 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
             a.col_blocks_per_cta = w->nt / w->cgroups;
             a.part = w->part2.d();
             a.first = first;
+            a.vvec = vvec;
+            a.rowq_part = rowpart;
+            a.rowkv_part = rowkv ? rowpart + (size_t)w->cgroups * w->rows2 : nullptr;
             a.coin_count = reinterpret_cast<int *>(w->coin.p);
             a.coin_list = reinterpret_cast<int *>(w->coin.p) + 16;
             a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
                                                       (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
             a.coin_cap = GaussWS::COIN_CAP;
             dim3 grid(w->rblocks, w->cgroups);
-#define CALL(D) km_reduce_kernel<D><<<grid, THREADS, smem, s>>>(a)
-            SRGP_D_SWITCH(d, CALL)
+            if (mode == MODE_GRAD) {
+#define CALL(D) km_reduce_kernel<D, MODE_GRAD><<<grid, THREADS, smem, s>>>(a)
+                SRGP_D_SWITCH(d, CALL)
 #undef CALL
+            } else {
+#define CALL(D) km_reduce_kernel<D, MODE_ROWFORM><<<grid, THREADS, smem, s>>>(a)
+                SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            }
             SRGP_LAUNCH_CHECK();
+        }
+        if (mode == MODE_ROWFORM) {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s, rowkv ? 2 : 1);
+            combine_rows_kernel<<<ceil_div(rows_valid, 256), 256, 0, s>>>(rowpart, w->cgroups, w->rows2, rows_valid,
+                                                                          rowq + r0);
+            SRGP_LAUNCH_CHECK();
+            if (rowkv) {
+                combine_rows_kernel<<<ceil_div(rows_valid, 256), 256, 0, s>>>(
+                    rowpart + (size_t)w->cgroups * w->rows2, w->cgroups, w->rows2, rows_valid, rowkv + r0);
+                SRGP_LAUNCH_CHECK();
+            }
         }
         first = 0;
     }
-    {
+    if (mode == MODE_GRAD && out) {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
         sum_part_kernel<<<d + 1, 32, 0, s>>>(w->part2.d(), slots, PART_STRIDE, d + 1, out);
         SRGP_LAUNCH_CHECK();
@@ -762,6 +861,21 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
     return SRGP_OK;
 }
 
+// out[0 .. d] <- sum over this shard's rows (see km_reduce_kernel); out == null defers the final sum to a
+// later call that accumulates into the same per-CTA slots.
+int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
+                const double *ra, const double *beta, double *out, bool accumulate_slots)
+{
+    return km_pass(ctx, w, gp, MODE_GRAD, Mop, rs, ra, beta, nullptr, out, accumulate_slots, nullptr, nullptr);
+}
+
+// Row quadratic forms over the shard: rowq_i = K_i Mop K_i^T (Mop symmetric), rowkv_i = K_i v (optional).
+int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
+                  double *rowq, double *rowkv)
+{
+    return km_pass(ctx, w, gp, MODE_ROWFORM, Mop, nullptr, nullptr, nullptr, vvec, nullptr, false, rowq,
+                   vvec ? rowkv : nullptr);
+}
 
 // ---- small launchers -----------------------------------------------------------------------------------
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,

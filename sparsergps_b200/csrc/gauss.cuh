@@ -30,6 +30,7 @@ struct GaussWS {
     DevBuf scal;     // device scalars
     DevBuf part2;    // pass-2 per-CTA partial sums
     DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
+    DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
     double *h_scal = nullptr;   // pinned mirror of scal
 
     enum { NMATS = 16, NVECS = 12, NROWV = 6, NSCAL = 256, COIN_CAP = 65536 };
@@ -65,6 +66,9 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
 // accumulate_slots: add to the per-CTA slots of a previous gauss_pass2 call instead of restarting them.
 int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
                 const double *ra, const double *beta, double *out, bool accumulate_slots);
+// Row quadratic forms over the shard: rowq_i = K_i Mop K_i^T (Mop symmetric), rowkv_i = K_i v (v may be null).
+int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
+                  double *rowq, double *rowkv);
 // out[0] = sum N o Kuu, out[1 + c] = sum N o Kuu o D_c, out[1 + d] = sum of N over bit-identical knot pairs
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
               double *out);
@@ -76,6 +80,8 @@ int set_scalar(srgp_ctx *ctx, double *dst, double v);
 int copy_scalar(srgp_ctx *ctx, double *dst, const double *src, int count);
 
 int comm_allreduce(srgp_ctx *ctx, double *buf, size_t count, cudaStream_t s);
+// D2H of the scalar block + stream sync; maps a failed m x m Cholesky to SRGP_ERR_NOT_PD
+int fetch_scalars(srgp_ctx *ctx, GaussWS *w);
 int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
              double *obj, double *grad);
 int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,

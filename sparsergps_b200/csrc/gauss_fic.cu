@@ -1,0 +1,211 @@
+// gauss_fic.cu -- Gaussian FIC objective + gradient on the resident shard.
+//
+// Reference: obj_fun_norm (R/laplace_approx_obj_funs.R:6-52), Z construction
+// (R/laplace_gradient_ascent.R:1259-1263), dlogp_dcov_par (R/laplace_approx_gradient.R:720-968).
+// Reduced form (oracle/reduced_model.py::fic_obj_grad == literal transcription to 1e-13):
+//   S = K_uu + delta I;  q_i = K_i S^-1 K_i^T;  Z_i = sigma^2 + tau^2 + delta - q_i;  B_i = 1/Z_i;  r = y - mu
+//   G_B = K^T diag(B) K, b = K^T (B r), C = (S + G_B)^-1, v = C b, beta = S^-1 (b - G_B v), M2 = C G_B S^-1
+//   obj = -sum B r^2/2 + b^T v/2 - (sum log Z - log|S| + log|S + G_B|)/2 - n log(2 pi)/2
+//   c_i = K_i C K_i^T, alpha_i = B_i (r_i - K_i v), w_i = B_i - B_i^2 c_i, rho_i = alpha_i^2/2 - w_i/2
+//   Omega = diag(-B - 2 rho) K S^-1 + diag(B) K M2 + alpha beta^T
+//   N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1,  G_rho = K^T diag(rho) K
+//   g_theta = sum Omega o dK + sum N o dS + A1(theta) sum rho   (A1 = 2 sigma^2, 0, 2 tau^2; dS(tau) = 0)
+// Row passes: q (K S^-1 row forms), weighted Gram, c and K v (row forms with C), two Omega terms, weighted Gram.
+#include <math.h>
+
+#include "dense.cuh"
+#include "gauss.cuh"
+
+namespace srgp {
+
+using W = GaussWS;
+
+__device__ __forceinline__ double block_reduce_256(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += red[k];
+    return t;
+}
+
+// Z, B, B r from q; per-block partial sums of B r^2 and log Z  (part[2 * block + {0, 1}])
+__global__ void __launch_bounds__(256)
+fic_rows1_kernel(const double *__restrict__ q, const double *__restrict__ r, int64_t n, double zconst,
+                 double *__restrict__ B, double *__restrict__ Br, double *__restrict__ part)
+{
+    __shared__ double red[8];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double z = zconst - q[i];
+        const double b = 1.0 / z, ri = r[i];
+        B[i] = b;
+        Br[i] = b * ri;
+        s0 = fma(b * ri, ri, s0);
+        s1 += log(z);
+    }
+    s0 = block_reduce_256(s0, red);
+    s1 = block_reduce_256(s1, red);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = s0;
+        part[2 * blockIdx.x + 1] = s1;
+    }
+}
+
+// alpha, rho, rs1 = -B - 2 rho from c, K v; per-block partial sums of rho
+__global__ void __launch_bounds__(256)
+fic_rows2_kernel(const double *__restrict__ c, const double *__restrict__ kv, const double *__restrict__ r,
+                 const double *__restrict__ B, int64_t n, double *__restrict__ alpha, double *__restrict__ rho,
+                 double *__restrict__ rs1, double *__restrict__ part)
+{
+    __shared__ double red[8];
+    double sr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double b = B[i];
+        const double a = b * (r[i] - kv[i]);
+        const double wi = b - b * b * c[i];
+        const double rh = 0.5 * a * a - 0.5 * wi;
+        alpha[i] = a;
+        rho[i] = rh;
+        rs1[i] = -b - 2.0 * rh;
+        sr += rh;
+    }
+    sr = block_reduce_256(sr, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = sr;
+}
+
+__global__ void sum_strided_kernel(const double *__restrict__ part, int count, int stride, int offset,
+                                   double *__restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += part[i * stride + offset];
+    s = block_reduce_256(s, red);
+    if (threadIdx.x == 0) *out = s;
+}
+
+constexpr int ROW_BLOCKS = 128;
+
+int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
+              double *obj, double *grad)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int64_t n = ctx->n;
+    const size_t mm = (size_t)mp * mp;
+    GenParams gp;
+    fill_gen(gp, kernel, d, sigma, l);
+    const double zconst = sigma * sigma + tau * tau + delta;
+
+    double *GB = w->red1.d(), *b = GB + mm, *tail = b + mp;   // allreduce buffer of pass 1
+    SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
+    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+
+    double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
+    double *Linv = w->mat(W::M_LINV), *LinvT = w->mat(W::M_X1), *tmp = w->mat(W::M_TMP);
+    double *CG = w->mat(W::M_CG), *M2 = w->mat(W::M_CGS), *SG = w->mat(W::M_SG), *SGS = w->mat(W::M_SGS);
+    double *N = w->mat(W::M_N), *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2), *Grho = w->mat(W::M_X2);
+    double *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP), *beta = w->vec(W::V_BETA);
+    double *gsc = w->gemv_scratch();
+    double *q = w->rowv(0, n), *Bv = w->rowv(1, n), *Br = w->rowv(2, n), *kv = w->rowv(3, n);
+    double *alpha = w->rowv(4, n), *rho = w->rowv(5, n);
+    double *cq = q, *rs1 = Br;   // reuse: q is dead once B exists, B r once b is reduced
+
+    // ---- S, S^-1 ----------------------------------------------------------------------------------------
+    SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
+    SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
+    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
+    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, LinvT, tmp, Sinv, w->info(0),
+                                 w->sc(W::S_LOGDET_S)));
+
+    // ---- pass 1a: q_i ; rows: Z, B, B r, sum B r^2, sum log Z ----------------------------------------------
+    SRGP_TRY(gauss_rowform(ctx, w, gp, Sinv, nullptr, q, nullptr));
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 3);
+        fic_rows1_kernel<<<ROW_BLOCKS, 256, 0, s>>>(q, w->r.d(), n, zconst, Bv, Br, w->part2.d());
+        SRGP_LAUNCH_CHECK();
+        sum_strided_kernel<<<1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, 2, 0, tail);
+        SRGP_LAUNCH_CHECK();
+        sum_strided_kernel<<<1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, 2, 1, tail + 1);
+        SRGP_LAUNCH_CHECK();
+    }
+    SRGP_TRY(set_scalar(ctx, tail + 2, (double)n));
+    // ---- pass 1b: G_B, b ---------------------------------------------------------------------------------
+    SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, GB, b));
+    SRGP_TRY(comm_allreduce(ctx, GB, mm + mp + 3, s));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_X), tail, 3));   // s0, s1, n (global)
+
+    // ---- m x m: C, v, beta, M2 -----------------------------------------------------------------------------
+    SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, 1.0, GB, 0.0, A));
+    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1),
+                                 w->sc(W::S_LOGDET_A)));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, C, b, 0.0, nullptr, v, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, GB, v, 0.0, nullptr, gv, gsc));
+    SRGP_TRY(axpby_vec(ctx, mp, 1.0, b, -1.0, gv, tv));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Sinv, tv, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::dot_v(ctx, s, m, b, v, w->sc(W::S_BV)));
+    if (grad) {
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, GB, mp, 0.0, CG, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, M2, mp));
+
+        // ---- pass 2a: c_i, (K v)_i ; rows: alpha, rho, -B - 2 rho, sum rho -----------------------------------
+        SRGP_TRY(gauss_rowform(ctx, w, gp, C, v, cq, kv));
+        double *p2 = w->sc(W::S_P2);
+        {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+            fic_rows2_kernel<<<ROW_BLOCKS, 256, 0, s>>>(cq, kv, w->r.d(), Bv, n, alpha, rho, rs1, w->part2.d());
+            SRGP_LAUNCH_CHECK();
+            sum_strided_kernel<<<1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, 1, 0, p2 + d + 2);
+            SRGP_LAUNCH_CHECK();
+        }
+        // ---- pass 2b: the two Omega terms share the per-CTA slots; G_rho --------------------------------------
+        SRGP_TRY(gauss_pass2(ctx, w, gp, Sinv, rs1, alpha, beta, nullptr, false));
+        SRGP_TRY(gauss_pass2(ctx, w, gp, M2, Bv, nullptr, beta, p2, true));
+        // quirk Q4: sum of Omega_ij over bit-identical (row, knot) pairs (both terms were recorded)
+        SRGP_TRY(coin_fix(ctx, w, gp, Sinv, 0.0, p2 + 1 + d));
+        double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho | p2 (d + 3)]
+        SRGP_TRY(gauss_pass1(ctx, w, gp, rho, rho, red2, tv));
+        SRGP_TRY(copy_scalar(ctx, red2 + mm, p2, d + 3));
+        SRGP_TRY(comm_allreduce(ctx, red2, mm + d + 3, s));
+        SRGP_TRY(copy_scalar(ctx, p2, red2 + mm, d + 3));
+        SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
+
+        // ---- N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1 ------------------------------
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, GB, mp, 0.0, SG, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, M2, mp, 0.0, T1, mp));     // M2 symmetric
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5, SGS, -0.5, T1, 0.0, N));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, Grho, mp, 0.0, SG, mp));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, N, 1.0, SGS, 0.0, N));
+        SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
+        SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS)));
+    }
+    SRGP_TRY(fetch_scalars(ctx, w));
+
+    const double *h = w->h_scal;
+    const double s0 = h[W::S_X], s1 = h[W::S_X + 1], ntot = h[W::S_X + 2];
+    *obj = -0.5 * s0 + 0.5 * h[W::S_BV] - 0.5 * (s1 - h[W::S_LOGDET_S] + h[W::S_LOGDET_A]) - 0.5 * ntot * log(2.0 * M_PI);
+    if (grad) {
+        const double *p2 = h + W::S_P2, *ns = h + W::S_NS;
+        const double sum_rho = p2[d + 2];
+        grad[0] = 2.0 * p2[0] + 2.0 * ns[0] + 2.0 * sigma * sigma * sum_rho;
+        if (kernel == SRGP_ARD) {
+            for (int c = 0; c < d; c++) grad[1 + c] = p2[1 + c] + ns[1 + c];
+        } else {
+            double g = 0.0;
+            for (int c = 0; c < d; c++) g += p2[1 + c] + ns[1 + c];
+            grad[1] = g;
+        }
+        const int ti = (kernel == SRGP_ARD) ? 1 + d : 2;
+        grad[ti] = 2.0 * tau * tau * sum_rho + 2.0 * tau * tau * p2[1 + d];
+    }
+    return SRGP_OK;
+}
+
+}  // namespace srgp

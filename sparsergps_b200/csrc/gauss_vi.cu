@@ -21,7 +21,7 @@ namespace srgp {
 
 using W = GaussWS;
 
-static int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
+int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
 {
     SRGP_CUDA(cudaMemcpyAsync(w->h_scal, w->scal.p, W::NSCAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -140,12 +140,6 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
                    2.0 * tau * tau * p2[1 + d];
     }
     return SRGP_OK;
-}
-
-int gauss_fic(srgp_ctx *, GaussWS *, int, double, const double *, double, double, double *, double *)
-{
-    set_error("FIC model: not implemented yet");
-    return SRGP_ERR_STATE;
 }
 
 }  // namespace srgp
