@@ -1007,7 +1007,8 @@ static int set_data_common(srgp_ctx *ctx, int64_t n, int d)
     ctx->n = n;
     ctx->d = d;
     SRGP_TRY(w->r.reserve(std::max<size_t>(8, (size_t)n * 8)));
-    SRGP_TRY(w->rowa.reserve(std::max<size_t>(8, (size_t)n * 8 * GaussWS::NROWV)));
+    SRGP_TRY(w->rowa.reserve(GaussWS::row_stride(n) * 8 * GaussWS::NROWV));
+    SRGP_CUDA(cudaMemsetAsync(w->rowa.p, 0, GaussWS::row_stride(n) * 8 * GaussWS::NROWV, ctx->stream));
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
     SRGP_TRY(w->part2.reserve((size_t)256 * PART_STRIDE * 8));
     // residual r = y - mu and s0 = r^T r: independent of theta, computed once per data upload

@@ -47,7 +47,10 @@ struct GaussWS {
     double *dinv(int which) const { return mats.d() + (size_t)NMATS * mp * mp + (size_t)which * ((size_t)2 * mp * 128 + 256); }
     double *vec(int i) const { return vecs.d() + (size_t)i * mp; }
     double *gemv_scratch() const { return vecs.d() + (size_t)NVECS * mp; }
-    double *rowv(int i, int64_t n) const { return rowa.d() + (size_t)i * n; }
+    // per-row vectors: stride padded to 128 doubles (16-byte aligned bulk copies of weight tiles) and followed
+    // by a zeroed tail, because the weighted SYRK reads weights for the zero rows that pad a chunk
+    static size_t row_stride(int64_t n) { return ((size_t)n + 127) / 128 * 128 + 1024; }
+    double *rowv(int i, int64_t n) const { return rowa.d() + (size_t)i * row_stride(n); }
     double *sc(int i) const { return scal.d() + i; }
     int *info(int which) const { return reinterpret_cast<int *>(scal.d() + S_INFO) + which; }
     void release();
