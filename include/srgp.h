@@ -119,6 +119,10 @@ double srgp_dtrace_term_dtau(double trace_term);
    Omega is n x m (host).  out has p entries ordered sigma, l (or l1..ld), tau. */
 int srgp_omega_dk_reduce(srgp_ctx *ctx, int kernel, const double *x, int64_t n, const double *xu, int64_t m,
                          int d, double sigma, const double *l, double tau, const double *Omega, double *out);
+/* Same with x, xu and Omega already in HBM (kernel-only timing: the kernel reads 8*n*m bytes of Omega once). */
+int srgp_omega_dk_reduce_dev(srgp_ctx *ctx, int kernel, const double *x_dev, int64_t n, const double *xu_dev,
+                             int64_t m, int d, double sigma, const double *l, double tau, const double *Omega_dev,
+                             double *out);
 
 /* ---------------------------------------------------------------- fused objective + gradient - */
 /* Resident data shard: xy (n x d), y (n), mu (n, NULL = 0).  Under multi-GPU each rank passes ITS rows. */

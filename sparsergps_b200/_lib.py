@@ -56,6 +56,7 @@ SIGNATURES = {
     "srgp_dtrace_term_dcov_par": (ci, [vp, cd, dp, i64, dp]),
     "srgp_dtrace_term_dtau": (cd, [cd]),
     "srgp_omega_dk_reduce": (ci, [vp, ci, dp, i64, dp, i64, ci, cd, dp, cd, dp, dp]),
+    "srgp_omega_dk_reduce_dev": (ci, [vp, ci, vp, i64, vp, i64, ci, cd, dp, cd, vp, dp]),
     "srgp_set_data": (ci, [vp, dp, i64, ci, dp, dp]),
     "srgp_set_data_dev": (ci, [vp, vp, i64, ci, vp, vp]),
     "srgp_gauss_obj_grad": (ci, [vp, ci, ci, dp, i64, cd, dp, cd, cd, dp, dp]),

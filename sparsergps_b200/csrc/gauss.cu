@@ -303,10 +303,12 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 
     pipeline_init(sm);
     // stage the scaled rows of this row block once
-    for (int t = tid; t < d * BM; t += THREADS) {
-        const int c = t / BM, ii = t - c * BM;
-        const int i = i0 + ii;
-        xs[c * BM + ii] = (i < a.rows_valid) ? a.X[a.r0 + i + a.ldx * c] * a.invl[c] : 0.0;
+    if (MODE == MODE_GRAD) {
+        for (int t = tid; t < d * BM; t += THREADS) {
+            const int c = t / BM, ii = t - c * BM;
+            const int i = i0 + ii;
+            xs[c * BM + ii] = (i < a.rows_valid) ? a.X[a.r0 + i + a.ldx * c] * a.invl[c] : 0.0;
+        }
     }
     if (!is_producer())
         for (int t = lane; t < PART_STRIDE; t += 32) red[warp * PART_STRIDE + t] = 0.0;
@@ -325,12 +327,14 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         mainloop<false, false, false>(sm, a.Kc + i0, a.ldc, a.Mop + j0, a.mp, nullptr, a.mp / BK, it, acc);
         // stage this column block's knots (all 288 threads), consumers then run the epilogue
         __syncthreads();
-        for (int t = tid; t < d * BN; t += THREADS) {
-            const int c = t / BN, jj = t - c * BN;
-            const int j = j0 + jj;
-            us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
+        if (MODE == MODE_GRAD) {
+            for (int t = tid; t < d * BN; t += THREADS) {
+                const int c = t / BN, jj = t - c * BN;
+                const int j = j0 + jj;
+                us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (MODE == MODE_ROWFORM) {
             // per-row sums over this column block: (K Mop^T)_ij K_ij and K_ij v_j
             if (!is_producer()) {
@@ -867,6 +871,40 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
                 const double *ra, const double *beta, double *out, bool accumulate_slots)
 {
     return km_pass(ctx, w, gp, MODE_GRAD, Mop, rs, ra, beta, nullptr, out, accumulate_slots, nullptr, nullptr);
+}
+
+// Row quadratic forms of ONE materialised chunk already sitting in w->chunk (column-major, ld = w->rows2,
+// zero padded): rowq[i] = chunk_i Mop chunk_i^T for i < rows_valid.  Used by srgp_trace_term.
+int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, double *rowq)
+{
+    cudaStream_t s = ctx->stream;
+    const int d = 1;
+    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
+    static bool configured = false;
+    if (!configured) {
+        SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<1, MODE_ROWFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(Smem) + sizeof(double) * (8 * (BM + BN) + CONSUMER_WARPS * PART_STRIDE))));
+        configured = true;
+    }
+    KmArgs a = {};
+    a.Kc = w->chunk.d();
+    a.ldc = w->rows2;
+    a.Mop = Mop;
+    a.mp = w->mp;
+    a.m = w->m;
+    a.d = d;
+    a.rows_valid = rows_valid;
+    a.col_blocks_per_cta = w->nt / w->cgroups;
+    a.rowq_part = w->rowpart.d();
+    {
+        KernelScope ks(ctx, SRGP_PROF_KM, s);
+        km_reduce_kernel<1, MODE_ROWFORM><<<dim3(w->rblocks, w->cgroups), THREADS, smem, s>>>(a);
+        SRGP_LAUNCH_CHECK();
+    }
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+    combine_rows_kernel<<<ceil_div(rows_valid, 256), 256, 0, s>>>(w->rowpart.d(), w->cgroups, w->rows2, rows_valid, rowq);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
 }
 
 // Row quadratic forms over the shard: rowq_i = K_i Mop K_i^T (Mop symmetric), rowkv_i = K_i v (optional).

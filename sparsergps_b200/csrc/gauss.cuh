@@ -72,6 +72,7 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
 // Row quadratic forms over the shard: rowq_i = K_i Mop K_i^T (Mop symmetric), rowkv_i = K_i v (v may be null).
 int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
                   double *rowq, double *rowkv);
+int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, double *rowq);
 // out[0] = sum N o Kuu, out[1 + c] = sum N o Kuu o D_c, out[1 + d] = sum of N over bit-identical knot pairs
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
               double *out);

@@ -3,9 +3,6 @@
 using namespace srgp;
 #define SRGP_TODO(name) do { set_error(name ": not implemented yet"); return SRGP_ERR_STATE; } while (0)
 extern "C" {
-int srgp_trace_term(srgp_ctx *, double, double, double, const double *, int64_t, int64_t, const double *, double *) { SRGP_TODO("srgp_trace_term"); }
-int srgp_dtrace_term_dcov_par(srgp_ctx *, double, const double *, int64_t, double *) { SRGP_TODO("srgp_dtrace_term_dcov_par"); }
-int srgp_omega_dk_reduce(srgp_ctx *, int, const double *, int64_t, const double *, int64_t, int, double, const double *, double, const double *, double *) { SRGP_TODO("srgp_omega_dk_reduce"); }
 int srgp_laplace_newton(srgp_ctx *, int, int, const double *, int64_t, const double *, double, const double *, double, double, double, int, double, double *, double *, int *, double *, double *, double *) { SRGP_TODO("srgp_laplace_newton"); }
 int srgp_laplace_grad(srgp_ctx *, int, int, const double *, int64_t, double, const double *, double, double, double, const double *, double *) { SRGP_TODO("srgp_laplace_grad"); }
 }
