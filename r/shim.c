@@ -1,0 +1,331 @@
+/*
+ * r/shim.c -- the R-side glue a sparseRGPs maintainer adds to bind libsrgp.so behind the package's own
+ * `.Call` routines (replaces src/RcppExports.cpp + the two Rcpp kernel files of the reference).
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE: R (Rinternals.h, libR) is not installed.
+ * It is marshalling only; every numerical statement lives behind include/srgp.h, which tests/ exercise through
+ * ctypes.  Build inside the package:   PKG_LIBS = -L<dir> -lsrgp   (src/Makevars), keep R/RcppExports.R as is.
+ *
+ * Registered routine names and arities are those of src/RcppExports.cpp:285-304, so R/RcppExports.R loads
+ * unchanged.  Error conventions: status != 0 -> Rf_error, EXCEPT unknown kernel /
+ * parameter names, which print the reference's message and return a 0 x 0 matrix.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "srgp.h"
+
+static srgp_ctx *g_ctx = NULL;
+
+static srgp_ctx *ctx(void)
+{
+    if (!g_ctx && srgp_ctx_create(0, &g_ctx) != SRGP_OK) Rf_error("sparseRGPs: %s", srgp_last_error());
+    return g_ctx;
+}
+
+static double list_get(SEXP lst, const char *name)
+{
+    SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+    for (R_xlen_t i = 0; i < Rf_xlength(lst); i++)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asReal(VECTOR_ELT(lst, i));
+    Rf_error("Index out of bounds: [index='%s'].", name);   /* Rcpp's index_out_of_bounds */
+    return NA_REAL;
+}
+
+static int kernel_id(SEXP cov_fun)
+{
+    const char *s = CHAR(STRING_ELT(cov_fun, 0));
+    if (!strcmp(s, "sqexp")) return SRGP_SQEXP;
+    if (!strcmp(s, "exp")) return SRGP_EXP;
+    if (!strcmp(s, "ard")) return SRGP_ARD;
+    return -1;
+}
+
+static SEXP empty_matrix(const char *msg)
+{
+    REprintf("%s", msg);
+    return Rf_allocMatrix(REALSXP, 0, 0);
+}
+
+/* x_pred = matrix() arrives as a 1 x 1 logical NA (src/covariance_functionsC.cpp:81) */
+static int is_empty(SEXP x_pred) { return ISNA(REAL(x_pred)[0]) || ISNAN(REAL(x_pred)[0]); }
+
+static SEXP assemble(SEXP x, SEXP x_pred, SEXP cov_par, int kernel, double delta, SEXP lnames, int par, int comp0,
+                     int derivative)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    x_pred = PROTECT(Rf_coerceVector(x_pred, REALSXP));
+    const int n1 = Rf_nrows(x), d = Rf_ncols(x);
+    const int self = is_empty(x_pred);
+    const int n2 = self ? n1 : Rf_nrows(x_pred);
+    double l[SRGP_MAX_D];
+    if (kernel == SRGP_ARD) {
+        if (d > SRGP_MAX_D) Rf_error("sparseRGPs: d = %d exceeds %d", d, SRGP_MAX_D);
+        for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    } else {
+        l[0] = list_get(cov_par, "l");
+    }
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n1, n2));
+    int st;
+    if (!derivative)
+        st = srgp_make_cov_mat(ctx(), kernel, REAL(x), n1, self ? NULL : REAL(x_pred), n2, d,
+                               list_get(cov_par, "sigma"), l, self ? list_get(cov_par, "tau") : 0.0, delta, REAL(out));
+    else
+        st = srgp_dsig_dtheta(ctx(), kernel, par, comp0, REAL(x), n1, self ? NULL : REAL(x_pred), n2, d,
+                              list_get(cov_par, "sigma"), l, par == SRGP_PAR_TAU ? list_get(cov_par, "tau") : 0.0,
+                              REAL(out));
+    UNPROTECT(3);
+    if (st == SRGP_ERR_UNKNOWN_PAR) return empty_matrix("Error: invalid parameter name for chosen covariance function");
+    if (st != SRGP_OK) Rf_error("sparseRGPs: %s", srgp_last_error());
+    return out;
+}
+
+SEXP _sparseRGPs_make_cov_matC(SEXP x, SEXP x_pred, SEXP cov_par, SEXP cov_fun, SEXP delta)
+{
+    const int k = kernel_id(cov_fun);
+    if (k != SRGP_SQEXP && k != SRGP_EXP) return empty_matrix("Error: invalid covariance function");
+    return assemble(x, x_pred, cov_par, k, Rf_asReal(delta), R_NilValue, 0, 0, 0);
+}
+
+SEXP _sparseRGPs_make_cov_mat_ardC(SEXP x, SEXP x_pred, SEXP cov_par, SEXP cov_fun, SEXP delta, SEXP lnames)
+{
+    if (kernel_id(cov_fun) != SRGP_ARD) return empty_matrix("Error: invalid covariance function");
+    return assemble(x, x_pred, cov_par, SRGP_ARD, Rf_asReal(delta), lnames, 0, 0, 0);
+}
+
+static int par_id(const char *name, int kernel, SEXP lnames, int *comp0)
+{
+    *comp0 = -1;
+    if (!strcmp(name, "sigma")) return SRGP_PAR_SIGMA;
+    if (!strcmp(name, "tau")) return SRGP_PAR_TAU;
+    if (kernel == SRGP_ARD) {
+        int found = -1;   /* the reference keeps the LAST match (covariance_function_derivativesC.cpp:596-605) */
+        for (int c = 0; c < Rf_length(lnames); c++)
+            if (!strcmp(name, CHAR(STRING_ELT(lnames, c)))) found = c;
+        if (found >= 0) { *comp0 = found; return SRGP_PAR_LC; }
+        return 99;
+    }
+    return strcmp(name, "l") ? 99 : SRGP_PAR_L;
+}
+
+SEXP _sparseRGPs_dsig_dthetaC(SEXP x, SEXP x_pred, SEXP cov_par, SEXP cov_fun, SEXP par_name)
+{
+    const int k = kernel_id(cov_fun);
+    if (k != SRGP_SQEXP && k != SRGP_EXP) return empty_matrix("Error: invalid covariance function");
+    int comp0;
+    const int par = par_id(CHAR(STRING_ELT(par_name, 0)), k, R_NilValue, &comp0);
+    return assemble(x, x_pred, cov_par, k, 0.0, R_NilValue, par, comp0, 1);
+}
+
+SEXP _sparseRGPs_dsig_dtheta_ardC(SEXP x, SEXP x_pred, SEXP cov_par, SEXP cov_fun, SEXP par_name, SEXP lnames)
+{
+    if (kernel_id(cov_fun) != SRGP_ARD) return empty_matrix("Error: invalid covariance function");
+    int comp0;
+    const int par = par_id(CHAR(STRING_ELT(par_name, 0)), SRGP_ARD, lnames, &comp0);
+    return assemble(x, x_pred, cov_par, SRGP_ARD, 0.0, lnames, par, comp0, 1);
+}
+
+/* transforms (vectors in, vectors out) */
+SEXP _sparseRGPs_real_to_pos(SEXP x)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_xlength(x)));
+    srgp_real_to_pos(REAL(x), Rf_xlength(x), REAL(out));
+    UNPROTECT(2);
+    return out;
+}
+SEXP _sparseRGPs_pos_to_real(SEXP x)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_xlength(x)));
+    srgp_pos_to_real(REAL(x), Rf_xlength(x), REAL(out));
+    UNPROTECT(2);
+    return out;
+}
+SEXP _sparseRGPs_real_to_bounded(SEXP x, SEXP ub, SEXP lb)
+{
+    x = PROTECT(Rf_coerceVector(x, REALSXP));
+    ub = PROTECT(Rf_coerceVector(ub, REALSXP));
+    lb = PROTECT(Rf_coerceVector(lb, REALSXP));
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, Rf_xlength(x)));
+    srgp_real_to_bounded(REAL(x), REAL(ub), REAL(lb), Rf_xlength(x), REAL(out));
+    UNPROTECT(4);
+    return out;
+}
+
+/* scalar covariance functions: (x1, x2, cov_par[, lnames]) -> double */
+SEXP _sparseRGPs_cov_fun_sqrd_expC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    return Rf_ScalarReal(srgp_cov_fun_sqrd_exp(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"),
+                                               list_get(cov_par, "l")));
+}
+SEXP _sparseRGPs_cov_fun_expC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    return Rf_ScalarReal(srgp_cov_fun_exp(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"),
+                                          list_get(cov_par, "l")));
+}
+SEXP _sparseRGPs_cov_fun_sqrd_exp_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+{
+    double l[SRGP_MAX_D];
+    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    return Rf_ScalarReal(srgp_cov_fun_sqrd_exp_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l));
+}
+
+/* per-pair derivative helpers return list(derivative, trans_par, inv_trans_par) like the Rcpp originals */
+static SEXP deriv_list(double deriv, double par)
+{
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)), nm = PROTECT(Rf_allocVector(STRSXP, 3));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarReal(deriv));
+    SET_VECTOR_ELT(out, 1, Rf_ScalarReal(log(par)));
+    SET_VECTOR_ELT(out, 2, Rf_ScalarReal(par));
+    SET_STRING_ELT(nm, 0, Rf_mkChar("derivative"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("trans_par"));
+    SET_STRING_ELT(nm, 2, Rf_mkChar("inv_trans_par"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+#define PAIR_SCALAR(NAME, FN, PARNAME)                                                                         \
+    SEXP _sparseRGPs_##NAME(SEXP x1, SEXP x2, SEXP cov_par)                                                    \
+    {                                                                                                          \
+        return deriv_list(FN(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), list_get(cov_par, "l")), \
+                          list_get(cov_par, PARNAME));                                                         \
+    }
+PAIR_SCALAR(dsqexp_dsigmaC, srgp_dsqexp_dsigma, "sigma")
+PAIR_SCALAR(dsqexp_dlC, srgp_dsqexp_dl, "l")
+PAIR_SCALAR(dexp_dsigmaC, srgp_dexp_dsigma, "sigma")
+PAIR_SCALAR(dexp_dlC, srgp_dexp_dl, "l")
+SEXP _sparseRGPs_dsqexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    return deriv_list(srgp_dsqexp_dtau(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "tau")), list_get(cov_par, "tau"));
+}
+SEXP _sparseRGPs_dexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    return deriv_list(srgp_dexp_dtau(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "tau")), list_get(cov_par, "tau"));
+}
+SEXP _sparseRGPs_dsqexp_dsigma_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+{
+    double l[SRGP_MAX_D];
+    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    return deriv_list(srgp_dsqexp_dsigma_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l),
+                      list_get(cov_par, "sigma"));
+}
+SEXP _sparseRGPs_dsqexp_dl_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames, SEXP comp)
+{
+    double l[SRGP_MAX_D];
+    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    const int c0 = (int)Rf_asReal(comp) - 1;   /* 1-based in R (covariance_function_derivativesC.cpp:121) */
+    return deriv_list(srgp_dsqexp_dl_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l, c0), l[c0]);
+}
+static SEXP dx2_list(SEXP x2, SEXP lb, SEXP ub, const double *deriv, const double *tp, int d)
+{
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)), nm = PROTECT(Rf_allocVector(STRSXP, 3));
+    SEXP a = PROTECT(Rf_allocVector(REALSXP, d)), b = PROTECT(Rf_allocVector(REALSXP, d)), c = PROTECT(Rf_allocVector(REALSXP, d));
+    memcpy(REAL(a), deriv, sizeof(double) * d);
+    memcpy(REAL(b), tp, sizeof(double) * d);
+    srgp_real_to_bounded(REAL(x2), REAL(ub), REAL(lb), d, REAL(c));
+    SET_VECTOR_ELT(out, 0, a); SET_VECTOR_ELT(out, 1, b); SET_VECTOR_ELT(out, 2, c);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("derivative")); SET_STRING_ELT(nm, 1, Rf_mkChar("trans_par"));
+    SET_STRING_ELT(nm, 2, Rf_mkChar("inv_trans_par"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+SEXP _sparseRGPs_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
+{
+    double deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
+    srgp_dsqexp_dx2(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), list_get(cov_par, "l"), REAL(lb),
+                    REAL(ub), deriv, tp);
+    return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
+}
+SEXP _sparseRGPs_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub, SEXP lnames)
+{
+    double l[SRGP_MAX_D], deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
+    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    srgp_dsqexp_dx2_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l, REAL(lb), REAL(ub), deriv, tp);
+    return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
+}
+
+/* ---- new fused entry points (R/patches/*.R delegate to them; the R signatures stay as they are) ---------- */
+/* .Call("_sparseRGPs_gauss_obj_grad", model, cov_fun, xy, y, mu, xu, cov_par, delta, lnames)
+     -> list(objective =, gradient = named numeric)  : one iteration's elbo_fun + delbo_dcov_par (model 0) or
+        obj_fun_norm + dlogp_dcov_par (model 1).  A failed Cholesky raises an R error (SRGP_ERR_NOT_PD), which
+        keeps the try() paths of R/knot_proposal_functions.R:1314-1354 working. */
+SEXP _sparseRGPs_gauss_obj_grad(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP cov_par,
+                                SEXP delta, SEXP lnames)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
+    double l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    const int p = (k == SRGP_ARD) ? d + 2 : 3;
+    SEXP grad = PROTECT(Rf_allocVector(REALSXP, p));
+    double obj = NA_REAL;
+    const int st = srgp_gauss_obj_grad_host(ctx(), Rf_asInteger(model), k, REAL(xy), n, d, REAL(y),
+                                            Rf_length(mu) == n ? REAL(mu) : NULL, REAL(xu), m,
+                                            list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta),
+                                            &obj, REAL(grad));
+    if (st != SRGP_OK) { UNPROTECT(5); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarReal(obj));
+    SET_VECTOR_ELT(out, 1, grad);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("objective"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("gradient"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(7);
+    return out;
+}
+
+/* .Call("_sparseRGPs_trace_term", sigma, tau, delta, Sigma12, Sigma22): body of trace_term_fun */
+SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP Sigma22)
+{
+    double out = NA_REAL;
+    if (srgp_trace_term(ctx(), Rf_asReal(sigma), Rf_asReal(tau), Rf_asReal(delta), REAL(Sigma12), Rf_nrows(Sigma12),
+                        Rf_ncols(Sigma12), REAL(Sigma22), &out) != SRGP_OK)
+        Rf_error("sparseRGPs: %s", srgp_last_error());
+    return Rf_ScalarReal(out);
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_sparseRGPs_real_to_pos", (DL_FUNC)&_sparseRGPs_real_to_pos, 1},
+    {"_sparseRGPs_pos_to_real", (DL_FUNC)&_sparseRGPs_pos_to_real, 1},
+    {"_sparseRGPs_real_to_bounded", (DL_FUNC)&_sparseRGPs_real_to_bounded, 3},
+    {"_sparseRGPs_dsqexp_dsigmaC", (DL_FUNC)&_sparseRGPs_dsqexp_dsigmaC, 3},
+    {"_sparseRGPs_dsqexp_dsigma_ardC", (DL_FUNC)&_sparseRGPs_dsqexp_dsigma_ardC, 4},
+    {"_sparseRGPs_dsqexp_dlC", (DL_FUNC)&_sparseRGPs_dsqexp_dlC, 3},
+    {"_sparseRGPs_dsqexp_dl_ardC", (DL_FUNC)&_sparseRGPs_dsqexp_dl_ardC, 5},
+    {"_sparseRGPs_dsqexp_dtauC", (DL_FUNC)&_sparseRGPs_dsqexp_dtauC, 3},
+    {"_sparseRGPs_dsqexp_dx2C", (DL_FUNC)&_sparseRGPs_dsqexp_dx2C, 5},
+    {"_sparseRGPs_dsqexp_dx2_ardC", (DL_FUNC)&_sparseRGPs_dsqexp_dx2_ardC, 6},
+    {"_sparseRGPs_dexp_dsigmaC", (DL_FUNC)&_sparseRGPs_dexp_dsigmaC, 3},
+    {"_sparseRGPs_dexp_dlC", (DL_FUNC)&_sparseRGPs_dexp_dlC, 3},
+    {"_sparseRGPs_dexp_dtauC", (DL_FUNC)&_sparseRGPs_dexp_dtauC, 3},
+    {"_sparseRGPs_dsig_dthetaC", (DL_FUNC)&_sparseRGPs_dsig_dthetaC, 5},
+    {"_sparseRGPs_dsig_dtheta_ardC", (DL_FUNC)&_sparseRGPs_dsig_dtheta_ardC, 6},
+    {"_sparseRGPs_cov_fun_sqrd_expC", (DL_FUNC)&_sparseRGPs_cov_fun_sqrd_expC, 3},
+    {"_sparseRGPs_cov_fun_sqrd_exp_ardC", (DL_FUNC)&_sparseRGPs_cov_fun_sqrd_exp_ardC, 4},
+    {"_sparseRGPs_cov_fun_expC", (DL_FUNC)&_sparseRGPs_cov_fun_expC, 3},
+    {"_sparseRGPs_make_cov_matC", (DL_FUNC)&_sparseRGPs_make_cov_matC, 5},
+    {"_sparseRGPs_make_cov_mat_ardC", (DL_FUNC)&_sparseRGPs_make_cov_mat_ardC, 6},
+    {"_sparseRGPs_gauss_obj_grad", (DL_FUNC)&_sparseRGPs_gauss_obj_grad, 9},
+    {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
+    {NULL, NULL, 0}};
+
+void R_init_sparseRGPs(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}
+
+void R_unload_sparseRGPs(DllInfo *dll)
+{
+    (void)dll;
+    if (g_ctx) srgp_ctx_destroy(g_ctx);
+    g_ctx = NULL;
+}
