@@ -594,7 +594,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -642,11 +642,11 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->gen_groups = std::max(1, std::min(192, (ctx->sm_count * 8) / w->nt));
     SRGP_TRY(w->b1part.reserve((size_t)w->gen_groups * mp * 8));
     SRGP_TRY(w->U.reserve((size_t)m * d * 8));
-    SRGP_TRY(w->red1.reserve(((size_t)mp * mp + mp + 16) * 8));
+    SRGP_TRY(w->red1.reserve(((size_t)mp * mp + 4 * (size_t)mp + 64) * 8));
     SRGP_TRY(w->mats.reserve((size_t)GaussWS::NMATS * mp * mp * 8 + ((size_t)4 * mp * dense::NB + 512) * 8));
     SRGP_TRY(w->vecs.reserve((size_t)GaussWS::NVECS * mp * 8 + (size_t)dense::GEMV_SCRATCH * mp * 8));
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
-    SRGP_TRY(w->part2.reserve((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE * 8));
+    SRGP_TRY(w->part2.reserve(std::max((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE, (size_t)128 * mp) * 8));
     SRGP_TRY(w->coin.reserve((size_t)GaussWS::COIN_CAP * (2 * sizeof(int) + sizeof(double)) + 64));
     SRGP_TRY(w->rowpart.reserve((size_t)2 * w->cgroups * w->rows2 * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
@@ -746,6 +746,63 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
         sum_rows_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->b1part.d(), w->gen_groups, mp, b1);
         SRGP_LAUNCH_CHECK();
     }
+    return SRGP_OK;
+}
+
+// ---- Laplace helpers: K materialised once per theta (it is reused by every Newton iteration) ----------------
+int materialise_k(srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int quantum = BK * w->splits;
+    const int64_t rows_alloc = round_up(std::max<int64_t>(ctx->n, 1), quantum);
+    SRGP_TRY(w->Kmat.reserve((size_t)rows_alloc * mp * 8));
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
+        const int rows_padded = (int)round_up(rows_valid, quantum);
+        KernelScope ks(ctx, SRGP_PROF_GEN, s);
+        dim3 grid(mp / 128, w->gen_groups);
+        const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
+#define CALL(D) launch_gen_rm<D>(s, grid, smem, ctx->Xp, ctx->n, w->r.d(), r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->Kmat.d() + (size_t)r0 * mp, w->b1part.d(), 1)
+        SRGP_D_SWITCH(d, CALL)
+#undef CALL
+        SRGP_LAUNCH_CHECK();
+    }
+    return SRGP_OK;
+}
+
+int gram_materialised(srgp_ctx *ctx, GaussWS *w, const double *rowweight, double *G)
+{
+    cudaStream_t s = ctx->stream;
+    static bool configured = false;
+    if (!configured) {
+        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(Smem)));
+        configured = true;
+    }
+    const int mp = w->mp;
+    const int quantum = BK * w->splits;
+    int first = 1;
+    if (ctx->n == 0) SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)w->pairs * w->splits * BM * BN * 8, s));
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
+        const int rows_padded = (int)round_up(rows_valid, quantum);
+        KernelScope ks(ctx, SRGP_PROF_GRAM, s);
+        dim3 grid(w->pairs, w->splits);
+        const int ktiles = rows_padded / quantum;
+        const double *chunk = w->Kmat.d() + (size_t)r0 * mp;
+        if (rowweight)
+            syrk_chunk_kernel<true><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, rowweight + r0, ktiles, w->Gpart.d(), first);
+        else
+            syrk_chunk_kernel<false><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, nullptr, ktiles, w->Gpart.d(), first);
+        SRGP_LAUNCH_CHECK();
+        first = 0;
+    }
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+    syrk_finalize_kernel<<<w->pairs, CONSUMER_THREADS, 0, s>>>(w->Gpart.d(), w->splits, mp, G);
+    SRGP_LAUNCH_CHECK();
     return SRGP_OK;
 }
 

@@ -31,11 +31,13 @@ struct GaussWS {
     DevBuf part2;    // pass-2 per-CTA partial sums
     DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
     DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
+    DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal
 
-    enum { NMATS = 16, NVECS = 12, NROWV = 6, NSCAL = 256, COIN_CAP = 65536 };
-    enum Mat { M_S = 0, M_SINV, M_A, M_C, M_LINV, M_TMP, M_CG, M_CGS, M_SG, M_SGS, M_N, M_MOP, M_T1, M_T2, M_X1, M_X2 };
-    enum Vec { V_B = 0, V_V, V_GV, V_TMP, V_BETA, V_T1, V_T2, V_T3 };
+    enum { NMATS = 24, NVECS = 16, NROWV = 20, NSCAL = 256, COIN_CAP = 65536 };
+    enum Mat { M_S = 0, M_SINV, M_A, M_C, M_LINV, M_TMP, M_CG, M_CGS, M_SG, M_SGS, M_N, M_MOP, M_T1, M_T2, M_X1, M_X2,
+               M_GZ, M_CZ, M_GWP, M_L1, M_L2, M_L3, M_L4, M_L5 };
+    enum Vec { V_B = 0, V_V, V_GV, V_TMP, V_BETA, V_T1, V_T2, V_T3, V_T4, V_T5, V_T6, V_T7 };
     enum Scal {
         S_S0 = 0, S_LOGDET_S, S_LOGDET_A, S_SUMQ, S_TRCG1, S_BV, S_B1V, S_VGV, S_INFO, S_INFO_HI, S_NTOT, S_S0TOT, S_Q4,
         S_P2 = 32,      // pass-2 sums: 1 + d entries, + q4 at S_P2 + 1 + d  (allreduced together)
@@ -73,6 +75,10 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
 int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
                   double *rowq, double *rowkv);
 int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, double *rowq);
+// Laplace: materialise the shard's K row-major into w->Kmat (rows padded with zeros to the SYRK quantum)
+int materialise_k(srgp_ctx *ctx, GaussWS *w, const GenParams &gp);
+// G = Kmat^T diag(rowweight) Kmat over the materialised shard (rowweight may be null)
+int gram_materialised(srgp_ctx *ctx, GaussWS *w, const double *rowweight, double *G);
 // out[0] = sum N o Kuu, out[1 + c] = sum N o Kuu o D_c, out[1 + d] = sum of N over bit-identical knot pairs
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
               double *out);

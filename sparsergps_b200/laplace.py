@@ -1,0 +1,51 @@
+"""Host-side mirror of the reference's sparse Laplace functions (R/newtrap_sparseGP.R,
+R/laplace_approx_gradient.R:25-339) on top of the C ABI: same argument meaning, GPU evaluation."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .context import default_context
+from .vi_functions import _theta
+
+FAMILIES = {"bernoulli": L.BERNOULLI, "poisson": L.POISSON}
+
+
+def newtrap_sparseGP(start_vals, family, cov_par, cov_fun, xy, xu, y, mu, muu, maxit=1000, tol=1e-6, delta=1e-6,
+                     m=1.0, ctx=None):
+    """R/newtrap_sparseGP.R:6-186.  Returns the reference's list as a dict: gp, objective_function_values,
+    gradient, u_posterior_mean, u_posterior_variance.  `m` is the Poisson offset of the reference's `...`."""
+    ctx = ctx or default_context()
+    xy, xu = L.fmat(xy), L.fmat(xu)
+    n, d = xy.shape
+    mk = xu.shape[0]
+    sigma, l, tau, _ = _theta(cov_par, cov_fun, d)
+    ctx.set_data(xy, y, mu)
+    ff = L.fvec(start_vals).copy()
+    assert ff.size == n
+    hist = np.zeros(int(maxit) + 1)
+    nit = L.ci()
+    gpsi, um, uv = np.zeros(n), np.zeros(mk), np.zeros((mk, mk), order="F")
+    muu = L.fvec(np.broadcast_to(np.asarray(muu, dtype=np.float64).reshape(-1), (mk,)))
+    lv = L.fvec(l)
+    L.check(ctx._lib.srgp_laplace_newton(ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), mk, L.ptr(muu),
+                                         sigma, L.ptr(lv), tau, float(delta), float(m), int(maxit), float(tol),
+                                         L.ptr(ff), L.ptr(hist), C.byref(nit), L.ptr(gpsi), L.ptr(um), L.ptr(uv)))
+    return {"gp": ff, "objective_function_values": hist[:nit.value].copy(), "gradient": gpsi,
+            "u_posterior_mean": um, "u_posterior_variance": uv}
+
+
+def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, m=1.0, ctx=None, **_ignored):
+    """R/laplace_approx_gradient.R:25-339 with dcov_fun_dknot = NA, transform = TRUE: list(gradient, trans_par)."""
+    ctx = ctx or default_context()
+    xy, xu = L.fmat(xy), L.fmat(xu)
+    n, d = xy.shape
+    sigma, l, tau, names = _theta(cov_par, cov_fun, d)
+    ctx.set_data(xy, y, mu)
+    ffv, lv = L.fvec(ff), L.fvec(l)
+    grad = np.zeros(len(names))
+    L.check(ctx._lib.srgp_laplace_grad(ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), xu.shape[0], sigma,
+                                       L.ptr(lv), tau, float(delta), float(m), L.ptr(ffv), L.ptr(grad)))
+    return {"gradient": dict(zip(names, grad)), "trans_par": {k: float(np.log(cov_par[k])) for k in names}}

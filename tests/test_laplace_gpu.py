@@ -1,0 +1,66 @@
+"""K7: sparse Laplace Newton mode finder and gradient (CUDA) against the literal oracle (quirks Q1, Q2 included)."""
+import numpy as np
+import pytest
+
+from oracle import ref_model as rm
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(family, n=900, m=40, coincident=True):
+    c = cases.config4(n=n, m=m)
+    if family == "poisson":
+        c["y"] = np.random.default_rng(3).poisson(np.exp(0.5 * np.sin(c["x"][:, 0]))).astype(np.float64)
+    if coincident:
+        c["xu"] = np.vstack([c["xu"], c["x"][5]])
+    return c
+
+
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_newton_matches_literal_oracle(ctx, family):
+    from sparsergps_b200 import laplace as Lp
+    c = _case(family)
+    cp, mk = c["cov_par"], len(c["xu"])
+    kw = {"m": 1.0} if family == "poisson" else {}
+    ref = rm.newtrap_sparseGP(np.zeros(900), family, cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(mk),
+                              maxit=40, tol=1e-5, delta=c["delta"], **kw)
+    got = Lp.newtrap_sparseGP(np.zeros(900), family, cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(mk),
+                              maxit=40, tol=1e-5, delta=c["delta"], ctx=ctx)
+    h_ref, h = ref["objective_function_values"], got["objective_function_values"]
+    assert len(h) == len(h_ref)                                  # same iteration count / stopping decision
+    np.testing.assert_allclose(h, h_ref, rtol=1e-8)
+    np.testing.assert_allclose(got["gp"], ref["gp"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(got["gradient"], ref["gradient"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(got["u_posterior_mean"], ref["u_posterior_mean"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(got["u_posterior_variance"], ref["u_posterior_variance"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_laplace_gradient_matches_literal_oracle(ctx, family):
+    from sparsergps_b200 import laplace as Lp
+    c = _case(family)
+    cp, mk = c["cov_par"], len(c["xu"])
+    kw = {"m": 1.0} if family == "poisson" else {}
+    fit = rm.newtrap_sparseGP(np.zeros(900), family, cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(mk),
+                              maxit=30, tol=1e-5, delta=c["delta"], **kw)
+    g_ref = rm.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], c["delta"], **kw)["gradient"]
+    got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], c["delta"], ctx=ctx)
+    scale = max(abs(v) for v in g_ref.values())
+    for k in g_ref:
+        assert got["gradient"][k] == pytest.approx(g_ref[k], rel=1e-8, abs=1e-9 * scale), k
+
+
+def test_newton_sqexp_1d_and_start_values(ctx):
+    from sparsergps_b200 import laplace as Lp
+    rng = np.random.default_rng(9)
+    n = 500
+    x = np.sort(rng.uniform(0, 10, n)).reshape(-1, 1)
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-2 * np.sin(x[:, 0])))).astype(np.float64)
+    xu = np.linspace(0.5, 9.5, 12).reshape(-1, 1)
+    cp = {"sigma": 2.0, "l": 1.0, "tau": 0.1}
+    ff0 = 0.1 * rng.normal(size=n)
+    ref = rm.newtrap_sparseGP(ff0, "bernoulli", cp, "sqexp", x, xu, y, np.zeros(n), np.zeros(12), maxit=25, tol=1e-5, delta=1e-3)
+    got = Lp.newtrap_sparseGP(ff0, "bernoulli", cp, "sqexp", x, xu, y, np.zeros(n), np.zeros(12), maxit=25, tol=1e-5, delta=1e-3, ctx=ctx)
+    np.testing.assert_allclose(got["objective_function_values"], ref["objective_function_values"], rtol=1e-8)
+    np.testing.assert_allclose(got["gp"], ref["gp"], rtol=1e-7, atol=1e-9)
