@@ -92,6 +92,11 @@ extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
+        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
+    }
     SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
     SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
     SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -120,11 +125,13 @@ extern "C" void srgp_ctx_destroy(srgp_ctx *ctx)
             cudaEventDestroy(pr.second);
         }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_a, ctx->ev_b, ctx->ev_fork, ctx->ev_join, ctx->tim0, ctx->tim1};
+    cudaEvent_t evs[] = {ctx->ev_a, ctx->ev_b, ctx->ev_fork, ctx->ev_join, ctx->tim0, ctx->tim1,
+                         ctx->ev_gen[0], ctx->ev_gen[1], ctx->ev_used[0], ctx->ev_used[1]};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     delete ctx;
 }
 
@@ -133,6 +140,7 @@ extern "C" int srgp_ctx_sync(srgp_ctx *ctx)
     SRGP_TRY(use_device(ctx));
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream2));
+    SRGP_CUDA(cudaStreamSynchronize(ctx->stream3));
     return SRGP_OK;
 }
 

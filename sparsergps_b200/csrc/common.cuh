@@ -81,6 +81,8 @@ struct srgp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;   // main stream: passes, dense chain
     cudaStream_t stream2 = nullptr;  // side stream: work independent of the main chain
+    cudaStream_t stream3 = nullptr;  // generator stream: K chunk c+1 is generated while the DMMA kernel eats chunk c
+    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t tim0 = nullptr, tim1 = nullptr;
 

@@ -594,7 +594,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -612,7 +612,7 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     // pass 1: pairs x splits CTAs ~ one wave; chunk ~ 48 MB so it stays in the 126 MB L2 with the Gram slots
     w->splits = std::max(1, ctx->sm_count / w->pairs);
     if (w->splits > 64) w->splits = 64;
-    int64_t chunk_mb = 48;
+    int64_t chunk_mb = 32;
     if (const char *e = getenv("SRGP_CHUNK_MB")) chunk_mb = std::max(4, atoi(e));
     const int64_t target_bytes = chunk_mb << 20;
     int64_t rows = target_bytes / (8 * (int64_t)mp);
@@ -637,7 +637,8 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->rblocks = std::max(1, ctx->sm_count / cg);
     w->rows2 = w->rblocks * BM;
     const size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
-    SRGP_TRY(w->chunk.reserve(chunk_elems * 8));
+    w->chunk_elems = chunk_elems;
+    SRGP_TRY(w->chunk.reserve(2 * chunk_elems * 8));   // double buffered: generation overlaps consumption
     SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));
     w->gen_groups = std::max(1, std::min(192, (ctx->sm_count * 8) / w->nt));
     SRGP_TRY(w->b1part.reserve((size_t)w->gen_groups * mp * 8));
@@ -649,6 +650,7 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     SRGP_TRY(w->part2.reserve(std::max((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE, (size_t)128 * mp) * 8));
     SRGP_TRY(w->coin.reserve((size_t)GaussWS::COIN_CAP * (2 * sizeof(int) + sizeof(double)) + 64));
     SRGP_TRY(w->rowpart.reserve((size_t)2 * w->cgroups * w->rows2 * 8));
+    SRGP_TRY(w->nspart.reserve((size_t)NS_BLOCKS * PART_STRIDE * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
     w->planned = true;
     return SRGP_OK;
@@ -713,30 +715,42 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
         SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)w->pairs * w->splits * BM * BN * 8, s));
         SRGP_CUDA(cudaMemsetAsync(w->b1part.p, 0, (size_t)w->gen_groups * mp * 8, s));
     }
-    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
+    // Generator on its own stream, two chunk buffers: chunk c+1 is generated while the SYRK kernel consumes
+    // chunk c (the generator CTAs are small enough to be co-resident with the DMMA CTAs and fill its FP64 bubbles).
+    cudaStream_t sg = ctx->stream3;
+    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    int cidx = 0;
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1, cidx++) {
         const int rows_valid = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
         const int rows_padded = (int)round_up(rows_valid, quantum);
+        const int b = cidx & 1;
+        double *chunk = w->chunk.d() + (size_t)b * w->chunk_elems;
+        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
         {
-            KernelScope ks(ctx, SRGP_PROF_GEN, s);
+            KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(mp / 128, w->gen_groups);
             const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
-#define CALL(D) launch_gen_rm<D>(s, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->chunk.d(), w->b1part.d(), first)
+#define CALL(D) launch_gen_rm<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, chunk, w->b1part.d(), first)
             SRGP_D_SWITCH(d, CALL)
 #undef CALL
             SRGP_LAUNCH_CHECK();
         }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
+        SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GRAM, s);
             dim3 grid(w->pairs, w->splits);
             const int ktiles = rows_padded / quantum;
             if (rowweight)
-                syrk_chunk_kernel<true><<<grid, THREADS, sizeof(Smem), s>>>(w->chunk.d(), mp, rowweight + r0, ktiles,
+                syrk_chunk_kernel<true><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, rowweight + r0, ktiles,
                                                                             w->Gpart.d(), first);
             else
-                syrk_chunk_kernel<false><<<grid, THREADS, sizeof(Smem), s>>>(w->chunk.d(), mp, nullptr, ktiles,
+                syrk_chunk_kernel<false><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, nullptr, ktiles,
                                                                              w->Gpart.d(), first);
             SRGP_LAUNCH_CHECK();
         }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
         first = 0;
     }
     {
@@ -848,22 +862,31 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
     if (mode == MODE_GRAD && ctx->n == 0 && first)
         SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
     double *rowpart = w->rowpart.d();
-    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2) {
+    cudaStream_t sg = ctx->stream3;
+    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    int cidx = 0;
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2, cidx++) {
         const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
         const int rows_padded = w->rows2;   // the K*M kernel always runs all row blocks of the chunk
+        const int b = cidx & 1;
+        double *chunk = w->chunk.d() + (size_t)b * w->chunk_elems;
+        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
         {
-            KernelScope ks(ctx, SRGP_PROF_GEN, s);
+            KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(ceil_div(rows_padded, GENC_ROWS), std::min(mp / GENC_COLS, 64));
             const size_t gs = sizeof(double) * GENC_COLS * d;
-#define CALL(D) launch_gen_cm<D>(s, grid, gs, ctx->Xp, ctx->n, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, w->chunk.d(), (int64_t)w->rows2)
+#define CALL(D) launch_gen_cm<D>(sg, grid, gs, ctx->Xp, ctx->n, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, chunk, (int64_t)w->rows2)
             SRGP_D_SWITCH(d, CALL)
 #undef CALL
             SRGP_LAUNCH_CHECK();
         }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
+        SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_KM, s);
             KmArgs a;
-            a.Kc = w->chunk.d();
+            a.Kc = chunk;
             a.ldc = w->rows2;
             a.Mop = Mop;
             a.mp = mp;
@@ -901,6 +924,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
             }
             SRGP_LAUNCH_CHECK();
         }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
         if (mode == MODE_ROWFORM) {
             KernelScope ks(ctx, SRGP_PROF_REDUCE, s, rowkv ? 2 : 1);
             combine_rows_kernel<<<ceil_div(rows_valid, 256), 256, 0, s>>>(rowpart, w->cgroups, w->rows2, rows_valid,
@@ -974,13 +998,13 @@ int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *
 
 // ---- small launchers -----------------------------------------------------------------------------------
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
-              double *out)
+              double *out, cudaStream_t s)
 {
-    cudaStream_t s = ctx->stream;
+    // own scratch (w->nspart): this runs on the side stream while pass 2 owns w->part2
     KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-    ns_reduce_kernel<<<NS_BLOCKS, 256, 0, s>>>(N, S, w->mp, w->m, w->d, w->U.d(), gp, nugget, w->part2.d());
+    ns_reduce_kernel<<<NS_BLOCKS, 256, 0, s>>>(N, S, w->mp, w->m, w->d, w->U.d(), gp, nugget, w->nspart.d());
     SRGP_LAUNCH_CHECK();
-    sum_part_kernel<<<w->d + 2, 32, 0, s>>>(w->part2.d(), NS_BLOCKS, PART_STRIDE, w->d + 2, out);
+    sum_part_kernel<<<w->d + 2, 32, 0, s>>>(w->nspart.d(), NS_BLOCKS, PART_STRIDE, w->d + 2, out);
     SRGP_LAUNCH_CHECK();
     return SRGP_OK;
 }

@@ -17,6 +17,7 @@ struct GaussWS {
     int m = 0, mp = 0, d = 0, nt = 0, pairs = 0;
     int splits = 1, rows1 = 0, gen_groups = 1;    // pass 1: SYRK split-K over the chunk rows
     int cgroups = 1, rblocks = 1, rows2 = 0;      // pass 2: row blocks x column groups
+    size_t chunk_elems = 0;                       // doubles per chunk buffer (two buffers)
 
     DevBuf U;        // knots, m x d column-major
     DevBuf chunk;    // L2-resident K chunk (row-major in pass 1, column-major in pass 2)
@@ -31,6 +32,7 @@ struct GaussWS {
     DevBuf part2;    // pass-2 per-CTA partial sums
     DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
     DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
+    DevBuf nspart;   // scratch of ns_reduce (runs on the side stream)
     DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal
 
@@ -81,7 +83,7 @@ int materialise_k(srgp_ctx *ctx, GaussWS *w, const GenParams &gp);
 int gram_materialised(srgp_ctx *ctx, GaussWS *w, const double *rowweight, double *G);
 // out[0] = sum N o Kuu, out[1 + c] = sum N o Kuu o D_c, out[1 + d] = sum of N over bit-identical knot pairs
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
-              double *out);
+              double *out, cudaStream_t s);
 // quirk Q4: *out = sum over recorded pairs of (omega_p - coef * (K S^-1)_{i_p j_p})
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
 int scale_vec(srgp_ctx *ctx, const double *x, int64_t n, double a, double *out);
@@ -92,6 +94,10 @@ int copy_scalar(srgp_ctx *ctx, double *dst, const double *src, int count);
 int comm_allreduce(srgp_ctx *ctx, double *buf, size_t count, cudaStream_t s);
 // D2H of the scalar block + stream sync; maps a failed m x m Cholesky to SRGP_ERR_NOT_PD
 int fetch_scalars(srgp_ctx *ctx, GaussWS *w);
+// side stream helpers: fork makes ctx->stream2 wait for everything issued so far on ctx->stream; join makes
+// ctx->stream wait for everything issued so far on ctx->stream2
+int stream_fork(srgp_ctx *ctx);
+int stream_join(srgp_ctx *ctx);
 int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
              double *obj, double *grad);
 int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,

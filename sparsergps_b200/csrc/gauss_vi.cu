@@ -21,6 +21,20 @@ namespace srgp {
 
 using W = GaussWS;
 
+int stream_fork(srgp_ctx *ctx)
+{
+    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SRGP_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    return SRGP_OK;
+}
+
+int stream_join(srgp_ctx *ctx)
+{
+    SRGP_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    SRGP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return SRGP_OK;
+}
+
 int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
 {
     SRGP_CUDA(cudaMemcpyAsync(w->h_scal, w->scal.p, W::NSCAL * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -53,28 +67,33 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
     SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
 
-    // ---- pass 1 -------------------------------------------------------------------------------------
-    SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G1, b1));
-    SRGP_TRY(copy_scalar(ctx, tail, w->sc(W::S_S0), 1));
-    SRGP_TRY(set_scalar(ctx, tail + 1, (double)ctx->n));
-    SRGP_TRY(comm_allreduce(ctx, G1, mm + mp + 2, s));
-    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_S0TOT), tail, 1));
-    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_NTOT), tail + 1, 1));
-
-    // ---- replicated m x m stage -----------------------------------------------------------------------
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
     double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP), *CG = w->mat(W::M_CG), *CGS = w->mat(W::M_CGS);
     double *SG = w->mat(W::M_SG), *SGS = w->mat(W::M_SGS), *N = w->mat(W::M_N), *Mop = w->mat(W::M_MOP);
     double *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2), *LinvT = w->mat(W::M_X1);
     double *bv = w->vec(W::V_B), *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP);
     double *beta = w->vec(W::V_BETA), *gsc = w->gemv_scratch();
+    cudaStream_t s2 = ctx->stream2;
 
-    // S = K_uu + delta I (self-covariance minus tau^2 I: R/vi_functions.R:736-741), identity on the padding
-    SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
-    SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
-    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
-    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, LinvT, tmp, Sinv, w->info(0),
-                                 w->sc(W::S_LOGDET_S)));
+    // ---- side stream: S = K_uu + delta I (self-covariance minus tau^2 I: R/vi_functions.R:736-741), identity on
+    //      the padding; Cholesky, S^-1, log|S|.  Independent of the data rows, so it overlaps pass 1. ----
+    SRGP_TRY(stream_fork(ctx));
+    SRGP_TRY(assemble_dev_ld(ctx, s2, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
+    SRGP_TRY(dense::pad_identity(ctx, s2, S, mp, m, 1.0));
+    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s2));
+    SRGP_TRY(dense::chol_inverse(ctx, s2, T1, mp, m, w->dinv(0), w->mat(W::M_L1), w->mat(W::M_L2), w->mat(W::M_L3), Sinv,
+                                 w->info(0), w->sc(W::S_LOGDET_S)));
+
+    // ---- pass 1 (main stream) --------------------------------------------------------------------------------
+    SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G1, b1));
+    SRGP_TRY(copy_scalar(ctx, tail, w->sc(W::S_S0), 1));
+    SRGP_TRY(set_scalar(ctx, tail + 1, (double)ctx->n));
+    SRGP_TRY(comm_allreduce(ctx, G1, mm + mp + 2, s));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_S0TOT), tail, 1));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W::S_NTOT), tail + 1, 1));
+    SRGP_TRY(stream_join(ctx));
+
+    // ---- replicated m x m stage: the chain pass 2 waits for ------------------------------------------------------
     // A = S + B G1 ; C = A^-1
     SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, B, G1, 0.0, A));
     SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1),
@@ -85,19 +104,30 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv, gsc));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, bv, -B, gv, tv));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Sinv, tv, 0.0, nullptr, beta, gsc));
-    SRGP_TRY(dense::dot_mm(ctx, s, mp, m, Sinv, G1, w->sc(W::S_SUMQ), w->part2.d()));
-    SRGP_TRY(dense::dot_mm(ctx, s, mp, m, C, G1, w->sc(W::S_TRCG1), w->part2.d()));
-    SRGP_TRY(dense::dot_v(ctx, s, m, bv, v, w->sc(W::S_BV)));
-    SRGP_TRY(dense::dot_v(ctx, s, m, b1, v, w->sc(W::S_B1V)));
-    SRGP_TRY(dense::dot_v(ctx, s, m, v, gv, w->sc(W::S_VGV)));
     if (grad) {
         // CG = C G1 ; CGS = C G1 S^-1 ; Mop = (1/tau^2 - B) S^-1 + B^2 CGS - B beta v^T
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, G1, mp, 0.0, CG, mp));
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, CGS, mp));
         SRGP_TRY(dense::axpby(ctx, s, mp, m, itau2 - B, Sinv, B * B, CGS, 0.0, Mop));
         SRGP_TRY(dense::ger(ctx, s, mp, -B, beta, v, Mop));
+    }
+    // ---- side stream: everything of the m x m stage that pass 2 does not need (scalars, N, sum N o dS) ----------
+    SRGP_TRY(stream_fork(ctx));
+    SRGP_TRY(dense::dot_mm(ctx, s2, mp, m, Sinv, G1, w->sc(W::S_SUMQ), w->nspart.d()));
+    SRGP_TRY(dense::dot_mm(ctx, s2, mp, m, C, G1, w->sc(W::S_TRCG1), w->nspart.d()));
+    SRGP_TRY(dense::dot_v(ctx, s2, m, bv, v, w->sc(W::S_BV)));
+    SRGP_TRY(dense::dot_v(ctx, s2, m, b1, v, w->sc(W::S_B1V)));
+    SRGP_TRY(dense::dot_v(ctx, s2, m, v, gv, w->sc(W::S_VGV)));
+    if (grad) {
+        SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, G1, mp, 0.0, SG, mp));
+        SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
+        // C G1 S^-1 is symmetric, so SG * CGS = SG * CGS^T: the tile engine's fast NT form
+        SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
+        SRGP_TRY(dense::axpby(ctx, s2, mp, m, 0.5 * B - 0.5 * itau2, SGS, -0.5 * B * B, T2, 0.0, N));
+        SRGP_TRY(dense::ger(ctx, s2, mp, -0.5, beta, beta, N));
+        SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS), s2));
 
-        // ---- pass 2 ---------------------------------------------------------------------------------
+        // ---- pass 2 (main stream) ---------------------------------------------------------------------------
         double *ra = w->rowv(0, ctx->n);
         SRGP_TRY(scale_vec(ctx, w->r.d(), ctx->n, B, ra));
         double *p2 = w->sc(W::S_P2);
@@ -106,16 +136,8 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
         // sum (Omega_ij - (K S^-1)_ij / tau^2) there (the trace-term part of Omega does not apply to tau)
         SRGP_TRY(coin_fix(ctx, w, gp, Sinv, itau2, p2 + 1 + d));
         SRGP_TRY(comm_allreduce(ctx, p2, d + 2, s));
-
-        // ---- N and sum N o dS -------------------------------------------------------------------------
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, G1, mp, 0.0, SG, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
-        // C G1 S^-1 is symmetric, so SG * CGS = SG * CGS^T: the tile engine's fast NT form
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
-        SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5 * B - 0.5 * itau2, SGS, -0.5 * B * B, T2, 0.0, N));
-        SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
-        SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS)));
     }
+    SRGP_TRY(stream_join(ctx));
     SRGP_TRY(fetch_scalars(ctx, w));
 
     // ---- host: a handful of scalars ---------------------------------------------------------------------

@@ -593,7 +593,7 @@ extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const do
     SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, N, 1.0, SGS, 0.0, N));
     SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
     SRGP_TRY(dense::ger(ctx, s, mp, 0.5, skt, GG, N));
-    SRGP_TRY(ns_reduce(ctx, w, L.gp, N, L.S, tau * tau + delta, w->sc(W_::S_NS)));
+    SRGP_TRY(ns_reduce(ctx, w, L.gp, N, L.S, tau * tau + delta, w->sc(W_::S_NS), s));
     SRGP_TRY(fetch_scalars(ctx, w));
 
     const double *h = w->h_scal, *hp2 = h + W_::S_P2, *ns = h + W_::S_NS;
