@@ -30,6 +30,10 @@ METRIC = "sparse-GP obj+grad evals/sec (n=1M,m=1024,d=8 ARD)"
 UNIT = "evals/s"
 
 
+def workload_name(n, m, d):
+    return "synthetic sparse ARD GP n=%d d=%d m=%d, VI objective+gradient (BASELINE configs[4])" % (n, d, m)
+
+
 def workload(n, m, d, seed=1312):
     """X, U ~ N(0, I_d); sigma 1, l_c = 0.8 + 0.05 c, tau 0.5, delta 1e-6, mu = 0."""
     rng = np.random.default_rng(seed)
@@ -115,6 +119,16 @@ def fp64_peak_tflops():
     return 2.0 * N ** 3 / (best * 1e-3) / 1e12
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return {"bytes_per_launch": t["bytes_per_launch"], "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_launch"],
+                "source": t["source"]}
+    except Exception:
+        return None
+
+
 def cpu_reference_time(n_sample, m, d, threads=None):
     """Seconds for ONE obj+grad evaluation of the oracle (literal NumPy/OpenBLAS transcription of elbo_fun +
     delbo_dcov_par, with the per-element assembly in single-threaded C as Rcpp is) at n = n_sample."""
@@ -152,7 +166,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_eval_full * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic sparse ARD GP n=%d d=%d m=%d, VI objective+gradient" % (n, d, m)},
+        "config": {"workload": workload_name(n, m, d)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "oracle (NumPy literal transcription + single-threaded C assembly, %s) on %d of "
                                    "%d rows, %.2f s per evaluation, extrapolated linearly in n" %
@@ -278,7 +292,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "km_reduce_kernel (K*M on DMMA + fused dK reductions)",
                 "achieved": km_flops / (km_ms * 1e-3) / 1e12 if km_ms > 0 else None, "peak": peak,
                 "unit": "TFLOP/s", "frac": (km_flops / (km_ms * 1e-3) / 1e12 / peak) if km_ms > 0 else None,
-                "traffic": None,
+                "traffic": ncu_traffic("km_reduce_kernel"),
                 "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 entry in MEASURED_PEAKS.json)",
                 "launches_per_step": km_launches / steps, "avg_launch_ms": km_ms / max(1, km_launches),
                 "share_of_step": km_ms / ms_max}
@@ -298,8 +312,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic sparse ARD GP n=%d d=%d m=%d, VI objective+gradient (BASELINE configs[4])"
-                                   % (n, d, m), "rows_per_gpu": nloc, "l2": "flushed between timed iterations "
+            "config": {"workload": workload_name(n, m, d), "rows_per_gpu": nloc, "l2": "flushed between timed iterations "
                        "(256 MiB write inside the timed region)", "parallelism": "rows sharded x%d, 2 NCCL allreduces/eval" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xs.nbytes + ys.nbytes + xu.nbytes + 8 * (d + 3)),

@@ -97,8 +97,6 @@ extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
         SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
         SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
     }
-    SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
-    SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
     SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     SRGP_CUDA(cudaEventCreate(&ctx->tim0));
@@ -116,7 +114,7 @@ extern "C" void srgp_ctx_destroy(srgp_ctx *ctx)
     cudaDeviceSynchronize();
     srgp_comm_destroy(ctx);
     if (ctx->ws && ctx->ws_free) ctx->ws_free(ctx->ws);
-    srgp::DevBuf *bufs[] = {&ctx->in_x, &ctx->in_xp, &ctx->in_l, &ctx->out_mat, &ctx->tmp0, &ctx->tmp1,
+    srgp::DevBuf *bufs[] = {&ctx->in_x, &ctx->in_xp, &ctx->out_mat, &ctx->tmp0, &ctx->tmp1,
                             &ctx->flush, &ctx->X, &ctx->y, &ctx->mu};
     for (auto *b : bufs) b->release();
     for (auto &slot : ctx->prof)
@@ -125,7 +123,7 @@ extern "C" void srgp_ctx_destroy(srgp_ctx *ctx)
             cudaEventDestroy(pr.second);
         }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_a, ctx->ev_b, ctx->ev_fork, ctx->ev_join, ctx->tim0, ctx->tim1,
+    cudaEvent_t evs[] = {ctx->ev_fork, ctx->ev_join, ctx->tim0, ctx->tim1,
                          ctx->ev_gen[0], ctx->ev_gen[1], ctx->ev_used[0], ctx->ev_used[1]};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);

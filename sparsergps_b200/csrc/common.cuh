@@ -83,16 +83,15 @@ struct srgp_ctx {
     cudaStream_t stream2 = nullptr;  // side stream: work independent of the main chain
     cudaStream_t stream3 = nullptr;  // generator stream: K chunk c+1 is generated while the DMMA kernel eats chunk c
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t tim0 = nullptr, tim1 = nullptr;
 
     // API-parity scratch (K1/K2/K5 with host pointers)
-    srgp::DevBuf in_x, in_xp, in_l, out_mat, tmp0, tmp1;
+    srgp::DevBuf in_x, in_xp, out_mat, tmp0, tmp1;
     srgp::DevBuf flush;
 
     // resident data shard
     srgp::DevBuf X, y, mu;  // X: n x d column-major, y/mu: n
-    bool x_borrowed = false;
     const double *Xp = nullptr, *yp = nullptr, *mup = nullptr;
     int64_t n = 0;
     int d = 0;

@@ -1,0 +1,42 @@
+"""Secondary metric: sparse Laplace Newton iterations/sec, Bernoulli, n=100000, d=8, m=512.
+   python tools/bench_newton.py [n] [m] [maxit]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sparsergps_b200 import laplace as Lp
+from sparsergps_b200.context import Context
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+maxit = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+d = 8
+rng = np.random.default_rng(1311)
+x = rng.normal(size=(n, d))
+f = 1.5 * np.sin(x[:, 0]) + x[:, 1] - 0.5 * x[:, 2]
+y = (rng.uniform(size=n) < 1 / (1 + np.exp(-f))).astype(np.float64)
+xu = rng.normal(size=(m, d))
+cp = {"sigma": 2.0}
+for c in range(d):
+    cp["l%d" % (c + 1)] = 1.5
+cp["tau"] = 0.1
+ctx = Context(0)
+res = None
+for rep in range(2):
+    t0 = time.perf_counter()
+    res = Lp.newtrap_sparseGP(np.zeros(n), "bernoulli", cp, "ard", x, xu, y, np.zeros(n), np.zeros(m), maxit=maxit,
+                              tol=1e-5, delta=1e-3, ctx=ctx)
+    dt = time.perf_counter() - t0
+t0 = time.perf_counter()
+g = Lp.dlogq_dcov_par(cp, "ard", xu, x, y, res["gp"], "bernoulli", np.zeros(n), 1e-3, ctx=ctx)
+dtg = time.perf_counter() - t0
+iters = len(res["objective_function_values"]) - 1
+print(json.dumps({"workload": "Bernoulli sparse Laplace Newton, n=%d d=8 m=%d (config 4)" % (n, m), "newton_iterations": iters,
+                  "seconds_incl_setup_and_h2d": round(dt, 4), "newton_iters_per_s": round(iters / dt, 1),
+                  "objective_first_last": [res["objective_function_values"][0], res["objective_function_values"][-1]],
+                  "max_abs_grad_psi": float(np.max(np.abs(res["gradient"]))), "laplace_gradient_seconds": round(dtg, 4),
+                  "grad": {k: float(v) for k, v in g["gradient"].items()}}))
