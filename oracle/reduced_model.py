@@ -15,15 +15,75 @@ from __future__ import annotations
 
 import math
 
+import contextlib
+
 import numpy as np
 import scipy.linalg as sla
+
+# Working precision.  `with extended_precision():` switches every array of this module to numpy.longdouble
+# (x87 80-bit here) with hand-written Cholesky / triangular inverse, giving a ~1e-19 reference for configurations
+# whose conditioning puts the literal (LU, float64) transcription itself at ~1e-8.
+_DT = np.float64
+
+
+@contextlib.contextmanager
+def extended_precision():
+    global _DT
+    old, _DT = _DT, np.longdouble
+    try:
+        yield
+    finally:
+        _DT = old
+
+
+def _arr(a):
+    return np.asarray(a, dtype=_DT)
+
+
+def _cholesky(A):
+    if _DT is np.float64:
+        return np.linalg.cholesky(A)
+    A = np.array(A, dtype=_DT)
+    n = A.shape[0]
+    L = np.zeros_like(A)
+    for j in range(n):
+        v = A[j:, j] - L[j:, :j] @ L[j, :j]
+        L[j:, j] = v / np.sqrt(v[0])
+    return L
+
+
+def _spd_inverse(A):
+    """(A^-1, log det A) through the Cholesky factor."""
+    L = _cholesky(A)
+    n = L.shape[0]
+    logdet = 2 * np.sum(np.log(np.diag(L)))
+    if _DT is np.float64:
+        return sla.cho_solve((L, True), np.eye(n)), logdet
+    X = np.zeros_like(L)                      # X = L^-1 by forward substitution, row by row
+    for i in range(n):
+        X[i, i] = 1 / L[i, i]
+        X[i, :i] = -(L[i, :i] @ X[:i, :i]) / L[i, i]
+    return X.T @ X, logdet
+
+
+def _inv(A):
+    if _DT is np.float64:
+        return np.linalg.inv(A)
+    return _spd_inverse(A)[0]
+
+
+def _solve(A, b):
+    if _DT is np.float64:
+        return np.linalg.solve(A, b)
+    return _spd_inverse(A)[0] @ b
 
 
 def kernel_matrix(x, u, sigma, l, cov_fun="ard"):
     """K_ij and the per-dimension scaled squared differences D_ijc = ((x_ic - u_jc)/l_c)^2."""
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
-    l = np.broadcast_to(np.asarray(l, dtype=np.float64).reshape(-1), (x.shape[1],))
+    x = _arr(x).reshape(len(x), -1)
+    u = _arr(u).reshape(len(u), -1)
+    sigma = _DT(sigma)
+    l = np.broadcast_to(_arr(l).reshape(-1), (x.shape[1],))
     D = ((x[:, None, :] - u[None, :, :]) / l[None, None, :]) ** 2
     K = sigma ** 2 * np.exp(-D.sum(axis=2) / 2)
     return K, D
@@ -41,7 +101,7 @@ def _coincident(x, u):
 def vi_pass1(x, r, u, sigma, l):
     """Per-shard partial sums: G1 = K^T K, b1 = K^T r, s0 = r^T r."""
     K, _ = kernel_matrix(x, u, sigma, l)
-    return {"G1": K.T @ K, "b1": K.T @ r, "s0": float(r @ r), "n": float(len(r))}
+    return {"G1": K.T @ K, "b1": K.T @ r, "s0": r @ r, "n": _DT(len(r))}
 
 
 def add_partials(parts):
@@ -53,53 +113,50 @@ def add_partials(parts):
 
 # ---------------------------------------------------------------- replicated m x m --------------
 def vi_mid(p1, u, sigma, l, tau, delta, cov_fun="ard"):
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     m = u.shape[0]
     Kuu, _ = kernel_matrix(u, u, sigma, l)
-    S = Kuu + delta * np.eye(m)                      # self-cov minus tau^2 I  (R/vi_functions.R:736-741)
+    sigma, tau, delta = _DT(sigma), _DT(tau), _DT(delta)
+    S = Kuu + delta * np.eye(m, dtype=_DT)           # self-cov minus tau^2 I  (R/vi_functions.R:736-741)
     Z = tau ** 2 + delta
-    B = 1.0 / Z
+    B = 1 / Z
     n = p1["n"]
-    LS = np.linalg.cholesky(S)
-    Sinv = sla.cho_solve((LS, True), np.eye(m))
-    logdetS = 2 * np.sum(np.log(np.diag(LS)))
+    Sinv, logdetS = _spd_inverse(S)
     G = B * p1["G1"]
-    LA = np.linalg.cholesky(S + G)
-    Cm = sla.cho_solve((LA, True), np.eye(m))
-    logdetA = 2 * np.sum(np.log(np.diag(LA)))
+    Cm, logdetA = _spd_inverse(S + G)
     b = B * p1["b1"]
     v = Cm @ b
     beta = Sinv @ (b - G @ v)
-    sum_q = float(np.sum(Sinv * p1["G1"]))
+    sum_q = np.sum(Sinv * p1["G1"])
     tt = -(1 / (2 * tau ** 2)) * (n * (sigma ** 2 + delta) - sum_q)
-    obj = -0.5 * B * p1["s0"] + 0.5 * float(b @ v) - 0.5 * (n * math.log(Z) - logdetS + logdetA) \
-        - (n / 2) * math.log(2 * math.pi) + tt
+    obj = -B * p1["s0"] / 2 + (b @ v) / 2 - (n * np.log(Z) - logdetS + logdetA) / 2 \
+        - (n / 2) * np.log(2 * _DT(np.pi) if _DT is np.float64 else 2 * np.arctan(_DT(1)) * 4) + tt
     CGS = Cm @ G @ Sinv
     M = (1 / tau ** 2 - B) * Sinv + B * CGS
     SGS = Sinv @ G @ Sinv
-    N = 0.5 * SGS - 0.5 * Sinv @ G @ CGS - 0.5 * np.outer(beta, beta) - (1 / (2 * tau ** 2)) * Sinv @ p1["G1"] @ Sinv
-    return dict(obj=obj, tt=tt, B=B, v=v, beta=beta, M=M, N=N, Sinv=Sinv, C=Cm, trCG1=float(np.sum(Cm * p1["G1"])),
-                n=n)
+    N = SGS / 2 - Sinv @ G @ CGS / 2 - np.outer(beta, beta) / 2 - (1 / (2 * tau ** 2)) * Sinv @ p1["G1"] @ Sinv
+    return dict(obj=obj, tt=tt, B=B, v=v, beta=beta, M=M, N=N, Sinv=Sinv, C=Cm, trCG1=np.sum(Cm * p1["G1"]), n=n)
 
 
 # ---------------------------------------------------------------- pass 2 (rows) -----------------
 def vi_pass2(x, r, u, sigma, l, tau, mid):
     """Per-shard partials: sum_ij Omega_ij dK_ij(theta) for sigma and each length scale, sum alpha^2,
     and the coincident-row correction of quirk Q4 (dK/dlog tau = 2 tau^2 where x_i == u_j bit-exactly)."""
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     K, D = kernel_matrix(x, u, sigma, l)
     alpha = mid["B"] * (r - K @ mid["v"])
     Omega = K @ mid["M"] + np.outer(alpha, mid["beta"])
     P = Omega * K
-    g_sigma = 2 * float(P.sum())
-    g_l = np.einsum("ij,ijc->c", P, D)
+    tau = _DT(tau)
+    g_sigma = 2 * P.sum()
+    g_l = np.array([np.sum(P * D[:, :, c]) for c in range(D.shape[2])], dtype=_DT)
     eq = _coincident(x, u)
-    g_tau_q4 = 0.0
+    g_tau_q4 = _DT(0)
     if eq.any():
         Om_tau = Omega - (1 / tau ** 2) * (K @ mid["Sinv"])
-        g_tau_q4 = 2 * tau ** 2 * float(Om_tau[eq].sum())
-    return {"g_sigma": g_sigma, "g_l": g_l, "sum_alpha2": float(alpha @ alpha), "g_tau_q4": g_tau_q4}
+        g_tau_q4 = 2 * tau ** 2 * Om_tau[eq].sum()
+    return {"g_sigma": g_sigma, "g_l": g_l, "sum_alpha2": alpha @ alpha, "g_tau_q4": g_tau_q4}
 
 
 def dS_dtheta(u, sigma, l, tau, name, cov_fun="ard"):
@@ -116,18 +173,19 @@ def dS_dtheta(u, sigma, l, tau, name, cov_fun="ard"):
 
 
 def vi_finish(p2, mid, u, sigma, l, tau, cov_fun="ard"):
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
+    sigma, tau = _DT(sigma), _DT(tau)
     d = u.shape[1]
     n, B, N = mid["n"], mid["B"], mid["N"]
     grad = {}
-    grad["sigma"] = p2["g_sigma"] + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "sigma"))) \
+    grad["sigma"] = p2["g_sigma"] + np.sum(N * dS_dtheta(u, sigma, l, tau, "sigma")) \
         - (1 / (2 * tau ** 2)) * 2 * sigma ** 2 * n
     if cov_fun == "ard":
         for c in range(d):
             nm = "l%d" % (c + 1)
-            grad[nm] = float(p2["g_l"][c]) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, nm)))
+            grad[nm] = p2["g_l"][c] + np.sum(N * dS_dtheta(u, sigma, l, tau, nm))
     else:
-        grad["l"] = float(np.sum(p2["g_l"])) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun)))
+        grad["l"] = np.sum(p2["g_l"]) + np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun))
     grad["tau"] = tau ** 2 * p2["sum_alpha2"] - tau ** 2 * (n * B - B ** 2 * mid["trCG1"]) - 2 * mid["tt"] \
         + p2["g_tau_q4"]
     return grad
@@ -135,8 +193,8 @@ def vi_finish(p2, mid, u, sigma, l, tau, cov_fun="ard"):
 
 def vi_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
     """Full evaluation; `shards` splits the rows into that many contiguous blocks (the multi-GPU layout)."""
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    r = np.asarray(y, dtype=np.float64).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (len(x),))
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    r = np.asarray(y, dtype=_DT).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=_DT).reshape(-1), (len(x),))
     bounds = shard_bounds(len(x), shards)
     p1 = add_partials([vi_pass1(x[a:b], r[a:b], u, sigma, l) for a, b in bounds])
     mid = vi_mid(p1, u, sigma, l, tau, delta, cov_fun)
@@ -167,19 +225,16 @@ def fic_rows_q(x, u, sigma, l, Sinv):
 def fic_pass1(x, r, u, sigma, l, Bv):
     """pass 1b (rows): G_B = K^T diag(B) K, b = K^T (B r), s0 = sum B r^2, s1 = sum log Z."""
     K, _ = kernel_matrix(x, u, sigma, l)
-    return {"GB": K.T @ (Bv[:, None] * K), "b": K.T @ (Bv * r), "s0": float(np.sum(Bv * r * r)),
-            "s1": float(np.sum(-np.log(Bv))), "n": float(len(r))}
+    return {"GB": K.T @ (Bv[:, None] * K), "b": K.T @ (Bv * r), "s0": np.sum(Bv * r * r),
+            "s1": np.sum(-np.log(Bv)), "n": _DT(len(r))}
 
 
 def fic_mid(p1, S, Sinv, logdetS):
-    m = S.shape[0]
-    LA = np.linalg.cholesky(S + p1["GB"])
-    Cm = sla.cho_solve((LA, True), np.eye(m))
-    logdetA = 2 * np.sum(np.log(np.diag(LA)))
+    Cm, logdetA = _spd_inverse(S + p1["GB"])
     v = Cm @ p1["b"]
     beta = Sinv @ (p1["b"] - p1["GB"] @ v)
     n = p1["n"]
-    obj = -0.5 * p1["s0"] + 0.5 * float(p1["b"] @ v) - 0.5 * (p1["s1"] - logdetS + logdetA) - (n / 2) * math.log(2 * math.pi)
+    obj = -p1["s0"] / 2 + (p1["b"] @ v) / 2 - (p1["s1"] - logdetS + logdetA) / 2 - (n / 2) * np.log(8 * np.arctan(_DT(1)))
     M2 = Cm @ p1["GB"] @ Sinv
     return dict(obj=obj, C=Cm, v=v, beta=beta, M2=M2, n=n)
 
@@ -189,49 +244,50 @@ def fic_rows_rho(x, r, u, sigma, l, Bv, mid):
     K, _ = kernel_matrix(x, u, sigma, l)
     c = np.sum((K @ mid["C"]) * K, axis=1)
     alpha = Bv * (r - K @ mid["v"])
-    rho = 0.5 * alpha ** 2 - 0.5 * (Bv - Bv ** 2 * c)
+    rho = alpha ** 2 / 2 - (Bv - Bv ** 2 * c) / 2
     return alpha, rho
 
 
 def fic_pass2(x, u, sigma, l, tau, Bv, alpha, rho, Sinv, mid):
     """pass 2b (rows): sum Omega o dK for sigma / l_c, G_rho = K^T diag(rho) K, sum rho, Q4 pairs."""
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     K, D = kernel_matrix(x, u, sigma, l)
     Omega = (-Bv - 2 * rho)[:, None] * (K @ Sinv) + Bv[:, None] * (K @ mid["M2"]) + np.outer(alpha, mid["beta"])
     P = Omega * K
     eq = _coincident(x, u)
-    return {"g_sigma": 2 * float(P.sum()), "g_l": np.einsum("ij,ijc->c", P, D), "Grho": K.T @ (rho[:, None] * K),
-            "sum_rho": float(rho.sum()), "g_tau_q4": 2 * tau ** 2 * float(Omega[eq].sum()) if eq.any() else 0.0}
+    tau = _DT(tau)
+    return {"g_sigma": 2 * P.sum(), "g_l": np.array([np.sum(P * D[:, :, c]) for c in range(D.shape[2])], dtype=_DT),
+            "Grho": K.T @ (rho[:, None] * K), "sum_rho": rho.sum(),
+            "g_tau_q4": 2 * tau ** 2 * Omega[eq].sum() if eq.any() else _DT(0)}
 
 
 def fic_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     m, d = u.shape
-    r = np.asarray(y, dtype=np.float64).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (len(x),))
+    r = np.asarray(y, dtype=_DT).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=_DT).reshape(-1), (len(x),))
     bounds = shard_bounds(len(x), shards)
+    sigma, tau, delta = _DT(sigma), _DT(tau), _DT(delta)
     Kuu, _ = kernel_matrix(u, u, sigma, l)
-    S = Kuu + delta * np.eye(m)
-    LS = np.linalg.cholesky(S)
-    Sinv = sla.cho_solve((LS, True), np.eye(m))
-    logdetS = 2 * np.sum(np.log(np.diag(LS)))
-    Bs = [1.0 / (sigma ** 2 + tau ** 2 + delta - fic_rows_q(x[a:b], u, sigma, l, Sinv)) for a, b in bounds]
+    S = Kuu + delta * np.eye(m, dtype=_DT)
+    Sinv, logdetS = _spd_inverse(S)
+    Bs = [1 / (sigma ** 2 + tau ** 2 + delta - fic_rows_q(x[a:b], u, sigma, l, Sinv)) for a, b in bounds]
     p1 = add_partials([fic_pass1(x[a:b], r[a:b], u, sigma, l, Bs[k]) for k, (a, b) in enumerate(bounds)])
     mid = fic_mid(p1, S, Sinv, logdetS)
     ar = [fic_rows_rho(x[a:b], r[a:b], u, sigma, l, Bs[k], mid) for k, (a, b) in enumerate(bounds)]
     p2 = add_partials([fic_pass2(x[a:b], u, sigma, l, tau, Bs[k], ar[k][0], ar[k][1], Sinv, mid)
                        for k, (a, b) in enumerate(bounds)])
     GB = p1["GB"]
-    N = 0.5 * Sinv @ GB @ Sinv - 0.5 * Sinv @ GB @ mid["M2"] - 0.5 * np.outer(mid["beta"], mid["beta"]) \
+    N = Sinv @ GB @ Sinv / 2 - Sinv @ GB @ mid["M2"] / 2 - np.outer(mid["beta"], mid["beta"]) / 2 \
         + Sinv @ p2["Grho"] @ Sinv
-    grad = {"sigma": p2["g_sigma"] + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "sigma"))) + 2 * sigma ** 2 * p2["sum_rho"]}
+    grad = {"sigma": p2["g_sigma"] + np.sum(N * dS_dtheta(u, sigma, l, tau, "sigma")) + 2 * sigma ** 2 * p2["sum_rho"]}
     if cov_fun == "ard":
         for c in range(d):
             nm = "l%d" % (c + 1)
-            grad[nm] = float(p2["g_l"][c]) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, nm)))
+            grad[nm] = p2["g_l"][c] + np.sum(N * dS_dtheta(u, sigma, l, tau, nm))
     else:
-        grad["l"] = float(np.sum(p2["g_l"])) + float(np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun)))
+        grad["l"] = np.sum(p2["g_l"]) + np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun))
     grad["tau"] = 2 * tau ** 2 * p2["sum_rho"] + p2["g_tau_q4"]
     return mid["obj"], grad
 
@@ -267,12 +323,11 @@ def laplace_setup(x, u, sigma, l, tau, delta):
     m = len(u)
     Kuu, _ = kernel_matrix(u, u, sigma, l)
     S = Kuu + (tau ** 2 + delta) * np.eye(m)          # tau^2 kept (R/newtrap_sparseGP.R:51-60)
-    LS = np.linalg.cholesky(S)
-    Sinv = sla.cho_solve((LS, True), np.eye(m))
+    Sinv, logdetS = _spd_inverse(S)
     Z = sigma ** 2 + tau ** 2 + delta - np.sum((K @ Sinv) * K, axis=1)
     GZ = K.T @ (K / Z[:, None])
-    CZ = np.linalg.inv(S + GZ)
-    return dict(K=K, S=S, Sinv=Sinv, Z=Z, GZ=GZ, CZ=CZ, logdetS=2 * np.sum(np.log(np.diag(LS))))
+    CZ = _inv(S + GZ)
+    return dict(K=K, S=S, Sinv=Sinv, Z=Z, GZ=GZ, CZ=CZ, logdetS=logdetS)
 
 
 def laplace_obj(st, family, ff, y, mu, pois_m=1.0):
@@ -282,7 +337,7 @@ def laplace_obj(st, family, ff, y, mu, pois_m=1.0):
     omega = -W / (1 - W * Z)
     Gw = K.T @ (omega[:, None] * K)
     a = K.T @ ((ff - mu) / Z)
-    logdetA = 2 * np.sum(np.log(np.diag(np.linalg.cholesky(st["S"] + Gw))))
+    logdetA = _spd_inverse(st["S"] + Gw)[1]
     obj = -0.5 * float(np.sum((ff - mu) ** 2 / Z)) + 0.5 * float(a @ st["CZ"] @ a) + logpy \
         - 0.5 * (-st["logdetS"] + logdetA) - 0.5 * float(np.sum(np.log(1 - W * Z)))
     return obj, Gw
@@ -291,7 +346,7 @@ def laplace_obj(st, family, ff, y, mu, pois_m=1.0):
 def laplace_newton(x, y, mu, muu, u, sigma, l, tau, delta, family, ff0, maxit=1000, tol=1e-6, pois_m=1.0):
     st = laplace_setup(x, u, sigma, l, tau, delta)
     K, Z, S = st["K"], st["Z"], st["S"]
-    ff = np.array(ff0, dtype=np.float64)
+    ff = np.array(ff0, dtype=_DT)
     obj, Gw = laplace_obj(st, family, ff, y, mu, pois_m)
     hist = [obj]
     it = 1
@@ -303,7 +358,7 @@ def laplace_newton(x, y, mu, muu, u, sigma, l, tau, delta, family, ff0, maxit=10
         h = st["CZ"] @ a
         Kh = K @ h
         grad_psi = d1 - (ff - mu) / Z + Kh / Z
-        g2 = np.linalg.solve(S + Gw, K.T @ (e * grad_psi))
+        g2 = _solve(S + Gw, K.T @ (e * grad_psi))
         Gw_used = Gw
         ff = ff + Z * e * d1 - e * (ff - mu) + e * Kh + e * (K @ g2)
         obj, Gw = laplace_obj(st, family, ff, y, mu, pois_m)
@@ -311,21 +366,21 @@ def laplace_newton(x, y, mu, muu, u, sigma, l, tau, delta, family, ff0, maxit=10
         if not (it < maxit and (abs(hist[-1] - hist[-2]) > tol or np.any(np.abs(grad_psi) > tol))):
             break
     a = K.T @ ((ff - mu) / Z)
-    u_mean = np.asarray(muu, dtype=np.float64) + a - st["GZ"] @ (st["CZ"] @ a)
-    u_var = S - Gw_used + Gw_used @ np.linalg.solve(S + Gw_used, Gw_used)      # TT = -G_omega of the last update
+    u_mean = np.asarray(muu, dtype=_DT) + a - st["GZ"] @ (st["CZ"] @ a)
+    u_var = S - Gw_used + Gw_used @ _solve(S + Gw_used, Gw_used)      # TT = -G_omega of the last update
     return dict(gp=ff, hist=np.array(hist), gradient=grad_psi, u_mean=u_mean, u_var=u_var)
 
 
 def laplace_grad(x, y, mu, u, sigma, l, tau, delta, family, ff, cov_fun="ard", pois_m=1.0):
-    x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
-    u = np.asarray(u, dtype=np.float64).reshape(len(u), -1)
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     d = u.shape[1]
     st = laplace_setup(x, u, sigma, l, tau, delta)
     K, Z, S, Sinv, CZ = st["K"], st["Z"], st["S"], st["Sinv"], st["CZ"]
     g, W, W3, _ = lik_terms(family, ff, y, pois_m)
     B = 1 / (Z - 1 / W)
     GB = K.T @ (B[:, None] * K)
-    C = np.linalg.inv(S + GB)
+    C = _inv(S + GB)
     a = K.T @ ((ff - mu) / Z)
     h = CZ @ a
     alpha = (ff - mu) / Z - (K @ h) / Z

@@ -717,7 +717,7 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
     }
     // Generator on its own stream, two chunk buffers: chunk c+1 is generated while the SYRK kernel consumes
     // chunk c (the generator CTAs are small enough to be co-resident with the DMMA CTAs and fill its FP64 bubbles).
-    cudaStream_t sg = ctx->stream3;
+    cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;   // diagnostic: serialise generator and DMMA kernels
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
     SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
     int cidx = 0;
@@ -862,7 +862,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
     if (mode == MODE_GRAD && ctx->n == 0 && first)
         SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
     double *rowpart = w->rowpart.d();
-    cudaStream_t sg = ctx->stream3;
+    cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;   // diagnostic: serialise generator and DMMA kernels
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
     SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
     int cidx = 0;
@@ -1213,4 +1213,49 @@ extern "C" int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, co
 {
     SRGP_TRY(srgp_set_data(ctx, xy, n, d, y, mu));
     return srgp_gauss_obj_grad(ctx, model, kernel, xu, m, sigma, l, tau, delta, obj, grad);
+}
+
+#include "srgp_internal.h"
+extern "C" int srgp_test_gen(srgp_ctx *ctx, const double *xu, int64_t m, double sigma, const double *l, int reps,
+                             double *ms_out)
+{
+    SRGP_TRY(use_device(ctx));
+    GaussWS *w = gauss_ws(ctx);
+    SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
+    cudaStream_t s = ctx->stream;
+    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, s));
+    GenParams gp;
+    fill_gen(gp, SRGP_ARD, ctx->d, sigma, l);
+    const int quantum = BK * w->splits, mp = w->mp, d = w->d;
+    for (int which = 0; which < 2; which++) {
+        for (int r = 0; r <= reps; r++) {
+            if (r == 1) SRGP_CUDA(cudaEventRecord(ctx->tim0, s));
+            if (which == 0) {
+                for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
+                    const int rv = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
+                    dim3 grid(mp / 128, w->gen_groups);
+                    const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
+#define CALL(D) launch_gen_rm<D>(s, grid, smem, ctx->Xp, ctx->n, w->r.d(), r0, rv, (int)round_up(rv, quantum), w->U.d(), w->m, mp, d, gp, w->chunk.d(), w->b1part.d(), 1)
+                    SRGP_D_SWITCH(d, CALL)
+#undef CALL
+                }
+            } else {
+                for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2) {
+                    const int rv = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
+                    dim3 grid(ceil_div(w->rows2, GENC_ROWS), std::min(mp / GENC_COLS, 64));
+                    const size_t gs = sizeof(double) * GENC_COLS * d;
+#define CALL(D) launch_gen_cm<D>(s, grid, gs, ctx->Xp, ctx->n, r0, rv, w->rows2, w->U.d(), w->m, mp, d, gp, w->chunk.d(), (int64_t)w->rows2)
+                    SRGP_D_SWITCH(d, CALL)
+#undef CALL
+                }
+            }
+            SRGP_LAUNCH_CHECK();
+        }
+        SRGP_CUDA(cudaEventRecord(ctx->tim1, s));
+        SRGP_CUDA(cudaEventSynchronize(ctx->tim1));
+        float f = 0.f;
+        SRGP_CUDA(cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1));
+        ms_out[which] = f / std::max(1, reps);
+    }
+    return SRGP_OK;
 }

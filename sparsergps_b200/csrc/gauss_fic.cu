@@ -120,7 +120,8 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
     SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
     SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
-    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, LinvT, tmp, Sinv, w->info(0),
+    double *LinvS = w->mat(W::M_L1), *LinvTS = w->mat(W::M_L2);   // kept: vector solves with S use the factors
+    SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), LinvS, LinvTS, tmp, Sinv, w->info(0),
                                  w->sc(W::S_LOGDET_S)));
 
     // ---- pass 1a: q_i ; rows: Z, B, B r, sum B r^2, sum log Z ----------------------------------------------
@@ -144,11 +145,15 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, 1.0, GB, 0.0, A));
     SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1),
                                  w->sc(W::S_LOGDET_A)));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, C, b, 0.0, nullptr, v, gsc));
+    // vector solves through the triangular factors (forward error ~ sqrt(cond) instead of cond)
+    double *t1 = w->vec(W::V_T1), *t2 = w->vec(W::V_T2);
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Linv, b, 0.0, nullptr, t1, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, GB, v, 0.0, nullptr, gv, gsc));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, b, -1.0, gv, tv));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Sinv, tv, 0.0, nullptr, beta, gsc));
-    SRGP_TRY(dense::dot_v(ctx, s, m, b, v, w->sc(W::S_BV)));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvS, tv, 0.0, nullptr, t2, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvTS, t2, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::dot_v(ctx, s, m, t1, t1, w->sc(W::S_BV)));   // b^T (S+G_B)^-1 b = |L^-1 b|^2
     if (grad) {
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, GB, mp, 0.0, CG, mp));
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, M2, mp));

@@ -99,11 +99,16 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1),
                                  w->sc(W::S_LOGDET_A)));
     // b = B b1 ; v = C b ; gv = G1 v ; beta = S^-1 (b - B gv)
+    // (vector solves go through the triangular factors, L^-T (L^-1 x): their forward error scales with
+    //  sqrt(cond) instead of cond for the explicit inverse -- matters for the OAT-shaped configs, cond(S) ~ 1e4+)
+    double *t1 = w->vec(W::V_T1), *t2 = w->vec(W::V_T2);
     SRGP_TRY(axpby_vec(ctx, mp, B, b1, 0.0, nullptr, bv));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, C, bv, 0.0, nullptr, v, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Linv, bv, 0.0, nullptr, t1, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv, gsc));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, bv, -B, gv, tv));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Sinv, tv, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L1), tv, 0.0, nullptr, t2, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L2), t2, 0.0, nullptr, beta, gsc));
     if (grad) {
         // CG = C G1 ; CGS = C G1 S^-1 ; Mop = (1/tau^2 - B) S^-1 + B^2 CGS - B beta v^T
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, G1, mp, 0.0, CG, mp));
@@ -115,7 +120,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(stream_fork(ctx));
     SRGP_TRY(dense::dot_mm(ctx, s2, mp, m, Sinv, G1, w->sc(W::S_SUMQ), w->nspart.d()));
     SRGP_TRY(dense::dot_mm(ctx, s2, mp, m, C, G1, w->sc(W::S_TRCG1), w->nspart.d()));
-    SRGP_TRY(dense::dot_v(ctx, s2, m, bv, v, w->sc(W::S_BV)));
+    SRGP_TRY(dense::dot_v(ctx, s2, m, t1, t1, w->sc(W::S_BV)));   // b^T (S+G)^-1 b = |L^-1 b|^2
     SRGP_TRY(dense::dot_v(ctx, s2, m, b1, v, w->sc(W::S_B1V)));
     SRGP_TRY(dense::dot_v(ctx, s2, m, v, gv, w->sc(W::S_VGV)));
     if (grad) {

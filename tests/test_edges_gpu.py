@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 def _problem(n, m, d, seed, cov_fun="ard"):
     rng = np.random.default_rng(seed)
-    x, xu = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    spread = max(1.0, 0.3 * m ** (1.0 / d))      # keep the knot spacing near the length scale: cond(S) moderate
+    x, xu = spread * rng.normal(size=(n, d)), spread * rng.normal(size=(m, d))
     y = np.sin(x[:, 0]) + 0.3 * rng.normal(size=n)
     if cov_fun == "ard":
         cp = cases.ard_par(1.1, rng.uniform(0.7, 1.6, d), 0.4)
@@ -28,6 +29,12 @@ def test_tiny_ragged_and_generic_d(ctx, n, m, d, model):
     obj, grad = ctx.gauss_obj_grad(model, "ard", xu, cp["sigma"], cases.lvec(cp), cp["tau"], 1e-4)
     f = rm.vi_obj_grad if model == "vi" else rm.fic_obj_grad
     obj_ref, g_ref = f(cp, "ard", xu, x, y, np.zeros(n), 1e-4)
+    if not np.isfinite(obj_ref):
+        # quirk Q6: the reference's log(det(Sigma22)) under/overflows (129 knots on a line); the product takes
+        # log|S| from the Cholesky factor, as the reduced-form oracle does -- the gradient is unaffected
+        from oracle import reduced_model as red
+        fr = red.vi_obj_grad if model == "vi" else red.fic_obj_grad
+        obj_ref = fr(x, y, np.zeros(n), xu, cp["sigma"], cases.lvec(cp), cp["tau"], 1e-4)[0]
     _check(obj, grad, obj_ref, g_ref, list(cp))
 
 

@@ -112,3 +112,16 @@ def test_newton_and_laplace_gradient_run():
     assert np.max(np.abs(fit["gradient"])) < 1e-3
     g = rm.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], "bernoulli", c["mu"], c["delta"])
     assert all(np.isfinite(v) for v in g["gradient"].values())
+
+
+def test_extended_precision_reference_agrees_when_well_conditioned():
+    c = cases.config2(n=300, m=16)
+    cp = c["cov_par"]
+    for f in (red.vi_obj_grad, red.fic_obj_grad):
+        o64, g64 = f(c["x"], c["y"], c["mu"], c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+        with red.extended_precision():
+            ox, gx = f(c["x"], c["y"], c["mu"], c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+        assert type(ox).__name__ == "longdouble"
+        assert float(o64) == pytest.approx(float(ox), rel=1e-13)
+        for k in g64:
+            assert float(g64[k]) == pytest.approx(float(gx[k]), rel=1e-11), k

@@ -4,7 +4,6 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdint.h>
-#include "../sparsergps_b200/csrc/kmath.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
@@ -69,14 +68,13 @@ __global__ void k_mixed(double *out, int iters, double a, double b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int WHICH>
 __global__ void k_exp(double *out, int iters, double x0)
 {
     double x = x0 - 1e-3 * threadIdx.x, s = 0;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            double v = WHICH == 0 ? exp(x) : srgp::exp_nonpos(x);
+            double v = exp(x);
             s += v;
             x -= 1e-4;
         }
@@ -129,9 +127,8 @@ int main()
     float t_f8 = time_it([&] { k_mixed<0, 8><<<blocks, threads>>>(out, iters, 1.0000001, 1e-9); });
 
     const int eiters = 512;
-    float t_exp0 = time_it([&] { k_exp<0><<<blocks, threads>>>(out, eiters, -0.1); });
-    float t_exp1 = time_it([&] { k_exp<1><<<blocks, threads>>>(out, eiters, -0.1); });
-    double exp0 = nthreads * 8 * eiters / (t_exp0 * 1e-3) / 1e12, exp1 = nthreads * 8 * eiters / (t_exp1 * 1e-3) / 1e12;
+    float t_exp0 = time_it([&] { k_exp<<<blocks, threads>>>(out, eiters, -0.1); });
+    double exp0 = nthreads * 8 * eiters / (t_exp0 * 1e-3) / 1e12;
 
     // occupancy sensitivity of DMMA: 8 warps per SM (the Gram kernel's shape)
     float t_mma8w = time_it([&] { k_dmma<16><<<sms, 256>>>(out, iters, 1.0000001, 1e-9); });
@@ -144,9 +141,9 @@ int main()
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d, "
            "\"dfma_tflops\": %.2f, \"dmma_tflops\": %.2f, "
            "\"ms_dmma8\": %.4f, \"ms_dmma8_plus_dfma8\": %.4f, \"ms_dmma8_plus_dfma16\": %.4f, \"ms_dfma8\": %.4f, "
-           "\"exp_libdevice_Tops\": %.3f, \"exp_nonpos_Tops\": %.3f, "
+           "\"exp_libdevice_Tops\": %.3f, "
            "\"dmma_tflops_4warps_per_sm\": %.2f, \"dmma_tflops_8warps_per_sm\": %.2f, \"dmma_tflops_16warps_per_sm\": %.2f}\n",
-           prop.name, sms, prop.clockRate, dfma_tflops, dmma_tflops, t_mix0, t_mix8, t_mix16, t_f8, exp0, exp1,
+           prop.name, sms, prop.clockRate, dfma_tflops, dmma_tflops, t_mix0, t_mix8, t_mix16, t_f8, exp0,
            dmma4w, dmma8w, dmma16w);
     cudaFree(out);
     return 0;
