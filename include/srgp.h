@@ -147,6 +147,22 @@ int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, const double 
                              const double *y, const double *mu, const double *xu, int64_t m, double sigma,
                              const double *l, double tau, double delta, double *obj, double *grad);
 
+/* ---------------------------------------------------------------- posterior at the knots, prediction ---- */
+/* Posterior of the process at the knots on the resident shard: the tail of norm_grad_ascent_vi
+   (R/vi_functions.R:1160-1180, model SRGP_VI) / norm_grad_ascent (R/laplace_gradient_ascent.R:1637-1656, SRGP_FIC).
+   muu (m, NULL = 0) is the prior mean at the knots; u_mean (m) and u_var (m x m) are global under multi-GPU. */
+int srgp_gauss_posterior_u(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, const double *muu,
+                           double sigma, const double *l, double tau, double delta, double *u_mean, double *u_var);
+/* predict_vi (R/vi_functions.R:1222-1336) and predict_laplace (R/laplace_approx_prediction.R:3-123) with
+   full_cov = FALSE:  pred_mean = mu_pred + K S22^-1 (u_mean - muu),
+                      pred_var_i = var_const + K_i (-S22^-1 + S22^-1 u_var S22^-1) K_i^T,  K = k(x_pred, xu).
+   s22_nugget is the diagonal added to K_uu: delta for Gaussian models, tau^2 + delta for the other families;
+   var_const is tau^2 + sigma^2 + delta (predict_vi) or sigma^2 + tau^2 (predict_laplace).  K is never built. */
+int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int64_t n_pred, int d, const double *mu_pred,
+                 const double *xu, int64_t m, const double *muu, const double *u_mean, const double *u_var,
+                 double sigma, const double *l, double s22_nugget, double var_const, double *pred_mean,
+                 double *pred_var);
+
 /* ---------------------------------------------------------------- sparse Laplace ------------- */
 /* newtrap_sparseGP (R/newtrap_sparseGP.R:6-186) on the resident shard.  ff (n) in: start values, out: mode.
    obj_hist receives up to maxit objective values, *n_iter their count.  grad_psi (n), u_mean (m),

@@ -551,3 +551,50 @@ def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, dcov
         grad[par_name] = (1 / 2) * comp2 - (1 / 2) * comp1 - \
             (1 / 2) * float((_col(comp4 * (-W3)).T @ comp3)[0, 0])                  # :333-335
     return {"gradient": grad, "trans_par": trans_par}
+
+
+# --------------------------------------------------------------------------------------------------
+# Posterior at the knots and prediction
+# --------------------------------------------------------------------------------------------------
+def gauss_posterior_u(cov_par, cov_fun, xu, xy, y, mu, muu, delta=1e-6, vi=True):
+    """Tail of norm_grad_ascent_vi (R/vi_functions.R:1160-1180) for vi = True, of norm_grad_ascent
+    (R/laplace_gradient_ascent.R:1637-1656) otherwise: posterior mean and variance of the process at the knots."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    mu = np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), y.shape)
+    Sigma12, Sigma22, _ = assemble(cov_par, cov_fun, xy, xu, delta)
+    if vi:
+        Z = np.repeat(cov_par["tau"] ** 2 + delta, Sigma12.shape[0])            # R/vi_functions.R:753
+    else:
+        Z = fic_Z(cov_par, Sigma12, Sigma22, delta)                               # R/laplace_gradient_ascent.R:1259-1263
+    ZSig12 = _rows(1 / Z, Sigma12)
+    R1 = chol(Sigma22 + Sigma12.T @ ZSig12)
+    rhs = ZSig12.T @ _col(y - mu)
+    u_mean = np.asarray(muu, dtype=np.float64).reshape(-1) + rhs.reshape(-1) - \
+        (Sigma12.T @ (ZSig12 @ solve(R1, solve(R1.T, rhs)))).reshape(-1)
+    W = solve(R1.T, Sigma12.T)
+    u_var = Sigma22 - Sigma12.T @ ZSig12 + (ZSig12.T @ W.T) @ (W @ ZSig12)
+    return u_mean, u_var
+
+
+def predict_vi(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, delta=1e-6):
+    """R/vi_functions.R:1222-1336, family = "gaussian", full_cov = FALSE."""
+    Sigma12, Sigma22, _ = assemble(cov_par, cov_fun, x_pred, xu, delta)           # Sigma22 = self-cov - tau^2 I
+    Sigma22_inv = solve(Sigma22)
+    pred_mean = np.asarray(mu, dtype=np.float64).reshape(-1) + \
+        (Sigma12 @ solve(Sigma22, _col(np.asarray(u_mean) - np.asarray(muu)))).reshape(-1)
+    temp22 = -Sigma22_inv + Sigma22_inv @ u_var @ Sigma22_inv
+    Sigma11 = cov_par["tau"] ** 2 + cov_par["sigma"] ** 2 + delta
+    pred_var = Sigma11 + np.sum(Sigma12 * (temp22 @ Sigma12.T).T, axis=1)
+    return pred_mean, pred_var
+
+
+def predict_laplace(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, family="gaussian", delta=1e-6):
+    """R/laplace_approx_prediction.R:3-123, full_cov = FALSE: Sigma22 keeps tau^2 for non-Gaussian families and
+    the predictive variance constant is sigma^2 + tau^2 (no delta)."""
+    Sigma12, Sigma22, _ = assemble(cov_par, cov_fun, x_pred, xu, delta, keep_tau_in_S=(family != "gaussian"))
+    Sigma22_inv = solve(Sigma22)
+    pred_mean = np.asarray(mu, dtype=np.float64).reshape(-1) + \
+        (Sigma12 @ solve(Sigma22, _col(np.asarray(u_mean) - np.asarray(muu)))).reshape(-1)
+    temp22 = -Sigma22_inv + Sigma22_inv @ u_var @ Sigma22_inv
+    pred_var = cov_par["sigma"] ** 2 + cov_par["tau"] ** 2 + np.sum((Sigma12 @ temp22) * Sigma12, axis=1)
+    return pred_mean, pred_var

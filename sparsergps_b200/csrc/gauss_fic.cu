@@ -214,3 +214,189 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
 }
 
 }  // namespace srgp
+
+// ====================================================================================================
+// posterior at the knots, and prediction
+// ====================================================================================================
+namespace srgp {
+
+// u_mean = muu + b - G v, u_var = S - G + G C G with G = K^T diag(1/Z) K, b = K^T ((y - mu)/Z), C = (S + G)^-1,
+// v = C b.  Z = tau^2 + delta (VI: R/vi_functions.R:753,1160-1180) or sigma^2 + tau^2 + delta - q_i
+// (FIC: R/laplace_gradient_ascent.R:1259-1263,1637-1656).
+int gauss_posterior(srgp_ctx *ctx, GaussWS *w, int model, int kernel, double sigma, const double *l, double tau,
+                    double delta, double *u_plus /* dev, mp: b - G v */, double *u_var_dev /* dev, mp x mp */)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int64_t n = ctx->n;
+    const size_t mm = (size_t)mp * mp;
+    GenParams gp;
+    fill_gen(gp, kernel, d, sigma, l);
+    double *G = w->red1.d(), *b = G + mm;
+    SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
+    double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
+    double *Linv = w->mat(W::M_LINV), *LinvT = w->mat(W::M_X1), *tmp = w->mat(W::M_TMP), *T1 = w->mat(W::M_T1);
+    double *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *t1 = w->vec(W::V_T1), *gsc = w->gemv_scratch();
+    SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
+    SRGP_TRY(dense::pad_identity(ctx, s, S, mp, m, 1.0));
+    if (model == SRGP_VI) {
+        const double B = 1.0 / (tau * tau + delta);
+        SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G, b));
+        SRGP_TRY(comm_allreduce(ctx, G, mm + mp, s));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, B, G, 0.0, nullptr, 0.0, G));
+        SRGP_TRY(axpby_vec(ctx, mp, B, b, 0.0, nullptr, b));
+    } else {
+        SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
+        SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), Linv, LinvT, tmp, Sinv, w->info(0),
+                                     w->sc(W::S_LOGDET_S)));
+        double *q = w->rowv(0, n), *Bv = w->rowv(1, n), *Br = w->rowv(2, n);
+        SRGP_TRY(gauss_rowform(ctx, w, gp, Sinv, nullptr, q, nullptr));
+        {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+            fic_rows1_kernel<<<ROW_BLOCKS, 256, 0, s>>>(q, w->r.d(), n, sigma * sigma + tau * tau + delta, Bv, Br,
+                                                        w->part2.d());
+            SRGP_LAUNCH_CHECK();
+        }
+        SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, G, b));
+        SRGP_TRY(comm_allreduce(ctx, G, mm + mp, s));
+    }
+    SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, 1.0, G, 0.0, A));
+    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, m, w->dinv(1), Linv, LinvT, tmp, C, w->info(1), w->sc(W::S_LOGDET_A)));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Linv, b, 0.0, nullptr, t1, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
+    SRGP_TRY(dense::gemv(ctx, s, mp, -1.0, G, v, 1.0, b, u_plus, gsc));       // b - G v
+    (void)gv;
+    // u_var = S - G + G C G
+    double *GC = w->mat(W::M_CG);
+    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, G, mp, C, mp, 0.0, GC, mp));
+    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, GC, mp, G, mp, 0.0, u_var_dev, mp));
+    SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, u_var_dev, -1.0, G, 0.0, u_var_dev));
+    SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, u_var_dev, 1.0, S, 0.0, u_var_dev));
+    return SRGP_OK;
+}
+
+__global__ void predict_finish_kernel(const double *__restrict__ kw, const double *__restrict__ kq, int64_t n,
+                                      const double *__restrict__ mu, double var_const, double *__restrict__ mean,
+                                      double *__restrict__ var)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        mean[i] = (mu ? mu[i] : 0.0) + kw[i];
+        var[i] = var_const + kq[i];
+    }
+}
+
+}  // namespace srgp
+
+using namespace srgp;
+
+extern "C" int srgp_gauss_posterior_u(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m,
+                                      const double *muu, double sigma, const double *l, double tau, double delta,
+                                      double *u_mean, double *u_var)
+{
+    if (!ctx || !xu || !l || !u_mean || !u_var || m <= 0 || m > 32768 || (model != SRGP_VI && model != SRGP_FIC)) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (!ctx->have_data) {
+        set_error("srgp_gauss_posterior_u called before srgp_set_data");
+        return SRGP_ERR_STATE;
+    }
+    if (kernel != SRGP_SQEXP && kernel != SRGP_ARD) {
+        set_error("Error: invalid covariance function");
+        return SRGP_ERR_UNKNOWN_KERNEL;
+    }
+    SRGP_TRY(use_device(ctx));
+    GaussWS *w = gauss_ws(ctx);
+    SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
+    cudaStream_t s = ctx->stream;
+    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, s));
+    double *uplus = w->vec(GaussWS::V_T3), *uvar = w->mat(GaussWS::M_N);
+    SRGP_TRY(gauss_posterior(ctx, w, model, kernel, sigma, l, tau, delta, uplus, uvar));
+    std::vector<double> up((size_t)w->mp);
+    SRGP_CUDA(cudaMemcpyAsync(up.data(), uplus, (size_t)w->mp * 8, cudaMemcpyDeviceToHost, s));
+    SRGP_CUDA(cudaMemcpy2DAsync(u_var, (size_t)m * 8, uvar, (size_t)w->mp * 8, (size_t)m * 8, m, cudaMemcpyDeviceToHost, s));
+    SRGP_TRY(fetch_scalars(ctx, w));
+    for (int64_t j = 0; j < m; j++) u_mean[j] = (muu ? muu[j] : 0.0) + up[j];
+    return SRGP_OK;
+}
+
+extern "C" int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int64_t n_pred, int d,
+                            const double *mu_pred, const double *xu, int64_t m, const double *muu,
+                            const double *u_mean, const double *u_var, double sigma, const double *l,
+                            double s22_nugget, double var_const, double *pred_mean, double *pred_var)
+{
+    if (!ctx || !x_pred || !xu || !u_mean || !u_var || !l || !pred_mean || !pred_var || n_pred <= 0 || m <= 0 ||
+        m > 32768 || d <= 0 || d > SRGP_MAX_D) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (kernel != SRGP_SQEXP && kernel != SRGP_ARD) {
+        set_error("Error: invalid covariance function");
+        return SRGP_ERR_UNKNOWN_KERNEL;
+    }
+    SRGP_TRY(use_device(ctx));
+    cudaStream_t s = ctx->stream;
+    GaussWS *w = gauss_ws(ctx);
+    // the prediction points temporarily take the place of the resident shard for one row-form pass
+    const double *Xsave = ctx->Xp;
+    const int64_t nsave = ctx->n;
+    const int dsave = ctx->d;
+    SRGP_TRY(ctx->in_x.reserve((size_t)n_pred * d * 8));
+    SRGP_CUDA(cudaMemcpyAsync(ctx->in_x.p, x_pred, (size_t)n_pred * d * 8, cudaMemcpyHostToDevice, s));
+    ctx->Xp = ctx->in_x.d();
+    ctx->n = n_pred;
+    ctx->d = d;
+    int st = plan(ctx, w, (int)m, d);
+    const int mp = w->mp;
+    const size_t mm = (size_t)mp * mp;
+    GenParams gp;
+    fill_gen(gp, kernel, d, sigma, l);
+    double *S = w->mat(GaussWS::M_S), *Sinv = w->mat(GaussWS::M_SINV), *UV = w->mat(GaussWS::M_A);
+    double *T1 = w->mat(GaussWS::M_T1), *T2 = w->mat(GaussWS::M_T2), *Tm = w->mat(GaussWS::M_MOP);
+    double *dv = w->vec(GaussWS::V_B), *wv = w->vec(GaussWS::V_V), *gsc = w->gemv_scratch();
+    std::vector<double> diff((size_t)mp, 0.0);
+    for (int64_t j = 0; j < m; j++) diff[j] = u_mean[j] - (muu ? muu[j] : 0.0);
+    if (st == SRGP_OK) st = ctx->tmp0.reserve((size_t)n_pred * 8 * 4 + 64) ;
+    auto run = [&]() -> int {
+        SRGP_CUDA(cudaMemsetAsync(w->scal.d() + GaussWS::S_INFO, 0, 16, s));
+        SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * d * 8, cudaMemcpyHostToDevice, s));
+        SRGP_CUDA(cudaMemcpyAsync(dv, diff.data(), (size_t)mp * 8, cudaMemcpyHostToDevice, s));
+        SRGP_CUDA(cudaMemsetAsync(UV, 0, mm * 8, s));
+        SRGP_CUDA(cudaMemcpy2DAsync(UV, (size_t)mp * 8, u_var, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice, s));
+        // Sigma22 (nugget delta for Gaussian models, tau^2 + delta otherwise), its inverse
+        SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, d, sigma, l, s22_nugget, S, mp));
+        SRGP_TRY(dense::pad_identity(ctx, s, S, mp, (int)m, 1.0));
+        SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
+        SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, (int)m, w->dinv(0), w->mat(GaussWS::M_LINV), w->mat(GaussWS::M_X1),
+                                     w->mat(GaussWS::M_TMP), Sinv, w->info(0), w->sc(GaussWS::S_LOGDET_S)));
+        // w = S^-1 (u_mean - muu) through the factors; T = -S^-1 + S^-1 u_var S^-1
+        SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(GaussWS::M_LINV), dv, 0.0, nullptr, w->vec(GaussWS::V_T1), gsc));
+        SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(GaussWS::M_X1), w->vec(GaussWS::V_T1), 0.0, nullptr, wv, gsc));
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, UV, mp, 0.0, T2, mp));      // u_var symmetric
+        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, T2, mp, Sinv, mp, 0.0, Tm, mp));
+        SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, Tm, -1.0, Sinv, 0.0, Tm));
+        // padding block of Tm must not contribute: K has zero columns there, nothing to do
+        double *kq = ctx->tmp0.d(), *kw = kq + n_pred, *pm = kw + n_pred, *pv = pm + n_pred;
+        SRGP_TRY(gauss_rowform(ctx, w, gp, Tm, wv, kq, kw));
+        const double *mu_dev = nullptr;
+        if (mu_pred) {
+            SRGP_TRY(ctx->tmp1.reserve((size_t)n_pred * 8));
+            SRGP_CUDA(cudaMemcpyAsync(ctx->tmp1.p, mu_pred, (size_t)n_pred * 8, cudaMemcpyHostToDevice, s));
+            mu_dev = ctx->tmp1.d();
+        }
+        {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+            predict_finish_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(kw, kq, n_pred, mu_dev, var_const, pm, pv);
+            SRGP_LAUNCH_CHECK();
+        }
+        SRGP_CUDA(cudaMemcpyAsync(pred_mean, pm, (size_t)n_pred * 8, cudaMemcpyDeviceToHost, s));
+        SRGP_CUDA(cudaMemcpyAsync(pred_var, pv, (size_t)n_pred * 8, cudaMemcpyDeviceToHost, s));
+        return fetch_scalars(ctx, w);
+    };
+    if (st == SRGP_OK) st = run();
+    if (st != SRGP_OK) cudaStreamSynchronize(s);
+    ctx->Xp = Xsave;
+    ctx->n = nsave;
+    ctx->d = dsave;
+    return st;
+}

@@ -49,3 +49,14 @@ def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, m=1.
     L.check(ctx._lib.srgp_laplace_grad(ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), xu.shape[0], sigma,
                                        L.ptr(lv), tau, float(delta), float(m), L.ptr(ffv), L.ptr(grad)))
     return {"gradient": dict(zip(names, grad)), "trans_par": {k: float(np.log(cov_par[k])) for k in names}}
+
+
+def predict_laplace(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, full_cov=False, family="gaussian",
+                    delta=1e-6, ctx=None):
+    """R/laplace_approx_prediction.R:3-123 (same argument list), full_cov = FALSE."""
+    from .vi_functions import _predict
+    if full_cov:
+        raise NotImplementedError("full_cov = TRUE builds a dense n_pred x n_pred matrix: out of the hot path")
+    tau, sigma = float(cov_par["tau"]), float(cov_par["sigma"])
+    nugget = delta if family == "gaussian" else tau ** 2 + delta
+    return _predict(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, nugget, sigma ** 2 + tau ** 2, ctx)

@@ -103,3 +103,49 @@ def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, **_ign
 def obj_norm_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
     """obj_fun_norm with Z built as norm_grad_ascent does (R/laplace_gradient_ascent.R:1241-1265)."""
     return _fused("fic", cov_par, cov_fun, xu, xy, y, mu, delta, False, ctx)["objective"]
+
+
+# ---- posterior at the knots and prediction (SURVEY.md section 8f item 2) ------------------------------
+def gauss_posterior_u(cov_par, cov_fun, xu, xy, y, mu, muu, delta=1e-6, vi=True, ctx=None):
+    """u_mean, u_var as the tails of norm_grad_ascent_vi (R/vi_functions.R:1160-1180, vi = True) and
+    norm_grad_ascent (R/laplace_gradient_ascent.R:1637-1656, vi = False) compute them."""
+    ctx = ctx or default_context()
+    xy, xu = L.fmat(xy), L.fmat(xu)
+    m = xu.shape[0]
+    sigma, l, tau, _ = _theta(cov_par, cov_fun, xy.shape[1])
+    ctx.set_data(xy, y, mu)
+    muu = L.fvec(np.broadcast_to(np.asarray(muu, dtype=np.float64).reshape(-1), (m,)))
+    lv = L.fvec(l)
+    um, uv = np.zeros(m), np.zeros((m, m), order="F")
+    L.check(ctx._lib.srgp_gauss_posterior_u(ctx.handle, L.VI if vi else L.FIC, L.KERNELS[cov_fun], L.ptr(xu), m,
+                                            L.ptr(muu), sigma, L.ptr(lv), tau, float(delta), L.ptr(um), L.ptr(uv)))
+    return um, uv
+
+
+def _predict(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, s22_nugget, var_const, ctx):
+    ctx = ctx or default_context()
+    xp, xu = L.fmat(x_pred), L.fmat(xu)
+    n, d = xp.shape
+    m = xu.shape[0]
+    sigma, l, tau, _ = _theta(cov_par, cov_fun, d)
+    lv = L.fvec(l)
+    mu = L.fvec(np.broadcast_to(np.asarray(mu, dtype=np.float64).reshape(-1), (n,)))
+    muu = L.fvec(np.broadcast_to(np.asarray(muu, dtype=np.float64).reshape(-1), (m,)))
+    um, uv = L.fvec(u_mean), L.fmat(u_var)
+    pm, pv = np.zeros(n), np.zeros(n)
+    L.check(ctx._lib.srgp_predict(ctx.handle, L.KERNELS[cov_fun], L.ptr(xp), n, d, L.ptr(mu), L.ptr(xu), m,
+                                  L.ptr(muu), L.ptr(um), L.ptr(uv), sigma, L.ptr(lv), float(s22_nugget),
+                                  float(var_const), L.ptr(pm), L.ptr(pv)))
+    return {"pred_mean": pm, "pred_var": pv}
+
+
+def predict_vi(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, full_cov=False, family="gaussian", delta=1e-6,
+               ctx=None):
+    """R/vi_functions.R:1222-1336 (same argument list).  full_cov = TRUE is the dense n_pred x n_pred branch of the
+    reference and is not on the GPU path."""
+    if family != "gaussian":
+        return "Error: Only Gaussian data currently supported."       # the reference returns this string
+    if full_cov:
+        raise NotImplementedError("full_cov = TRUE builds a dense n_pred x n_pred matrix: out of the hot path")
+    tau, sigma = float(cov_par["tau"]), float(cov_par["sigma"])
+    return _predict(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, delta, tau ** 2 + sigma ** 2 + delta, ctx)
