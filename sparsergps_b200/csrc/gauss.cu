@@ -612,7 +612,9 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     // pass 1: pairs x splits CTAs ~ one wave; chunk ~ 48 MB so it stays in the 126 MB L2 with the Gram slots
     w->splits = std::max(1, ctx->sm_count / w->pairs);
     if (w->splits > 64) w->splits = 64;
-    int64_t chunk_mb = 32;
+    // 64 MB per buffer (two buffers): measured sweep 24..160 MB in profiles/r01_chunk_sweep.txt -- larger chunks
+    // mean fewer launches / pipeline fills; beyond L2 the re-reads come from HBM, which has headroom here
+    int64_t chunk_mb = 64;
     if (const char *e = getenv("SRGP_CHUNK_MB")) chunk_mb = std::max(4, atoi(e));
     const int64_t target_bytes = chunk_mb << 20;
     int64_t rows = target_bytes / (8 * (int64_t)mp);
@@ -620,10 +622,10 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     rows = std::max<int64_t>(quantum, rows / quantum * quantum);
     w->rows1 = (int)rows;
     // pass 2: row blocks x column groups ~ one wave
-    // column groups: each CTA owns nt / cg column blocks of one 128-row block; cg = 4 keeps the chunk
-    // (sm_count / cg row blocks) near 40 MB at m = 1024 and gives every CTA two tiles per launch
+    // column groups: each CTA owns nt / cg column blocks of one 128-row block; cg = 2 -> 74 row blocks x 2 groups
+    // = 148 CTAs, four tiles per CTA per launch at m = 1024 (sweep in profiles/r01_chunk_sweep.txt)
     int cg = 1;
-    for (int c : {4, 2, 8}) {
+    for (int c : {2, 4, 8}) {
         if (w->nt % c == 0) {
             cg = c;
             break;
