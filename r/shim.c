@@ -292,6 +292,67 @@ SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP
     return Rf_ScalarReal(out);
 }
 
+/* .Call("_sparseRGPs_laplace_newton", family, cov_fun, xy, y, mu, xu, muu, cov_par, delta, lnames, start_vals,
+         maxit, tol, pois_m) -> the list newtrap_sparseGP returns (R/newtrap_sparseGP.R:183-184) */
+SEXP _sparseRGPs_laplace_newton(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP muu, SEXP cov_par,
+                                SEXP delta, SEXP lnames, SEXP start_vals, SEXP maxit, SEXP tol, SEXP pois_m)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    muu = PROTECT(Rf_coerceVector(muu, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu), mi = Rf_asInteger(maxit);
+    double l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    if (srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL) != SRGP_OK)
+        Rf_error("sparseRGPs: %s", srgp_last_error());
+    SEXP ff = PROTECT(Rf_duplicate(Rf_coerceVector(start_vals, REALSXP)));
+    SEXP hist = PROTECT(Rf_allocVector(REALSXP, mi + 1)), gpsi = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP um = PROTECT(Rf_allocVector(REALSXP, m)), uv = PROTECT(Rf_allocMatrix(REALSXP, m, m));
+    int nit = 0;
+    const int fam = strcmp(CHAR(STRING_ELT(family, 0)), "poisson") ? SRGP_BERNOULLI : SRGP_POISSON;
+    const int st = srgp_laplace_newton(ctx(), fam, k, REAL(xu), m, Rf_length(muu) == m ? REAL(muu) : NULL,
+                                       list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta),
+                                       Rf_asReal(pois_m), mi, Rf_asReal(tol), REAL(ff), REAL(hist), &nit, REAL(gpsi),
+                                       REAL(um), REAL(uv));
+    if (st != SRGP_OK) { UNPROTECT(10); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP h = PROTECT(Rf_lengthgets(hist, nit));
+    const char *nms[] = {"gp", "objective_function_values", "gradient", "u_posterior_mean", "u_posterior_variance"};
+    SEXP vals[] = {ff, h, gpsi, um, uv};
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 5)), nm = PROTECT(Rf_allocVector(STRSXP, 5));
+    for (int i = 0; i < 5; i++) { SET_VECTOR_ELT(out, i, vals[i]); SET_STRING_ELT(nm, i, Rf_mkChar(nms[i])); }
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(13);
+    return out;
+}
+
+/* .Call("_sparseRGPs_predict", cov_fun, x_pred, mu_pred, xu, muu, u_mean, u_var, cov_par, lnames, s22_nugget,
+         var_const) -> list(pred_mean, pred_var): bodies of predict_vi / predict_laplace with full_cov = FALSE */
+SEXP _sparseRGPs_predict(SEXP cov_fun, SEXP x_pred, SEXP mu_pred, SEXP xu, SEXP muu, SEXP u_mean, SEXP u_var,
+                         SEXP cov_par, SEXP lnames, SEXP s22_nugget, SEXP var_const)
+{
+    x_pred = PROTECT(Rf_coerceVector(x_pred, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(x_pred), d = Rf_ncols(x_pred), m = Rf_nrows(xu);
+    double l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    SEXP pm = PROTECT(Rf_allocVector(REALSXP, n)), pv = PROTECT(Rf_allocVector(REALSXP, n));
+    const int st = srgp_predict(ctx(), k, REAL(x_pred), n, d, Rf_length(mu_pred) == n ? REAL(mu_pred) : NULL, REAL(xu),
+                                m, Rf_length(muu) == m ? REAL(muu) : NULL, REAL(u_mean), REAL(u_var),
+                                list_get(cov_par, "sigma"), l, Rf_asReal(s22_nugget), Rf_asReal(var_const), REAL(pm),
+                                REAL(pv));
+    if (st != SRGP_OK) { UNPROTECT(4); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, pm); SET_VECTOR_ELT(out, 1, pv);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("pred_mean")); SET_STRING_ELT(nm, 1, Rf_mkChar("pred_var"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(6);
+    return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_real_to_pos", (DL_FUNC)&_sparseRGPs_real_to_pos, 1},
     {"_sparseRGPs_pos_to_real", (DL_FUNC)&_sparseRGPs_pos_to_real, 1},
@@ -315,6 +376,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_make_cov_mat_ardC", (DL_FUNC)&_sparseRGPs_make_cov_mat_ardC, 6},
     {"_sparseRGPs_gauss_obj_grad", (DL_FUNC)&_sparseRGPs_gauss_obj_grad, 9},
     {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
+    {"_sparseRGPs_laplace_newton", (DL_FUNC)&_sparseRGPs_laplace_newton, 14},
+    {"_sparseRGPs_predict", (DL_FUNC)&_sparseRGPs_predict, 11},
     {NULL, NULL, 0}};
 
 void R_init_sparseRGPs(DllInfo *dll)
