@@ -149,7 +149,7 @@ gen_colmajor_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0, int r
                     }
                 } else {
                     for (int c = 0; c < d; c++) {
-                        const double t = X[r0 + i + ldx * c] * p.invl[c] - su[jj * d + c];
+                        const double t = __dmul_rn(X[r0 + i + ldx * c], p.invl[c]) - su[jj * d + c];
                         s = fma(t, t, s);
                     }
                 }

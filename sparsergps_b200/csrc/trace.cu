@@ -55,30 +55,37 @@ static int sum_vec(srgp_ctx *ctx, const double *x, int64_t n, double *scratch, d
 // knots broadcast from shared memory, K and the scaled differences regenerated in registers.
 //   part[block][0] = sum Omega K, [1 + c] = sum Omega K ((x_c - u_c)/l_c)^2, [1 + d] = sum Omega [x == u]
 // ------------------------------------------------------------------------------------------------
-constexpr int OD_ROWS = 256;
+constexpr int OD_THREADS = 128;
+constexpr int OD_RPT = 2;                       // rows per thread: the knot loads from shared memory serve both
+constexpr int OD_ROWS = OD_THREADS * OD_RPT;    // rows per CTA
 constexpr int OD_COLS = 32;
 constexpr int OD_STRIDE = SRGP_MAX_D + 8;
 
+// FP64-pipe budget per entry (d = 8): 8 DADD + 8 DFMA (distance) + 17 (libdevice exp) + 8 DMUL + 8 DFMA
+// (per-dimension sums) + 5 = 54 instructions for 8 bytes of Omega: on B200 (37 TF/s FP64 vs 6.5 TB/s HBM, ridge
+// = 22 instructions per 8-byte entry) this kernel is bound by the FP64 pipe, not by HBM.
 template <int DT>
-__global__ void __launch_bounds__(OD_ROWS)
+__global__ void __launch_bounds__(OD_THREADS)
 omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__restrict__ X, int64_t ldx,
                 int64_t rows, const double *__restrict__ U, int m, int d_rt, GenParams p,
                 double *__restrict__ part, int first)
 {
-    extern __shared__ double su[];   // [OD_COLS][d] scaled knots, then [OD_COLS][d] raw knots
-    __shared__ double red[8][OD_STRIDE];
+    extern __shared__ double su[];   // [OD_COLS][d] scaled knots
+    __shared__ double red[OD_THREADS / 32][OD_STRIDE];
     const int d = DT > 0 ? DT : d_rt;
-    double *sraw = su + OD_COLS * d;
-    const int64_t i = (int64_t)blockIdx.x * OD_ROWS + threadIdx.x;
-    const bool iv = i < rows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = lane; t < OD_STRIDE; t += 32) red[warp][t] = 0.0;
-    double xi[DT > 0 ? DT : 1], xr[DT > 0 ? DT : 1];
-    if (DT > 0) {
+    const double logs2 = log(p.sigma2);
+    int64_t irow[OD_RPT];
+    bool iv[OD_RPT];
+    double xi[OD_RPT][DT > 0 ? DT : 1];
 #pragma unroll
-        for (int c = 0; c < DT; c++) {
-            xr[c] = iv ? X[i + ldx * c] : 0.0;
-            xi[c] = xr[c] * p.invl[c];
+    for (int q = 0; q < OD_RPT; q++) {
+        irow[q] = (int64_t)blockIdx.x * OD_ROWS + q * OD_THREADS + threadIdx.x;
+        iv[q] = irow[q] < rows;
+        if (DT > 0) {
+#pragma unroll
+            for (int c = 0; c < DT; c++) xi[q][c] = iv[q] ? X[irow[q] + ldx * c] * p.invl[c] : 0.0;
         }
     }
     double g0 = 0.0, gt = 0.0, gl[DT > 0 ? DT : 1];
@@ -88,50 +95,55 @@ omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__r
     for (int jt = blockIdx.y; jt < col_tiles; jt += gridDim.y) {
         const int j0 = jt * OD_COLS;
         __syncthreads();
-        for (int t = threadIdx.x; t < OD_COLS * d; t += OD_ROWS) {
+        for (int t = threadIdx.x; t < OD_COLS * d; t += OD_THREADS) {
             const int jj = t / d, c = t - jj * d;
-            const double u = (j0 + jj < m) ? U[j0 + jj + (int64_t)m * c] : 0.0;
-            sraw[t] = u;
-            su[t] = u * p.invl[c];
+            su[t] = (j0 + jj < m) ? U[j0 + jj + (int64_t)m * c] * p.invl[c] : 0.0;
         }
         __syncthreads();
-        if (!iv) continue;
         const int jmax = min(OD_COLS, m - j0);
-#pragma unroll 2
         for (int jj = 0; jj < jmax; jj++) {
-            const double om = __ldcs(Omega + i + ldo * (int64_t)(j0 + jj));
-            double sq = 0.0, t2[DT > 0 ? DT : 1];
-            bool alleq = true;
             if (DT > 0) {
+                double uj[DT > 0 ? DT : 1];
 #pragma unroll
-                for (int c = 0; c < DT; c++) {
-                    const double t = xi[c] - su[jj * DT + c];
-                    t2[c] = t * t;
-                    sq += t2[c];
-                    alleq = alleq && (xr[c] == sraw[jj * DT + c]);
+                for (int c = 0; c < DT; c++) uj[c] = su[jj * DT + c];
+#pragma unroll
+                for (int q = 0; q < OD_RPT; q++) {
+                    const double om = iv[q] ? __ldcs(Omega + irow[q] + ldo * (int64_t)(j0 + jj)) : 0.0;
+                    double t[DT > 0 ? DT : 1], sq = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DT; c++) {
+                        t[c] = xi[q][c] - uj[c];
+                        sq = fma(t[c], t[c], sq);
+                    }
+                    const double pk = om * exp(fma(-0.5, sq, logs2));
+                    g0 += pk;
+                    // identical scaled coordinates <=> sq == 0 (exact differences): quirk Q4 pairs
+                    if (sq == 0.0) gt += om;
+#pragma unroll
+                    for (int c = 0; c < DT; c++) gl[c] = fma(pk * t[c], t[c], gl[c]);
                 }
-                const double pk = om * p.sigma2 * exp(-0.5 * sq);
-                g0 += pk;
-#pragma unroll
-                for (int c = 0; c < DT; c++) gl[c] = fma(pk, t2[c], gl[c]);
             } else {
-                for (int c = 0; c < d; c++) {
-                    const double xv = X[i + ldx * c];
-                    const double t = xv * p.invl[c] - su[jj * d + c];
-                    sq = fma(t, t, sq);
-                    alleq = alleq && (xv == sraw[jj * d + c]);
-                }
-                const double pk = om * p.sigma2 * exp(-0.5 * sq);
-                g0 += pk;
-                for (int c = 0; c < d; c++) {
-                    const double t = X[i + ldx * c] * p.invl[c] - su[jj * d + c];
-                    atomicAdd(&red[warp][1 + c], pk * t * t);   // generic-d slow path (d > 8)
+                for (int q = 0; q < OD_RPT; q++) {
+                    if (!iv[q]) continue;
+                    const double om = __ldcs(Omega + irow[q] + ldo * (int64_t)(j0 + jj));
+                    double sq = 0.0;
+                    for (int c = 0; c < d; c++) {
+                        // __dmul_rn: no FMA contraction, so identical points give exactly t = 0 (quirk Q4)
+                        const double t = __dmul_rn(X[irow[q] + ldx * c], p.invl[c]) - su[jj * d + c];
+                        sq = fma(t, t, sq);
+                    }
+                    const double pk = om * exp(fma(-0.5, sq, logs2));
+                    g0 += pk;
+                    if (sq == 0.0) gt += om;
+                    for (int c = 0; c < d; c++) {
+                        const double t = __dmul_rn(X[irow[q] + ldx * c], p.invl[c]) - su[jj * d + c];
+                        atomicAdd(&red[warp][1 + c], pk * t * t);   // generic-d slow path (d > 8)
+                    }
                 }
             }
-            if (alleq) gt += om;
         }
     }
-    // warp-shuffle reductions, then the 8 warps through shared memory
+    // warp-shuffle reductions, then the warps through shared memory
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         g0 += __shfl_xor_sync(0xffffffffu, g0, o);
@@ -153,7 +165,7 @@ omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__r
     __syncthreads();
     if (threadIdx.x < 2 + d) {
         double v = 0.0;
-        for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+        for (int w = 0; w < OD_THREADS / 32; w++) v += red[w][threadIdx.x];
         double *slot = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * OD_STRIDE + threadIdx.x;
         *slot = first ? v : (*slot + v);
     }
@@ -176,10 +188,10 @@ static int omega_dk_dev(srgp_ctx *ctx, const GenParams &gp, const double *x_dev,
                         int grid_x, int grid_y, int first)
 {
     cudaStream_t s = ctx->stream;
-    const size_t smem = sizeof(double) * 2 * OD_COLS * d;
+    const size_t smem = sizeof(double) * OD_COLS * d;
     KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
     dim3 grid(grid_x, grid_y);
-#define CALL(D) omega_dk_kernel<D><<<grid, OD_ROWS, smem, s>>>(omega_dev, ldo, x_dev, ldx, rows, u_dev, m, d, gp, part, first)
+#define CALL(D) omega_dk_kernel<D><<<grid, OD_THREADS, smem, s>>>(omega_dev, ldo, x_dev, ldx, rows, u_dev, m, d, gp, part, first)
     switch (d) {
     case 1: CALL(1); break;
     case 2: CALL(2); break;
