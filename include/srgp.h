@@ -147,6 +147,24 @@ int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, const double 
                              const double *y, const double *mu, const double *xu, int64_t m, double sigma,
                              const double *l, double tau, double delta, double *obj, double *grad);
 
+/* The same evaluation plus the knot-location gradient: delbo_dcov_par / dlogp_dcov_par called with
+   dcov_fun_dknot = dsqexp_dx2 / dsqexp_dx2_ard (R/vi_functions.R:425-592, R/laplace_approx_gradient.R:965-1126,
+   closures R/covariance_function_derivatives.R:178-320; installed by R/optimize_gp.R:246,261).
+     knot_lb, knot_ub : d bounds each, the reference's knot_bounds = [min - range/10, max + range/10] of xy per
+                        dimension (R/vi_functions.R:175-178), computed by the caller from the WHOLE data set;
+                        both NULL = transform FALSE (plain d/du, trans_knot = xu).
+     knot_opt, n_opt  : 0-based indices of the knots being optimised (R: 1-based `knot_opt`); NULL = all.
+                        Other knots get gradient 0.
+     knot_grad        : m*d entries, knot-major ([k*d + c]) like the reference's `knot_gradient`.
+     trans_knot       : m x d column-major (may be NULL), the reference's `trans_knot`:
+                        log(u - lb + 1e-4) - log(ub - u + 1e-4).
+   The Jacobian keeps the reference's guard, (ub - lb) / ((u - lb)(ub - u) + 1e-4)  (SURVEY.md quirk Q12).
+   grad is required.  Cost: the pass-2 epilogue also sums P_ik (x_ic - u_kc) per knot; no extra pass. */
+int srgp_gauss_obj_grad_knots(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
+                              const double *l, double tau, double delta, const double *knot_lb,
+                              const double *knot_ub, const int *knot_opt, int64_t n_opt, double *obj, double *grad,
+                              double *knot_grad, double *trans_knot);
+
 /* ---------------------------------------------------------------- posterior at the knots, prediction ---- */
 /* Posterior of the process at the knots on the resident shard: the tail of norm_grad_ascent_vi
    (R/vi_functions.R:1160-1180, model SRGP_VI) / norm_grad_ascent (R/laplace_gradient_ascent.R:1637-1656, SRGP_FIC).

@@ -156,7 +156,37 @@ def vi_pass2(x, r, u, sigma, l, tau, mid):
     if eq.any():
         Om_tau = Omega - (1 / tau ** 2) * (K @ mid["Sinv"])
         g_tau_q4 = 2 * tau ** 2 * Om_tau[eq].sum()
-    return {"g_sigma": g_sigma, "g_l": g_l, "sum_alpha2": alpha @ alpha, "g_tau_q4": g_tau_q4}
+    return {"g_sigma": g_sigma, "g_l": g_l, "sum_alpha2": alpha @ alpha, "g_tau_q4": g_tau_q4,
+            "g_knot": knot_colsums(P, x, u, l)}
+
+
+def knot_colsums(P, x, u, l):
+    """Row-shard partial of the knot gradient: G[k, c] = sum_i P_ik (x_ic - u_kc) / l_c^2 with P = Omega o K, i.e.
+    sum_i Omega_ik dK_ik / du_kc before the Jacobian of the knot transform."""
+    l = np.broadcast_to(np.asarray(l, dtype=_DT).reshape(-1), (u.shape[1],))
+    return (P.T @ x - P.sum(axis=0)[:, None] * u) / l ** 2
+
+
+def knot_bounds(x):
+    """[min - range/10, max + range/10] per dimension (R/vi_functions.R:175-178)."""
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    lo, hi = x.min(axis=0), x.max(axis=0)
+    return np.stack([lo - (hi - lo) / 10, hi + (hi - lo) / 10], axis=1)
+
+
+def knot_finish(g_knot, N, u, sigma, l, bounds, transform=True):
+    """Adds the m x m part, sum_j (N_jk + N_kj) Kuu_jk (u_jc - u_kc) / l_c^2 (dSigma22/du_kc has row k and column k
+    filled with the same vector, zero on the diagonal: R/vi_functions.R:446-474), then the Jacobian
+    (ub - lb) / ((u - lb)(ub - u) + 1e-4) of the bounded-logit knot transform (quirk Q12)."""
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
+    Kuu, _ = kernel_matrix(u, u, sigma, l)
+    lv = np.broadcast_to(np.asarray(l, dtype=_DT).reshape(-1), (u.shape[1],))
+    Q = (N + N.T) * Kuu
+    g = g_knot + (Q.T @ u - Q.sum(axis=0)[:, None] * u) / lv ** 2
+    if transform:
+        b = np.asarray(bounds, dtype=_DT)
+        g = g * ((b[:, 1] - b[:, 0]) / ((u - b[:, 0]) * (b[:, 1] - u) + _DT(1e-4)))
+    return g
 
 
 def dS_dtheta(u, sigma, l, tau, name, cov_fun="ard"):
@@ -191,15 +221,19 @@ def vi_finish(p2, mid, u, sigma, l, tau, cov_fun="ard"):
     return grad
 
 
-def vi_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
-    """Full evaluation; `shards` splits the rows into that many contiguous blocks (the multi-GPU layout)."""
+def vi_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1, knots=False, bounds=None):
+    """Full evaluation; `shards` splits the rows into that many contiguous blocks (the multi-GPU layout).
+    knots = True appends the m x d knot gradient (bounds default to knot_bounds(x))."""
     x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
     r = np.asarray(y, dtype=_DT).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=_DT).reshape(-1), (len(x),))
-    bounds = shard_bounds(len(x), shards)
+    kb, bounds = bounds, shard_bounds(len(x), shards)
     p1 = add_partials([vi_pass1(x[a:b], r[a:b], u, sigma, l) for a, b in bounds])
     mid = vi_mid(p1, u, sigma, l, tau, delta, cov_fun)
     p2 = add_partials([vi_pass2(x[a:b], r[a:b], u, sigma, l, tau, mid) for a, b in bounds])
-    return mid["obj"], vi_finish(p2, mid, u, sigma, l, tau, cov_fun)
+    grad = vi_finish(p2, mid, u, sigma, l, tau, cov_fun)
+    if not knots:
+        return mid["obj"], grad
+    return mid["obj"], grad, knot_finish(p2["g_knot"], mid["N"], u, sigma, l, knot_bounds(x) if kb is None else kb)
 
 
 def shard_bounds(n, world):
@@ -259,10 +293,11 @@ def fic_pass2(x, u, sigma, l, tau, Bv, alpha, rho, Sinv, mid):
     tau = _DT(tau)
     return {"g_sigma": 2 * P.sum(), "g_l": np.array([np.sum(P * D[:, :, c]) for c in range(D.shape[2])], dtype=_DT),
             "Grho": K.T @ (rho[:, None] * K), "sum_rho": rho.sum(),
-            "g_tau_q4": 2 * tau ** 2 * Omega[eq].sum() if eq.any() else _DT(0)}
+            "g_tau_q4": 2 * tau ** 2 * Omega[eq].sum() if eq.any() else _DT(0), "g_knot": knot_colsums(P, x, u, l)}
 
 
-def fic_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
+def fic_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1, knots=False, bounds=None):
+    kb = bounds
     x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
     u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
     m, d = u.shape
@@ -289,7 +324,9 @@ def fic_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1):
     else:
         grad["l"] = np.sum(p2["g_l"]) + np.sum(N * dS_dtheta(u, sigma, l, tau, "l", cov_fun))
     grad["tau"] = 2 * tau ** 2 * p2["sum_rho"] + p2["g_tau_q4"]
-    return mid["obj"], grad
+    if not knots:
+        return mid["obj"], grad
+    return mid["obj"], grad, knot_finish(p2["g_knot"], N, u, sigma, l, knot_bounds(x) if kb is None else kb)
 
 
 # ====================================================================================================

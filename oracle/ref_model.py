@@ -99,6 +99,105 @@ def dsqexp_dl(x1, x2, cov_par):
             "trans_par": math.log(l)}
 
 
+def _knot_l(x2, cov_par, ard):
+    if ard:
+        return np.array([cov_par["l%d" % (i + 1)] for i in range(len(x2))])
+    return cov_par["l"]
+
+
+def _dx2(x1, x2, cov_par, transform, bounds, ard):
+    sigma = cov_par["sigma"]
+    x1 = np.asarray(x1, dtype=np.float64).reshape(-1)
+    x2 = np.asarray(x2, dtype=np.float64).reshape(-1)
+    l = _knot_l(x2, cov_par, ard)
+    bounds = np.asarray(bounds, dtype=np.float64)
+    dx2_dx2t = (bounds[:, 1] - bounds[:, 0]) / (((x2 - bounds[:, 0]) * (bounds[:, 1] - x2)) + 1e-4)
+    if ard:
+        e = np.exp(-1 / 2 * np.sum((x1 - x2) ** 2 / l ** 2))
+    else:
+        e = np.exp(-np.sum((x1 - x2) ** 2) / (2 * l ** 2))
+    der = (1 / (l ** 2)) * (x1 - x2) * sigma ** 2 * e
+    if transform:
+        with np.errstate(invalid="ignore", divide="ignore"):      # a knot outside the bounds gives NaN, as in R
+            tp = np.log((x2 - bounds[:, 0]) + 1e-4) - np.log((bounds[:, 1] - x2) + 1e-4)
+        return {"derivative": der * dx2_dx2t, "trans_par": tp}
+    return {"derivative": der, "trans_par": x2}
+
+
+def dsqexp_dx2(x1, x2, cov_par, transform=False, bounds=None):
+    """R/covariance_function_derivatives.R:178-236 (the R closure optimize_gp installs as dcov_fun_dknot, not the
+    unused Rcpp dsqexp_dx2C): derivative of k(x1, x2) wrt each coordinate of x2, times d x2 / d x2t when
+    transform = TRUE (quirk Q12: the 1e-4 guard sits in the Jacobian and in the logit, not in the map)."""
+    return _dx2(x1, x2, cov_par, transform, bounds, ard=False)
+
+
+def dsqexp_dx2_ard(x1, x2, cov_par, transform=False, bounds=None):
+    """R/covariance_function_derivatives.R:238-320."""
+    return _dx2(x1, x2, cov_par, transform, bounds, ard=True)
+
+
+def dcov_fun_dknot_for(cov_fun):
+    """R/optimize_gp.R:246,261."""
+    return {"sqexp": dsqexp_dx2, "ard": dsqexp_dx2_ard}[cov_fun]
+
+
+def knot_bounds_for(xy):
+    """R/vi_functions.R:175-178, R/laplace_approx_gradient.R (same four lines in every gradient function)."""
+    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
+    lo, hi = xy.min(axis=0), xy.max(axis=0)
+    diffs = hi - lo
+    return np.stack([lo - diffs / 10, hi + diffs / 10], axis=1)
+
+
+def _dsig12_dknot(k, d, cov_par, dcov_fun_dknot, xu, xy, bounds, transform):
+    """R/vi_functions.R:427-445: n x m, only column k non-zero."""
+    mat = np.zeros((xy.shape[0], xu.shape[0]))
+    for i in range(xy.shape[0]):
+        mat[i, k] = dcov_fun_dknot(xy[i], xu[k], cov_par, transform, bounds)["derivative"][d]
+    return mat
+
+
+def _dsig22_dknot(k, d, cov_par, dcov_fun_dknot, xu, bounds, transform):
+    """R/vi_functions.R:446-474: column k, then row k, both filled with d k(xu[i], xu[k]) / d xu[k, d]."""
+    m = xu.shape[0]
+    mat = np.zeros((m, m))
+    for i in range(m):
+        mat[i, k] = dcov_fun_dknot(xu[i], xu[k], cov_par, transform, bounds)["derivative"][d]
+    for i in range(m):
+        mat[k, i] = dcov_fun_dknot(xu[i], xu[k], cov_par, transform, bounds)["derivative"][d]
+    return mat
+
+
+def _knot_gradient(vi, cov_par, dcov_fun_dknot, xu, xy, knot_opt, transform, B, C, Sigma12, Sigma22, FF, comp2_1):
+    """Knot loop shared by delbo_dcov_par (R/vi_functions.R:475-581, vi = True: A = 0 and the trace-term
+    derivative is added) and dlogp_dcov_par (R/laplace_approx_gradient.R:1011-1115, vi = False: A = -A2)."""
+    m, dd = xu.shape
+    n = xy.shape[0]
+    bounds = knot_bounds_for(xy)
+    grad_knot = np.zeros(m * dd)
+    trans_knot = xu.copy()
+    p = 0
+    for k in range(m):
+        if transform:
+            trans_knot[k] = dcov_fun_dknot(0, xu[k], cov_par, transform, bounds)["trans_par"]
+        for d in range(dd):
+            p += 1
+            if k not in knot_opt:
+                continue
+            dK = _dsig12_dknot(k, d, cov_par, dcov_fun_dknot, xu, xy, bounds, transform)
+            dS = _dsig22_dknot(k, d, cov_par, dcov_fun_dknot, xu, bounds, transform)
+            temp1 = 2 * dK - FF.T @ dS
+            A2 = np.sum(temp1 * FF.T, axis=1)
+            A = np.zeros(n) if vi else -A2
+            comp1 = _comp1(A, B, C, Sigma12, Sigma22, FF, dK, dS)
+            comp2 = _comp2(A, comp2_1, Sigma12, Sigma22, FF, dK, dS)
+            g = (1 / 2) * comp2 - (1 / 2) * comp1
+            if vi:
+                g += dtrace_term_dcov_par(cov_par, 0 - A2)
+            grad_knot[p - 1] = g
+    return grad_knot, trans_knot
+
+
 def dcov_fun_dtheta_for(cov_fun):
     """R/optimize_gp.R:236-261 (nugget = TRUE)."""
     if cov_fun == "sqexp":
@@ -241,9 +340,12 @@ def _comp2(A, comp2_1, Sigma12, Sigma22, FF, dSigma12, dSigma22):
     return float((comp2_1.T @ comp2_2)[0, 0])
 
 
-def delbo_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=None):
-    """R/vi_functions.R:126-420 with dcov_fun_dknot = NA, transform = TRUE.
-    Returns {"gradient": dict by parameter name, "trans_par": dict}."""
+def delbo_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=None, dcov_fun_dknot=None,
+                   knot_opt=None, transform=True):
+    """R/vi_functions.R:126-592, transform = TRUE for the covariance parameters.  dcov_fun_dknot = None stands for
+    R's NA (no knot gradient).  Returns {"gradient": dict by parameter name, "trans_par": dict} plus, with a
+    dcov_fun_dknot, "knot_gradient" (length m*d, knot-major like R's p counter) and "trans_knot" (m x d);
+    knot_opt holds 0-based knot indices (R: 1-based)."""
     xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
     xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
@@ -284,11 +386,16 @@ def delbo_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=
         else:
             dtrace_term = dtrace_term_dcov_par(cov_par, A_trace)
         grad[par_name] = (1 / 2) * comp2 - (1 / 2) * comp1 + dtrace_term            # :416-417
-    return {"gradient": grad, "trans_par": trans_par}
+    if dcov_fun_dknot is None:
+        return {"gradient": grad, "trans_par": trans_par}
+    gk, tk = _knot_gradient(True, cov_par, dcov_fun_dknot, xu, xy, range(len(xu)) if knot_opt is None else knot_opt,
+                            transform, B, C, Sigma12, Sigma22, FF, comp2_1)         # :425-581
+    return {"gradient": grad, "knot_gradient": gk, "trans_par": trans_par, "trans_knot": tk}
 
 
-def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=None):
-    """R/laplace_approx_gradient.R:720-968 (FIC Gaussian) with dcov_fun_dknot = NA, transform = TRUE."""
+def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=None, dcov_fun_dknot=None,
+                   knot_opt=None, transform=True):
+    """R/laplace_approx_gradient.R:720-1126 (FIC Gaussian), transform = TRUE; knot outputs as in delbo_dcov_par."""
     xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
     xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
@@ -321,7 +428,11 @@ def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=
         comp1 = _comp1(A, B, C, Sigma12, Sigma22, FF, dSigma12, dSigma22)           # :937-951
         comp2 = _comp2(A, comp2_1, Sigma12, Sigma22, FF, dSigma12, dSigma22)        # :957-960
         grad[par_name] = (1 / 2) * comp2 - (1 / 2) * comp1                          # :964-965
-    return {"gradient": grad, "trans_par": trans_par}
+    if dcov_fun_dknot is None:
+        return {"gradient": grad, "trans_par": trans_par}
+    gk, tk = _knot_gradient(False, cov_par, dcov_fun_dknot, xu, xy, range(len(xu)) if knot_opt is None else knot_opt,
+                            transform, B, C, Sigma12, Sigma22, FF, comp2_1)         # :965-1115
+    return {"gradient": grad, "knot_gradient": gk, "trans_par": trans_par, "trans_knot": tk}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -11,31 +11,41 @@ trace_term_fun <- function(cov_par, Sigma12, Sigma22, delta)
 ##   dtrace_term_dtau(cov_par, trace_term)     = -2 * trace_term
 ##   dtrace_term_dcov_par(cov_par, A_trace)    = -(1/(2 * tau^2)) * sum(A_trace)
 
-## R/vi_functions.R:126 -- signature unchanged; fixed knots (dcov_fun_dknot = NA) go to the GPU, the knot-gradient
-## branch keeps the original body (delbo_dcov_par_R is the renamed original).
+## Shared body: dcov_fun_dknot = NA -> fused objective + gradient; a function -> the same evaluation plus the
+## knot-location gradient (R/vi_functions.R:425-592 / R/laplace_approx_gradient.R:965-1126), knot_bounds as in
+## R/vi_functions.R:175-178.  The original R bodies (renamed *_R) remain the fall-back for argument combinations
+## the GPU path does not take (dcov_fun_dtheta not a list).
+.srgp_gauss_grad <- function(model, fallback, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y,
+                             ff, mu, transform, delta, ...)
+{
+  if(!is.list(dcov_fun_dtheta) || (!is.function(dcov_fun_dknot) && !transform))
+    return(fallback(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff, mu, transform,
+                    delta, ...))
+  lnames <- if(cov_fun == "ard") paste("l", 1:ncol(xy), sep = "") else character()
+  if(!is.function(dcov_fun_dknot))
+  {
+    res <- .Call('_sparseRGPs_gauss_obj_grad', model, cov_fun, xy, as.numeric(y), as.numeric(mu), xu, cov_par, delta,
+                 lnames, PACKAGE = 'sparseRGPs')
+    grad <- res$gradient; names(grad) <- names(cov_par)
+    return(list("gradient" = grad, "trans_par" = lapply(cov_par, log), "objective" = res$objective))
+  }
+  lo <- apply(X = xy, MARGIN = 2, FUN = min); hi <- apply(X = xy, MARGIN = 2, FUN = max)
+  knot_bounds <- cbind(lo - (hi - lo)/10, hi + (hi - lo)/10)
+  res <- .Call('_sparseRGPs_gauss_obj_grad_knots', model, cov_fun, xy, as.numeric(y), as.numeric(mu), xu, cov_par,
+               delta, lnames, knot_bounds, as.integer(knot_opt), transform, PACKAGE = 'sparseRGPs')
+  grad <- res$gradient; names(grad) <- names(cov_par)
+  list("gradient" = grad, "knot_gradient" = res$knot_gradient, "trans_par" = lapply(cov_par, log),
+       "trans_knot" = res$trans_knot, "objective" = res$objective)
+}
+
+## R/vi_functions.R:126 -- signature unchanged
 delbo_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = NA, knot_opt, xu, xy, y, ff = NA,
                            mu, transform = TRUE, delta = 1e-6, ...)
-{
-  if(is.function(dcov_fun_dknot) || !transform || !is.list(dcov_fun_dtheta))
-    return(delbo_dcov_par_R(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff, mu,
-                            transform, delta, ...))
-  lnames <- if(cov_fun == "ard") paste("l", 1:ncol(xy), sep = "") else character()
-  res <- .Call('_sparseRGPs_gauss_obj_grad', 0L, cov_fun, xy, as.numeric(y), as.numeric(mu), xu, cov_par, delta,
-               lnames, PACKAGE = 'sparseRGPs')
-  grad <- res$gradient; names(grad) <- names(cov_par)
-  list("gradient" = grad, "trans_par" = lapply(cov_par, log), "objective" = res$objective)
-}
+  .srgp_gauss_grad(0L, delbo_dcov_par_R, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
+                   mu, transform, delta, ...)
 
 ## R/laplace_approx_gradient.R:720 -- same for the FIC gradient (model 1)
 dlogp_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = NA, knot_opt, xu, xy, y, ff = NA,
                            mu, transform = TRUE, delta = 1e-6, ...)
-{
-  if(is.function(dcov_fun_dknot) || !transform || !is.list(dcov_fun_dtheta))
-    return(dlogp_dcov_par_R(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff, mu,
-                            transform, delta, ...))
-  lnames <- if(cov_fun == "ard") paste("l", 1:ncol(xy), sep = "") else character()
-  res <- .Call('_sparseRGPs_gauss_obj_grad', 1L, cov_fun, xy, as.numeric(y), as.numeric(mu), xu, cov_par, delta,
-               lnames, PACKAGE = 'sparseRGPs')
-  grad <- res$gradient; names(grad) <- names(cov_par)
-  list("gradient" = grad, "trans_par" = lapply(cov_par, log), "objective" = res$objective)
-}
+  .srgp_gauss_grad(1L, dlogp_dcov_par_R, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
+                   mu, transform, delta, ...)

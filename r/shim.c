@@ -282,6 +282,51 @@ SEXP _sparseRGPs_gauss_obj_grad(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP 
     return out;
 }
 
+/* .Call("_sparseRGPs_gauss_obj_grad_knots", model, cov_fun, xy, y, mu, xu, cov_par, delta, lnames, knot_bounds,
+         knot_opt, transform) -> list(objective, gradient, knot_gradient, trans_knot): the branch of delbo_dcov_par /
+   dlogp_dcov_par taken when dcov_fun_dknot is a function (R/vi_functions.R:425-592,
+   R/laplace_approx_gradient.R:965-1126).  knot_bounds is the d x 2 matrix of R/vi_functions.R:175-178; knot_opt is
+   R's 1-based index vector. */
+SEXP _sparseRGPs_gauss_obj_grad_knots(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP cov_par,
+                                      SEXP delta, SEXP lnames, SEXP knot_bounds, SEXP knot_opt, SEXP transform)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    knot_bounds = PROTECT(Rf_coerceVector(knot_bounds, REALSXP));
+    knot_opt = PROTECT(Rf_coerceVector(knot_opt, INTSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
+    const int tr = Rf_asLogical(transform), n_opt = Rf_length(knot_opt);
+    double l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    int *opt0 = (int *)R_alloc(n_opt > 0 ? n_opt : 1, sizeof(int));
+    for (int t = 0; t < n_opt; t++) opt0[t] = INTEGER(knot_opt)[t] - 1;
+    const int p = (k == SRGP_ARD) ? d + 2 : 3;
+    SEXP grad = PROTECT(Rf_allocVector(REALSXP, p));
+    SEXP kgrad = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)m * d));
+    SEXP tknot = PROTECT(Rf_allocMatrix(REALSXP, m, d));
+    double obj = NA_REAL;
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    if (st == SRGP_OK)
+        st = srgp_gauss_obj_grad_knots(ctx(), Rf_asInteger(model), k, REAL(xu), m, list_get(cov_par, "sigma"), l,
+                                       list_get(cov_par, "tau"), Rf_asReal(delta),
+                                       tr ? REAL(knot_bounds) : NULL, tr ? REAL(knot_bounds) + d : NULL,  /* cbind(lb, ub) */
+                                       opt0, n_opt, &obj, REAL(grad), REAL(kgrad), REAL(tknot));
+    if (st != SRGP_OK) { UNPROTECT(9); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    const char *names[] = {"objective", "gradient", "knot_gradient", "trans_knot"};
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4)), nm = PROTECT(Rf_allocVector(STRSXP, 4));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarReal(obj));
+    SET_VECTOR_ELT(out, 1, grad);
+    SET_VECTOR_ELT(out, 2, kgrad);
+    SET_VECTOR_ELT(out, 3, tknot);
+    for (int t = 0; t < 4; t++) SET_STRING_ELT(nm, t, Rf_mkChar(names[t]));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(11);
+    return out;
+}
+
 /* .Call("_sparseRGPs_trace_term", sigma, tau, delta, Sigma12, Sigma22): body of trace_term_fun */
 SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP Sigma22)
 {
@@ -375,6 +420,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_make_cov_matC", (DL_FUNC)&_sparseRGPs_make_cov_matC, 5},
     {"_sparseRGPs_make_cov_mat_ardC", (DL_FUNC)&_sparseRGPs_make_cov_mat_ardC, 6},
     {"_sparseRGPs_gauss_obj_grad", (DL_FUNC)&_sparseRGPs_gauss_obj_grad, 9},
+    {"_sparseRGPs_gauss_obj_grad_knots", (DL_FUNC)&_sparseRGPs_gauss_obj_grad_knots, 12},
     {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
     {"_sparseRGPs_laplace_newton", (DL_FUNC)&_sparseRGPs_laplace_newton, 14},
     {"_sparseRGPs_predict", (DL_FUNC)&_sparseRGPs_predict, 11},

@@ -68,6 +68,32 @@ class Context:
                                               C.byref(obj), L.ptr(grad) if want_grad else None))
         return obj.value, (grad if want_grad else None)
 
+    def gauss_obj_grad_knots(self, model, cov_fun, xu, sigma, l, tau, delta, knot_bounds=None, knot_opt=None):
+        """Objective, gradient wrt log theta and the knot-location gradient in one evaluation.
+        knot_bounds: d x 2 array [lb, ub] (None = transform FALSE); knot_opt: 0-based indices (None = all).
+        Returns (obj, grad, knot_gradient (m*d, knot-major), trans_knot (m x d))."""
+        xu = L.fmat(xu)
+        m, d = xu.shape
+        assert d == self.d, "knots and data disagree on the input dimension"
+        lv = L.fvec(l)
+        p = (d + 2) if cov_fun == "ard" else 3
+        obj = L.cd()
+        grad, kgrad, tk = np.zeros(p), np.zeros(m * d), np.zeros((m, d), order="F")
+        lb = ub = None
+        if knot_bounds is not None:
+            kb = np.asarray(knot_bounds, dtype=np.float64).reshape(d, 2)
+            lb, ub = L.fvec(kb[:, 0]), L.fvec(kb[:, 1])
+        opt, n_opt = None, 0
+        if knot_opt is not None:
+            opt = np.ascontiguousarray(np.asarray(list(knot_opt), dtype=np.int32))
+            n_opt = len(opt)
+        L.check(self._lib.srgp_gauss_obj_grad_knots(
+            self.handle, L.VI if model == "vi" else L.FIC, L.KERNELS[cov_fun], L.ptr(xu), m, float(sigma), L.ptr(lv),
+            float(tau), float(delta), L.ptr(lb) if lb is not None else None, L.ptr(ub) if ub is not None else None,
+            opt.ctypes.data_as(C.POINTER(C.c_int)) if opt is not None and n_opt else None, n_opt, C.byref(obj),
+            L.ptr(grad), L.ptr(kgrad), L.ptr(tk)))
+        return obj.value, grad, kgrad, tk
+
     def gauss_obj_grad_host(self, model, cov_fun, xy, y, mu, xu, sigma, l, tau, delta, want_grad=True):
         """One-shot call with the reference's argument list (uploads xy / y / mu inside the call)."""
         xy, y, xu, lv = L.fmat(xy), L.fvec(y), L.fmat(xu), L.fvec(l)

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gauss.cuh"
+#include <vector>
 #include "gemm.cuh"
 
 namespace srgp {
@@ -270,6 +271,7 @@ struct KmArgs {
     int *coin_list;         // (i_global_lo, j) pairs, capacity coin_cap
     double *coin_omega;
     int coin_cap;
+    double *knot_part;      // MODE_GRAD_KNOT: [gridDim.x][d][mp] per-row-block column sums of P_ij (x_ic - u_jc) / l_c
 };
 
 
@@ -284,7 +286,18 @@ __device__ __noinline__ void record_coincident(const KmArgs &a, int i_local, int
     }
 }
 
-enum { MODE_GRAD = 0, MODE_ROWFORM = 1 };
+enum { MODE_GRAD = 0, MODE_ROWFORM = 1, MODE_GRAD_KNOT = 2 };
+
+// this CTA's column sums of one finished column block (both warp rows) -> its rows of knot_part
+__device__ __forceinline__ void flush_knot_sums(const KmArgs &a, const double *kn, int d, int j0, int tid)
+{
+    for (int t = tid; t < d * BN; t += THREADS) {
+        const int c = t / BN, jj = t - c * BN;
+        double *slot = a.knot_part + ((int64_t)blockIdx.x * d + c) * a.mp + j0 + jj;
+        const double v = kn[c * BN + jj] + kn[(d + c) * BN + jj];
+        *slot = a.first ? v : (*slot + v);
+    }
+}
 
 template <int DT, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
@@ -296,6 +309,10 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     double *us = xs + a.d * BM;
     double *red = us + a.d * BN;
     const int d = DT > 0 ? DT : a.d;
+    constexpr bool GRAD = (MODE == MODE_GRAD || MODE == MODE_GRAD_KNOT);
+    constexpr bool KNOT = (MODE == MODE_GRAD_KNOT);
+    // KNOT: per-column sums of this column block, one copy per warp row: kn[wm][c][BN]
+    double *kn = red + CONSUMER_WARPS * PART_STRIDE;
     const int rb = blockIdx.x;
     const int i0 = rb * BM;
     const int tid = threadIdx.x;
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 
     pipeline_init(sm);
     // stage the scaled rows of this row block once
-    if (MODE == MODE_GRAD) {
+    if (GRAD) {
         for (int t = tid; t < d * BM; t += THREADS) {
             const int c = t / BM, ii = t - c * BM;
             const int i = i0 + ii;
@@ -312,6 +329,8 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     }
     if (!is_producer())
         for (int t = lane; t < PART_STRIDE; t += 32) red[warp * PART_STRIDE + t] = 0.0;
+    if (KNOT)
+        for (int t = tid; t < 2 * d * BN; t += THREADS) kn[t] = 0.0;
     __syncthreads();
 
     uint32_t it = 0;
@@ -327,7 +346,8 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         mainloop<false, false, false>(sm, a.Kc + i0, a.ldc, a.Mop + j0, a.mp, nullptr, a.mp / BK, it, acc);
         // stage this column block's knots (all 288 threads), consumers then run the epilogue
         __syncthreads();
-        if (MODE == MODE_GRAD) {
+        if (KNOT && cbi > 0) flush_knot_sums(a, kn, d, j0 - BN, tid);
+        if (GRAD) {
             for (int t = tid; t < d * BN; t += THREADS) {
                 const int c = t / BN, jj = t - c * BN;
                 const int j = j0 + jj;
@@ -394,6 +414,9 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
                     uv[ni][1] = us[c * BN + frag_col(ni) + 1];
                 }
                 double sc = 0.0;
+                double kc[4][2];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) kc[ni][0] = kc[ni][1] = 0.0;
 #pragma unroll
                 for (int mi = 0; mi < 8; mi++)
 #pragma unroll
@@ -402,11 +425,25 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
                         for (int e = 0; e < 2; e++) {
                             const double t = xv[mi] - uv[ni][e];
                             sc = fma(acc[mi][ni][e], t * t, sc);
+                            if (KNOT) kc[ni][e] = fma(acc[mi][ni][e], t, kc[ni][e]);
                             if (t != 0.0) eqmask &= ~(1ull << ((mi * 4 + ni) * 2 + e));
                         }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
                 if (lane == 0) red[warp * PART_STRIDE + 1 + c] += sc;
+                if (KNOT) {
+                    // a column of the warp tile lives in the 8 lanes that share lane & 3
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            double v = kc[ni][e];
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (lane < 4) kn[((warp & 1) * d + c) * BN + frag_col(ni) + e] = v;
+                        }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -427,6 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         }
     }
     __syncthreads();
+    if (KNOT) flush_knot_sums(a, kn, d, (cb0 + a.col_blocks_per_cta - 1) * BN, tid);
     if (MODE == MODE_ROWFORM) {
         // rows are shared by the 4 lanes of a quad and by the 4 warps of one warp row: quad shuffle, then
         // shared memory (xs is free now: [4 warp columns][128 rows] x 2 <= d * 128 doubles needs d >= 8, so
@@ -594,7 +632,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -840,15 +878,21 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
 {
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
-    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
+    const bool grad_like = (mode == MODE_GRAD || mode == MODE_GRAD_KNOT);
+    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE +
+                                                         (mode == MODE_GRAD_KNOT ? (size_t)2 * d * BN : 0));
     if (smem > 227 * 1024) {
         set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
         return SRGP_ERR_ARG;
     }
-    static size_t configured_smem[2][9] = {{0}};   // per template instantiation (index 0 = runtime d)
+    static size_t configured_smem[3][9] = {{0}};   // per template instantiation (index 0 = runtime d)
     const int slot_d = (d >= 1 && d <= 8) ? d : 0;
     if (configured_smem[mode][slot_d] < smem) {
-        if (mode == MODE_GRAD) {
+        if (mode == MODE_GRAD_KNOT) {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_GRAD_KNOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
+        } else if (mode == MODE_GRAD) {
 #define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
             SRGP_D_SWITCH(d, CALL)
 #undef CALL
@@ -861,8 +905,12 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
     }
     const int slots = w->rblocks * w->cgroups;
     int first = accumulate_slots ? 0 : 1;
-    if (mode == MODE_GRAD && ctx->n == 0 && first)
+    if (grad_like && ctx->n == 0 && first)
         SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
+    if (mode == MODE_GRAD_KNOT) {
+        SRGP_TRY(w->knotpart.reserve((size_t)w->rblocks * d * mp * 8));
+        if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->knotpart.p, 0, (size_t)w->rblocks * d * mp * 8, s));
+    }
     double *rowpart = w->rowpart.d();
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;   // diagnostic: serialise generator and DMMA kernels
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
@@ -914,8 +962,13 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
             a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
                                                       (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
             a.coin_cap = GaussWS::COIN_CAP;
+            a.knot_part = mode == MODE_GRAD_KNOT ? w->knotpart.d() : nullptr;
             dim3 grid(w->rblocks, w->cgroups);
-            if (mode == MODE_GRAD) {
+            if (mode == MODE_GRAD_KNOT) {
+#define CALL(D) km_reduce_kernel<D, MODE_GRAD_KNOT><<<grid, THREADS, smem, s>>>(a)
+                SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            } else if (mode == MODE_GRAD) {
 #define CALL(D) km_reduce_kernel<D, MODE_GRAD><<<grid, THREADS, smem, s>>>(a)
                 SRGP_D_SWITCH(d, CALL)
 #undef CALL
@@ -940,7 +993,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
         }
         first = 0;
     }
-    if (mode == MODE_GRAD && out) {
+    if (grad_like && out) {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
         sum_part_kernel<<<d + 1, 32, 0, s>>>(w->part2.d(), slots, PART_STRIDE, d + 1, out);
         SRGP_LAUNCH_CHECK();
@@ -953,7 +1006,8 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
 int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
                 const double *ra, const double *beta, double *out, bool accumulate_slots)
 {
-    return km_pass(ctx, w, gp, MODE_GRAD, Mop, rs, ra, beta, nullptr, out, accumulate_slots, nullptr, nullptr);
+    return km_pass(ctx, w, gp, w->want_knots ? MODE_GRAD_KNOT : MODE_GRAD, Mop, rs, ra, beta, nullptr, out,
+                   accumulate_slots, nullptr, nullptr);
 }
 
 // Row quadratic forms of ONE materialised chunk already sitting in w->chunk (column-major, ld = w->rows2,
@@ -996,6 +1050,97 @@ int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *
 {
     return km_pass(ctx, w, gp, MODE_ROWFORM, Mop, nullptr, nullptr, nullptr, vvec, nullptr, false, rowq,
                    vvec ? rowkv : nullptr);
+}
+
+// ---- knot-location gradient ----------------------------------------------
+// knot_part [rblocks][d][mp] -> sums [d][mp] over the row blocks of this shard
+__global__ void knot_colsum_kernel(const double *__restrict__ part, int rblocks, int64_t dm, double *__restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= dm) return;
+    double s = 0.0;
+    for (int rb = 0; rb < rblocks; rb++) s += part[(int64_t)rb * dm + t];
+    out[t] = s;
+}
+
+struct KnotBounds {
+    int transform;
+    double lb[SRGP_MAX_D], ub[SRGP_MAX_D];
+};
+
+// One CTA per knot k:  g[k][c] = ( sums[c][k] / l_c  +  sum_j (N_jk + N_kj) Kuu_jk (u_jc - u_kc) / l_c^2 ) * J_kc
+//   sums  = sum_i P_ik (x_ic - u_kc) / l_c from pass 2 (all ranks),
+//   the second term is sum N o dSigma22/du_kc: dSigma22_dknot fills row k and column k with the same vector
+//   (R/vi_functions.R:446-474), zero where j == k,
+//   J_kc  = (ub_c - lb_c) / ((u_kc - lb_c)(ub_c - u_kc) + 1e-4) when the knots are optimised on the bounded-logit
+//   scale (R/covariance_function_derivatives.R:184), else 1.
+// Output is knot-major ([k * d + c]) like the reference's p counter (R/vi_functions.R:487-499).
+__global__ void __launch_bounds__(128)
+knot_finish_kernel(const double *__restrict__ sums, const double *__restrict__ N, const double *__restrict__ S, int mp,
+                   int m, int d, const double *__restrict__ U, GenParams p, KnotBounds kb, double *__restrict__ out)
+{
+    __shared__ double red[4][8];
+    const int k = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int c0 = 0; c0 < d; c0 += 8) {
+        double g[8], uk[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+            g[cc] = 0.0;
+            uk[cc] = (c0 + cc < d) ? U[k + (int64_t)m * (c0 + cc)] : 0.0;
+        }
+        for (int j = tid; j < m; j += 128) {
+            if (j == k) continue;
+            const double q = (N[j + (int64_t)k * mp] + N[k + (int64_t)j * mp]) * S[j + (int64_t)k * mp];
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++)
+                if (c0 + cc < d) g[cc] = fma(q, U[j + (int64_t)m * (c0 + cc)] - uk[cc], g[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) g[cc] += __shfl_xor_sync(0xffffffffu, g[cc], o);
+            if (lane == 0) red[warp][cc] = g[cc];
+        }
+        __syncthreads();
+        if (tid < 8 && c0 + tid < d) {
+            const int c = c0 + tid;
+            const double il = p.invl[c];
+            double v = sums[(int64_t)c * mp + k] * il + (red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]) * il * il;
+            if (kb.transform) {
+                const double u = U[k + (int64_t)m * c];
+                v *= (kb.ub[c] - kb.lb[c]) / ((u - kb.lb[c]) * (kb.ub[c] - u) + 1e-4);
+            }
+            out[(int64_t)k * d + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// After pass 2 (which ran with w->want_knots) and once N is complete on ctx->stream: reduce, allreduce, finish.
+// The m x d result stays in w->knotsum after the [d][mp] sums.
+int knot_finish(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int64_t dm = (int64_t)d * mp;
+    SRGP_TRY(w->knotsum.reserve((size_t)(dm + (int64_t)m * d) * 8));
+    double *sums = w->knotsum.d(), *out = sums + dm;
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        knot_colsum_kernel<<<(unsigned)ceil_div(dm, (int64_t)256), 256, 0, s>>>(w->knotpart.d(), w->rblocks, dm, sums);
+        SRGP_LAUNCH_CHECK();
+    }
+    SRGP_TRY(comm_allreduce(ctx, sums, dm, s));
+    KnotBounds kb;
+    kb.transform = w->knot_transform ? 1 : 0;
+    for (int c = 0; c < SRGP_MAX_D; c++) {
+        kb.lb[c] = (w->knot_transform && c < d) ? w->knot_lb[c] : 0.0;
+        kb.ub[c] = (w->knot_transform && c < d) ? w->knot_ub[c] : 0.0;
+    }
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+    knot_finish_kernel<<<m, 128, 0, s>>>(sums, N, S, mp, m, d, w->U.d(), gp, kb, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
 }
 
 // ---- small launchers -----------------------------------------------------------------------------------
@@ -1179,8 +1324,9 @@ extern "C" int srgp_set_data_dev(srgp_ctx *ctx, const double *xy_dev, int64_t n,
     return set_data_common(ctx, n, d);
 }
 
-extern "C" int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
-                                   const double *l, double tau, double delta, double *obj, double *grad)
+static int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma, const double *l,
+                      double tau, double delta, double *obj, double *grad, bool knots, const double *knot_lb,
+                      const double *knot_ub, double *knot_grad)
 {
     if (!ctx || !xu || !l || !obj || m <= 0) {
         set_error("bad argument");
@@ -1198,14 +1344,70 @@ extern "C" int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const d
         set_error("m = %lld knots exceeds the supported 32768", (long long)m);
         return SRGP_ERR_ARG;
     }
+    if (model != SRGP_VI && model != SRGP_FIC) {
+        set_error("unknown model %d", model);
+        return SRGP_ERR_ARG;
+    }
     SRGP_TRY(use_device(ctx));
     GaussWS *w = gauss_ws(ctx);
     SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
     SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (model == SRGP_VI) return gauss_vi(ctx, w, kernel, sigma, l, tau, delta, obj, grad);
-    if (model == SRGP_FIC) return gauss_fic(ctx, w, kernel, sigma, l, tau, delta, obj, grad);
-    set_error("unknown model %d", model);
-    return SRGP_ERR_ARG;
+    w->want_knots = knots;
+    w->knot_transform = knots && knot_lb && knot_ub;
+    if (w->knot_transform)
+        for (int c = 0; c < ctx->d; c++) {
+            w->knot_lb[c] = knot_lb[c];
+            w->knot_ub[c] = knot_ub[c];
+        }
+    const int rc = (model == SRGP_VI) ? gauss_vi(ctx, w, kernel, sigma, l, tau, delta, obj, grad)
+                                      : gauss_fic(ctx, w, kernel, sigma, l, tau, delta, obj, grad);
+    w->want_knots = false;
+    if (rc != SRGP_OK || !knots) return rc;
+    const double *dev = w->knotsum.d() + (int64_t)ctx->d * w->mp;
+    SRGP_CUDA(cudaMemcpyAsync(knot_grad, dev, (size_t)m * ctx->d * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SRGP_OK;
+}
+
+extern "C" int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
+                                   const double *l, double tau, double delta, double *obj, double *grad)
+{
+    return gauss_eval(ctx, model, kernel, xu, m, sigma, l, tau, delta, obj, grad, false, nullptr, nullptr, nullptr);
+}
+
+extern "C" int srgp_gauss_obj_grad_knots(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m,
+                                         double sigma, const double *l, double tau, double delta,
+                                         const double *knot_lb, const double *knot_ub, const int *knot_opt,
+                                         int64_t n_opt, double *obj, double *grad, double *knot_grad,
+                                         double *trans_knot)
+{
+    if (!grad || !knot_grad || (knot_lb == nullptr) != (knot_ub == nullptr) || n_opt < 0 || (n_opt > 0 && !knot_opt)) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (knot_opt)
+        for (int64_t t = 0; t < n_opt; t++)
+            if (knot_opt[t] < 0 || knot_opt[t] >= m) {
+                set_error("knot_opt[%lld] = %d outside [0, %lld)", (long long)t, knot_opt[t], (long long)m);
+                return SRGP_ERR_ARG;
+            }
+    SRGP_TRY(gauss_eval(ctx, model, kernel, xu, m, sigma, l, tau, delta, obj, grad, true, knot_lb, knot_ub, knot_grad));
+    const int d = ctx->d;
+    if (knot_opt) {   // knots outside knot_opt keep gradient 0 (R/vi_functions.R:500-503)
+        std::vector<char> keep((size_t)m, 0);
+        for (int64_t t = 0; t < n_opt; t++) keep[knot_opt[t]] = 1;
+        for (int64_t k = 0; k < m; k++)
+            if (!keep[k])
+                for (int c = 0; c < d; c++) knot_grad[k * d + c] = 0.0;
+    }
+    if (trans_knot) {   // the knots on the optimiser's scale: inv_trans_fun of dsqexp_dx2 (m x d column-major like xu)
+        for (int c = 0; c < d; c++)
+            for (int64_t k = 0; k < m; k++) {
+                const double u = xu[k + m * c];
+                trans_knot[k + m * c] = knot_lb ? log((u - knot_lb[c]) + 1e-4) - log((knot_ub[c] - u) + 1e-4) : u;
+            }
+    }
+    return SRGP_OK;
 }
 
 extern "C" int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, const double *xy, int64_t n, int d,

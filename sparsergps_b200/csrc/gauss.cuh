@@ -33,6 +33,11 @@ struct GaussWS {
     DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
     DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
     DevBuf nspart;   // scratch of ns_reduce (runs on the side stream)
+    DevBuf knotpart; // pass 2 with knot gradients: [rblocks][d][mp] column sums of P o (x - u) / l
+    DevBuf knotsum;  // [d][mp] sums over the shard (allreduced), then the m x d knot gradient (knot-major)
+    // knot-gradient request of the current call (set by the entry point, read by gauss_pass2 / knot_finish)
+    bool want_knots = false, knot_transform = false;
+    double knot_lb[SRGP_MAX_D], knot_ub[SRGP_MAX_D];
     DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal
 
@@ -86,6 +91,8 @@ int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, c
               double *out, cudaStream_t s);
 // quirk Q4: *out = sum over recorded pairs of (omega_p - coef * (K S^-1)_{i_p j_p})
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
+// knot-location gradient from the pass-2 column sums (w->knotpart) and N: see knot_finish_kernel
+int knot_finish(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S);
 int scale_vec(srgp_ctx *ctx, const double *x, int64_t n, double a, double *out);
 int axpby_vec(srgp_ctx *ctx, int n, double a, const double *x, double b, const double *z, double *y);
 int set_scalar(srgp_ctx *ctx, double *dst, double v);

@@ -190,6 +190,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, N, 1.0, SGS, 0.0, N));
         SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
         SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS), s));
+        if (w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));
     }
     SRGP_TRY(fetch_scalars(ctx, w));
 

@@ -143,6 +143,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
         SRGP_TRY(comm_allreduce(ctx, p2, d + 2, s));
     }
     SRGP_TRY(stream_join(ctx));
+    if (grad && w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));
     SRGP_TRY(fetch_scalars(ctx, w));
 
     // ---- host: a handful of scalars ---------------------------------------------------------------------

@@ -72,21 +72,40 @@ def omega_dk_reduce(cov_par, cov_fun, xy, xu, Omega, ctx=None):
 
 
 # ---- fused objective + gradient -----------------------------------------------------------------------
-def _fused(model, cov_par, cov_fun, xu, xy, y, mu, delta, want_grad, ctx):
+def knot_bounds(xy):
+    """[min - range/10, max + range/10] per input dimension: R/vi_functions.R:175-178 (host side, like the R code)."""
+    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
+    lo, hi = xy.min(axis=0), xy.max(axis=0)
+    return np.stack([lo - (hi - lo) / 10, hi + (hi - lo) / 10], axis=1)
+
+
+def _fused(model, cov_par, cov_fun, xu, xy, y, mu, delta, want_grad, ctx, dcov_fun_dknot=None, knot_opt=None,
+           transform=True):
     ctx = ctx or default_context()
     xy = L.fmat(xy)
     sigma, l, tau, names = _theta(cov_par, cov_fun, xy.shape[1])
-    obj, grad = ctx.gauss_obj_grad_host(model, cov_fun, xy, y, mu, xu, sigma, l, tau, delta, want_grad=want_grad)
-    out = {"objective": obj, "trans_par": {k: float(np.log(cov_par[k])) for k in names}}
+    out = {"trans_par": {k: float(np.log(cov_par[k])) for k in names}}
+    if dcov_fun_dknot is None or dcov_fun_dknot is False:
+        obj, grad = ctx.gauss_obj_grad_host(model, cov_fun, xy, y, mu, xu, sigma, l, tau, delta, want_grad=want_grad)
+    else:
+        ctx.set_data(xy, y, mu)
+        obj, grad, kgrad, tk = ctx.gauss_obj_grad_knots(model, cov_fun, xu, sigma, l, tau, delta,
+                                                        knot_bounds(xy) if transform else None, knot_opt)
+        out["knot_gradient"], out["trans_knot"] = kgrad, tk
+    out["objective"] = obj
     if want_grad:
         out["gradient"] = dict(zip(names, grad))
     return out
 
 
-def delbo_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, **_ignored):
-    """R/vi_functions.R:126-420 with dcov_fun_dknot = NA, transform = TRUE: list(gradient, trans_par); the
-    ELBO of the same theta (elbo_fun, :64-121) comes back as "objective" from the same two passes."""
-    return _fused("vi", cov_par, cov_fun, xu, xy, y, mu, delta, True, ctx)
+def delbo_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, dcov_fun_dknot=None, knot_opt=None,
+                   transform=True, **_ignored):
+    """R/vi_functions.R:126-592, transform = TRUE for the covariance parameters: list(gradient, trans_par); the
+    ELBO of the same theta (elbo_fun, :64-121) comes back as "objective" from the same two passes.
+    dcov_fun_dknot: None / False = R's NA; anything else (R passes dsqexp_dx2 / dsqexp_dx2_ard, chosen by cov_fun)
+    adds "knot_gradient" (m*d, knot-major) and "trans_knot" (:425-592).  knot_opt: 0-based indices (R: 1-based),
+    None = all knots; `transform` is the knot transform flag of the reference."""
+    return _fused("vi", cov_par, cov_fun, xu, xy, y, mu, delta, True, ctx, dcov_fun_dknot, knot_opt, transform)
 
 
 def elbo_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
@@ -95,9 +114,11 @@ def elbo_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
     return _fused("vi", cov_par, cov_fun, xu, xy, y, mu, delta, False, ctx)["objective"]
 
 
-def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, **_ignored):
-    """R/laplace_approx_gradient.R:720-968 (FIC Gaussian) + obj_fun_norm (R/laplace_approx_obj_funs.R:6-52)."""
-    return _fused("fic", cov_par, cov_fun, xu, xy, y, mu, delta, True, ctx)
+def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, dcov_fun_dknot=None, knot_opt=None,
+                   transform=True, **_ignored):
+    """R/laplace_approx_gradient.R:720-1126 (FIC Gaussian) + obj_fun_norm (R/laplace_approx_obj_funs.R:6-52); knot
+    arguments as in delbo_dcov_par."""
+    return _fused("fic", cov_par, cov_fun, xu, xy, y, mu, delta, True, ctx, dcov_fun_dknot, knot_opt, transform)
 
 
 def obj_norm_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):

@@ -46,11 +46,14 @@ def _cpu_worker(rank, world, port, q):
     mid = red.vi_mid(p1, c["xu"], cp["sigma"], l, cp["tau"], c["delta"])
     p2 = _allreduce_dict(red.vi_pass2(x, r, c["xu"], cp["sigma"], l, cp["tau"], mid))
     grad = red.vi_finish(p2, mid, c["xu"], cp["sigma"], l, cp["tau"])
-    q.put((rank, mid["obj"], grad))
+    # knot gradient: the per-knot column sums travel in the same allreduce; bounds come from the WHOLE data set
+    kgrad = red.knot_finish(p2["g_knot"], mid["N"], c["xu"], cp["sigma"], l, red.knot_bounds(c["x"]))
+    q.put((rank, mid["obj"], grad, kgrad))
     dist.destroy_process_group()
 
 
 def test_sharded_reduction_logic_gloo_world2():
+    from oracle import reduced_model as red
     from oracle import ref_model as rm
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -64,12 +67,16 @@ def test_sharded_reduction_logic_gloo_world2():
         assert p.exitcode == 0
     c = cases.config3(n=900, m=40)
     obj_ref, g_ref = rm.vi_obj_grad(c["cov_par"], "ard", c["xu"], c["x"], c["y"], c["mu"], c["delta"])
-    for rank, obj, grad in res:
+    _, _, kg_ref = red.vi_obj_grad(c["x"], c["y"], c["mu"], c["xu"], c["cov_par"]["sigma"], cases.lvec(c["cov_par"]),
+                                   c["cov_par"]["tau"], c["delta"], knots=True)
+    for rank, obj, grad, kgrad in res:
         assert obj == pytest.approx(obj_ref, rel=1e-10)
         for k in g_ref:
             assert grad[k] == pytest.approx(g_ref[k], rel=1e-8, abs=1e-9)
+        np.testing.assert_allclose(kgrad, kg_ref, rtol=1e-9, atol=1e-9 * np.abs(kg_ref).max())
     # every rank holds the same global result
     assert res[0][1] == res[1][1]
+    np.testing.assert_array_equal(res[0][3], res[1][3])
 
 
 def test_shard_bounds_cover_rows():
@@ -95,8 +102,10 @@ def _gpu_worker(rank, world, port, q, model):
     ctx.comm_init(world, rank, uid[0])
     lo, hi = shard_bounds(len(c["x"]), world, rank)
     ctx.set_data(c["x"][lo:hi], c["y"][lo:hi], None)
-    obj, grad = ctx.gauss_obj_grad(model, "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
-    q.put((rank, obj, grad))
+    from sparsergps_b200.vi_functions import knot_bounds
+    obj, grad, kg, _ = ctx.gauss_obj_grad_knots(model, "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"],
+                                                knot_bounds(c["x"]))
+    q.put((rank, obj, grad, kg))
     ctx.close()
     dist.destroy_process_group()
 
@@ -109,7 +118,9 @@ def test_two_gpus_match_one_gpu(ctx, model):
     c = cases.config5(n=30011, m=300)
     cp = c["cov_par"]
     ctx.set_data(c["x"], c["y"], None)
-    obj1, g1 = ctx.gauss_obj_grad(model, "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+    from sparsergps_b200.vi_functions import knot_bounds
+    obj1, g1, kg1, _ = ctx.gauss_obj_grad_knots(model, "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"],
+                                                knot_bounds(c["x"]))
     mctx = mp.get_context("spawn")
     q = mctx.Queue()
     port = _free_port()
@@ -120,6 +131,7 @@ def test_two_gpus_match_one_gpu(ctx, model):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, obj, grad in res:
+    for rank, obj, grad, kg in res:
         assert obj == pytest.approx(obj1, rel=1e-11)               # summation order differs across shards
         np.testing.assert_allclose(grad, g1, rtol=1e-9, atol=1e-9 * np.abs(g1).max())
+        np.testing.assert_allclose(kg, kg1, rtol=1e-9, atol=1e-9 * np.abs(kg1).max())
