@@ -165,6 +165,19 @@ int srgp_gauss_obj_grad_knots(srgp_ctx *ctx, int model, int kernel, const double
                               const double *knot_ub, const int *knot_opt, int64_t n_opt, double *obj, double *grad,
                               double *knot_grad, double *trans_knot);
 
+/* OAT candidate scoring: the loops of knot_prop_random_norm_vi (R/vi_functions.R:2211-2298, model SRGP_VI, elbo_fun)
+   and knot_prop_random_norm (R/knot_proposal_functions.R:1283-1353, model SRGP_FIC, obj_fun_norm with the FIC Z):
+   scores[t] = objective with candidate row t appended to the knots, theta fixed, on the resident shard.
+   cand is n_cand x d column-major (the reference samples TTmax rows of xy that are not knots; the sampling stays
+   with the caller).  obj0 (may be NULL) receives the objective with the m knots alone.
+   SRGP_VI: all candidates are scored from ONE pass over the data (Gram of [knots | candidates]) plus bordered
+   Cholesky updates, 128 candidates per pass.  SRGP_FIC: one objective-only evaluation per candidate.
+   A candidate whose bordered / full Cholesky fails (the reference's try-error, after which it resamples that
+   candidate with jitter) gets scores[t] = NaN; a failure with the CURRENT knots returns SRGP_ERR_NOT_PD. */
+int srgp_oat_scores(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, const double *cand,
+                    int64_t n_cand, double sigma, const double *l, double tau, double delta, double *obj0,
+                    double *scores);
+
 /* ---------------------------------------------------------------- posterior at the knots, prediction ---- */
 /* Posterior of the process at the knots on the resident shard: the tail of norm_grad_ascent_vi
    (R/vi_functions.R:1160-1180, model SRGP_VI) / norm_grad_ascent (R/laplace_gradient_ascent.R:1637-1656, SRGP_FIC).

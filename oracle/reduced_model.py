@@ -236,6 +236,64 @@ def vi_obj_grad(x, y, mu, u, sigma, l, tau, delta, cov_fun="ard", shards=1, knot
     return mid["obj"], grad, knot_finish(p2["g_knot"], mid["N"], u, sigma, l, knot_bounds(x) if kb is None else kb)
 
 
+def vi_oat_scores(x, y, mu, u, cand, sigma, l, tau, delta, shards=1):
+    """OAT candidate scoring for the VI objective by bordered updates: ONE Gram of [knots | candidates] over the
+    data rows (sharded like pass 1), then per candidate O(m^2) Schur-complement algebra instead of a full
+    (m+1)-knot evaluation.  Returns (objective with the m knots, objective with each candidate appended)."""
+    x = np.asarray(x, dtype=_DT).reshape(len(x), -1)
+    u = np.asarray(u, dtype=_DT).reshape(len(u), -1)
+    cand = np.asarray(cand, dtype=_DT).reshape(len(cand), -1)
+    m, T = len(u), len(cand)
+    ua = np.vstack([u, cand])
+    r = np.asarray(y, dtype=_DT).reshape(-1) - np.broadcast_to(np.asarray(mu, dtype=_DT).reshape(-1), (len(x),))
+    p1 = add_partials([vi_pass1(x[a:b], r[a:b], ua, sigma, l) for a, b in shard_bounds(len(x), shards)])
+    sigma, tau, delta = _DT(sigma), _DT(tau), _DT(delta)
+    Ka, _ = kernel_matrix(ua, ua, sigma, l)
+    Sa = Ka + delta * np.eye(m + T, dtype=_DT)
+    Z = tau ** 2 + delta
+    B = 1 / Z
+    n, s0 = p1["n"], p1["s0"]
+    G1, b1 = p1["G1"][:m, :m], p1["b1"][:m]
+    LS = _cholesky(Sa[:m, :m])
+    LA = _cholesky(Sa[:m, :m] + B * G1)
+    LSi, LAi = _inv_lower(LS), _inv_lower(LA)
+    t1 = LAi @ (B * b1)
+    Sinv = LSi.T @ LSi
+    logdetS, logdetA = 2 * np.sum(np.log(np.diag(LS))), 2 * np.sum(np.log(np.diag(LA)))
+    sumq = np.sum(Sinv * G1)
+    log2pi = np.log(2 * _DT(np.pi) if _DT is np.float64 else 8 * np.arctan(_DT(1)))
+
+    def objective(bCb, ldS, ldA, sq):
+        tt = -(1 / (2 * tau ** 2)) * (n * (sigma ** 2 + delta) - sq)
+        return -B * s0 / 2 + bCb / 2 - (n * np.log(Z) - ldS + ldA) / 2 - (n / 2) * log2pi + tt
+
+    obj0 = objective(t1 @ t1, logdetS, logdetA, sumq)
+    sT, gT = Sa[:m, m:], p1["G1"][:m, m:]
+    kap, gam, kcr = np.diag(Sa)[m:], np.diag(p1["G1"])[m:], p1["b1"][m:]
+    ES = LSi @ sT
+    w = LSi.T @ ES
+    H = G1 @ w
+    EA = LAi @ (sT + B * gT)
+    schurS = kap - np.sum(ES * ES, axis=0)
+    schurA = kap + B * gam - np.sum(EA * EA, axis=0)
+    out = np.full(T, np.nan, dtype=_DT)
+    for t in range(T):
+        if schurS[t] > 0 and schurA[t] > 0:
+            tr_inc = (w[:, t] @ H[:, t] - 2 * (w[:, t] @ gT[:, t]) + gam[t]) / schurS[t]
+            quad = (B * kcr[t] - EA[:, t] @ t1) ** 2 / schurA[t]
+            out[t] = objective(t1 @ t1 + quad, logdetS + np.log(schurS[t]), logdetA + np.log(schurA[t]), sumq + tr_inc)
+    return obj0, out
+
+
+def _inv_lower(L):
+    n = L.shape[0]
+    X = np.zeros_like(L)
+    for i in range(n):
+        X[i, i] = 1 / L[i, i]
+        X[i, :i] = -(L[i, :i] @ X[:i, :i]) / L[i, i]
+    return X
+
+
 def shard_bounds(n, world):
     """Contiguous row blocks, sizes differing by at most one (rank r gets rows [lo, hi))."""
     base, rem = divmod(n, world)

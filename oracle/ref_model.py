@@ -436,6 +436,40 @@ def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=
 
 
 # --------------------------------------------------------------------------------------------------
+# OAT candidate scoring: knot_prop_random_norm_vi (R/vi_functions.R:2108-2304) and knot_prop_random_norm
+# (R/knot_proposal_functions.R:1176-1357) without their RNG (the candidate rows are an argument here)
+# --------------------------------------------------------------------------------------------------
+def oat_candidate_scores(cov_par, cov_fun, xu, xy, y, mu, pseudo_prop, delta=1e-6, vi=True):
+    """For each candidate row: the objective with that row appended to the knots, objective only
+    (R/vi_functions.R:2211-2245 with elbo_fun; R/knot_proposal_functions.R:1283-1310 with obj_fun_norm and the FIC
+    Z).  A failed chol() -- R's try-error, which makes the caller resample -- is reported as NaN."""
+    xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
+    pseudo_prop = np.asarray(pseudo_prop, dtype=np.float64).reshape(len(pseudo_prop), -1)
+    out = np.full(len(pseudo_prop), np.nan)
+    for i in range(len(pseudo_prop)):
+        pseudo_xu = np.vstack([xu, pseudo_prop[i]])
+        Sigma12, Sigma22, _ = assemble(cov_par, cov_fun, xy, pseudo_xu, delta)
+        try:
+            if vi:
+                Z = np.repeat(cov_par["tau"] ** 2 + delta, Sigma12.shape[0])
+                out[i] = elbo_fun(mu, Z, Sigma12, Sigma22, y, cov_par, delta)
+            else:
+                out[i] = obj_fun_norm(mu, fic_Z(cov_par, Sigma12, Sigma22, delta), Sigma12, Sigma22, y)
+        except np.linalg.LinAlgError:
+            pass
+    return out
+
+
+def knot_prop_choice(xu, pseudo_prop, obj_current, scores):
+    """obj_fun_x[which.max(c(rep(obj_current, nrow(xu)), scores)), ] (R/vi_functions.R:2164,2299-2303): the best
+    candidate, or the FIRST existing knot when no candidate beats the current objective."""
+    xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
+    vals = np.concatenate([np.repeat(obj_current, len(xu)), scores])
+    vals = np.where(np.isnan(vals), -np.inf, vals)               # which.max skips NA / NaN
+    return np.vstack([xu, np.asarray(pseudo_prop).reshape(len(scores), -1)])[int(np.argmax(vals))].reshape(1, -1)
+
+
+# --------------------------------------------------------------------------------------------------
 # One "objective + gradient evaluation" exactly as one optimiser iteration performs it
 # --------------------------------------------------------------------------------------------------
 def vi_obj_grad(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6):

@@ -49,3 +49,21 @@ dlogp_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = N
                            mu, transform = TRUE, delta = 1e-6, ...)
   .srgp_gauss_grad(1L, dlogp_dcov_par_R, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
                    mu, transform, delta, ...)
+
+## R/vi_functions.R:2211-2298 and R/knot_proposal_functions.R:1283-1353 -- inside knot_prop_random_norm_vi /
+## knot_prop_random_norm, the `for(i in 1:nrow(pseudo_prop))` loop that rebuilds Sigma12 / Sigma22 and calls obj_fun
+## once per candidate becomes one call; the sampling above it and the which.max below it stay as they are:
+##
+##   res <- .Call('_sparseRGPs_oat_scores', 0L,      # 1L in knot_prop_random_norm
+##                norm_opt$cov_fun, norm_opt$xy, as.numeric(y), as.numeric(norm_opt$mu), xu, pseudo_prop,
+##                norm_opt$cov_par, delta, lnames, PACKAGE = 'sparseRGPs')
+##   bad <- which(is.nan(res$scores))                # the reference's try-error branch: resample with jitter
+##   while(length(bad) > 0) {
+##     pseudo_prop[bad,] <- xy_setminus_xu[sample.int(nrow(xy_setminus_xu), length(bad)),, drop = FALSE] +
+##       rnorm(n = length(bad) * ncol(xu), mean = 0, sd = 1e-6)
+##     res$scores[bad] <- .Call('_sparseRGPs_oat_scores', 0L, norm_opt$cov_fun, norm_opt$xy, as.numeric(y),
+##                              as.numeric(norm_opt$mu), xu, pseudo_prop[bad,, drop = FALSE], norm_opt$cov_par, delta,
+##                              lnames, PACKAGE = 'sparseRGPs')$scores
+##     bad <- bad[is.nan(res$scores[bad])]
+##   }
+##   obj_fun_vals <- c(obj_fun_vals, res$scores)

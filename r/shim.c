@@ -327,6 +327,41 @@ SEXP _sparseRGPs_gauss_obj_grad_knots(SEXP model, SEXP cov_fun, SEXP xy, SEXP y,
     return out;
 }
 
+/* .Call("_sparseRGPs_oat_scores", model, cov_fun, xy, y, mu, xu, pseudo_prop, cov_par, delta, lnames)
+     -> list(objective = <objective with xu>, scores = numeric(nrow(pseudo_prop))): the candidate loop of
+   knot_prop_random_norm_vi (R/vi_functions.R:2211-2298, model 0) / knot_prop_random_norm
+   (R/knot_proposal_functions.R:1283-1353, model 1).  NaN scores mark candidates whose chol()/solve() would have
+   raised; the R side resamples those exactly as before. */
+SEXP _sparseRGPs_oat_scores(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP pseudo_prop,
+                            SEXP cov_par, SEXP delta, SEXP lnames)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    pseudo_prop = PROTECT(Rf_coerceVector(pseudo_prop, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu), T = Rf_nrows(pseudo_prop);
+    double l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    SEXP scores = PROTECT(Rf_allocVector(REALSXP, T));
+    double obj0 = NA_REAL;
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    if (st == SRGP_OK)
+        st = srgp_oat_scores(ctx(), Rf_asInteger(model), k, REAL(xu), m, REAL(pseudo_prop), T,
+                             list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta), &obj0,
+                             REAL(scores));
+    if (st != SRGP_OK) { UNPROTECT(6); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarReal(obj0));
+    SET_VECTOR_ELT(out, 1, scores);
+    SET_STRING_ELT(nm, 0, Rf_mkChar("objective"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("scores"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(8);
+    return out;
+}
+
 /* .Call("_sparseRGPs_trace_term", sigma, tau, delta, Sigma12, Sigma22): body of trace_term_fun */
 SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP Sigma22)
 {
@@ -421,6 +456,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_make_cov_mat_ardC", (DL_FUNC)&_sparseRGPs_make_cov_mat_ardC, 6},
     {"_sparseRGPs_gauss_obj_grad", (DL_FUNC)&_sparseRGPs_gauss_obj_grad, 9},
     {"_sparseRGPs_gauss_obj_grad_knots", (DL_FUNC)&_sparseRGPs_gauss_obj_grad_knots, 12},
+    {"_sparseRGPs_oat_scores", (DL_FUNC)&_sparseRGPs_oat_scores, 10},
     {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
     {"_sparseRGPs_laplace_newton", (DL_FUNC)&_sparseRGPs_laplace_newton, 14},
     {"_sparseRGPs_predict", (DL_FUNC)&_sparseRGPs_predict, 11},

@@ -62,6 +62,7 @@ SIGNATURES = {
     "srgp_gauss_obj_grad": (ci, [vp, ci, ci, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_obj_grad_host": (ci, [vp, ci, ci, dp, i64, ci, dp, dp, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_obj_grad_knots": (ci, [vp, ci, ci, dp, i64, cd, dp, cd, cd, dp, dp, C.POINTER(ci), i64, dp, dp, dp, dp]),
+    "srgp_oat_scores": (ci, [vp, ci, ci, dp, i64, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_posterior_u": (ci, [vp, ci, ci, dp, i64, dp, cd, dp, cd, cd, dp, dp]),
     "srgp_predict": (ci, [vp, ci, dp, i64, ci, dp, dp, i64, dp, dp, dp, cd, dp, cd, cd, dp, dp]),
     "srgp_laplace_newton": (ci, [vp, ci, ci, dp, i64, dp, cd, dp, cd, cd, cd, ci, cd, dp, dp, C.POINTER(ci), dp, dp, dp]),

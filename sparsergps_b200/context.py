@@ -94,6 +94,19 @@ class Context:
             L.ptr(grad), L.ptr(kgrad), L.ptr(tk)))
         return obj.value, grad, kgrad, tk
 
+    def oat_scores(self, model, cov_fun, xu, cand, sigma, l, tau, delta):
+        """Objective with each candidate row appended to the knots (theta fixed) on the resident shard.
+        Returns (objective with the knots alone, scores ndarray; NaN = that candidate's Cholesky failed)."""
+        xu, cand = L.fmat(xu), L.fmat(cand)
+        assert xu.shape[1] == self.d and cand.shape[1] == self.d
+        lv = L.fvec(l)
+        obj0 = L.cd()
+        scores = np.zeros(cand.shape[0])
+        L.check(self._lib.srgp_oat_scores(self.handle, L.VI if model == "vi" else L.FIC, L.KERNELS[cov_fun], L.ptr(xu),
+                                          xu.shape[0], L.ptr(cand), cand.shape[0], float(sigma), L.ptr(lv), float(tau),
+                                          float(delta), C.byref(obj0), L.ptr(scores)))
+        return obj0.value, scores
+
     def gauss_obj_grad_host(self, model, cov_fun, xy, y, mu, xu, sigma, l, tau, delta, want_grad=True):
         """One-shot call with the reference's argument list (uploads xy / y / mu inside the call)."""
         xy, y, xu, lv = L.fmat(xy), L.fvec(y), L.fmat(xu), L.fvec(l)

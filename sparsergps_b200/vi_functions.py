@@ -126,6 +126,41 @@ def obj_norm_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
     return _fused("fic", cov_par, cov_fun, xu, xy, y, mu, delta, False, ctx)["objective"]
 
 
+# ---- OAT candidate scoring -----------------------------------------------------
+def oat_candidate_scores(cov_par, cov_fun, xu, xy, y, mu, pseudo_prop, delta=1e-6, vi=True, ctx=None):
+    """The candidate loop of knot_prop_random_norm_vi (R/vi_functions.R:2211-2298, vi = True) / knot_prop_random_norm
+    (R/knot_proposal_functions.R:1283-1353, vi = False): (objective with xu, objective with each row of pseudo_prop
+    appended to xu).  NaN marks a candidate the reference would resample (its chol() error)."""
+    ctx = ctx or default_context()
+    xy = L.fmat(xy)
+    sigma, l, tau, _ = _theta(cov_par, cov_fun, xy.shape[1])
+    ctx.set_data(xy, y, mu)
+    return ctx.oat_scores("vi" if vi else "fic", cov_fun, xu, pseudo_prop, sigma, l, tau, delta)
+
+
+def _knot_prop_random(norm_opt, pseudo_prop, vi, opt, ctx, y):
+    delta = (opt or {}).get("delta", 1e-6)
+    xu = np.asarray(norm_opt["xu"], dtype=np.float64).reshape(len(norm_opt["xu"]), -1)
+    pseudo_prop = np.asarray(pseudo_prop, dtype=np.float64).reshape(-1, xu.shape[1])
+    _, scores = oat_candidate_scores(norm_opt["cov_par"], norm_opt["cov_fun"], xu, norm_opt["xy"], y, norm_opt["mu"],
+                                     pseudo_prop, delta, vi, ctx)
+    vals = np.concatenate([np.repeat(norm_opt["obj_fun"][-1], len(xu)), scores])
+    vals = np.where(np.isnan(vals), -np.inf, vals)
+    return np.vstack([xu, pseudo_prop])[int(np.argmax(vals))].reshape(1, -1)
+
+
+def knot_prop_random_norm_vi(norm_opt, pseudo_prop, opt=None, ctx=None, y=None, **_ignored):
+    """R/vi_functions.R:2108-2304 with the sampled rows `pseudo_prop` (:2209) passed in instead of drawn by R's RNG:
+    returns obj_fun_x[which.max(c(rep(last objective, nrow(xu)), scores)), ] as a 1 x d matrix.  norm_opt is the
+    optimiser's list (xu, cov_par, xy, mu, cov_fun, obj_fun); y arrives through `...` in the reference."""
+    return _knot_prop_random(norm_opt, pseudo_prop, True, opt, ctx, y)
+
+
+def knot_prop_random_norm(norm_opt, pseudo_prop, opt=None, ctx=None, y=None, **_ignored):
+    """R/knot_proposal_functions.R:1176-1357 (FIC objective), same conventions."""
+    return _knot_prop_random(norm_opt, pseudo_prop, False, opt, ctx, y)
+
+
 # ---- posterior at the knots and prediction (SURVEY.md section 8f item 2) ------------------------------
 def gauss_posterior_u(cov_par, cov_fun, xu, xy, y, mu, muu, delta=1e-6, vi=True, ctx=None):
     """u_mean, u_var as the tails of norm_grad_ascent_vi (R/vi_functions.R:1160-1180, vi = True) and

@@ -147,3 +147,19 @@ def test_reduced_knot_gradient_equals_literal(model, case):
     rest = [k for k in range(m) if k not in sel]
     assert not ref[rest].any()
     assert lit["trans_knot"].shape == (m, d)
+
+
+def test_bordered_oat_scores_equal_per_candidate_loop():
+    """OAT scoring: one Gram of [knots | candidates] + Schur complements == the reference's loop of full
+    (m+1)-knot elbo_fun evaluations (R/vi_functions.R:2211-2298)."""
+    c = cases.config2(n=500, m=24)
+    cp = c["cov_par"]
+    cand = c["x"][[3, 77, 210, 499]]
+    lit = rm.oat_candidate_scores(cp, "ard", c["xu"], c["x"], c["y"], c["mu"], cand, c["delta"], vi=True)
+    obj0, bordered = red.vi_oat_scores(c["x"], c["y"], c["mu"], c["xu"], cand, cp["sigma"], cases.lvec(cp), cp["tau"],
+                                       c["delta"], shards=2)
+    np.testing.assert_allclose(bordered, lit, rtol=1e-12)
+    assert obj0 == pytest.approx(rm.vi_obj_grad(cp, "ard", c["xu"], c["x"], c["y"], c["mu"], c["delta"])[0], rel=1e-12)
+    pick = rm.knot_prop_choice(c["xu"], cand, obj0, lit)
+    np.testing.assert_array_equal(pick[0], cand[int(np.argmax(lit))])          # every candidate raises the bound
+    np.testing.assert_array_equal(rm.knot_prop_choice(c["xu"], cand, 1e9, lit)[0], c["xu"][0])   # none does: first knot
