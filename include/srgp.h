@@ -36,7 +36,9 @@ enum srgp_status {
     SRGP_ERR_CUDA = 4,           /* CUDA runtime / launch failure, or no device */
     SRGP_ERR_NOT_PD = 5,         /* an m x m Cholesky failed; the R shim must raise an R error (R's chol() does) */
     SRGP_ERR_STATE = 6,          /* call order (e.g. obj_grad before set_data) */
-    SRGP_ERR_COMM = 7            /* NCCL failure / libnccl not loadable */
+    SRGP_ERR_COMM = 7,           /* NCCL failure / libnccl not loadable */
+    SRGP_ERR_NUMERIC = 8         /* non-finite objective / gradient inside srgp_gauss_fit (R: "missing value where
+                                    TRUE/FALSE needed" in the loop condition) */
 };
 
 enum srgp_kernel { SRGP_SQEXP = 0, SRGP_EXP = 1, SRGP_ARD = 2 };          /* cov_fun = "sqexp" | "exp" | "ard" */
@@ -177,6 +179,29 @@ int srgp_gauss_obj_grad_knots(srgp_ctx *ctx, int model, int kernel, const double
 int srgp_oat_scores(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, const double *cand,
                     int64_t n_cand, double sigma, const double *l, double tau, double delta, double *obj0,
                     double *scores);
+
+/* The optimiser loops norm_grad_ascent_vi (R/vi_functions.R:596-1218, model SRGP_VI) and norm_grad_ascent
+   (R/laplace_gradient_ascent.R:1111-1696, model SRGP_FIC) with a fixed number of knots, transform = TRUE (hard-coded
+   in the reference, R/vi_functions.R:640).  Defaults of the reference (`opt_master`, :641-643): adadelta, decay 0.95,
+   epsilon 1e-6, learn_rate 1e-2, eta 1e3, maxit 1000, obj_tol 1e-3, grad_tol Inf. */
+enum srgp_optim_method { SRGP_OPT_ADADELTA = 0, SRGP_OPT_GA = 1 };
+typedef struct srgp_fit_opt {
+    int optim_method;                            /* "adadelta" | "ga" */
+    double decay, epsilon, eta, learn_rate;      /* optim_par */
+    int maxit;
+    double obj_tol, grad_tol;                    /* grad_tol = INFINITY disables the gradient test, as in R */
+    int opt_theta;                               /* is.list(dcov_fun_dtheta): optimise log(theta) */
+    int opt_knots;                               /* is.function(dcov_fun_dknot): optimise the knots too */
+} srgp_fit_opt;
+/* In/out: xu (m x d column-major), *sigma, l (d entries for ard, 1 otherwise), *tau.  knot_lb / knot_ub / knot_opt as
+   in srgp_gauss_obj_grad_knots (required when opt_knots).  *iter_out = the reference's `iter` (evaluations done);
+   obj_hist needs maxit entries (`obj_fun`); par_hist / grad_hist (may be NULL) maxit x p, one row per iteration
+   (`cov_par_history`, `grad`).  Each iteration is one fused evaluation on the resident shard; the posterior at the
+   knots that the reference returns with the fit is srgp_gauss_posterior_u at the returned theta / xu. */
+int srgp_gauss_fit(srgp_ctx *ctx, int model, int kernel, double *xu, int64_t m, double *sigma, double *l, double *tau,
+                   double delta, const srgp_fit_opt *opt, const double *knot_lb, const double *knot_ub,
+                   const int *knot_opt, int64_t n_opt, int *iter_out, double *obj_hist, double *par_hist,
+                   double *grad_hist);
 
 /* ---------------------------------------------------------------- posterior at the knots, prediction ---- */
 /* Posterior of the process at the knots on the resident shard: the tail of norm_grad_ascent_vi

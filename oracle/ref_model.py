@@ -436,6 +436,99 @@ def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, dcov_fun_dtheta=
 
 
 # --------------------------------------------------------------------------------------------------
+# Optimiser loops: norm_grad_ascent_vi (R/vi_functions.R:596-1218) and norm_grad_ascent
+# (R/laplace_gradient_ascent.R:1111-1696), fixed knot count, transform = TRUE (hard-coded there, :640)
+# --------------------------------------------------------------------------------------------------
+FIT_DEFAULTS = {"optim_method": "adadelta", "decay": 0.95, "epsilon": 1e-6, "learn_rate": 1e-2, "eta": 1e3,
+                "maxit": 1000, "obj_tol": 1e-3, "grad_tol": float("inf"), "delta": 1e-6}     # R/vi_functions.R:641-643
+
+
+def _knot_trans_fun(t, bounds):
+    """dsqexp_dx2(...)$trans_fun (R/covariance_function_derivatives.R:189-194), applied to one row."""
+    return bounds[:, 1] * (1 / (1 + np.exp(-t))) + bounds[:, 0] * (1 / (1 + np.exp(t)))
+
+
+def norm_grad_ascent(cov_par_start, cov_fun, xu, xy, y, mu, opt=None, vi=True, opt_theta=True, opt_knots=False,
+                     knot_opt=None):
+    """Gradient ascent on the ELBO (vi = True: R/vi_functions.R:703-1158) or the FIC marginal likelihood
+    (vi = False: R/laplace_gradient_ascent.R:1219-1633).  opt_theta stands for is.list(dcov_fun_dtheta), opt_knots
+    for is.function(dcov_fun_dknot).  Returns cov_par, xu, iter, obj_fun, grad, knot_grad histories; the posterior at
+    the knots (the functions' tail) is gauss_posterior_u."""
+    o = dict(FIT_DEFAULTS)
+    o.update({k: v for k, v in (opt or {}).items() if k in o})
+    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
+    xu = np.array(xu, dtype=np.float64).reshape(len(xu), -1)
+    delta, decay, eps, eta = o["delta"], o["decay"], o["epsilon"], o["eta"]
+    names = list(cov_par_start)
+    cov_par = dict(cov_par_start)
+    grad_fun = delbo_dcov_par if vi else dlogp_dcov_par
+    dknot = dcov_fun_dknot_for(cov_fun) if opt_knots else None
+
+    def evaluate(cp, knots):
+        Sigma12, Sigma22, _ = assemble(cp, cov_fun, xy, knots, delta)
+        if vi:
+            Z = np.repeat(cp["tau"] ** 2 + delta, Sigma12.shape[0])
+            obj = elbo_fun(mu, Z, Sigma12, Sigma22, y, cp, delta)
+        else:
+            obj = obj_fun_norm(mu, fic_Z(cp, Sigma12, Sigma22, delta), Sigma12, Sigma22, y)
+        return obj, grad_fun(cp, cov_fun, knots, xy, y, mu, delta, dcov_fun_dknot=dknot, knot_opt=knot_opt)
+
+    obj, ev = evaluate(cov_par, xu)
+    obj_vals = [obj]
+    g_theta = np.array([ev["gradient"][k] for k in names]) if opt_theta else np.zeros(1)
+    trans = np.array([ev["trans_par"][k] for k in names])
+    g_knot = np.asarray(ev["knot_gradient"]) if opt_knots else np.zeros(1)
+    if opt_knots:
+        bounds = knot_bounds_for(xy)
+        xu_trans = np.array(ev["trans_knot"])
+    grad_hist, knot_hist, par_hist = [g_theta.copy()], [g_knot.copy()], [np.array([cov_par[k] for k in names])]
+    sg2_t = sd2_t = sc_t = np.zeros(len(names))
+    sg2_k = sd2_k = sc_k = np.zeros(xu.size)
+    it = 1
+    while it < o["maxit"] and (np.any(np.abs(np.concatenate([g_theta, g_knot])) > o["grad_tol"]) or
+                               (abs(obj - obj_vals[it - 2]) > o["obj_tol"] if it > 1 else True)):
+        it += 1
+        if o["optim_method"] == "adadelta":
+            if opt_theta:
+                sg2_t = decay * sg2_t + (1 - decay) * g_theta ** 2
+                d_t = ((1 / eta) ** sc_t) * (np.sqrt(sd2_t + eps) / np.sqrt(sg2_t + eps)) * g_theta
+                sd2_t = decay * sd2_t + (1 - decay) * d_t ** 2
+                trans = trans + d_t
+            if opt_knots:
+                sg2_k = decay * sg2_k + (1 - decay) * g_knot ** 2
+                d_k = ((1 / eta) ** sc_k) * (np.sqrt(sd2_k + eps) / np.sqrt(sg2_k + eps)) * g_knot
+                sd2_k = decay * sd2_k + (1 - decay) * d_k ** 2
+                xu_trans = xu_trans + d_k.reshape(xu.shape)                     # matrix(..., byrow = TRUE)
+        else:                                                                   # "ga"
+            if opt_theta:
+                trans = trans + o["learn_rate"] * g_theta
+            if opt_knots:
+                xu_trans = xu_trans + o["learn_rate"] * g_knot.reshape(xu.shape)
+        if opt_knots:
+            xu = np.vstack([_knot_trans_fun(xu_trans[k], bounds) for k in range(len(xu))])
+        if opt_theta:
+            cov_par = {k: float(np.exp(trans[j])) for j, k in enumerate(names)}  # real_to_pos / trans_fun = exp
+        obj, ev = evaluate(cov_par, xu)
+        obj_vals.append(obj)
+        if opt_theta:
+            g_new = np.array([ev["gradient"][k] for k in names])
+            if o["optim_method"] == "adadelta":
+                sc_t = decay * sc_t + (1 - decay) * np.abs(np.sign(g_new) - np.sign(g_theta)) / 2
+            g_theta = g_new
+            trans = np.array([ev["trans_par"][k] for k in names])
+        if opt_knots:
+            gk_new = np.asarray(ev["knot_gradient"])
+            if o["optim_method"] == "adadelta":
+                sc_k = decay * sc_k + (1 - decay) * np.abs(np.sign(gk_new) - np.sign(g_knot))   # no /2 (:1147)
+            g_knot = gk_new
+        grad_hist.append(g_theta.copy())
+        knot_hist.append(g_knot.copy())
+        par_hist.append(np.array([cov_par[k] for k in names]))
+    return {"cov_par": cov_par, "xu": xu, "iter": it, "obj_fun": np.array(obj_vals), "grad": np.array(grad_hist),
+            "knot_grad": np.array(knot_hist), "cov_par_history": np.array(par_hist)}
+
+
+# --------------------------------------------------------------------------------------------------
 # OAT candidate scoring: knot_prop_random_norm_vi (R/vi_functions.R:2108-2304) and knot_prop_random_norm
 # (R/knot_proposal_functions.R:1176-1357) without their RNG (the candidate rows are an argument here)
 # --------------------------------------------------------------------------------------------------

@@ -67,3 +67,14 @@ dlogp_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = N
 ##     bad <- bad[is.nan(res$scores[bad])]
 ##   }
 ##   obj_fun_vals <- c(obj_fun_vals, res$scores)
+
+## R/vi_functions.R:596 / R/laplace_gradient_ascent.R:1111 -- norm_grad_ascent_vi / norm_grad_ascent: the
+## `while(iter < maxit && ...)` loops (:963-1158 / :1453-1633) become ONE call; argument handling above the loop and
+## the u_mean / u_var tail (-> '_sparseRGPs_gauss_posterior_u') stay.  With `o` = the merged opt_master list:
+##
+##   fit <- .Call('_sparseRGPs_gauss_fit', 0L,        # 1L in norm_grad_ascent
+##                cov_fun, xy, as.numeric(y), as.numeric(mu), xu, cov_par_start, o$delta, lnames,
+##                o$optim_method, c(o$decay, o$epsilon, o$eta, o$learn_rate), as.integer(o$maxit), o$obj_tol, o$grad_tol,
+##                is.list(dcov_fun_dtheta), is.function(dcov_fun_dknot), knot_bounds, as.integer(knot_opt),
+##                PACKAGE = 'sparseRGPs')
+##   ## fit: list(cov_par, xu, iter, obj_fun, grad, cov_par_history)

@@ -34,6 +34,14 @@ static double list_get(SEXP lst, const char *name)
     return NA_REAL;
 }
 
+/* overwrite the named element of a list of scalars (the list must be freshly duplicated by the caller) */
+static void set_list(SEXP lst, const char *name, double v)
+{
+    SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+    for (R_xlen_t i = 0; i < Rf_xlength(lst); i++)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) { SET_VECTOR_ELT(lst, i, Rf_ScalarReal(v)); return; }
+}
+
 static int kernel_id(SEXP cov_fun)
 {
     const char *s = CHAR(STRING_ELT(cov_fun, 0));
@@ -362,6 +370,70 @@ SEXP _sparseRGPs_oat_scores(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, 
     return out;
 }
 
+/* .Call("_sparseRGPs_gauss_fit", model, cov_fun, xy, y, mu, xu, cov_par_start, delta, lnames, optim_method,
+         optim_par = c(decay, epsilon, eta, learn_rate), maxit, obj_tol, grad_tol, opt_theta, opt_knots, knot_bounds,
+         knot_opt) -> list(cov_par, xu, iter, obj_fun, grad, cov_par_history): the loops of norm_grad_ascent_vi
+   (R/vi_functions.R:963-1158) / norm_grad_ascent (R/laplace_gradient_ascent.R:1453-1633). */
+SEXP _sparseRGPs_gauss_fit(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP cov_par, SEXP delta,
+                           SEXP lnames, SEXP optim_method, SEXP optim_par, SEXP maxit, SEXP obj_tol, SEXP grad_tol,
+                           SEXP opt_theta, SEXP opt_knots, SEXP knot_bounds, SEXP knot_opt)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    knot_bounds = PROTECT(Rf_coerceVector(knot_bounds, REALSXP));
+    knot_opt = PROTECT(Rf_coerceVector(knot_opt, INTSXP));
+    SEXP xu_out = PROTECT(Rf_duplicate(Rf_coerceVector(xu, REALSXP)));          /* in/out */
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu_out);
+    const int nl = (k == SRGP_ARD) ? d : 1, p = nl + 2, mi = Rf_asInteger(maxit), n_opt = Rf_length(knot_opt);
+    double sigma = list_get(cov_par, "sigma"), tau = list_get(cov_par, "tau"), l[SRGP_MAX_D];
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    else l[0] = list_get(cov_par, "l");
+    srgp_fit_opt o;
+    o.optim_method = strcmp(CHAR(STRING_ELT(optim_method, 0)), "ga") ? SRGP_OPT_ADADELTA : SRGP_OPT_GA;
+    o.decay = REAL(optim_par)[0]; o.epsilon = REAL(optim_par)[1]; o.eta = REAL(optim_par)[2];
+    o.learn_rate = REAL(optim_par)[3];
+    o.maxit = mi; o.obj_tol = Rf_asReal(obj_tol); o.grad_tol = Rf_asReal(grad_tol);
+    o.opt_theta = Rf_asLogical(opt_theta); o.opt_knots = Rf_asLogical(opt_knots);
+    int *opt0 = (int *)R_alloc(n_opt > 0 ? n_opt : 1, sizeof(int));
+    for (int t = 0; t < n_opt; t++) opt0[t] = INTEGER(knot_opt)[t] - 1;
+    double *obj_h = (double *)R_alloc(mi, sizeof(double));
+    double *par_h = (double *)R_alloc((size_t)mi * p, sizeof(double)), *grad_h = (double *)R_alloc((size_t)mi * p, sizeof(double));
+    int iter = 0;
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    if (st == SRGP_OK)
+        st = srgp_gauss_fit(ctx(), Rf_asInteger(model), k, REAL(xu_out), m, &sigma, l, &tau, Rf_asReal(delta), &o,
+                            o.opt_knots ? REAL(knot_bounds) : NULL, o.opt_knots ? REAL(knot_bounds) + d : NULL,
+                            opt0, n_opt, &iter, obj_h, par_h, grad_h);
+    if (st != SRGP_OK) { UNPROTECT(6); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    /* cov_par: same names and order as cov_par_start */
+    SEXP cp = PROTECT(Rf_duplicate(cov_par));
+    set_list(cp, "sigma", sigma); set_list(cp, "tau", tau);
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) set_list(cp, CHAR(STRING_ELT(lnames, c)), l[c]);
+    else set_list(cp, "l", l[0]);
+    SEXP objv = PROTECT(Rf_allocVector(REALSXP, iter));
+    SEXP gh = PROTECT(Rf_allocMatrix(REALSXP, iter, p)), ph = PROTECT(Rf_allocMatrix(REALSXP, iter, p));
+    for (int i = 0; i < iter; i++) {
+        REAL(objv)[i] = obj_h[i];
+        for (int j = 0; j < p; j++) {               /* row-major history -> R's column-major matrix */
+            REAL(gh)[i + (size_t)iter * j] = grad_h[(size_t)i * p + j];
+            REAL(ph)[i + (size_t)iter * j] = par_h[(size_t)i * p + j];
+        }
+    }
+    const char *names[] = {"cov_par", "xu", "iter", "obj_fun", "grad", "cov_par_history"};
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 6)), nm = PROTECT(Rf_allocVector(STRSXP, 6));
+    SET_VECTOR_ELT(out, 0, cp);
+    SET_VECTOR_ELT(out, 1, xu_out);
+    SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(iter));
+    SET_VECTOR_ELT(out, 3, objv);
+    SET_VECTOR_ELT(out, 4, gh);
+    SET_VECTOR_ELT(out, 5, ph);
+    for (int t = 0; t < 6; t++) SET_STRING_ELT(nm, t, Rf_mkChar(names[t]));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(12);
+    return out;
+}
+
 /* .Call("_sparseRGPs_trace_term", sigma, tau, delta, Sigma12, Sigma22): body of trace_term_fun */
 SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP Sigma22)
 {
@@ -457,6 +529,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_gauss_obj_grad", (DL_FUNC)&_sparseRGPs_gauss_obj_grad, 9},
     {"_sparseRGPs_gauss_obj_grad_knots", (DL_FUNC)&_sparseRGPs_gauss_obj_grad_knots, 12},
     {"_sparseRGPs_oat_scores", (DL_FUNC)&_sparseRGPs_oat_scores, 10},
+    {"_sparseRGPs_gauss_fit", (DL_FUNC)&_sparseRGPs_gauss_fit, 18},
     {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
     {"_sparseRGPs_laplace_newton", (DL_FUNC)&_sparseRGPs_laplace_newton, 14},
     {"_sparseRGPs_predict", (DL_FUNC)&_sparseRGPs_predict, 11},

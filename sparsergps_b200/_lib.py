@@ -15,7 +15,8 @@ ci = C.c_int
 cd = C.c_double
 vp = C.c_void_p
 
-OK, ERR_ARG, ERR_UNKNOWN_KERNEL, ERR_UNKNOWN_PAR, ERR_CUDA, ERR_NOT_PD, ERR_STATE, ERR_COMM = range(8)
+OK, ERR_ARG, ERR_UNKNOWN_KERNEL, ERR_UNKNOWN_PAR, ERR_CUDA, ERR_NOT_PD, ERR_STATE, ERR_COMM, ERR_NUMERIC = range(9)
+OPT_ADADELTA, OPT_GA = 0, 1
 SQEXP, EXP, ARD = 0, 1, 2
 PAR_SIGMA, PAR_L, PAR_TAU, PAR_LC = 0, 1, 2, 3
 VI, FIC = 0, 1
@@ -24,6 +25,13 @@ UNIQUE_ID_BYTES = 128
 PROF = {"assemble": 0, "gen": 1, "gram": 2, "km": 3, "dense": 4, "reduce": 5, "comm": 6}
 
 KERNELS = {"sqexp": SQEXP, "exp": EXP, "ard": ARD}
+
+
+class FitOpt(C.Structure):
+    """srgp_fit_opt (include/srgp.h); defaults = the reference's opt_master (R/vi_functions.R:641-643)."""
+    _fields_ = [("optim_method", ci), ("decay", cd), ("epsilon", cd), ("eta", cd), ("learn_rate", cd), ("maxit", ci),
+                ("obj_tol", cd), ("grad_tol", cd), ("opt_theta", ci), ("opt_knots", ci)]
+
 
 # name -> (restype, argtypes); must list every symbol include/srgp.h declares (tests/test_abi.py checks).
 SIGNATURES = {
@@ -62,6 +70,8 @@ SIGNATURES = {
     "srgp_gauss_obj_grad": (ci, [vp, ci, ci, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_obj_grad_host": (ci, [vp, ci, ci, dp, i64, ci, dp, dp, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_obj_grad_knots": (ci, [vp, ci, ci, dp, i64, cd, dp, cd, cd, dp, dp, C.POINTER(ci), i64, dp, dp, dp, dp]),
+    "srgp_gauss_fit": (ci, [vp, ci, ci, dp, i64, dp, dp, dp, cd, C.POINTER(FitOpt), dp, dp, C.POINTER(ci), i64,
+                            C.POINTER(ci), dp, dp, dp]),
     "srgp_oat_scores": (ci, [vp, ci, ci, dp, i64, dp, i64, cd, dp, cd, cd, dp, dp]),
     "srgp_gauss_posterior_u": (ci, [vp, ci, ci, dp, i64, dp, cd, dp, cd, cd, dp, dp]),
     "srgp_predict": (ci, [vp, ci, dp, i64, ci, dp, dp, i64, dp, dp, dp, cd, dp, cd, cd, dp, dp]),

@@ -94,6 +94,43 @@ class Context:
             L.ptr(grad), L.ptr(kgrad), L.ptr(tk)))
         return obj.value, grad, kgrad, tk
 
+    def gauss_fit(self, model, cov_fun, xu, sigma, l, tau, delta, opt=None, opt_theta=True, opt_knots=False,
+                  knot_bounds=None, knot_opt=None):
+        """norm_grad_ascent_vi / norm_grad_ascent on the resident shard (one fused evaluation per iteration).
+        opt: dict with the reference's option names (optim_method, decay, epsilon, eta, learn_rate, maxit, obj_tol,
+        grad_tol).  Returns dict(sigma, l, tau, xu, iter, obj_fun, cov_par_history, grad)."""
+        o = {"optim_method": "adadelta", "decay": 0.95, "epsilon": 1e-6, "learn_rate": 1e-2, "eta": 1e3, "maxit": 1000,
+             "obj_tol": 1e-3, "grad_tol": float("inf")}
+        o.update({k: v for k, v in (opt or {}).items() if k in o})
+        xu = np.array(L.fmat(xu), order="F", copy=True)
+        m, d = xu.shape
+        assert d == self.d
+        nl = d if cov_fun == "ard" else 1
+        lv = np.array(np.broadcast_to(np.asarray(l, dtype=np.float64).reshape(-1), (nl,)), copy=True)
+        p = nl + 2
+        fo = L.FitOpt({"adadelta": L.OPT_ADADELTA, "ga": L.OPT_GA}[o["optim_method"]], o["decay"], o["epsilon"],
+                      o["eta"], o["learn_rate"], int(o["maxit"]), o["obj_tol"], o["grad_tol"], int(bool(opt_theta)),
+                      int(bool(opt_knots)))
+        lb = ub = None
+        if knot_bounds is not None:
+            kb = np.asarray(knot_bounds, dtype=np.float64).reshape(d, 2)
+            lb, ub = L.fvec(kb[:, 0]), L.fvec(kb[:, 1])
+        ko, n_opt = None, 0
+        if knot_opt is not None:
+            ko = np.ascontiguousarray(np.asarray(list(knot_opt), dtype=np.int32))
+            n_opt = len(ko)
+        sg, ta, it = L.cd(float(sigma)), L.cd(float(tau)), C.c_int(0)
+        maxit = int(o["maxit"])
+        obj_hist, par_hist, grad_hist = np.full(maxit, np.nan), np.full((maxit, p), np.nan), np.full((maxit, p), np.nan)
+        L.check(self._lib.srgp_gauss_fit(
+            self.handle, L.VI if model == "vi" else L.FIC, L.KERNELS[cov_fun], L.ptr(xu), m, C.byref(sg), L.ptr(lv),
+            C.byref(ta), float(delta), C.byref(fo), L.ptr(lb) if lb is not None else None,
+            L.ptr(ub) if ub is not None else None, ko.ctypes.data_as(C.POINTER(C.c_int)) if n_opt else None, n_opt,
+            C.byref(it), L.ptr(obj_hist), L.ptr(par_hist), L.ptr(grad_hist)))
+        k = it.value
+        return {"sigma": sg.value, "l": lv, "tau": ta.value, "xu": xu, "iter": k, "obj_fun": obj_hist[:k],
+                "cov_par_history": par_hist[:k], "grad": grad_hist[:k]}
+
     def oat_scores(self, model, cov_fun, xu, cand, sigma, l, tau, delta):
         """Objective with each candidate row appended to the knots (theta fixed) on the resident shard.
         Returns (objective with the knots alone, scores ndarray; NaN = that candidate's Cholesky failed)."""

@@ -1324,9 +1324,10 @@ extern "C" int srgp_set_data_dev(srgp_ctx *ctx, const double *xy_dev, int64_t n,
     return set_data_common(ctx, n, d);
 }
 
-static int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma, const double *l,
-                      double tau, double delta, double *obj, double *grad, bool knots, const double *knot_lb,
-                      const double *knot_ub, double *knot_grad)
+namespace srgp {
+int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma, const double *l,
+               double tau, double delta, double *obj, double *grad, bool knots, const double *knot_lb,
+               const double *knot_ub, double *knot_grad)
 {
     if (!ctx || !xu || !l || !obj || m <= 0) {
         set_error("bad argument");
@@ -1368,6 +1369,7 @@ static int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, in
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
     return SRGP_OK;
 }
+}  // namespace srgp
 
 extern "C" int srgp_gauss_obj_grad(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma,
                                    const double *l, double tau, double delta, double *obj, double *grad)

@@ -109,6 +109,11 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
              double *obj, double *grad);
 int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
               double *obj, double *grad);
+// One evaluation on the resident shard behind srgp_gauss_obj_grad / srgp_gauss_obj_grad_knots (argument checks,
+// plan, knot upload, model dispatch; knot_grad is a HOST buffer of m * d doubles when knots is set)
+int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m, double sigma, const double *l,
+               double tau, double delta, double *obj, double *grad, bool knots, const double *knot_lb,
+               const double *knot_ub, double *knot_grad);
 // K1 with an explicit output leading dimension (assemble.cu)
 int assemble_dev_ld(srgp_ctx *ctx, cudaStream_t s, int kernel, const double *x_dev, int64_t n1, int d, double sigma,
                     const double *l, double nugget, double *out_dev, int64_t ldo);

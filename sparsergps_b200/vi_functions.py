@@ -126,6 +126,43 @@ def obj_norm_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
     return _fused("fic", cov_par, cov_fun, xu, xy, y, mu, delta, False, ctx)["objective"]
 
 
+# ---- optimiser loops ----------------------------------------------------------
+def _grad_ascent(model, cov_par_start, cov_fun, xu, xy, y, mu, muu, opt, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, ctx):
+    ctx = ctx or default_context()
+    xy = L.fmat(xy)
+    opt = dict(opt or {})
+    delta = opt.get("delta", 1e-6)
+    sigma, l, tau, names = _theta(cov_par_start, cov_fun, xy.shape[1])
+    ctx.set_data(xy, y, mu)
+    knots = not (dcov_fun_dknot is None or dcov_fun_dknot is False)
+    res = ctx.gauss_fit(model, cov_fun, xu, sigma, l, tau, delta, opt, opt_theta=dcov_fun_dtheta is not False,
+                        opt_knots=knots, knot_bounds=knot_bounds(xy) if knots else None, knot_opt=knot_opt)
+    cov_par = dict(zip(names, [res["sigma"], *res["l"], res["tau"]]))
+    m = res["xu"].shape[0]
+    muu = np.zeros(m) if muu is None else muu
+    um, uv = gauss_posterior_u(cov_par, cov_fun, res["xu"], xy, y, mu, muu, delta, vi=(model == "vi"), ctx=ctx)
+    return {"cov_par": cov_par, "cov_fun": cov_fun, "xu": res["xu"], "xy": xy, "mu": mu, "muu": muu, "u_mean": um,
+            "u_var": uv, "iter": res["iter"], "obj_fun": res["obj_fun"], "grad": res["grad"],
+            "cov_par_history": res["cov_par_history"]}
+
+
+def norm_grad_ascent_vi(cov_par_start, cov_fun, xu, xy, y, mu=0.0, muu=None, opt=None, dcov_fun_dtheta=True,
+                        dcov_fun_dknot=None, knot_opt=None, ctx=None, **_ignored):
+    """R/vi_functions.R:596-1218: the whole fit in one call -- ADADELTA / gradient ascent on log(theta) (and the
+    knots when dcov_fun_dknot is given), one fused GPU evaluation per iteration, then u_mean / u_var.  Returns the
+    reference's list (cov_par, xu, u_mean, u_var, iter, obj_fun, grad, cov_par_history ...).  mu / muu must be
+    numeric here (the reference's mean(y) default for non-numeric mu is the caller's one-liner)."""
+    return _grad_ascent("vi", cov_par_start, cov_fun, xu, xy, y, mu, muu, opt, dcov_fun_dtheta, dcov_fun_dknot,
+                        knot_opt, ctx)
+
+
+def norm_grad_ascent(cov_par_start, cov_fun, xu, xy, y, mu=0.0, muu=None, opt=None, dcov_fun_dtheta=True,
+                     dcov_fun_dknot=None, knot_opt=None, ctx=None, **_ignored):
+    """R/laplace_gradient_ascent.R:1111-1696 (FIC marginal likelihood), same conventions."""
+    return _grad_ascent("fic", cov_par_start, cov_fun, xu, xy, y, mu, muu, opt, dcov_fun_dtheta, dcov_fun_dknot,
+                        knot_opt, ctx)
+
+
 # ---- OAT candidate scoring (SURVEY.md section 8f item 3) -----------------------------------------------------
 def oat_candidate_scores(cov_par, cov_fun, xu, xy, y, mu, pseudo_prop, delta=1e-6, vi=True, ctx=None):
     """The candidate loop of knot_prop_random_norm_vi (R/vi_functions.R:2211-2298, vi = True) / knot_prop_random_norm

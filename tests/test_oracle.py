@@ -163,3 +163,22 @@ def test_bordered_oat_scores_equal_per_candidate_loop():
     pick = rm.knot_prop_choice(c["xu"], cand, obj0, lit)
     np.testing.assert_array_equal(pick[0], cand[int(np.argmax(lit))])          # every candidate raises the bound
     np.testing.assert_array_equal(rm.knot_prop_choice(c["xu"], cand, 1e9, lit)[0], c["xu"][0])   # none does: first knot
+
+
+def test_optimiser_loop_transcription_basics():
+    """norm_grad_ascent: ascent on the ELBO, the documented stop rule, and the sign-flip state staying inert while
+    no gradient component changes sign (R/vi_functions.R:963-965,981-986,1132-1147)."""
+    c = cases.config1(n=200)
+    start = {"sigma": 1.0, "l": 0.5, "tau": 0.7}
+    r = rm.norm_grad_ascent(start, "sqexp", c["xu"], c["x"], c["y"], c["mu"], {"maxit": 8, "obj_tol": 1e-9}, vi=True)
+    assert r["iter"] == 8 and np.all(np.diff(r["obj_fun"]) > 0)
+    # first ADADELTA step: sd2 = 0, sc = 0  ->  step_j = sqrt(eps) / sqrt(0.05 g_j^2 + eps) * g_j on log(theta)
+    g0 = r["grad"][0]
+    step = np.sqrt(1e-6) / np.sqrt(0.05 * g0 ** 2 + 1e-6) * g0
+    np.testing.assert_allclose(np.log(r["cov_par_history"][1]), np.log(r["cov_par_history"][0]) + step, rtol=1e-12)
+    r2 = rm.norm_grad_ascent(start, "sqexp", c["xu"], c["x"], c["y"], c["mu"], {"maxit": 50, "obj_tol": 1e9}, vi=True)
+    assert r2["iter"] == 2                                   # iter = 1 always proceeds; |obj_2 - obj_1| <= tol stops
+    ga = rm.norm_grad_ascent(start, "sqexp", c["xu"], c["x"], c["y"], c["mu"],
+                             {"maxit": 3, "optim_method": "ga", "learn_rate": 1e-4}, vi=False)
+    np.testing.assert_allclose(np.log(ga["cov_par_history"][1]), np.log(ga["cov_par_history"][0]) + 1e-4 * ga["grad"][0],
+                               rtol=1e-12)
