@@ -1,5 +1,6 @@
 // common.cuh -- context, error plumbing, scratch buffers, per-kernel accounting.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -147,6 +148,18 @@ struct KernelScope {
         cudaEvent_t e;
         cudaEventCreate(&e);
         return e;
+    }
+};
+
+// cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold contexts on several GPUs:
+// a call site keeps one of these (static) and configures its kernels once per device.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool need(int device)
+    {
+        if (device < 0 || device >= 64) return true;
+        const unsigned long long bit = 1ull << device;
+        return (mask.fetch_or(bit) & bit) == 0;
     }
 };
 

@@ -68,12 +68,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g)
 template <bool A_KC, bool B_KC>
 static int launch_gemm(srgp_ctx *ctx, cudaStream_t s, dim3 grid, const GemmArgs &g)
 {
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
+    static DeviceOnce once;   // per template instantiation
+    if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(gemm_kernel<A_KC, B_KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
-        configured = true;
-    }
     KernelScope ks(ctx, SRGP_PROF_DENSE, s);
     gemm_kernel<A_KC, B_KC><<<grid, THREADS, sizeof(Smem), s>>>(g);
     SRGP_LAUNCH_CHECK();
@@ -256,12 +254,10 @@ __global__ void sum_parts_kernel(const double *parts, int n, double *out)
 
 int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, int *info, double *logdet)
 {
-    static bool configured = false;
+    static DeviceOnce once;
     const size_t smem = sizeof(double) * (NB * DLD + 3 * NB);   // factor + 2 broadcast vectors + pivots
-    if (!configured) {
+    if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     const int nb = mp / NB;
     // dinv area layout (caller allocates 2*mp*NB + nb doubles): [X_kk blocks | X_kk^T blocks | logdet partials]
     double *dinvT = dinv + (size_t)mp * NB;

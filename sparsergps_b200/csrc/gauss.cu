@@ -740,13 +740,12 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
                 double *G, double *b1)
 {
     cudaStream_t s = ctx->stream;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.need(ctx->device)) {
         SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
-        configured = true;
     }
     const int mp = w->mp, m = w->m, d = w->d;
     const int quantum = BK * w->splits;
@@ -828,13 +827,12 @@ int materialise_k(srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
 int gram_materialised(srgp_ctx *ctx, GaussWS *w, const double *rowweight, double *G)
 {
     cudaStream_t s = ctx->stream;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.need(ctx->device)) {
         SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
         SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(Smem)));
-        configured = true;
     }
     const int mp = w->mp;
     const int quantum = BK * w->splits;
@@ -885,7 +883,10 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
         set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
         return SRGP_ERR_ARG;
     }
-    static size_t configured_smem[3][9] = {{0}};   // per template instantiation (index 0 = runtime d)
+    // largest size configured so far per device and template instantiation (index 0 = runtime d)
+    static size_t configured_all[64][3][9] = {{{0}}};
+    size_t untracked[3][9] = {{0}};
+    size_t (*configured_smem)[9] = (ctx->device >= 0 && ctx->device < 64) ? configured_all[ctx->device] : untracked;
     const int slot_d = (d >= 1 && d <= 8) ? d : 0;
     if (configured_smem[mode][slot_d] < smem) {
         if (mode == MODE_GRAD_KNOT) {
@@ -1017,12 +1018,10 @@ int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, 
     cudaStream_t s = ctx->stream;
     const int d = 1;
     const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<1, MODE_ROWFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(Smem) + sizeof(double) * (8 * (BM + BN) + CONSUMER_WARPS * PART_STRIDE))));
-        configured = true;
-    }
     KmArgs a = {};
     a.Kc = w->chunk.d();
     a.ldc = w->rows2;

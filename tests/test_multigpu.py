@@ -135,3 +135,25 @@ def test_two_gpus_match_one_gpu(ctx, model):
         assert obj == pytest.approx(obj1, rel=1e-11)               # summation order differs across shards
         np.testing.assert_allclose(grad, g1, rtol=1e-9, atol=1e-9 * np.abs(g1).max())
         np.testing.assert_allclose(kg, kg1, rtol=1e-9, atol=1e-9 * np.abs(kg1).max())
+
+
+@pytest.mark.gpu
+def test_contexts_on_two_devices_in_one_process(ctx):
+    """One process may hold a context per GPU (include/srgp.h): per-device kernel attributes must be set on both."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from sparsergps_b200.context import Context
+    c = cases.config5(n=5000, m=200)
+    cp = c["cov_par"]
+    ctx.set_data(c["x"], c["y"], None)
+    ref = ctx.gauss_obj_grad("vi", "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+    other = Context(1)
+    try:
+        other.set_data(c["x"], c["y"], None)
+        got = other.gauss_obj_grad("vi", "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+        fic = other.gauss_obj_grad("fic", "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+    finally:
+        other.close()
+    assert got[0] == ref[0]
+    np.testing.assert_array_equal(got[1], ref[1])
+    assert np.isfinite(fic[0])
