@@ -155,8 +155,8 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvTS, t2, 0.0, nullptr, beta, gsc));
     SRGP_TRY(dense::dot_v(ctx, s, m, t1, t1, w->sc(W::S_BV)));   // b^T (S+G_B)^-1 b = |L^-1 b|^2
     if (grad) {
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, GB, mp, 0.0, CG, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, M2, mp));
+        // M2 = C G_B S^-1 = S^-1 - C   (G_B = A - S, C A = I): no product needed
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, Sinv, -1.0, C, 0.0, M2));
 
         // ---- pass 2a: c_i, (K v)_i ; rows: alpha, rho, -B - 2 rho, sum rho -----------------------------------
         SRGP_TRY(gauss_rowform(ctx, w, gp, C, v, cq, kv));
@@ -180,14 +180,11 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         SRGP_TRY(copy_scalar(ctx, p2, red2 + mm, d + 3));
         SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
 
-        // ---- N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1 ------------------------------
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, GB, mp, 0.0, SG, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, M2, mp, 0.0, T1, mp));     // M2 symmetric
-        SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5, SGS, -0.5, T1, 0.0, N));
+        // ---- N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1; with M2 = S^-1 - C and
+        //      S^-1 G_B C = S^-1 (A - S) C = S^-1 - C the first two terms collapse to M2/2 --------------------------
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, Grho, mp, 0.0, SG, mp));
         SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
-        SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, N, 1.0, SGS, 0.0, N));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 0.5, M2, 1.0, SGS, 0.0, N));
         SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
         SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS), s));
         if (w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));

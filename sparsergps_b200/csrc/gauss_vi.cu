@@ -6,8 +6,9 @@
 //   C = (S + G)^-1, b = B b1, v = C b, beta = S^-1 (b - G v), sum_q = tr(S^-1 G1)
 //   tt  = -(n (sigma^2 + delta) - sum_q) / (2 tau^2)
 //   obj = -B s0/2 + b^T v/2 - (n log Z - log|S| + log|S + G|)/2 - n log(2 pi)/2 + tt
-//   M   = (1/tau^2 - B) S^-1 + B C G S^-1 ;  Omega = K (M - B v beta^T) + B r beta^T
+//   M   = (1/tau^2 - B) S^-1 + B C G S^-1 = S^-1/tau^2 - B C ;  Omega = K (M - B v beta^T) + B r beta^T
 //   N   = S^-1 G S^-1/2 - S^-1 G C G S^-1/2 - beta beta^T/2 - S^-1 G1 S^-1/(2 tau^2)
+//       = (S^-1 - C)/2 - beta beta^T/2 - S^-1 G1 S^-1/(2 tau^2)          (G = A - S, A C = I)
 //   g_sigma = 2 sum Omega o K + 2 sum N o K_uu - sigma^2 n / tau^2
 //   g_l_c   = sum Omega o K o D_c + sum N o K_uu o D_c(u)
 //   g_tau   = tau^2 sum alpha^2 - tau^2 (n B - B^2 tr(C G1)) - 2 tt  [+ quirk Q4 pairs],
@@ -68,9 +69,9 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
 
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
-    double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP), *CG = w->mat(W::M_CG), *CGS = w->mat(W::M_CGS);
+    double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP);
     double *SG = w->mat(W::M_SG), *SGS = w->mat(W::M_SGS), *N = w->mat(W::M_N), *Mop = w->mat(W::M_MOP);
-    double *T1 = w->mat(W::M_T1), *T2 = w->mat(W::M_T2), *LinvT = w->mat(W::M_X1);
+    double *T1 = w->mat(W::M_T1), *LinvT = w->mat(W::M_X1);
     double *bv = w->vec(W::V_B), *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP);
     double *beta = w->vec(W::V_BETA), *gsc = w->gemv_scratch();
     cudaStream_t s2 = ctx->stream2;
@@ -110,10 +111,9 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L1), tv, 0.0, nullptr, t2, gsc));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L2), t2, 0.0, nullptr, beta, gsc));
     if (grad) {
-        // CG = C G1 ; CGS = C G1 S^-1 ; Mop = (1/tau^2 - B) S^-1 + B^2 CGS - B beta v^T
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, G1, mp, 0.0, CG, mp));
-        SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, Sinv, mp, 0.0, CGS, mp));
-        SRGP_TRY(dense::axpby(ctx, s, mp, m, itau2 - B, Sinv, B * B, CGS, 0.0, Mop));
+        // Mop = (1/tau^2 - B) S^-1 + B^2 C G1 S^-1 - B beta v^T.  With C (S + B G1) = I,  B C G1 S^-1 = S^-1 - C, so
+        // Mop = S^-1 / tau^2 - B C - B beta v^T: no product on the chain pass 2 waits for
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, itau2, Sinv, -B, C, 0.0, Mop));
         SRGP_TRY(dense::ger(ctx, s, mp, -B, beta, v, Mop));
     }
     // ---- side stream: everything of the m x m stage that pass 2 does not need (scalars, N, sum N o dS) ----------
@@ -124,11 +124,13 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(dense::dot_v(ctx, s2, m, b1, v, w->sc(W::S_B1V)));
     SRGP_TRY(dense::dot_v(ctx, s2, m, v, gv, w->sc(W::S_VGV)));
     if (grad) {
+        // N = (B/2 - 1/(2 tau^2)) X - (B^2/2) S^-1 G1 C G1 S^-1 - beta beta^T/2 with X = S^-1 G1 S^-1.  Since
+        // B G1 = A - S and A C = I:  B^2 S^-1 G1 C G1 S^-1 = B X - (S^-1 - C), hence
+        // N = -X / (2 tau^2) + (S^-1 - C)/2 - beta beta^T/2   (two products instead of five, no cancelling pair)
         SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, Sinv, mp, G1, mp, 0.0, SG, mp));
         SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, SG, mp, Sinv, mp, 0.0, SGS, mp));
-        // C G1 S^-1 is symmetric, so SG * CGS = SG * CGS^T: the tile engine's fast NT form
-        SRGP_TRY(dense::gemm(ctx, s2, 'N', 'T', mp, mp, mp, 1.0, SG, mp, CGS, mp, 0.0, T2, mp));
-        SRGP_TRY(dense::axpby(ctx, s2, mp, m, 0.5 * B - 0.5 * itau2, SGS, -0.5 * B * B, T2, 0.0, N));
+        SRGP_TRY(dense::axpby(ctx, s2, mp, m, 0.5, Sinv, -0.5, C, 0.0, N));
+        SRGP_TRY(dense::axpby(ctx, s2, mp, m, 1.0, N, -0.5 * itau2, SGS, 0.0, N));
         SRGP_TRY(dense::ger(ctx, s2, mp, -0.5, beta, beta, N));
         SRGP_TRY(ns_reduce(ctx, w, gp, N, S, delta, w->sc(W::S_NS), s2));
 
