@@ -272,6 +272,13 @@ struct KmArgs {
     double *coin_omega;
     int coin_cap;
     double *knot_part;      // MODE_GRAD_KNOT: [gridDim.x][d][mp] per-row-block column sums of P_ij (x_ic - u_jc) / l_c
+    // MODE_ROWD: per-row, per-dimension sums, one partial per (column block, warp column), written once:
+    //   rowd_part[((column block * 4 + warp column) * nslots + slot) * ldc + row]
+    //   slot c (0..d)          : sum_j T_ij K_ij D_ijc            (D_ij0 = 1;  T = K Mop)
+    //   slot d+1+c (beta given): sum_j beta_j K_ij D_ijc
+    //   last slot (vvec given) : sum_j K_ij v_j
+    double *rowd_part;
+    int nslots;
 };
 
 
@@ -286,7 +293,7 @@ __device__ __noinline__ void record_coincident(const KmArgs &a, int i_local, int
     }
 }
 
-enum { MODE_GRAD = 0, MODE_ROWFORM = 1, MODE_GRAD_KNOT = 2 };
+enum { MODE_GRAD = 0, MODE_ROWFORM = 1, MODE_GRAD_KNOT = 2, MODE_ROWD = 3 };
 
 // this CTA's column sums of one finished column block (both warp rows) -> its rows of knot_part
 __device__ __forceinline__ void flush_knot_sums(const KmArgs &a, const double *kn, int d, int j0, int tid)
@@ -296,6 +303,108 @@ __device__ __forceinline__ void flush_knot_sums(const KmArgs &a, const double *k
         double *slot = a.knot_part + ((int64_t)blockIdx.x * d + c) * a.mp + j0 + jj;
         const double v = kn[c * BN + jj] + kn[(d + c) * BN + jj];
         *slot = a.first ? v : (*slot + v);
+    }
+}
+
+// MODE_ROWD epilogue of one 128 x 128 tile (consumer warps only): see KmArgs::rowd_part.  acc holds T = K Mop on
+// entry.  Each quad owns 8 rows x 8 columns of the warp tile; row sums are reduced over the quad by shuffles and
+// stored by its first lane to the (column block, warp column) partial -- stores only, nothing to wait for.
+// Bit-identical (row, knot) pairs are appended to the coincidence list with T_ij (quirk Q4).
+template <int DT>
+__device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][4][2], const double *xs,
+                                              const double *us, int d, int i0, int j0)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wn = warp >> 1;
+    double *part = a.rowd_part + ((int64_t)((j0 / BN) * 4 + wn) * a.nslots) * a.ldc + i0;
+    auto flush = [&](int slot, double (&s)[8]) {
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            double v = s[mi];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if ((lane & 3) == 0) part[(int64_t)slot * a.ldc + frag_row(mi)] = v;
+        }
+    };
+    // weighted row sums of the values currently in acc, for c = 0 (weight 1) and every dimension
+    auto sums = [&](int slot0, unsigned long long *eqmask) {
+        double s[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            s[mi] = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) s[mi] += acc[mi][ni][0] + acc[mi][ni][1];
+        }
+        flush(slot0, s);
+        for (int c = 0; c < d; c++) {
+            double xv[8], uv[4][2];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) xv[mi] = xs[c * BM + frag_row(mi)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                uv[ni][0] = us[c * BN + frag_col(ni)];
+                uv[ni][1] = us[c * BN + frag_col(ni) + 1];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                s[mi] = 0.0;
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const double t = xv[mi] - uv[ni][e];
+                        s[mi] = fma(acc[mi][ni][e], t * t, s[mi]);
+                        if (eqmask && t != 0.0) *eqmask &= ~(1ull << ((mi * 4 + ni) * 2 + e));
+                    }
+            }
+            flush(slot0 + 1 + c, s);
+        }
+    };
+    // phase 1: acc <- T o K
+    unsigned long long eqmask = 0ull;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++) {
+        const int ii = frag_row(mi);
+        const bool iv = (i0 + ii) < a.rows_valid;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = j0 + frag_col(ni) + e;
+                acc[mi][ni][e] *= a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                if (iv && j < a.m) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
+            }
+    }
+    sums(0, &eqmask);
+    if (eqmask) {
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if ((eqmask >> ((mi * 4 + ni) * 2 + e)) & 1ull)
+                        record_coincident(a, i0 + frag_row(mi), j0 + frag_col(ni) + e, acc[mi][ni][e]);
+    }
+    // phase 2: acc <- beta_j K_ij (and the K v row sums on the way)
+    if (a.beta || a.vvec) {
+        double skv[8];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            const int ii = frag_row(mi);
+            skv[mi] = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = j0 + frag_col(ni) + e;
+                    const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                    if (a.vvec) skv[mi] = fma(k, a.vvec[j], skv[mi]);
+                    acc[mi][ni][e] = a.beta ? k * a.beta[j] : 0.0;
+                }
+        }
+        if (a.vvec) flush(a.nslots - 1, skv);
+        if (a.beta) sums(d + 1, nullptr);
     }
 }
 
@@ -311,6 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     const int d = DT > 0 ? DT : a.d;
     constexpr bool GRAD = (MODE == MODE_GRAD || MODE == MODE_GRAD_KNOT);
     constexpr bool KNOT = (MODE == MODE_GRAD_KNOT);
+    constexpr bool STAGE_XU = GRAD || (MODE == MODE_ROWD);   // epilogues that need the scaled coordinates
     // KNOT: per-column sums of this column block, one copy per warp row: kn[wm][c][BN]
     double *kn = red + CONSUMER_WARPS * PART_STRIDE;
     const int rb = blockIdx.x;
@@ -320,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 
     pipeline_init(sm);
     // stage the scaled rows of this row block once
-    if (GRAD) {
+    if (STAGE_XU) {
         for (int t = tid; t < d * BM; t += THREADS) {
             const int c = t / BM, ii = t - c * BM;
             const int i = i0 + ii;
@@ -347,13 +457,17 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         // stage this column block's knots (all 288 threads), consumers then run the epilogue
         __syncthreads();
         if (KNOT && cbi > 0) flush_knot_sums(a, kn, d, j0 - BN, tid);
-        if (GRAD) {
+        if (STAGE_XU) {
             for (int t = tid; t < d * BN; t += THREADS) {
                 const int c = t / BN, jj = t - c * BN;
                 const int j = j0 + jj;
                 us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
             }
             __syncthreads();
+        }
+        if (MODE == MODE_ROWD) {
+            if (!is_producer()) rowd_epilogue<DT>(a, acc, xs, us, d, i0, j0);
+            continue;
         }
         if (MODE == MODE_ROWFORM) {
             // per-row sums over this column block: (K Mop^T)_ij K_ij and K_ij v_j
@@ -465,6 +579,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     }
     __syncthreads();
     if (KNOT) flush_knot_sums(a, kn, d, (cb0 + a.col_blocks_per_cta - 1) * BN, tid);
+    if (MODE == MODE_ROWD) return;
     if (MODE == MODE_ROWFORM) {
         // rows are shared by the 4 lanes of a quad and by the 4 warps of one warp row: quad shuffle, then
         // shared memory (xs is free now: [4 warp columns][128 rows] x 2 <= d * 128 doubles needs d >= 8, so
@@ -632,7 +747,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -870,9 +985,21 @@ __global__ void combine_rows_kernel(const double *__restrict__ part, int groups,
     out[i] = s;
 }
 
+// MODE_ROWD: out[slot][i] = sum over the (column group, warp column) partials of one chunk
+__global__ void combine_rowd_kernel(const double *__restrict__ part, int groups, int nslots, int64_t ld, int rows,
+                                    double *__restrict__ out, int64_t out_stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, slot = blockIdx.y;
+    if (i >= rows) return;
+    double s = 0.0;
+    for (int g = 0; g < groups; g++) s += part[((int64_t)g * nslots + slot) * ld + i];
+    out[(int64_t)slot * out_stride + i] = s;
+}
+
+// MODE_ROWD: rowd receives nslots vectors of stride rowd_stride (see KmArgs::rowd_part for the slot order)
 static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, const double *Mop, const double *rs,
                    const double *ra, const double *beta, const double *vvec, double *out, bool accumulate_slots,
-                   double *rowq, double *rowkv)
+                   double *rowq, double *rowkv, double *rowd = nullptr, int64_t rowd_stride = 0)
 {
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
@@ -884,8 +1011,8 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
         return SRGP_ERR_ARG;
     }
     // largest size configured so far per device and template instantiation (index 0 = runtime d)
-    static size_t configured_all[64][3][9] = {{{0}}};
-    size_t untracked[3][9] = {{0}};
+    static size_t configured_all[64][4][9] = {{{0}}};
+    size_t untracked[4][9] = {{0}};
     size_t (*configured_smem)[9] = (ctx->device >= 0 && ctx->device < 64) ? configured_all[ctx->device] : untracked;
     const int slot_d = (d >= 1 && d <= 8) ? d : 0;
     if (configured_smem[mode][slot_d] < smem) {
@@ -897,6 +1024,10 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
 #define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
             SRGP_D_SWITCH(d, CALL)
 #undef CALL
+        } else if (mode == MODE_ROWD) {
+#define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_ROWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            SRGP_D_SWITCH(d, CALL)
+#undef CALL
         } else {
 #define CALL(D) SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<D, MODE_ROWFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
             SRGP_D_SWITCH(d, CALL)
@@ -905,6 +1036,8 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
         configured_smem[mode][slot_d] = smem;
     }
     const int slots = w->rblocks * w->cgroups;
+    const int nslots = (d + 1) * (beta ? 2 : 1) + (vvec ? 1 : 0);
+    if (mode == MODE_ROWD) SRGP_TRY(w->rowdpart.reserve((size_t)w->nt * 4 * nslots * w->rows2 * 8));
     int first = accumulate_slots ? 0 : 1;
     if (grad_like && ctx->n == 0 && first)
         SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
@@ -964,6 +1097,8 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
                                                       (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
             a.coin_cap = GaussWS::COIN_CAP;
             a.knot_part = mode == MODE_GRAD_KNOT ? w->knotpart.d() : nullptr;
+            a.rowd_part = mode == MODE_ROWD ? w->rowdpart.d() : nullptr;
+            a.nslots = nslots;
             dim3 grid(w->rblocks, w->cgroups);
             if (mode == MODE_GRAD_KNOT) {
 #define CALL(D) km_reduce_kernel<D, MODE_GRAD_KNOT><<<grid, THREADS, smem, s>>>(a)
@@ -971,6 +1106,10 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
 #undef CALL
             } else if (mode == MODE_GRAD) {
 #define CALL(D) km_reduce_kernel<D, MODE_GRAD><<<grid, THREADS, smem, s>>>(a)
+                SRGP_D_SWITCH(d, CALL)
+#undef CALL
+            } else if (mode == MODE_ROWD) {
+#define CALL(D) km_reduce_kernel<D, MODE_ROWD><<<grid, THREADS, smem, s>>>(a)
                 SRGP_D_SWITCH(d, CALL)
 #undef CALL
             } else {
@@ -981,6 +1120,12 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
             SRGP_LAUNCH_CHECK();
         }
         SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
+        if (mode == MODE_ROWD) {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+            combine_rowd_kernel<<<dim3((unsigned)ceil_div(rows_valid, 256), nslots), 256, 0, s>>>(
+                w->rowdpart.d(), w->nt * 4, nslots, w->rows2, rows_valid, rowd + r0, rowd_stride);
+            SRGP_LAUNCH_CHECK();
+        }
         if (mode == MODE_ROWFORM) {
             KernelScope ks(ctx, SRGP_PROF_REDUCE, s, rowkv ? 2 : 1);
             combine_rows_kernel<<<ceil_div(rows_valid, 256), 256, 0, s>>>(rowpart, w->cgroups, w->rows2, rows_valid,
@@ -1049,6 +1194,16 @@ int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *
 {
     return km_pass(ctx, w, gp, MODE_ROWFORM, Mop, nullptr, nullptr, nullptr, vvec, nullptr, false, rowq,
                    vvec ? rowkv : nullptr);
+}
+
+// Per-row, per-dimension sums over the shard (FIC): out[slot * stride + i], slots as in KmArgs::rowd_part --
+// T = K Mop (Mop symmetric): sum_j T_ij K_ij D_ijc (c = 0..d, D_ij0 = 1); with beta: sum_j beta_j K_ij D_ijc;
+// with vvec: sum_j K_ij v_j.  Bit-identical (row, knot) pairs are appended to w->coin together with T_ij.
+int gauss_rowd(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta,
+               const double *vvec, double *out, int64_t stride)
+{
+    return km_pass(ctx, w, gp, MODE_ROWD, Mop, nullptr, nullptr, beta, vvec, nullptr, false, nullptr, nullptr, out,
+                   stride);
 }
 
 // ---- knot-location gradient ----------------------------------------------
@@ -1209,6 +1364,51 @@ int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv,
     KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
     coin_fix_kernel<<<64, 256, 0, s>>>(count, list, omega, GaussWS::COIN_CAP, ctx->Xp, ctx->n, w->U.d(), w->m, w->mp,
                                        w->d, gp, Sinv, coef, omega);
+    SRGP_LAUNCH_CHECK();
+    coin_sum_kernel<<<1, 256, 0, s>>>(count, GaussWS::COIN_CAP, omega, out);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+// FIC, quirk Q4: the pairs were recorded by the K C pass with T_ij = (K C)_ij;
+//   Omega_ij = -2 rho_i (K S^-1)_ij - B_i (K C)_ij + alpha_i beta_j,  (K S^-1)_ij evaluated directly (one warp per pair)
+__global__ void __launch_bounds__(256)
+coin_fix_fic_kernel(const int *__restrict__ count, const int *__restrict__ list, const double *__restrict__ kc, int cap,
+                    const double *__restrict__ X, int64_t ldx, const double *__restrict__ U, int m, int mp, int d,
+                    GenParams p, const double *__restrict__ Sinv, const double *__restrict__ B,
+                    const double *__restrict__ rho, const double *__restrict__ alpha, const double *__restrict__ beta,
+                    double *__restrict__ vals)
+{
+    const int lane = threadIdx.x & 31;
+    const int npairs = min(*count, cap);
+    for (int pr = blockIdx.x * 8 + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8) {
+        const int i = list[2 * pr], j = list[2 * pr + 1];
+        double acc = 0.0;
+        for (int k = lane; k < m; k += 32) {
+            double sq = 0.0;
+            for (int c = 0; c < d; c++) {
+                const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
+                sq = fma(t, t, sq);
+            }
+            acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) vals[pr] = -2.0 * rho[i] * acc - B[i] * kc[pr] + alpha[i] * beta[j];
+    }
+}
+
+int coin_fix_fic(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, const double *B, const double *rho,
+                 const double *alpha, const double *beta, double *out)
+{
+    cudaStream_t s = ctx->stream;
+    int *count = reinterpret_cast<int *>(w->coin.p);
+    int *list = count + 16;
+    double *omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
+                                               (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
+    KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+    coin_fix_fic_kernel<<<64, 256, 0, s>>>(count, list, omega, GaussWS::COIN_CAP, ctx->Xp, ctx->n, w->U.d(), w->m,
+                                           w->mp, w->d, gp, Sinv, B, rho, alpha, beta, omega);
     SRGP_LAUNCH_CHECK();
     coin_sum_kernel<<<1, 256, 0, s>>>(count, GaussWS::COIN_CAP, omega, out);
     SRGP_LAUNCH_CHECK();

@@ -33,6 +33,8 @@ struct GaussWS {
     DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
     DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
     DevBuf nspart;   // scratch of ns_reduce (runs on the side stream)
+    DevBuf rowdpart; // per-(column group, warp column) partials of one chunk in the per-row / per-dimension mode
+    DevBuf rowd;     // FIC: per-row, per-dimension sums of passes 1a and 2a
     DevBuf knotpart; // pass 2 with knot gradients: [rblocks][d][mp] column sums of P o (x - u) / l
     DevBuf knotsum;  // [d][mp] sums over the shard (allreduced), then the m x d knot gradient (knot-major)
     // knot-gradient request of the current call (set by the entry point, read by gauss_pass2 / knot_finish)
@@ -82,6 +84,9 @@ int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mo
 int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
                   double *rowq, double *rowkv);
 int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, double *rowq);
+// Per-row, per-dimension sums over the shard (see gauss.cu): out[slot * stride + i]
+int gauss_rowd(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta,
+               const double *vvec, double *out, int64_t stride);
 // Laplace: materialise the shard's K row-major into w->Kmat (rows padded with zeros to the SYRK quantum)
 int materialise_k(srgp_ctx *ctx, GaussWS *w, const GenParams &gp);
 // G = Kmat^T diag(rowweight) Kmat over the materialised shard (rowweight may be null)
@@ -91,6 +96,9 @@ int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, c
               double *out, cudaStream_t s);
 // quirk Q4: *out = sum over recorded pairs of (omega_p - coef * (K S^-1)_{i_p j_p})
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
+// FIC variant: pairs recorded by gauss_rowd(C, ...) carry (K C)_ij; *out = sum of Omega_ij over the pairs
+int coin_fix_fic(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, const double *B, const double *rho,
+                 const double *alpha, const double *beta, double *out);
 // knot-location gradient from the pass-2 column sums (w->knotpart) and N: see knot_finish_kernel
 int knot_finish(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S);
 int scale_vec(srgp_ctx *ctx, const double *x, int64_t n, double a, double *out);

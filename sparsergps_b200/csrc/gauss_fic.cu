@@ -10,7 +10,14 @@
 //   Omega = diag(-B - 2 rho) K S^-1 + diag(B) K M2 + alpha beta^T
 //   N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1,  G_rho = K^T diag(rho) K
 //   g_theta = sum Omega o dK + sum N o dS + A1(theta) sum rho   (A1 = 2 sigma^2, 0, 2 tau^2; dS(tau) = 0)
-// Row passes: q (K S^-1 row forms), weighted Gram, c and K v (row forms with C), two Omega terms, weighted Gram.
+// With C (S + G_B) = I:  M2 = S^-1 - C,  Omega = -2 diag(rho) K S^-1 - diag(B) K C + alpha beta^T,
+//   N = M2/2 - beta beta^T/2 + S^-1 G_rho S^-1,  and
+//   sum Omega o K o D_c = sum_i ( -2 rho_i R_ic - B_i U_ic + alpha_i E_ic ),
+//   R_ic = sum_j (K S^-1)_ij K_ij D_ijc,  U_ic = sum_j (K C)_ij K_ij D_ijc,  E_ic = sum_j beta_j K_ij D_ijc  (D_ij0 = 1)
+// -- per-row sums of the two products the row forms q_i = R_i0 and c_i = U_i0 need anyway.
+// Row passes: K S^-1 (q, R), weighted Gram G_B, K C (c, U, E, K v), weighted Gram G_rho: 2 K*M + 2 SYRK.
+// With the knot-location gradient (column sums of Omega o K need rho, alpha first): q, G_B, c / K v, the two
+// explicit Omega passes, G_rho.
 #include <math.h>
 
 #include "dense.cuh"
@@ -79,6 +86,16 @@ fic_rows2_kernel(const double *__restrict__ c, const double *__restrict__ kv, co
     if (threadIdx.x == 0) part[blockIdx.x] = sr;
 }
 
+// out[c] = sum over the blocks of part[c * ROW_BLOCKS + block]   (one block per c)
+__global__ void sum_part_rows_kernel(const double *__restrict__ part, int count, double *__restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += part[blockIdx.x * count + i];
+    s = block_reduce_256(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 __global__ void sum_strided_kernel(const double *__restrict__ part, int count, int stride, int offset,
                                    double *__restrict__ out)
 {
@@ -90,6 +107,23 @@ __global__ void sum_strided_kernel(const double *__restrict__ part, int count, i
 }
 
 constexpr int ROW_BLOCKS = 128;
+
+// g[c] = sum_i ( -2 rho_i R_ic - B_i U_ic + alpha_i E_ic ),  c = 0..d  (= sum Omega o K o D_c with D_0 = 1):
+// one block column per c; per-block partials part[c * ROW_BLOCKS + block]
+__global__ void __launch_bounds__(256)
+fic_rowd_reduce_kernel(const double *__restrict__ R, const double *__restrict__ U, const double *__restrict__ E,
+                       int64_t stride, const double *__restrict__ B, const double *__restrict__ rho,
+                       const double *__restrict__ alpha, int64_t n, double *__restrict__ part)
+{
+    __shared__ double red[8];
+    const int c = blockIdx.y;
+    const double *Rc = R + (int64_t)c * stride, *Uc = U + (int64_t)c * stride, *Ec = E + (int64_t)c * stride;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += -2.0 * rho[i] * Rc[i] - B[i] * Uc[i] + alpha[i] * Ec[i];
+    s = block_reduce_256(s, red);
+    if (threadIdx.x == 0) part[c * ROW_BLOCKS + blockIdx.x] = s;
+}
 
 int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *l, double tau, double delta,
               double *obj, double *grad)
@@ -124,8 +158,25 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     SRGP_TRY(dense::chol_inverse(ctx, s, T1, mp, m, w->dinv(0), LinvS, LinvTS, tmp, Sinv, w->info(0),
                                  w->sc(W::S_LOGDET_S)));
 
-    // ---- pass 1a: q_i ; rows: Z, B, B r, sum B r^2, sum log Z ----------------------------------------------
-    SRGP_TRY(gauss_rowform(ctx, w, gp, Sinv, nullptr, q, nullptr));
+    // ---- pass 1a: q_i (and, when a gradient without knot terms is wanted, R_ic = sum_j (K S^-1)_ij K_ij D_ijc) ;
+    //      rows: Z, B, B r, sum B r^2, sum log Z --------------------------------------------------------------------
+    // Omega = -2 diag(rho) K S^-1 - diag(B) K C + alpha beta^T (M2 = S^-1 - C), so sum Omega o K o D_c splits into
+    // per-row sums of the two products the row forms q_i, c_i need anyway: no third / fourth K * M pass.  The
+    // knot-location gradient needs column sums of Omega o K, i.e. rho and alpha BEFORE the products: it keeps the
+    // two explicit Omega passes.
+    const bool rowd_path = grad && !w->want_knots;
+    const int64_t rstride = (int64_t)W::row_stride(n);
+    double *Rd = nullptr, *Ud = nullptr, *Ed = nullptr;
+    if (rowd_path) {
+        SRGP_TRY(w->rowd.reserve((size_t)(3 * (d + 1) + 1) * rstride * 8));
+        Rd = w->rowd.d();
+        Ud = Rd + (int64_t)(d + 1) * rstride;
+        Ed = Ud + (int64_t)(d + 1) * rstride;      // followed by K v
+        SRGP_TRY(gauss_rowd(ctx, w, gp, Sinv, nullptr, nullptr, Rd, rstride));
+        q = Rd;
+    } else {
+        SRGP_TRY(gauss_rowform(ctx, w, gp, Sinv, nullptr, q, nullptr));
+    }
     {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 3);
         fic_rows1_kernel<<<ROW_BLOCKS, 256, 0, s>>>(q, w->r.d(), n, zconst, Bv, Br, w->part2.d());
@@ -159,8 +210,16 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, Sinv, -1.0, C, 0.0, M2));
 
         // ---- pass 2a: c_i, (K v)_i ; rows: alpha, rho, -B - 2 rho, sum rho -----------------------------------
-        SRGP_TRY(gauss_rowform(ctx, w, gp, C, v, cq, kv));
         double *p2 = w->sc(W::S_P2);
+        if (rowd_path) {
+            // pairs recorded by pass 1a carry (K S^-1)_ij; restart the list so that it holds (K C)_ij only
+            SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+            SRGP_TRY(gauss_rowd(ctx, w, gp, C, beta, v, Ud, rstride));
+            cq = Ud;
+            kv = Ed + (int64_t)(d + 1) * rstride;
+        } else {
+            SRGP_TRY(gauss_rowform(ctx, w, gp, C, v, cq, kv));
+        }
         {
             KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
             fic_rows2_kernel<<<ROW_BLOCKS, 256, 0, s>>>(cq, kv, w->r.d(), Bv, n, alpha, rho, rs1, w->part2.d());
@@ -168,11 +227,25 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
             sum_strided_kernel<<<1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, 1, 0, p2 + d + 2);
             SRGP_LAUNCH_CHECK();
         }
-        // ---- pass 2b: the two Omega terms share the per-CTA slots; G_rho --------------------------------------
-        SRGP_TRY(gauss_pass2(ctx, w, gp, Sinv, rs1, alpha, beta, nullptr, false));
-        SRGP_TRY(gauss_pass2(ctx, w, gp, M2, Bv, nullptr, beta, p2, true));
-        // quirk Q4: sum of Omega_ij over bit-identical (row, knot) pairs (both terms were recorded)
-        SRGP_TRY(coin_fix(ctx, w, gp, Sinv, 0.0, p2 + 1 + d));
+        if (rowd_path) {
+            // ---- sum Omega o K o D_c from the per-row sums; quirk Q4 pairs ---------------------------------------
+            {
+                KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+                fic_rowd_reduce_kernel<<<dim3(ROW_BLOCKS, d + 1), 256, 0, s>>>(Rd, Ud, Ed, rstride, Bv, rho, alpha, n,
+                                                                              w->part2.d());
+                SRGP_LAUNCH_CHECK();
+                sum_part_rows_kernel<<<d + 1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, p2);
+                SRGP_LAUNCH_CHECK();
+            }
+            SRGP_TRY(coin_fix_fic(ctx, w, gp, Sinv, Bv, rho, alpha, beta, p2 + 1 + d));
+        } else {
+            // ---- pass 2b: the two Omega terms share the per-CTA slots ------------------------------------------
+            SRGP_TRY(gauss_pass2(ctx, w, gp, Sinv, rs1, alpha, beta, nullptr, false));
+            SRGP_TRY(gauss_pass2(ctx, w, gp, M2, Bv, nullptr, beta, p2, true));
+            // quirk Q4: sum of Omega_ij over bit-identical (row, knot) pairs (both terms were recorded)
+            SRGP_TRY(coin_fix(ctx, w, gp, Sinv, 0.0, p2 + 1 + d));
+        }
+        // ---- G_rho ----------------------------------------------------------------------------------------------
         double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho | p2 (d + 3)]
         SRGP_TRY(gauss_pass1(ctx, w, gp, rho, rho, red2, tv));
         SRGP_TRY(copy_scalar(ctx, red2 + mm, p2, d + 3));

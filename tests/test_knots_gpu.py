@@ -90,8 +90,8 @@ def test_knot_gradient_all_knots_against_reduced_oracle(ctx, model, shape):
     np.testing.assert_allclose(kg[big], kg_ref[big], rtol=RTOL)
     # and the plain evaluation still gives the same objective / gradient (the knot epilogue is a separate instantiation)
     obj2, grad2 = ctx.gauss_obj_grad(model, "ard", c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
-    assert obj2 == obj
-    np.testing.assert_allclose(grad2, grad, rtol=1e-12)
+    assert obj2 == pytest.approx(obj, rel=1e-13)     # different epilogues, different summation order
+    np.testing.assert_allclose(grad2, grad, rtol=1e-10, atol=1e-12 * np.abs(grad).max())
 
 
 def test_knot_gradient_finite_difference_at_scale(ctx):
