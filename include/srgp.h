@@ -231,6 +231,13 @@ int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const double *xu,
 int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
                       const double *l, double tau, double delta, double pois_m, const double *ff, double *grad);
 
+/* dlogq_dcov_par with dcov_fun_dknot (R/laplace_approx_gradient.R:345-705): the same gradient plus the knot-location
+   gradient at the mode ff.  Knot arguments and outputs as in srgp_gauss_obj_grad_knots. */
+int srgp_laplace_grad_knots(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                            const double *l, double tau, double delta, double pois_m, const double *ff,
+                            const double *knot_lb, const double *knot_ub, const int *knot_opt, int64_t n_opt,
+                            double *grad, double *knot_grad, double *trans_knot);
+
 /* ---------------------------------------------------------------- multi-GPU ------------------ */
 /* Row sharding over ranks with NCCL sum-allreduce of the pass partials (m x m Gram, m-vectors, scalars,
    gradient partials).  Rank 0 calls srgp_comm_unique_id and distributes the bytes out of band

@@ -740,8 +740,10 @@ def newtrap_sparseGP(start_vals, family, cov_par, cov_fun, xy, xu, y, mu, muu, m
 # --------------------------------------------------------------------------------------------------
 # Sparse Laplace gradient: R/laplace_approx_gradient.R:25-339
 # --------------------------------------------------------------------------------------------------
-def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, dcov_fun_dtheta=None, **kw):
-    """R/laplace_approx_gradient.R:25-339 with dcov_fun_dknot = NA, transform = TRUE (quirk Q2 verbatim)."""
+def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, dcov_fun_dtheta=None, dcov_fun_dknot=None,
+                   knot_opt=None, transform=True, **kw):
+    """R/laplace_approx_gradient.R:25-715, transform = TRUE for the covariance parameters (quirk Q2 verbatim);
+    dcov_fun_dknot / knot_opt / knot outputs as in delbo_dcov_par (:345-705)."""
     fam = FAMILIES[family]
     xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
     xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
@@ -788,7 +790,31 @@ def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, dcov
         comp3 = _col(-(1 / W) * B) * comp3_1 + _col(1 / W) * (BK @ (C @ (Sigma12.T @ (_col(B) * comp3_1))))   # :306-307
         grad[par_name] = (1 / 2) * comp2 - (1 / 2) * comp1 - \
             (1 / 2) * float((_col(comp4 * (-W3)).T @ comp3)[0, 0])                  # :333-335
-    return {"gradient": grad, "trans_par": trans_par}
+    if dcov_fun_dknot is None:
+        return {"gradient": grad, "trans_par": trans_par}
+    m, dd = xu.shape                                                                # :345-705
+    bounds = knot_bounds_for(xy)
+    grad_knot = np.zeros(m * dd)
+    trans_knot = xu.copy()
+    BK = _rows(B, Sigma12)
+    sel = range(m) if knot_opt is None else knot_opt
+    p = 0
+    for k in range(m):
+        if transform:
+            trans_knot[k] = dcov_fun_dknot(0, xu[k], cov_par, transform, bounds)["trans_par"]
+        for dk in range(dd):
+            p += 1
+            if k not in sel:
+                continue
+            dK = _dsig12_dknot(k, dk, cov_par, dcov_fun_dknot, xu, xy, bounds, transform)
+            dS = _dsig22_dknot(k, dk, cov_par, dcov_fun_dknot, xu, bounds, transform)
+            A = 0 - np.sum((2 * dK - FF.T @ dS) * FF.T, axis=1)                     # A1 = 0
+            comp1 = _comp1(A, B, C, Sigma12, Sigma22, FF, dK, dS)
+            comp2 = _comp2(A, comp2_1, Sigma12, Sigma22, FF, dK, dS)
+            comp3_1 = _col(A * grad_log_py_ff) + 2 * dK @ GG - FF.T @ dS @ GG
+            comp3 = _col(-(1 / W) * B) * comp3_1 + _col(1 / W) * (BK @ (C @ (Sigma12.T @ (_col(B) * comp3_1))))
+            grad_knot[p - 1] = (1 / 2) * comp2 - (1 / 2) * comp1 - (1 / 2) * float((_col(comp4 * (-W3)).T @ comp3)[0, 0])
+    return {"gradient": grad, "knot_gradient": grad_knot, "trans_par": trans_par, "trans_knot": trans_knot}
 
 
 # --------------------------------------------------------------------------------------------------

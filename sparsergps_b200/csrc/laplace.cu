@@ -14,6 +14,8 @@
 // Algebra checked against the literal transcription by tests/test_oracle.py (oracle/reduced_model.py).
 #include <math.h>
 
+#include <vector>
+
 #include "dense.cuh"
 #include "gauss.cuh"
 
@@ -504,9 +506,11 @@ extern "C" int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const 
     return SRGP_OK;
 }
 
-extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
-                                 const double *l, double tau, double delta, double pois_m, const double *ff,
-                                 double *grad)
+// dlogq_dcov_par on the resident shard; knot_grad (host, m * d, knot-major; null = none) adds the knot-location
+// gradient, which reuses Omega (the two pass-2 launches collect its per-knot column sums) and N.
+static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                             const double *l, double tau, double delta, double pois_m, const double *ff, double *grad,
+                             const double *knot_lb, const double *knot_ub, double *knot_grad)
 {
     SRGP_TRY(lap_check(ctx, family, kernel, xu, m, l));
     if (!ff || !grad) {
@@ -530,8 +534,8 @@ extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const do
     SRGP_TRY(L.ktv(L.d1, ktg));
     SRGP_TRY(gram_materialised(ctx, w, L.om, GB));
     SRGP_TRY(comm_allreduce(ctx, GB, mm + 2 * mp, s));
-    double *C = w->mat(W_::M_C), *M2 = w->mat(W_::M_CGS), *CG = w->mat(W_::M_CG), *SG = w->mat(W_::M_SG);
-    double *SGS = w->mat(W_::M_SGS), *N = w->mat(W_::M_N), *T1 = w->mat(W_::M_T1), *Grho = w->mat(W_::M_X2);
+    double *C = w->mat(W_::M_C), *M2 = w->mat(W_::M_CGS), *SG = w->mat(W_::M_SG);
+    double *SGS = w->mat(W_::M_SGS), *N = w->mat(W_::M_N), *Grho = w->mat(W_::M_X2);
     double *beta = w->vec(W_::V_BETA), *GG = w->vec(W_::V_T4), *c2 = w->vec(W_::V_T5), *Cc2 = w->vec(W_::V_T6);
     double *skt = w->vec(W_::V_T7);
     SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, L.S, 1.0, GB, 0.0, L.A));
@@ -566,11 +570,19 @@ extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const do
         sum_strided2_kernel<<<1, 256, 0, s>>>(w->part2.d(), LROW_BLOCKS, 1, 0, p2 + d + 2);
         SRGP_LAUNCH_CHECK();
     }
-    // M2 = C G_B S^-1 ; Omega = diag(-B - 2 rho) K S^-1 + diag(B) K M2 + alpha beta^T - t GG^T
-    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, C, mp, GB, mp, 0.0, CG, mp));
-    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, CG, mp, L.Sinv, mp, 0.0, M2, mp));
-    SRGP_TRY(gauss_pass2(ctx, w, L.gp, L.Sinv, rs1, alpha, beta, nullptr, false));
-    SRGP_TRY(gauss_pass2(ctx, w, L.gp, M2, L.om, negt, GG, p2, true));
+    // M2 = C G_B S^-1 = S^-1 - C (C (S + G_B) = I) ; Omega = diag(-B - 2 rho) K S^-1 + diag(B) K M2 + alpha beta^T - t GG^T
+    SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, L.Sinv, -1.0, C, 0.0, M2));
+    w->want_knots = knot_grad != nullptr;
+    w->knot_transform = knot_grad && knot_lb && knot_ub;
+    if (w->knot_transform)
+        for (int c = 0; c < d; c++) {
+            w->knot_lb[c] = knot_lb[c];
+            w->knot_ub[c] = knot_ub[c];
+        }
+    int rc2 = gauss_pass2(ctx, w, L.gp, L.Sinv, rs1, alpha, beta, nullptr, false);
+    if (rc2 == SRGP_OK) rc2 = gauss_pass2(ctx, w, L.gp, M2, L.om, negt, GG, p2, true);
+    w->want_knots = false;
+    SRGP_TRY(rc2);
     SRGP_TRY(coin_fix(ctx, w, L.gp, L.Sinv, 0.0, p2 + 1 + d));
     // G_rho, K^T t -> one allreduce with the gradient partials
     double *red2 = w->mat(W_::M_T2);   // [G_rho (mm)] then M_X1.. is LinvT: use a separate tail buffer
@@ -583,18 +595,20 @@ extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const do
     SRGP_TRY(copy_scalar(ctx, p2, tail2 + mp, d + 3));
     SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, L.Sinv, tail2, 0.0, nullptr, skt, L.gsc));
-    // N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1 + (S^-1 K^T t) GG^T/2
-    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, L.Sinv, mp, GB, mp, 0.0, SG, mp));
-    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, L.Sinv, mp, 0.0, SGS, mp));
-    SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, M2, mp, 0.0, T1, mp));
-    SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 0.5, SGS, -0.5, T1, 0.0, N));
+    // N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1 + (S^-1 K^T t) GG^T/2, and
+    // S^-1 G_B (S^-1 - M2) = S^-1 G_B C = S^-1 - C = M2, so the first two terms are M2/2
     SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, L.Sinv, mp, Grho, mp, 0.0, SG, mp));
     SRGP_TRY(dense::gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, SG, mp, L.Sinv, mp, 0.0, SGS, mp));
-    SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, N, 1.0, SGS, 0.0, N));
+    SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 0.5, M2, 1.0, SGS, 0.0, N));
     SRGP_TRY(dense::ger(ctx, s, mp, -0.5, beta, beta, N));
     SRGP_TRY(dense::ger(ctx, s, mp, 0.5, skt, GG, N));
     SRGP_TRY(ns_reduce(ctx, w, L.gp, N, L.S, tau * tau + delta, w->sc(W_::S_NS), s));
+    if (knot_grad) SRGP_TRY(knot_finish(ctx, w, L.gp, N, L.S));
     SRGP_TRY(fetch_scalars(ctx, w));
+    if (knot_grad) {
+        SRGP_CUDA(cudaMemcpyAsync(knot_grad, w->knotsum.d() + (int64_t)d * mp, (size_t)m * d * 8, cudaMemcpyDeviceToHost, s));
+        SRGP_CUDA(cudaStreamSynchronize(s));
+    }
 
     const double *h = w->h_scal, *hp2 = h + W_::S_P2, *ns = h + W_::S_NS;
     const double sum_rho = hp2[d + 2];
@@ -609,5 +623,47 @@ extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const do
     const int ti = (kernel == SRGP_ARD) ? 1 + d : 2;
     // dS(tau) = 2 tau^2 on identical knot pairs is NOT zeroed in the Laplace gradient (R/laplace_approx_gradient.R:214-237)
     grad[ti] = 2.0 * tau * tau * (sum_rho + ns[1 + d] + hp2[1 + d]);
+    return SRGP_OK;
+}
+
+extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                                 const double *l, double tau, double delta, double pois_m, const double *ff,
+                                 double *grad)
+{
+    return laplace_grad_impl(ctx, family, kernel, xu, m, sigma, l, tau, delta, pois_m, ff, grad, nullptr, nullptr,
+                             nullptr);
+}
+
+extern "C" int srgp_laplace_grad_knots(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                                       const double *l, double tau, double delta, double pois_m, const double *ff,
+                                       const double *knot_lb, const double *knot_ub, const int *knot_opt,
+                                       int64_t n_opt, double *grad, double *knot_grad, double *trans_knot)
+{
+    if (!knot_grad || (knot_lb == nullptr) != (knot_ub == nullptr) || n_opt < 0 || (n_opt > 0 && !knot_opt)) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (knot_opt)
+        for (int64_t t = 0; t < n_opt; t++)
+            if (knot_opt[t] < 0 || knot_opt[t] >= m) {
+                set_error("knot_opt[%lld] = %d outside [0, %lld)", (long long)t, knot_opt[t], (long long)m);
+                return SRGP_ERR_ARG;
+            }
+    SRGP_TRY(laplace_grad_impl(ctx, family, kernel, xu, m, sigma, l, tau, delta, pois_m, ff, grad, knot_lb, knot_ub,
+                               knot_grad));
+    const int d = ctx->d;
+    if (knot_opt) {
+        std::vector<char> keep((size_t)m, 0);
+        for (int64_t t = 0; t < n_opt; t++) keep[knot_opt[t]] = 1;
+        for (int64_t k = 0; k < m; k++)
+            if (!keep[k])
+                for (int c = 0; c < d; c++) knot_grad[k * d + c] = 0.0;
+    }
+    if (trans_knot)
+        for (int c = 0; c < d; c++)
+            for (int64_t k = 0; k < m; k++) {
+                const double u = xu[k + m * c];
+                trans_knot[k + m * c] = knot_lb ? log((u - knot_lb[c]) + 1e-4) - log((knot_ub[c] - u) + 1e-4) : u;
+            }
     return SRGP_OK;
 }

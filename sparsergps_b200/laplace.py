@@ -37,18 +37,41 @@ def newtrap_sparseGP(start_vals, family, cov_par, cov_fun, xy, xu, y, mu, muu, m
             "u_posterior_mean": um, "u_posterior_variance": uv}
 
 
-def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, m=1.0, ctx=None, **_ignored):
-    """R/laplace_approx_gradient.R:25-339 with dcov_fun_dknot = NA, transform = TRUE: list(gradient, trans_par)."""
+def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, m=1.0, ctx=None, dcov_fun_dknot=None,
+                   knot_opt=None, transform=True, **_ignored):
+    """R/laplace_approx_gradient.R:25-715, transform = TRUE for the covariance parameters: list(gradient, trans_par)
+    and, with a dcov_fun_dknot (None / False = R's NA), knot_gradient (m*d, knot-major) and trans_knot (:345-705).
+    knot_opt: 0-based indices (R: 1-based), None = all; `transform` is the knot transform flag."""
+    from .vi_functions import knot_bounds
     ctx = ctx or default_context()
     xy, xu = L.fmat(xy), L.fmat(xu)
     n, d = xy.shape
+    mk = xu.shape[0]
     sigma, l, tau, names = _theta(cov_par, cov_fun, d)
     ctx.set_data(xy, y, mu)
     ffv, lv = L.fvec(ff), L.fvec(l)
     grad = np.zeros(len(names))
-    L.check(ctx._lib.srgp_laplace_grad(ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), xu.shape[0], sigma,
-                                       L.ptr(lv), tau, float(delta), float(m), L.ptr(ffv), L.ptr(grad)))
-    return {"gradient": dict(zip(names, grad)), "trans_par": {k: float(np.log(cov_par[k])) for k in names}}
+    out = {"trans_par": {k: float(np.log(cov_par[k])) for k in names}}
+    if dcov_fun_dknot is None or dcov_fun_dknot is False:
+        L.check(ctx._lib.srgp_laplace_grad(ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), mk, sigma,
+                                           L.ptr(lv), tau, float(delta), float(m), L.ptr(ffv), L.ptr(grad)))
+    else:
+        kgrad, tk = np.zeros(mk * d), np.zeros((mk, d), order="F")
+        lb = ub = None
+        if transform:
+            kb = knot_bounds(xy)
+            lb, ub = L.fvec(kb[:, 0]), L.fvec(kb[:, 1])
+        opt, n_opt = None, 0
+        if knot_opt is not None:
+            opt = np.ascontiguousarray(np.asarray(list(knot_opt), dtype=np.int32))
+            n_opt = len(opt)
+        L.check(ctx._lib.srgp_laplace_grad_knots(
+            ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), mk, sigma, L.ptr(lv), tau, float(delta),
+            float(m), L.ptr(ffv), L.ptr(lb) if lb is not None else None, L.ptr(ub) if ub is not None else None,
+            opt.ctypes.data_as(C.POINTER(C.c_int)) if n_opt else None, n_opt, L.ptr(grad), L.ptr(kgrad), L.ptr(tk)))
+        out["knot_gradient"], out["trans_knot"] = kgrad, tk
+    out["gradient"] = dict(zip(names, grad))
+    return out
 
 
 def predict_laplace(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, full_cov=False, family="gaussian",

@@ -64,3 +64,32 @@ def test_newton_sqexp_1d_and_start_values(ctx):
     got = Lp.newtrap_sparseGP(ff0, "bernoulli", cp, "sqexp", x, xu, y, np.zeros(n), np.zeros(12), maxit=25, tol=1e-5, delta=1e-3, ctx=ctx)
     np.testing.assert_allclose(got["objective_function_values"], ref["objective_function_values"], rtol=1e-8)
     np.testing.assert_allclose(got["gp"], ref["gp"], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_laplace_knot_gradient_matches_literal_oracle(ctx, family):
+    """dlogq_dcov_par with dcov_fun_dknot (R/laplace_approx_gradient.R:345-705): selected knots against the
+    literal per-knot loop, the rest exactly 0, theta gradient unchanged."""
+    from sparsergps_b200 import laplace as Lp
+    c = _case(family, n=600, m=24, coincident=False)
+    cp, mk = c["cov_par"], len(c["xu"])
+    kw = {"m": 1.0} if family == "poisson" else {}
+    fit = rm.newtrap_sparseGP(np.zeros(600), family, cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(mk),
+                              maxit=30, tol=1e-5, delta=c["delta"], **kw)
+    opt = [0, 11, 23]
+    ref = rm.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], c["delta"],
+                            dcov_fun_dknot=rm.dsqexp_dx2_ard, knot_opt=opt, **kw)
+    got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], c["delta"], ctx=ctx,
+                            dcov_fun_dknot=True, knot_opt=opt)
+    d = c["x"].shape[1]
+    g, g_ref = got["knot_gradient"].reshape(mk, d), ref["knot_gradient"].reshape(mk, d)
+    np.testing.assert_allclose(g[opt], g_ref[opt], rtol=1e-8, atol=1e-11 * np.abs(g_ref).max())
+    rest = [k for k in range(mk) if k not in opt]
+    assert not g[rest].any()
+    np.testing.assert_allclose(got["trans_knot"], ref["trans_knot"], rtol=1e-13, atol=1e-13)
+    scale = max(abs(v) for v in ref["gradient"].values())
+    for k in ref["gradient"]:
+        assert got["gradient"][k] == pytest.approx(ref["gradient"][k], rel=1e-8, abs=1e-9 * scale), k
+    plain = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], c["delta"], ctx=ctx)
+    for k in ref["gradient"]:
+        assert plain["gradient"][k] == pytest.approx(got["gradient"][k], rel=1e-12)
