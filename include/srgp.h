@@ -238,6 +238,18 @@ int srgp_laplace_grad_knots(srgp_ctx *ctx, int family, int kernel, const double 
                             const double *knot_lb, const double *knot_ub, const int *knot_opt, int64_t n_opt,
                             double *grad, double *knot_grad, double *trans_knot);
 
+/* laplace_grad_ascent (R/laplace_gradient_ascent.R:10-628): the optimiser loop of srgp_gauss_fit around the sparse
+   Laplace evaluation -- a Newton mode search (newtrap_sparseGP with maxit_nr / tol_nr, warm-started from the previous
+   mode) and dlogq_dcov_par at that mode per iteration; the objective is the last Newton objective value.
+   In/out: xu, *sigma, l, *tau and ff (n: start values in, `fmax` out).  nr_iter (may be NULL) needs maxit entries
+   (`nr_iter`: Newton iterations per step); u_mean (m) / u_var (m x m) (may be NULL) are those of the last Newton run.
+   Other arguments as in srgp_gauss_fit.  Reference defaults: maxit_nr 1000, tol_nr 1e-6 (:77-80). */
+int srgp_laplace_fit(srgp_ctx *ctx, int family, int kernel, double *xu, int64_t m, const double *muu, double *sigma,
+                     double *l, double *tau, double delta, double pois_m, int maxit_nr, double tol_nr,
+                     const srgp_fit_opt *opt, const double *knot_lb, const double *knot_ub, const int *knot_opt,
+                     int64_t n_opt, double *ff, int *iter_out, double *obj_hist, double *par_hist, double *grad_hist,
+                     int *nr_iter, double *u_mean, double *u_var);
+
 /* ---------------------------------------------------------------- multi-GPU ------------------ */
 /* Row sharding over ranks with NCCL sum-allreduce of the pass partials (m x m Gram, m-vectors, scalars,
    gradient partials).  Rank 0 calls srgp_comm_unique_id and distributes the bytes out of band

@@ -448,31 +448,13 @@ def _knot_trans_fun(t, bounds):
     return bounds[:, 1] * (1 / (1 + np.exp(-t))) + bounds[:, 0] * (1 / (1 + np.exp(t)))
 
 
-def norm_grad_ascent(cov_par_start, cov_fun, xu, xy, y, mu, opt=None, vi=True, opt_theta=True, opt_knots=False,
-                     knot_opt=None):
-    """Gradient ascent on the ELBO (vi = True: R/vi_functions.R:703-1158) or the FIC marginal likelihood
-    (vi = False: R/laplace_gradient_ascent.R:1219-1633).  opt_theta stands for is.list(dcov_fun_dtheta), opt_knots
-    for is.function(dcov_fun_dknot).  Returns cov_par, xu, iter, obj_fun, grad, knot_grad histories; the posterior at
-    the knots (the functions' tail) is gauss_posterior_u."""
-    o = dict(FIT_DEFAULTS)
-    o.update({k: v for k, v in (opt or {}).items() if k in o})
-    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
-    xu = np.array(xu, dtype=np.float64).reshape(len(xu), -1)
-    delta, decay, eps, eta = o["delta"], o["decay"], o["epsilon"], o["eta"]
+def _grad_ascent_loop(evaluate, cov_par_start, xu, xy, o, opt_theta, opt_knots):
+    """The optimiser skeleton shared verbatim by norm_grad_ascent_vi (R/vi_functions.R:753-1158), norm_grad_ascent
+    (R/laplace_gradient_ascent.R:1267-1633) and laplace_grad_ascent (:100-568).  evaluate(cov_par, xu) returns
+    (objective, gradient-function result)."""
+    decay, eps, eta = o["decay"], o["epsilon"], o["eta"]
     names = list(cov_par_start)
     cov_par = dict(cov_par_start)
-    grad_fun = delbo_dcov_par if vi else dlogp_dcov_par
-    dknot = dcov_fun_dknot_for(cov_fun) if opt_knots else None
-
-    def evaluate(cp, knots):
-        Sigma12, Sigma22, _ = assemble(cp, cov_fun, xy, knots, delta)
-        if vi:
-            Z = np.repeat(cp["tau"] ** 2 + delta, Sigma12.shape[0])
-            obj = elbo_fun(mu, Z, Sigma12, Sigma22, y, cp, delta)
-        else:
-            obj = obj_fun_norm(mu, fic_Z(cp, Sigma12, Sigma22, delta), Sigma12, Sigma22, y)
-        return obj, grad_fun(cp, cov_fun, knots, xy, y, mu, delta, dcov_fun_dknot=dknot, knot_opt=knot_opt)
-
     obj, ev = evaluate(cov_par, xu)
     obj_vals = [obj]
     g_theta = np.array([ev["gradient"][k] for k in names]) if opt_theta else np.zeros(1)
@@ -526,6 +508,62 @@ def norm_grad_ascent(cov_par_start, cov_fun, xu, xy, y, mu, opt=None, vi=True, o
         par_hist.append(np.array([cov_par[k] for k in names]))
     return {"cov_par": cov_par, "xu": xu, "iter": it, "obj_fun": np.array(obj_vals), "grad": np.array(grad_hist),
             "knot_grad": np.array(knot_hist), "cov_par_history": np.array(par_hist)}
+
+
+def norm_grad_ascent(cov_par_start, cov_fun, xu, xy, y, mu, opt=None, vi=True, opt_theta=True, opt_knots=False,
+                     knot_opt=None):
+    """Gradient ascent on the ELBO (vi = True: R/vi_functions.R:703-1158) or the FIC marginal likelihood
+    (vi = False: R/laplace_gradient_ascent.R:1219-1633).  opt_theta stands for is.list(dcov_fun_dtheta), opt_knots
+    for is.function(dcov_fun_dknot).  Returns cov_par, xu, iter, obj_fun, grad, knot_grad histories; the posterior at
+    the knots (the functions' tail) is gauss_posterior_u."""
+    o = dict(FIT_DEFAULTS)
+    o.update({k: v for k, v in (opt or {}).items() if k in o})
+    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
+    xu = np.array(xu, dtype=np.float64).reshape(len(xu), -1)
+    delta = o["delta"]
+    grad_fun = delbo_dcov_par if vi else dlogp_dcov_par
+    dknot = dcov_fun_dknot_for(cov_fun) if opt_knots else None
+
+    def evaluate(cp, knots):
+        Sigma12, Sigma22, _ = assemble(cp, cov_fun, xy, knots, delta)
+        if vi:
+            Z = np.repeat(cp["tau"] ** 2 + delta, Sigma12.shape[0])
+            obj = elbo_fun(mu, Z, Sigma12, Sigma22, y, cp, delta)
+        else:
+            obj = obj_fun_norm(mu, fic_Z(cp, Sigma12, Sigma22, delta), Sigma12, Sigma22, y)
+        return obj, grad_fun(cp, cov_fun, knots, xy, y, mu, delta, dcov_fun_dknot=dknot, knot_opt=knot_opt)
+
+    return _grad_ascent_loop(evaluate, cov_par_start, xu, xy, o, opt_theta, opt_knots)
+
+
+LAPLACE_FIT_DEFAULTS = dict(FIT_DEFAULTS, maxit_nr=1000, tol_nr=1e-6)            # R/laplace_gradient_ascent.R:77-80
+
+
+def laplace_grad_ascent(cov_par_start, cov_fun, xu, xy, y, ff, family, mu, muu, opt=None, opt_theta=True,
+                        opt_knots=False, knot_opt=None, **kw):
+    """R/laplace_gradient_ascent.R:10-628: every evaluation is a Newton mode search (newtrap_sparseGP, warm-started
+    from the previous mode) followed by dlogq_dcov_par at that mode; the objective is the last value of the Newton
+    history.  Adds fmax, nr_iter, u_mean, u_var of the last Newton run to the result."""
+    o = dict(LAPLACE_FIT_DEFAULTS)
+    o.update({k: v for k, v in (opt or {}).items() if k in o})
+    xy = np.asarray(xy, dtype=np.float64).reshape(len(xy), -1)
+    xu = np.array(xu, dtype=np.float64).reshape(len(xu), -1)
+    dknot = dcov_fun_dknot_for(cov_fun) if opt_knots else None
+    state = {"ff": np.asarray(ff, dtype=np.float64).reshape(-1), "nr_iter": []}
+
+    def evaluate(cp, knots):
+        nr = newtrap_sparseGP(state["ff"], family, cp, cov_fun, xy, knots, y, mu, muu, maxit=o["maxit_nr"],
+                              tol=o["tol_nr"], delta=o["delta"], **kw)
+        state["ff"], state["nr"] = nr["gp"], nr
+        state["nr_iter"].append(len(nr["objective_function_values"]))
+        g = dlogq_dcov_par(cp, cov_fun, knots, xy, y, nr["gp"], family, mu, o["delta"], dcov_fun_dknot=dknot,
+                           knot_opt=knot_opt, **kw)
+        return nr["objective_function_values"][-1], g
+
+    res = _grad_ascent_loop(evaluate, cov_par_start, xu, xy, o, opt_theta, opt_knots)
+    res.update(fmax=state["ff"], nr_iter=np.array(state["nr_iter"]), u_mean=state["nr"]["u_posterior_mean"],
+               u_var=state["nr"]["u_posterior_variance"])
+    return res
 
 
 # --------------------------------------------------------------------------------------------------

@@ -18,9 +18,11 @@
 //             :1146-1147 sc_knot  = decay sc + (1 - decay) |sign(g_new) - sign(g_old)|        (no / 2, as written)
 #include <math.h>
 
+#include <functional>
 #include <vector>
 
 #include "gauss.cuh"
+#include "srgp.h"
 
 using namespace srgp;
 
@@ -28,24 +30,14 @@ namespace {
 inline double sgn(double v) { return (v > 0.0) - (v < 0.0); }   // R's sign(); NaN is caught before it gets here
 }
 
-extern "C" int srgp_gauss_fit(srgp_ctx *ctx, int model, int kernel, double *xu, int64_t m, double *sigma, double *l,
-                              double *tau, double delta, const srgp_fit_opt *opt, const double *knot_lb,
-                              const double *knot_ub, const int *knot_opt, int64_t n_opt, int *iter_out,
-                              double *obj_hist, double *par_hist, double *grad_hist)
+// One optimiser run.  th: p parameters (in/out) in the reference's order; xu: m x d column-major (in/out);
+// evaluate(obj, g_theta[p], g_knot[m*d]) runs one evaluation at the current th / xu.
+typedef std::function<int(double *, double *, double *)> EvalFn;
+
+static int fit_loop(const srgp_fit_opt *opt, int p, int64_t m, int d, std::vector<double> &th, double *xu,
+                    const double *knot_lb, const double *knot_ub, const int *knot_opt, int64_t n_opt,
+                    const EvalFn &evaluate_raw, int *iter_out, double *obj_hist, double *par_hist, double *grad_hist)
 {
-    if (!ctx || !xu || !sigma || !l || !tau || !opt || !iter_out || !obj_hist || m <= 0 || opt->maxit < 1 ||
-        (opt->optim_method != SRGP_OPT_ADADELTA && opt->optim_method != SRGP_OPT_GA) ||
-        (opt->opt_knots && (!knot_lb || !knot_ub)) || n_opt < 0 || (n_opt > 0 && !knot_opt)) {
-        set_error("bad argument");
-        return SRGP_ERR_ARG;
-    }
-    if (!ctx->have_data) {
-        set_error("srgp_gauss_fit called before srgp_set_data");
-        return SRGP_ERR_STATE;
-    }
-    const int d = ctx->d;
-    const bool ard = (kernel == SRGP_ARD);
-    const int nl = ard ? d : 1, p = nl + 2;
     const int64_t md = m * d;
     const bool ok = opt->opt_knots != 0, ot = opt->opt_theta != 0;
     std::vector<char> keep;
@@ -59,18 +51,12 @@ extern "C" int srgp_gauss_fit(srgp_ctx *ctx, int model, int kernel, double *xu, 
             keep[knot_opt[t]] = 1;
         }
     }
-    // theta in the reference's order: sigma, l / l1..ld, tau
-    std::vector<double> th(p), trans(p), g(p, 0.0), gnew(p), sg2(p, 0.0), sd2(p, 0.0), sc(p, 0.0), lfull(std::max(d, 1));
-    th[0] = *sigma;
-    for (int c = 0; c < nl; c++) th[1 + c] = l[c];
-    th[p - 1] = *tau;
+    std::vector<double> trans(p), g(p, 0.0), gnew(p), sg2(p, 0.0), sd2(p, 0.0), sc(p, 0.0);
     std::vector<double> gk(ok ? md : 0, 0.0), gknew(ok ? md : 0), ksg2(ok ? md : 0, 0.0), ksd2(ok ? md : 0, 0.0),
         ksc(ok ? md : 0, 0.0), xt(ok ? md : 0);
 
     auto evaluate = [&](double *obj) -> int {
-        for (int c = 0; c < d; c++) lfull[c] = th[1 + (ard ? c : 0)];
-        int rc = gauss_eval(ctx, model, kernel, xu, m, th[0], lfull.data(), th[p - 1], delta, obj, gnew.data(), ok,
-                            knot_lb, knot_ub, ok ? gknew.data() : nullptr);
+        int rc = evaluate_raw(obj, gnew.data(), ok ? gknew.data() : nullptr);
         if (rc != SRGP_OK) return rc;
         if (ok && !keep.empty())
             for (int64_t k = 0; k < m; k++)
@@ -165,6 +151,93 @@ extern "C" int srgp_gauss_fit(srgp_ctx *ctx, int model, int kernel, double *xu, 
         record(it, obj);
     }
     *iter_out = it;
+    return SRGP_OK;
+}
+
+static bool fit_args_ok(const srgp_fit_opt *opt, const double *knot_lb, const double *knot_ub, const int *knot_opt,
+                        int64_t n_opt)
+{
+    return opt && opt->maxit >= 1 && (opt->optim_method == SRGP_OPT_ADADELTA || opt->optim_method == SRGP_OPT_GA) &&
+           !(opt->opt_knots && (!knot_lb || !knot_ub)) && n_opt >= 0 && !(n_opt > 0 && !knot_opt);
+}
+
+extern "C" int srgp_gauss_fit(srgp_ctx *ctx, int model, int kernel, double *xu, int64_t m, double *sigma, double *l,
+                              double *tau, double delta, const srgp_fit_opt *opt, const double *knot_lb,
+                              const double *knot_ub, const int *knot_opt, int64_t n_opt, int *iter_out,
+                              double *obj_hist, double *par_hist, double *grad_hist)
+{
+    if (!ctx || !xu || !sigma || !l || !tau || !iter_out || !obj_hist || m <= 0 ||
+        !fit_args_ok(opt, knot_lb, knot_ub, knot_opt, n_opt)) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (!ctx->have_data) {
+        set_error("srgp_gauss_fit called before srgp_set_data");
+        return SRGP_ERR_STATE;
+    }
+    const int d = ctx->d;
+    const bool ard = (kernel == SRGP_ARD);
+    const int nl = ard ? d : 1, p = nl + 2;
+    std::vector<double> th(p), lfull(std::max(d, 1));   // theta in the reference's order: sigma, l / l1..ld, tau
+    th[0] = *sigma;
+    for (int c = 0; c < nl; c++) th[1 + c] = l[c];
+    th[p - 1] = *tau;
+    const bool ok = opt->opt_knots != 0;
+    EvalFn eval = [&](double *obj, double *g, double *gk) -> int {
+        for (int c = 0; c < d; c++) lfull[c] = th[1 + (ard ? c : 0)];
+        return gauss_eval(ctx, model, kernel, xu, m, th[0], lfull.data(), th[p - 1], delta, obj, g, ok, knot_lb, knot_ub,
+                          gk);
+    };
+    SRGP_TRY(fit_loop(opt, p, m, d, th, xu, knot_lb, knot_ub, knot_opt, n_opt, eval, iter_out, obj_hist, par_hist,
+                      grad_hist));
+    *sigma = th[0];
+    for (int c = 0; c < nl; c++) l[c] = th[1 + c];
+    *tau = th[p - 1];
+    return SRGP_OK;
+}
+
+// laplace_grad_ascent (R/laplace_gradient_ascent.R:10-628): the same optimiser skeleton; one evaluation = a Newton
+// mode search warm-started from the previous mode (newtrap_sparseGP, :475-487) + dlogq_dcov_par at that mode
+// (:493-508); the objective is the last value of the Newton history (:489).
+extern "C" int srgp_laplace_fit(srgp_ctx *ctx, int family, int kernel, double *xu, int64_t m, const double *muu,
+                                double *sigma, double *l, double *tau, double delta, double pois_m, int maxit_nr,
+                                double tol_nr, const srgp_fit_opt *opt, const double *knot_lb, const double *knot_ub,
+                                const int *knot_opt, int64_t n_opt, double *ff, int *iter_out, double *obj_hist,
+                                double *par_hist, double *grad_hist, int *nr_iter, double *u_mean, double *u_var)
+{
+    if (!ctx || !xu || !sigma || !l || !tau || !ff || !iter_out || !obj_hist || m <= 0 || maxit_nr < 1 ||
+        !fit_args_ok(opt, knot_lb, knot_ub, knot_opt, n_opt)) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (!ctx->have_data) {
+        set_error("srgp_laplace_fit called before srgp_set_data");
+        return SRGP_ERR_STATE;
+    }
+    const int d = ctx->d;
+    const bool ard = (kernel == SRGP_ARD);
+    const int nl = ard ? d : 1, p = nl + 2;
+    std::vector<double> th(p), lfull(std::max(d, 1)), nr_hist((size_t)maxit_nr + 1);
+    th[0] = *sigma;
+    for (int c = 0; c < nl; c++) th[1 + c] = l[c];
+    th[p - 1] = *tau;
+    const bool ok = opt->opt_knots != 0;
+    int evals = 0;
+    EvalFn eval = [&](double *obj, double *g, double *gk) -> int {
+        for (int c = 0; c < d; c++) lfull[c] = th[1 + (ard ? c : 0)];
+        int n_nr = 0;
+        SRGP_TRY(srgp_laplace_newton(ctx, family, kernel, xu, m, muu, th[0], lfull.data(), th[p - 1], delta, pois_m,
+                                     maxit_nr, tol_nr, ff, nr_hist.data(), &n_nr, nullptr, u_mean, u_var));
+        *obj = nr_hist[n_nr - 1];
+        if (nr_iter) nr_iter[evals] = n_nr;
+        evals++;
+        if (ok)
+            return srgp_laplace_grad_knots(ctx, family, kernel, xu, m, th[0], lfull.data(), th[p - 1], delta, pois_m, ff,
+                                           knot_lb, knot_ub, nullptr, 0, g, gk, nullptr);
+        return srgp_laplace_grad(ctx, family, kernel, xu, m, th[0], lfull.data(), th[p - 1], delta, pois_m, ff, g);
+    };
+    SRGP_TRY(fit_loop(opt, p, m, d, th, xu, knot_lb, knot_ub, knot_opt, n_opt, eval, iter_out, obj_hist, par_hist,
+                      grad_hist));
     *sigma = th[0];
     for (int c = 0; c < nl; c++) l[c] = th[1 + c];
     *tau = th[p - 1];

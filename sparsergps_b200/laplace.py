@@ -74,6 +74,60 @@ def dlogq_dcov_par(cov_par, cov_fun, xu, xy, y, ff, family, mu, delta=1e-6, m=1.
     return out
 
 
+def laplace_grad_ascent(cov_par_start, cov_fun, xu, xy, y, ff, family, mu, muu, opt=None, m=1.0, dcov_fun_dtheta=True,
+                        dcov_fun_dknot=None, knot_opt=None, ctx=None, **_ignored):
+    """R/laplace_gradient_ascent.R:10-628 in one call: ADADELTA / gradient ascent on log(theta) (and the knots when
+    dcov_fun_dknot is given); every iteration is a warm-started Newton mode search + dlogq_dcov_par on the GPU.
+    opt: the reference's option names (optim_method, decay, epsilon, eta, learn_rate, maxit, obj_tol, grad_tol,
+    maxit_nr, tol_nr, delta).  Returns the reference's list: cov_par, xu, fmax, iter, obj_fun, u_mean, u_var, grad,
+    cov_par_history (+ nr_iter)."""
+    from .vi_functions import knot_bounds
+    ctx = ctx or default_context()
+    xy = L.fmat(xy)
+    n, d = xy.shape
+    o = {"optim_method": "adadelta", "decay": 0.95, "epsilon": 1e-6, "learn_rate": 1e-2, "eta": 1e3, "maxit": 1000,
+         "obj_tol": 1e-3, "grad_tol": float("inf"), "maxit_nr": 1000, "delta": 1e-6, "tol_nr": 1e-6}
+    o.update({k: v for k, v in (opt or {}).items() if k in o})
+    sigma, l, tau, names = _theta(cov_par_start, cov_fun, d)
+    ctx.set_data(xy, y, mu)
+    xu = np.array(L.fmat(xu), order="F", copy=True)
+    mk = xu.shape[0]
+    nl = d if cov_fun == "ard" else 1
+    lv = np.array(np.broadcast_to(np.asarray(l, dtype=np.float64).reshape(-1), (nl,)), copy=True)
+    p = nl + 2
+    knots = not (dcov_fun_dknot is None or dcov_fun_dknot is False)
+    fo = L.FitOpt({"adadelta": L.OPT_ADADELTA, "ga": L.OPT_GA}[o["optim_method"]], o["decay"], o["epsilon"], o["eta"],
+                  o["learn_rate"], int(o["maxit"]), o["obj_tol"], o["grad_tol"], int(dcov_fun_dtheta is not False),
+                  int(knots))
+    lb = ub = None
+    if knots:
+        kb = knot_bounds(xy)
+        lb, ub = L.fvec(kb[:, 0]), L.fvec(kb[:, 1])
+    ko, n_opt = None, 0
+    if knot_opt is not None:
+        ko = np.ascontiguousarray(np.asarray(list(knot_opt), dtype=np.int32))
+        n_opt = len(ko)
+    muu_v = L.fvec(np.broadcast_to(np.asarray(muu, dtype=np.float64).reshape(-1), (mk,)))
+    ffv = L.fvec(ff).copy()
+    assert ffv.size == n
+    maxit = int(o["maxit"])
+    sg, ta, it = L.cd(float(sigma)), L.cd(float(tau)), C.c_int(0)
+    obj_hist, par_hist, grad_hist = np.full(maxit, np.nan), np.full((maxit, p), np.nan), np.full((maxit, p), np.nan)
+    nr_iter = np.zeros(maxit, dtype=np.int32)
+    um, uv = np.zeros(mk), np.zeros((mk, mk), order="F")
+    L.check(ctx._lib.srgp_laplace_fit(
+        ctx.handle, FAMILIES[family], L.KERNELS[cov_fun], L.ptr(xu), mk, L.ptr(muu_v), C.byref(sg), L.ptr(lv),
+        C.byref(ta), float(o["delta"]), float(m), int(o["maxit_nr"]), float(o["tol_nr"]), C.byref(fo),
+        L.ptr(lb) if lb is not None else None, L.ptr(ub) if ub is not None else None,
+        ko.ctypes.data_as(C.POINTER(C.c_int)) if n_opt else None, n_opt, L.ptr(ffv), C.byref(it), L.ptr(obj_hist),
+        L.ptr(par_hist), L.ptr(grad_hist), nr_iter.ctypes.data_as(C.POINTER(C.c_int)), L.ptr(um), L.ptr(uv)))
+    k = it.value
+    cov_par = dict(zip(names, [sg.value, *lv, ta.value]))
+    return {"cov_par": cov_par, "cov_fun": cov_fun, "xu": xu, "xy": xy, "mu": mu, "muu": muu, "fmax": ffv, "iter": k,
+            "obj_fun": obj_hist[:k], "u_mean": um, "u_var": uv, "grad": grad_hist[:k], "cov_par_history": par_hist[:k],
+            "nr_iter": nr_iter[:k]}
+
+
 def predict_laplace(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, full_cov=False, family="gaussian",
                     delta=1e-6, ctx=None):
     """R/laplace_approx_prediction.R:3-123 (same argument list), full_cov = FALSE."""

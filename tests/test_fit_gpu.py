@@ -78,3 +78,40 @@ def test_fit_at_scale_improves_objective(ctx):
                                  {"maxit": 20, "obj_tol": 1e-12, "delta": c["delta"]}, ctx=ctx)
     assert got["iter"] == 20 and got["obj_fun"][-1] > got["obj_fun"][0]
     assert np.all(np.isfinite(got["u_mean"]))
+
+
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_laplace_fit_trajectory_matches_reference_loop(ctx, family):
+    """laplace_grad_ascent (R/laplace_gradient_ascent.R:10-628): warm-started Newton + dlogq_dcov_par per iteration."""
+    from sparsergps_b200 import laplace as Lp
+    c = cases.config4(n=500, m=16)
+    if family == "poisson":
+        c["y"] = np.random.default_rng(3).poisson(np.exp(0.5 * np.sin(c["x"][:, 0]))).astype(np.float64)
+    start = dict(c["cov_par"])
+    start["sigma"] *= 0.8
+    kw = {"m": 1.0} if family == "poisson" else {}
+    opt = {"maxit": 6, "obj_tol": 1e-9, "delta": c["delta"], "maxit_nr": 40, "tol_nr": 1e-5}
+    ref = rm.laplace_grad_ascent(start, "ard", c["xu"], c["x"], c["y"], np.zeros(500), family, c["mu"], np.zeros(16),
+                                 opt, **kw)
+    got = Lp.laplace_grad_ascent(start, "ard", c["xu"], c["x"], c["y"], np.zeros(500), family, c["mu"], np.zeros(16),
+                                 opt, ctx=ctx)
+    assert got["iter"] == ref["iter"] == 6
+    np.testing.assert_array_equal(got["nr_iter"], ref["nr_iter"])
+    np.testing.assert_allclose(got["obj_fun"], ref["obj_fun"], rtol=1e-8)
+    np.testing.assert_allclose(got["cov_par_history"], ref["cov_par_history"], rtol=1e-7)
+    np.testing.assert_allclose(got["fmax"], ref["fmax"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(got["u_mean"], ref["u_mean"], rtol=1e-6, atol=1e-8)
+
+
+def test_laplace_fit_with_knots(ctx):
+    from sparsergps_b200 import laplace as Lp
+    c = cases.config4(n=400, m=10)
+    start = dict(c["cov_par"])
+    opt = {"maxit": 4, "obj_tol": 1e-9, "delta": c["delta"], "maxit_nr": 30, "tol_nr": 1e-5}
+    ref = rm.laplace_grad_ascent(start, "ard", c["xu"], c["x"], c["y"], np.zeros(400), "bernoulli", c["mu"], np.zeros(10),
+                                 opt, opt_knots=True, knot_opt=[1, 8])
+    got = Lp.laplace_grad_ascent(start, "ard", c["xu"], c["x"], c["y"], np.zeros(400), "bernoulli", c["mu"], np.zeros(10),
+                                 opt, dcov_fun_dknot=True, knot_opt=[1, 8], ctx=ctx)
+    assert got["iter"] == ref["iter"]
+    np.testing.assert_allclose(got["obj_fun"], ref["obj_fun"], rtol=1e-8)
+    np.testing.assert_allclose(got["xu"], ref["xu"], rtol=1e-7)
