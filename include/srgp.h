@@ -250,6 +250,13 @@ int srgp_laplace_fit(srgp_ctx *ctx, int family, int kernel, double *xu, int64_t 
                      int64_t n_opt, double *ff, int *iter_out, double *obj_hist, double *par_hist, double *grad_hist,
                      int *nr_iter, double *u_mean, double *u_var);
 
+/* Candidate loop of knot_prop_random (R/knot_proposal_functions.R:1096-1120) for the sparse Laplace models:
+   scores[t] = last Newton objective with candidate row t appended to the knots, every search warm-started from
+   fmax (n, the current mode).  cand is n_cand x d column-major.  NaN = that candidate's Cholesky failed. */
+int srgp_laplace_oat_scores(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, const double *cand,
+                            int64_t n_cand, double sigma, const double *l, double tau, double delta, double pois_m,
+                            int maxit_nr, double tol_nr, const double *fmax, double *scores);
+
 /* ---------------------------------------------------------------- multi-GPU ------------------ */
 /* Row sharding over ranks with NCCL sum-allreduce of the pass partials (m x m Gram, m-vectors, scalars,
    gradient partials).  Rank 0 calls srgp_comm_unique_id and distributes the bytes out of band

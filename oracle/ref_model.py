@@ -591,6 +591,24 @@ def oat_candidate_scores(cov_par, cov_fun, xu, xy, y, mu, pseudo_prop, delta=1e-
     return out
 
 
+def laplace_oat_candidate_scores(cov_par, cov_fun, xu, xy, y, fmax, family, mu, muu, pseudo_prop, delta=1e-6,
+                                 maxit=1000, tol=1e-6, **kw):
+    """Candidate loop of knot_prop_random (R/knot_proposal_functions.R:1096-1120): newtrap_sparseGP warm-started from
+    fmax with the candidate appended to the knots (muu extended by muu[1]); the score is the last objective value."""
+    xu = np.asarray(xu, dtype=np.float64).reshape(len(xu), -1)
+    pseudo_prop = np.asarray(pseudo_prop, dtype=np.float64).reshape(len(pseudo_prop), -1)
+    muu = np.asarray(muu, dtype=np.float64).reshape(-1)
+    out = np.full(len(pseudo_prop), np.nan)
+    for i in range(len(pseudo_prop)):
+        try:
+            nr = newtrap_sparseGP(fmax, family, cov_par, cov_fun, xy, np.vstack([xu, pseudo_prop[i]]), y, mu,
+                                  np.concatenate([muu, muu[:1]]), maxit=maxit, tol=tol, delta=delta, **kw)
+            out[i] = nr["objective_function_values"][-1]
+        except np.linalg.LinAlgError:
+            pass
+    return out
+
+
 def knot_prop_choice(xu, pseudo_prop, obj_current, scores):
     """obj_fun_x[which.max(c(rep(obj_current, nrow(xu)), scores)), ] (R/vi_functions.R:2164,2299-2303): the best
     candidate, or the FIRST existing knot when no candidate beats the current objective."""

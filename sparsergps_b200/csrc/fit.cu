@@ -18,6 +18,7 @@
 //             :1146-1147 sc_knot  = decay sc + (1 - decay) |sign(g_new) - sign(g_old)|        (no / 2, as written)
 #include <math.h>
 
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -241,5 +242,41 @@ extern "C" int srgp_laplace_fit(srgp_ctx *ctx, int family, int kernel, double *x
     *sigma = th[0];
     for (int c = 0; c < nl; c++) l[c] = th[1 + c];
     *tau = th[p - 1];
+    return SRGP_OK;
+}
+
+// knot_prop_random (R/knot_proposal_functions.R:1001-1175), candidate loop :1096-1120: for every candidate row a Newton
+// mode search with the knots [U; c], warm-started from the current mode; score = last Newton objective value.
+// A failed Cholesky (the reference's try-error, after which it resamples) gives NaN.
+extern "C" int srgp_laplace_oat_scores(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m,
+                                       const double *cand, int64_t n_cand, double sigma, const double *l, double tau,
+                                       double delta, double pois_m, int maxit_nr, double tol_nr, const double *fmax,
+                                       double *scores)
+{
+    if (!ctx || !xu || !cand || !l || !fmax || !scores || m <= 0 || n_cand <= 0 || maxit_nr < 1) {
+        set_error("bad argument");
+        return SRGP_ERR_ARG;
+    }
+    if (!ctx->have_data) {
+        set_error("srgp_laplace_oat_scores called before srgp_set_data");
+        return SRGP_ERR_STATE;
+    }
+    const int d = ctx->d;
+    const int64_t ma = m + 1, n = ctx->n;
+    std::vector<double> ua((size_t)ma * d), ff((size_t)std::max<int64_t>(n, 1)), hist((size_t)maxit_nr + 1);
+    for (int64_t t = 0; t < n_cand; t++) {
+        for (int c = 0; c < d; c++) {
+            for (int64_t k = 0; k < m; k++) ua[k + (size_t)ma * c] = xu[k + m * c];
+            ua[m + (size_t)ma * c] = cand[t + n_cand * c];
+        }
+        std::copy(fmax, fmax + n, ff.begin());
+        int n_nr = 0;
+        // muu only enters u_mean (not requested here): R passes c(muu, muu[1])
+        const int rc = srgp_laplace_newton(ctx, family, kernel, ua.data(), ma, nullptr, sigma, l, tau, delta, pois_m,
+                                           maxit_nr, tol_nr, ff.data(), hist.data(), &n_nr, nullptr, nullptr, nullptr);
+        if (rc == SRGP_ERR_NOT_PD) scores[t] = NAN;
+        else if (rc != SRGP_OK) return rc;
+        else scores[t] = hist[n_nr - 1];
+    }
     return SRGP_OK;
 }

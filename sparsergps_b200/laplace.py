@@ -128,6 +128,30 @@ def laplace_grad_ascent(cov_par_start, cov_fun, xu, xy, y, ff, family, mu, muu, 
             "nr_iter": nr_iter[:k]}
 
 
+def knot_prop_random(laplace_opt, pseudo_prop, family, y, opt=None, m=1.0, maxit=1000, tol=1e-6, ctx=None,
+                     return_scores=False, **_ignored):
+    """R/knot_proposal_functions.R:1001-1175 with the sampled rows `pseudo_prop` (:1093) passed in: one warm-started
+    Newton search per candidate on the GPU, then obj_fun_x[which.max(c(rep(last objective, nrow(xu)), scores)), ].
+    laplace_opt: the optimiser's list (xu, cov_par, xy, mu, muu, cov_fun, fmax, obj_fun); maxit / tol are
+    newtrap_sparseGP's (they reach it through `...` in the reference)."""
+    ctx = ctx or default_context()
+    delta = (opt or {}).get("delta", 1e-6)
+    xy = L.fmat(laplace_opt["xy"])
+    xu = L.fmat(laplace_opt["xu"])
+    cand = L.fmat(np.asarray(pseudo_prop, dtype=np.float64).reshape(-1, xu.shape[1]))
+    sigma, l, tau, _ = _theta(laplace_opt["cov_par"], laplace_opt["cov_fun"], xy.shape[1])
+    ctx.set_data(xy, y, laplace_opt["mu"])
+    lv, fm = L.fvec(l), L.fvec(laplace_opt["fmax"])
+    scores = np.zeros(cand.shape[0])
+    L.check(ctx._lib.srgp_laplace_oat_scores(ctx.handle, FAMILIES[family], L.KERNELS[laplace_opt["cov_fun"]], L.ptr(xu),
+                                             xu.shape[0], L.ptr(cand), cand.shape[0], sigma, L.ptr(lv), tau, float(delta),
+                                             float(m), int(maxit), float(tol), L.ptr(fm), L.ptr(scores)))
+    vals = np.concatenate([np.repeat(laplace_opt["obj_fun"][-1], xu.shape[0]), scores])
+    vals = np.where(np.isnan(vals), -np.inf, vals)
+    pick = np.vstack([xu, cand])[int(np.argmax(vals))].reshape(1, -1)
+    return (pick, scores) if return_scores else pick
+
+
 def predict_laplace(u_mean, u_var, xu, x_pred, cov_fun, cov_par, mu, muu, full_cov=False, family="gaussian",
                     delta=1e-6, ctx=None):
     """R/laplace_approx_prediction.R:3-123 (same argument list), full_cov = FALSE."""

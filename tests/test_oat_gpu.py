@@ -76,3 +76,25 @@ def test_oat_duplicate_candidate_is_flagged(ctx):
         _, scores = ctx.oat_scores(model, "ard", c["xu"], cand, cp["sigma"], l, cp["tau"], 0.0)
         _, clean = ctx.oat_scores(model, "ard", c["xu"], cand[:3], cp["sigma"], l, cp["tau"], 0.0)
         np.testing.assert_allclose(scores[:3], clean, rtol=1e-12)
+
+
+@pytest.mark.parametrize("family", ["bernoulli", "poisson"])
+def test_laplace_oat_scores_match_per_candidate_newton(ctx, family):
+    """knot_prop_random's candidate loop (R/knot_proposal_functions.R:1096-1120) for the sparse Laplace models."""
+    from sparsergps_b200 import laplace as Lp
+    c = cases.config4(n=600, m=20)
+    if family == "poisson":
+        c["y"] = np.random.default_rng(3).poisson(np.exp(0.5 * np.sin(c["x"][:, 0]))).astype(np.float64)
+    cp = c["cov_par"]
+    kw = {"m": 1.0} if family == "poisson" else {}
+    fit = rm.newtrap_sparseGP(np.zeros(600), family, cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(20),
+                              maxit=40, tol=1e-5, delta=c["delta"], **kw)
+    cand = _candidates(c, 5)
+    ref = rm.laplace_oat_candidate_scores(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], family, c["mu"], np.zeros(20),
+                                          cand, c["delta"], maxit=40, tol=1e-5, **kw)
+    lo = dict(xu=c["xu"], cov_par=cp, xy=c["x"], mu=c["mu"], muu=np.zeros(20), cov_fun="ard", fmax=fit["gp"],
+              obj_fun=fit["objective_function_values"])
+    pick, scores = Lp.knot_prop_random(lo, cand, family, c["y"], opt={"delta": c["delta"]}, maxit=40, tol=1e-5, ctx=ctx,
+                                       return_scores=True)
+    np.testing.assert_allclose(scores, ref, rtol=1e-8)
+    np.testing.assert_array_equal(pick, rm.knot_prop_choice(c["xu"], cand, fit["objective_function_values"][-1], ref))
