@@ -40,11 +40,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmArgs g)
     A += A_KC ? (int64_t)kt0 * BK : (int64_t)kt0 * BK * g.lda;
     B += B_KC ? (int64_t)kt0 * BK : (int64_t)kt0 * BK * g.ldb;
     pipeline_init(sm);
+    uint32_t it = 0;
+    const int nk = max(0, kt1 - kt0);
+    if (is_producer()) {
+        reg_dec<PRODUCER_REGS>();
+        if (is_producer_lead()) producer_issue<A_KC, B_KC, false>(sm, A, g.lda, B, g.ldb, nullptr, nk, it);
+        return;
+    }
+    reg_inc<CONSUMER_REGS>();
     double acc[8][4][2];
     zero_acc(acc);
-    uint32_t it = 0;
-    mainloop<A_KC, B_KC, false>(sm, A, g.lda, B, g.ldb, nullptr, max(0, kt1 - kt0), it, acc);
-    if (is_producer()) return;
+    consumer_mma<A_KC, B_KC, false>(sm, nk, it, acc);
     double *C = g.C + blockIdx.z * g.sC + (int64_t)tm * BM + (int64_t)tn * BN * g.ldc;
     double *Ct = g.Ct ? g.Ct + blockIdx.z * g.sCt + (int64_t)tn * BN + (int64_t)tm * BM * g.ldct : nullptr;
 #pragma unroll

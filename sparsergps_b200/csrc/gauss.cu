@@ -187,11 +187,17 @@ syrk_chunk_kernel(const double *__restrict__ Kr, int mp, const double *__restric
     const double *A = Kr + (int64_t)tm * BM + k0 * mp;
     const double *B = Kr + (int64_t)tn * BN + k0 * mp;
     pipeline_init(sm);
+    uint32_t it = 0;
+    if (is_producer()) {
+        reg_dec<PRODUCER_REGS>();
+        if (is_producer_lead())
+            producer_issue<false, false, WEIGHT>(sm, A, mp, B, mp, WEIGHT ? w + k0 : nullptr, ktiles_per_split, it);
+        return;
+    }
+    reg_inc<CONSUMER_REGS>();
     double acc[8][4][2];
     zero_acc(acc);
-    uint32_t it = 0;
-    mainloop<false, false, WEIGHT>(sm, A, mp, B, mp, WEIGHT ? w + k0 : nullptr, ktiles_per_split, it, acc);
-    if (is_producer()) return;
+    consumer_mma<false, false, WEIGHT>(sm, ktiles_per_split, it, acc);
     // accumulate into this CTA's own slot, stored in fragment order (fully coalesced)
     double *slot = Gpart + ((int64_t)blockIdx.x * gridDim.y + split) * (BM * BN);
 #pragma unroll
@@ -279,26 +285,35 @@ struct KmArgs {
     //   last slot (vvec given) : sum_j K_ij v_j
     double *rowd_part;
     int nslots;
+    double sigma2;          // K_ij == sigma2 flags a candidate for the coincidence test
 };
 
 
-__device__ __noinline__ void record_coincident(const KmArgs &a, int i_local, int j, double p_ij)
+// Rare path of quirk Q4.  The epilogues flag entries whose K_ij equals sigma^2 bit for bit (exp(0) = 1: every
+// identical pair qualifies, and so does a pair closer than ~1e-8 length scales); this function decides by the
+// reference's own test -- all coordinates equal (src/covariance_function_derivativesC.cpp:157-163) -- and appends
+// (row, knot, Omega_ij).  Arguments by value: taking the address of the kernel parameter struct would move it to
+// local memory for the whole kernel.
+__device__ __noinline__ void record_if_coincident(const double *X, int64_t ldx, int64_t i_shard, const double *U, int m,
+                                                  int j, int d, int *coin_count, int *coin_list, double *coin_omega,
+                                                  int coin_cap, double omega_ij)
 {
-    const double k = a.Kc[i_local + (int64_t)j * a.ldc];
-    const int slot = atomicAdd(a.coin_count, 1);
-    if (slot < a.coin_cap) {
-        a.coin_list[2 * slot] = (int)(a.r0 + i_local);
-        a.coin_list[2 * slot + 1] = j;
-        a.coin_omega[slot] = p_ij / k;   // Omega_ij; k = sigma^2 > 0 for identical points
+    for (int c = 0; c < d; c++)
+        if (X[i_shard + ldx * c] != U[j + (int64_t)m * c]) return;
+    const int slot = atomicAdd(coin_count, 1);
+    if (slot < coin_cap) {
+        coin_list[2 * slot] = (int)i_shard;
+        coin_list[2 * slot + 1] = j;
+        coin_omega[slot] = omega_ij;
     }
 }
 
 enum { MODE_GRAD = 0, MODE_ROWFORM = 1, MODE_GRAD_KNOT = 2, MODE_ROWD = 3 };
 
-// this CTA's column sums of one finished column block (both warp rows) -> its rows of knot_part
+// this CTA's column sums of one finished column block (both warp rows) -> its rows of knot_part (consumer threads)
 __device__ __forceinline__ void flush_knot_sums(const KmArgs &a, const double *kn, int d, int j0, int tid)
 {
-    for (int t = tid; t < d * BN; t += THREADS) {
+    for (int t = tid; t < d * BN; t += CONSUMER_THREADS) {
         const int c = t / BN, jj = t - c * BN;
         double *slot = a.knot_part + ((int64_t)blockIdx.x * d + c) * a.mp + j0 + jj;
         const double v = kn[c * BN + jj] + kn[(d + c) * BN + jj];
@@ -327,7 +342,7 @@ __device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][
         }
     };
     // weighted row sums of the values currently in acc, for c = 0 (weight 1) and every dimension
-    auto sums = [&](int slot0, unsigned long long *eqmask) {
+    auto sums = [&](int slot0) {
         double s[8];
 #pragma unroll
         for (int mi = 0; mi < 8; mi++) {
@@ -354,7 +369,6 @@ __device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][
                     for (int e = 0; e < 2; e++) {
                         const double t = xv[mi] - uv[ni][e];
                         s[mi] = fma(acc[mi][ni][e], t * t, s[mi]);
-                        if (eqmask && t != 0.0) *eqmask &= ~(1ull << ((mi * 4 + ni) * 2 + e));
                     }
             }
             flush(slot0 + 1 + c, s);
@@ -365,17 +379,17 @@ __device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][
 #pragma unroll
     for (int mi = 0; mi < 8; mi++) {
         const int ii = frag_row(mi);
-        const bool iv = (i0 + ii) < a.rows_valid;
 #pragma unroll
         for (int ni = 0; ni < 4; ni++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int j = j0 + frag_col(ni) + e;
-                acc[mi][ni][e] *= a.Kc[i0 + ii + (int64_t)j * a.ldc];
-                if (iv && j < a.m) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
+                const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
+                acc[mi][ni][e] *= k;
+                if (k == a.sigma2) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
             }
     }
-    sums(0, &eqmask);
+    sums(0);
     if (eqmask) {
 #pragma unroll
         for (int mi = 0; mi < 8; mi++)
@@ -384,7 +398,9 @@ __device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][
 #pragma unroll
                 for (int e = 0; e < 2; e++)
                     if ((eqmask >> ((mi * 4 + ni) * 2 + e)) & 1ull)
-                        record_coincident(a, i0 + frag_row(mi), j0 + frag_col(ni) + e, acc[mi][ni][e]);
+                        record_if_coincident(a.X, a.ldx, a.r0 + i0 + frag_row(mi), a.U, a.m, j0 + frag_col(ni) + e, d,
+                                             a.coin_count, a.coin_list, a.coin_omega, a.coin_cap,
+                                             acc[mi][ni][e] / a.sigma2);
     }
     // phase 2: acc <- beta_j K_ij (and the K v row sums on the way)
     if (a.beta || a.vvec) {
@@ -404,7 +420,7 @@ __device__ __forceinline__ void rowd_epilogue(const KmArgs &a, double (&acc)[8][
                 }
         }
         if (a.vvec) flush(a.nslots - 1, skv);
-        if (a.beta) sums(d + 1, nullptr);
+        if (a.beta) sums(d + 1);
     }
 }
 
@@ -415,8 +431,8 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     // only the first d rows of xs / us are used; the struct is sized for SRGP_MAX_D but allocated for d
     double *xs = reinterpret_cast<double *>(smem_raw + sizeof(Smem));
-    double *us = xs + a.d * BM;
-    double *red = us + a.d * BN;
+    double *us2 = xs + a.d * BM;            // two buffers of d * BN: the producer warp stages the next column block
+    double *red = us2 + 2 * a.d * BN;
     const int d = DT > 0 ? DT : a.d;
     constexpr bool GRAD = (MODE == MODE_GRAD || MODE == MODE_GRAD_KNOT);
     constexpr bool KNOT = (MODE == MODE_GRAD_KNOT);
@@ -437,6 +453,16 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
             xs[c * BM + ii] = (i < a.rows_valid) ? a.X[a.r0 + i + a.ldx * c] * a.invl[c] : 0.0;
         }
     }
+    const int cb0 = blockIdx.y * a.col_blocks_per_cta;
+    // scaled knots of one column block -> dst (d x BN); `nthreads` threads with index t0 take part
+    auto stage_knots = [&](double *dst, int j0, int t0, int nthreads) {
+        for (int t = t0; t < d * BN; t += nthreads) {
+            const int c = t / BN, jj = t - c * BN;
+            const int j = j0 + jj;
+            dst[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
+        }
+    };
+    if (STAGE_XU) stage_knots(us2, cb0 * BN, tid, THREADS);
     if (!is_producer())
         for (int t = lane; t < PART_STRIDE; t += 32) red[warp * PART_STRIDE + t] = 0.0;
     if (KNOT)
@@ -444,7 +470,26 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
     __syncthreads();
 
     uint32_t it = 0;
-    const int cb0 = blockIdx.y * a.col_blocks_per_cta;
+    // ---- producer warpgroup: one __syncthreads per column block + the final one, like the consumers -------------
+    if (is_producer()) {
+        reg_dec<PRODUCER_REGS>();
+        for (int cbi = 0; cbi < a.col_blocks_per_cta; cbi++) {
+            const int j0 = (cb0 + cbi) * BN;
+            if (is_producer_lead()) {
+                producer_issue<false, false, false>(sm, a.Kc + i0, a.ldc, a.Mop + j0, a.mp, nullptr, a.mp / BK, it);
+                // Every k-tile of this block is issued while the consumers still work on the last STAGES of them:
+                // stage the NEXT block's knots now.  That buffer was last read in the epilogue of block cbi - 1,
+                // which every consumer warp left before it released its first stage of this block.
+                if (STAGE_XU && cbi + 1 < a.col_blocks_per_cta)
+                    stage_knots(us2 + ((cbi + 1) & 1) * d * BN, j0 + BN, lane, 32);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        return;
+    }
+    // ---- consumer warpgroups ---------------------------------------------------------------------------------
+    reg_inc<CONSUMER_REGS>();
     double rq[8], rkv[8];
 #pragma unroll
     for (int mi = 0; mi < 8; mi++) rq[mi] = rkv[mi] = 0.0;
@@ -453,20 +498,15 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
         const int j0 = cb * BN;
         double acc[8][4][2];
         zero_acc(acc);
-        mainloop<false, false, false>(sm, a.Kc + i0, a.ldc, a.Mop + j0, a.mp, nullptr, a.mp / BK, it, acc);
-        // stage this column block's knots (all 288 threads), consumers then run the epilogue
+        consumer_mma<false, false, false>(sm, a.mp / BK, it, acc);
         __syncthreads();
-        if (KNOT && cbi > 0) flush_knot_sums(a, kn, d, j0 - BN, tid);
-        if (STAGE_XU) {
-            for (int t = tid; t < d * BN; t += THREADS) {
-                const int c = t / BN, jj = t - c * BN;
-                const int j = j0 + jj;
-                us[c * BN + jj] = (j < a.m) ? a.U[j + (int64_t)a.m * c] * a.invl[c] : 0.0;
-            }
-            __syncthreads();
+        const double *us = us2 + (cbi & 1) * d * BN;
+        if (KNOT && cbi > 0) {
+            flush_knot_sums(a, kn, d, j0 - BN, tid);
+            consumer_bar();   // kn is rewritten by this block's epilogue
         }
         if (MODE == MODE_ROWD) {
-            if (!is_producer()) rowd_epilogue<DT>(a, acc, xs, us, d, i0, j0);
+            rowd_epilogue<DT>(a, acc, xs, us, d, i0, j0);
             continue;
         }
         if (MODE == MODE_ROWFORM) {
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
                         const double k = a.Kc[i0 + ii + (int64_t)j * a.ldc];
                         const double om = fma(rsi, acc[mi][ni][e], rai * a.beta[j]);
                         acc[mi][ni][e] = om * k;
-                        if (iv && j < a.m) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
+                        if (k == a.sigma2) eqmask |= 1ull << ((mi * 4 + ni) * 2 + e);
                     }
                 }
             }
@@ -527,7 +567,7 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
                     uv[ni][0] = us[c * BN + frag_col(ni)];
                     uv[ni][1] = us[c * BN + frag_col(ni) + 1];
                 }
-                double sc = 0.0;
+                double scp[4] = {0.0, 0.0, 0.0, 0.0};   // four independent chains, not one of 64 dependent FMAs
                 double kc[4][2];
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) kc[ni][0] = kc[ni][1] = 0.0;
@@ -538,10 +578,10 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
                             const double t = xv[mi] - uv[ni][e];
-                            sc = fma(acc[mi][ni][e], t * t, sc);
+                            scp[ni] = fma(acc[mi][ni][e], t * t, scp[ni]);
                             if (KNOT) kc[ni][e] = fma(acc[mi][ni][e], t, kc[ni][e]);
-                            if (t != 0.0) eqmask &= ~(1ull << ((mi * 4 + ni) * 2 + e));
                         }
+                double sc = (scp[0] + scp[1]) + (scp[2] + scp[3]);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
                 if (lane == 0) red[warp * PART_STRIDE + 1 + c] += sc;
@@ -562,9 +602,9 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
             if (lane == 0) red[warp * PART_STRIDE + 0] += s0;
-            // quirk Q4: bit-identical data row / knot pairs (rare): record them for the tau derivative.
-            // The selection is fully unrolled so that acc[][][] is never indexed dynamically (that would
-            // move the accumulators to local memory for the whole kernel).
+            // quirk Q4: bit-identical data row / knot pairs (rare): record them for the tau derivative.  Candidates
+            // are the entries with K_ij == sigma^2; the selection is fully unrolled so that acc[][][] is never
+            // indexed dynamically (that would move the accumulators to local memory for the whole kernel).
             if (eqmask) {
 #pragma unroll
                 for (int mi = 0; mi < 8; mi++)
@@ -573,7 +613,9 @@ __global__ void __launch_bounds__(THREADS, 1) km_reduce_kernel(KmArgs a)
 #pragma unroll
                         for (int e = 0; e < 2; e++)
                             if ((eqmask >> ((mi * 4 + ni) * 2 + e)) & 1ull)
-                                record_coincident(a, i0 + frag_row(mi), j0 + frag_col(ni) + e, acc[mi][ni][e]);
+                                record_if_coincident(a.X, a.ldx, a.r0 + i0 + frag_row(mi), a.U, a.m,
+                                                     j0 + frag_col(ni) + e, d, a.coin_count, a.coin_list, a.coin_omega,
+                                                     a.coin_cap, acc[mi][ni][e] / a.sigma2);
             }
         }
     }
@@ -1004,7 +1046,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
     const bool grad_like = (mode == MODE_GRAD || mode == MODE_GRAD_KNOT);
-    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE +
+    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + 2 * BN) + CONSUMER_WARPS * PART_STRIDE +
                                                          (mode == MODE_GRAD_KNOT ? (size_t)2 * d * BN : 0));
     if (smem > 227 * 1024) {
         set_error("d = %d needs %zu bytes of shared memory in the K*M pass (limit 227 KB)", d, smem);
@@ -1099,6 +1141,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
             a.knot_part = mode == MODE_GRAD_KNOT ? w->knotpart.d() : nullptr;
             a.rowd_part = mode == MODE_ROWD ? w->rowdpart.d() : nullptr;
             a.nslots = nslots;
+            a.sigma2 = gp.sigma2;
             dim3 grid(w->rblocks, w->cgroups);
             if (mode == MODE_GRAD_KNOT) {
 #define CALL(D) km_reduce_kernel<D, MODE_GRAD_KNOT><<<grid, THREADS, smem, s>>>(a)
@@ -1162,11 +1205,11 @@ int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, 
 {
     cudaStream_t s = ctx->stream;
     const int d = 1;
-    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + BN) + CONSUMER_WARPS * PART_STRIDE);
+    const size_t smem = sizeof(Smem) + sizeof(double) * ((size_t)d * (BM + 2 * BN) + CONSUMER_WARPS * PART_STRIDE);
     static DeviceOnce once;
     if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(km_reduce_kernel<1, MODE_ROWFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(Smem) + sizeof(double) * (8 * (BM + BN) + CONSUMER_WARPS * PART_STRIDE))));
+                                       (int)(sizeof(Smem) + sizeof(double) * (8 * (BM + 2 * BN) + CONSUMER_WARPS * PART_STRIDE))));
     KmArgs a = {};
     a.Kc = w->chunk.d();
     a.ldc = w->rows2;

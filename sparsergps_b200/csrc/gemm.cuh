@@ -26,7 +26,13 @@ constexpr int LDKC = BK + 4;   // K-contiguous shared row stride (doubles)
 constexpr int TILE_DOUBLES = BM * LDKC;   // 2560 >= BK * LDMN = 2112
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int THREADS = CONSUMER_THREADS + 32;   // + 1 producer warp
+// + one producer WARPGROUP.  Only its first warp issues copies; the group exists so that registers can move between
+// the roles (setmaxnreg works on warpgroups): a CTA of 384 threads starts with 168 registers per thread, the producer
+// group drops to 40 and the two consumer groups rise to 232 -- enough for 64 accumulators plus double-buffered
+// fragments, where 168 made ptxas rotate accumulators through ~100 moves per k-tile and spill in the main loop.
+constexpr int PRODUCER_THREADS = 128;
+constexpr int THREADS = CONSUMER_THREADS + PRODUCER_THREADS;
+constexpr int CONSUMER_REGS = 232, PRODUCER_REGS = 40;
 
 struct __align__(128) Smem {
     double a[STAGES][TILE_DOUBLES];
@@ -80,6 +86,16 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+template <int N>
+__device__ __forceinline__ void reg_inc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
 
 // ---- pipeline state -------------------------------------------------------------------------------
@@ -99,6 +115,7 @@ __device__ __forceinline__ void pipeline_init(Smem &sm)
 }
 
 __device__ __forceinline__ bool is_producer() { return threadIdx.x >= CONSUMER_THREADS; }
+__device__ __forceinline__ bool is_producer_lead() { return (threadIdx.x >> 5) == CONSUMER_WARPS; }
 
 // Accumulator fragment coordinates of this thread inside the 128 x 128 CTA tile.
 __device__ __forceinline__ int frag_row(int mi)
@@ -115,46 +132,55 @@ __device__ __forceinline__ int frag_col(int ni)   // column of element 0; elemen
 // acc += op(A)[128 x K] * op(B)[128 x K]^T over `ktiles` k-tiles starting at the given tile origins.
 //   A_KC / B_KC : operand is K-contiguous (see header).   WEIGHT : B fragments are scaled by w[k].
 // A, B point at the tile origin: MN-contiguous -> &p[mn0 + k0*ld]; K-contiguous -> &p[k0 + mn0*ld].
+// The two halves of the main loop.  Kernels split into roles right after their common prologue:
+//     if (is_producer()) { reg_dec<PRODUCER_REGS>(); if (is_producer_lead()) producer_issue(...); ... return; }
+//     reg_inc<CONSUMER_REGS>(); ... consumer_mma(...); epilogue
+// A, B point at the tile origin: MN-contiguous -> &p[mn0 + k0*ld]; K-contiguous -> &p[k0 + mn0*ld].
+//   A_KC / B_KC : operand is K-contiguous (see header).   WEIGHT : B fragments are scaled by w[k].
 template <bool A_KC, bool B_KC, bool WEIGHT>
-__device__ __forceinline__ void mainloop(Smem &sm, const double *__restrict__ A, int64_t lda,
-                                         const double *__restrict__ B, int64_t ldb, const double *__restrict__ w,
-                                         int ktiles, uint32_t &it, double (&acc)[8][4][2])
+__device__ __forceinline__ void producer_issue(Smem &sm, const double *__restrict__ A, int64_t lda,
+                                               const double *__restrict__ B, int64_t ldb, const double *__restrict__ w,
+                                               int ktiles, uint32_t &it)
 {
     const int lane = threadIdx.x & 31;
-    if (is_producer()) {
-        constexpr uint32_t bytes = (uint32_t)(2 * BM * BK * sizeof(double)) + (WEIGHT ? BK * sizeof(double) : 0);
-        for (int kt = 0; kt < ktiles; kt++, it++) {
-            const int s = it % STAGES;
-            const uint32_t round = it / STAGES;
-            if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1);
-            if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);
-            __syncwarp();
-            const int64_t k0 = (int64_t)kt * BK;
-            if (!A_KC) {
-                if (lane < BK) bulk_g2s(&sm.a[s][lane * LDMN], A + (k0 + lane) * lda, BM * sizeof(double), &sm.full[s]);
-            } else {
+    constexpr uint32_t bytes = (uint32_t)(2 * BM * BK * sizeof(double)) + (WEIGHT ? BK * sizeof(double) : 0);
+    for (int kt = 0; kt < ktiles; kt++, it++) {
+        const int s = it % STAGES;
+        const uint32_t round = it / STAGES;
+        if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1);
+        if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);
+        __syncwarp();
+        const int64_t k0 = (int64_t)kt * BK;
+        if (!A_KC) {
+            if (lane < BK) bulk_g2s(&sm.a[s][lane * LDMN], A + (k0 + lane) * lda, BM * sizeof(double), &sm.full[s]);
+        } else {
 #pragma unroll
-                for (int r = 0; r < BM / 32; r++) {
-                    const int row = lane + 32 * r;
-                    bulk_g2s(&sm.a[s][row * LDKC], A + k0 + (int64_t)row * lda, BK * sizeof(double), &sm.full[s]);
-                }
+            for (int r = 0; r < BM / 32; r++) {
+                const int row = lane + 32 * r;
+                bulk_g2s(&sm.a[s][row * LDKC], A + k0 + (int64_t)row * lda, BK * sizeof(double), &sm.full[s]);
             }
-            if (!B_KC) {
-                if (lane >= 32 - BK) {
-                    const int row = lane - (32 - BK);
-                    bulk_g2s(&sm.b[s][row * LDMN], B + (k0 + row) * ldb, BN * sizeof(double), &sm.full[s]);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < BN / 32; r++) {
-                    const int row = lane + 32 * r;
-                    bulk_g2s(&sm.b[s][row * LDKC], B + k0 + (int64_t)row * ldb, BK * sizeof(double), &sm.full[s]);
-                }
-            }
-            if (WEIGHT && lane == 0) bulk_g2s(&sm.w[s][0], w + k0, BK * sizeof(double), &sm.full[s]);
         }
-        return;
+        if (!B_KC) {
+            if (lane >= 32 - BK) {
+                const int row = lane - (32 - BK);
+                bulk_g2s(&sm.b[s][row * LDMN], B + (k0 + row) * ldb, BN * sizeof(double), &sm.full[s]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < BN / 32; r++) {
+                const int row = lane + 32 * r;
+                bulk_g2s(&sm.b[s][row * LDKC], B + k0 + (int64_t)row * ldb, BK * sizeof(double), &sm.full[s]);
+            }
+        }
+        if (WEIGHT && lane == 0) bulk_g2s(&sm.w[s][0], w + k0, BK * sizeof(double), &sm.full[s]);
     }
+}
+
+// acc += op(A)[128 x K] * op(B)[128 x K]^T over `ktiles` k-tiles (consumer warps)
+template <bool A_KC, bool B_KC, bool WEIGHT>
+__device__ __forceinline__ void consumer_mma(Smem &sm, int ktiles, uint32_t &it, double (&acc)[8][4][2])
+{
+    const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int am = (warp & 1) * 64 + g;    // + mi*8
