@@ -804,12 +804,13 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->d = d;
     w->nt = mp / BM;
     w->pairs = w->nt * (w->nt + 1) / 2;
-    // pass 1: pairs x splits CTAs ~ one wave; chunk ~ 48 MB so it stays in the 126 MB L2 with the Gram slots
+    // pass 1: pairs x splits CTAs ~ one wave; a 96 MB chunk plus the Gram slots (19 MB) still fits the 126 MB L2
+    // (sweep in profiles/r01_chunk_sweep.txt: 64 / 96 / 128 MB -> 110.7 / 110.1 / 109.7 ms per evaluation)
     w->splits = std::max(1, ctx->sm_count / w->pairs);
     if (w->splits > 64) w->splits = 64;
     // 64 MB per buffer (two buffers): measured sweep 24..160 MB in profiles/r01_chunk_sweep.txt -- larger chunks
     // mean fewer launches / pipeline fills; beyond L2 the re-reads come from HBM, which has headroom here
-    int64_t chunk_mb = 64;
+    int64_t chunk_mb = 96;
     if (const char *e = getenv("SRGP_CHUNK_MB")) chunk_mb = std::max(4, atoi(e));
     const int64_t target_bytes = chunk_mb << 20;
     int64_t rows = target_bytes / (8 * (int64_t)mp);
