@@ -7,10 +7,13 @@
  *     src/covariance_function_derivativesC.cpp   (dsig_dthetaC, dsig_dtheta_ardC, helpers)
  * Every function cites the reference file:line whose operation order it follows.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
- * fixtures and R is not installed in this image, so the
- * reference itself cannot be run.  This file is pinned only against analytic
- * known answers derived from the formulas (tests/test_oracle.py).
+ * PARITY PINNED (this file only): the reference ships no golden vectors and R is
+ * not installed here, but its two C++ sources compile unmodified against a small
+ * Rcpp stand-in header (oracle/rcpp_shim/Rcpp.h -> oracle/_ref/, oracle/ref_native.py).
+ * tests/test_reference_pin.py checks this restatement BIT FOR BIT against that
+ * compiled reference on fresh seeded inputs and against the vectors recorded from
+ * it (tests/golden/rcpp_layer.*, tools/make_golden.py), plus the analytic known
+ * answers of tests/test_oracle.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product never does.

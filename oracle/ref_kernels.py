@@ -4,7 +4,8 @@ Mirrors the R-level signatures of the reference's Rcpp exports
 (R/RcppExports.R:7-127 -> src/covariance_functionsC.cpp, src/covariance_function_derivativesC.cpp)
 on NumPy arrays, evaluated by the plain-C restatement in ref_kernels.c on the CPU.
 
-PARITY UNPINNED: see the header of ref_kernels.c.
+PARITY PINNED against the reference's own compiled sources (oracle/ref_native.py, tests/test_reference_pin.py):
+see the header of ref_kernels.c.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """

@@ -7,8 +7,10 @@ Restates, statement by statement, the pure-R functions of luisdamiano/sparseRGPs
 (SURVEY.md Appendix C).  The dense covariance / derivative matrices come from the C restatement of the Rcpp
 kernels (ref_kernels.c) exactly as the R code obtains them through `.Call`.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path and R is not
-installed here, so nothing in this file has been compared with output of the reference itself.  It is pinned
+PARITY UNPINNED for the R-level algebra in this file: the reference ships no tests, golden vectors or fixtures
+for this path and no R interpreter exists here, so the model algebra below has not been compared with output of
+the reference itself. (The Rcpp layer it calls -- make_cov_mat*C, dsig_dtheta*C via oracle/ref_kernels.py -- IS
+pinned bit for bit against the reference's compiled C++ sources, tests/test_reference_pin.py.)  It is pinned
 against (i) analytic known answers, (ii) finite differences of its own Gaussian objectives, (iii) the
 independent reduced-form algebra in oracle/reduced_model.py (tests/test_oracle.py).
 

@@ -187,7 +187,11 @@ static SEXP deriv_list(double deriv, double par)
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)), nm = PROTECT(Rf_allocVector(STRSXP, 3));
     SET_VECTOR_ELT(out, 0, Rf_ScalarReal(deriv));
     SET_VECTOR_ELT(out, 1, Rf_ScalarReal(log(par)));
-    SET_VECTOR_ELT(out, 2, Rf_ScalarReal(par));
+    /* inv_trans_par = real_to_pos(par) on the UNtransformed value, i.e. exp(par)
+       (src/covariance_function_derivativesC.cpp:49,80,101,136,168; golden vectors in tests/golden) */
+    double inv;
+    srgp_real_to_pos(&par, 1, &inv);
+    SET_VECTOR_ELT(out, 2, Rf_ScalarReal(inv));
     SET_STRING_ELT(nm, 0, Rf_mkChar("derivative"));
     SET_STRING_ELT(nm, 1, Rf_mkChar("trans_par"));
     SET_STRING_ELT(nm, 2, Rf_mkChar("inv_trans_par"));

@@ -163,8 +163,10 @@ def cov_fun_expC(x1, x2, cov_par):
 
 
 def _deriv_list(value, par):
-    # the Rcpp helpers return list(derivative, trans_par = log(par), inv_trans_par = par)
-    return {"derivative": value, "trans_par": float(np.log(par)), "inv_trans_par": float(par)}
+    # the Rcpp helpers return list(derivative, trans_par = log(par), inv_trans_par = real_to_pos(par)): the R
+    # closure is applied to the UNtransformed value, i.e. exp(par), not par
+    # (src/covariance_function_derivativesC.cpp:49,80,101,136,168 -- pinned by tests/golden/rcpp_layer.json)
+    return {"derivative": value, "trans_par": float(np.log(par)), "inv_trans_par": float(real_to_pos([par])[0])}
 
 
 def dsqexp_dsigmaC(x1, x2, cov_par):

@@ -1,4 +1,5 @@
-"""Pin the oracle (the reference ships no golden vectors -> 'parity unpinned'):
+"""Pin the oracle's R-level algebra (no R here -> 'parity unpinned' for it; the Rcpp layer is
+pinned against the compiled reference in tests/test_reference_pin.py):
 analytic known answers, quirks, finite differences of the Gaussian objectives, and literal == reduced form."""
 import math
 
