@@ -2,9 +2,10 @@
  * r/shim.c -- the R-side glue a sparseRGPs maintainer adds to bind libsrgp.so behind the package's own
  * `.Call` routines (replaces src/RcppExports.cpp + the two Rcpp kernel files of the reference).
  *
- * NOT COMPILED IN THIS REPOSITORY'S IMAGE: R (Rinternals.h, libR) is not installed.
- * It is marshalling only; every numerical statement lives behind include/srgp.h, which tests/ exercise through
- * ctypes.  Build inside the package:   PKG_LIBS = -L<dir> -lsrgp   (src/Makevars), keep R/RcppExports.R as is.
+ * R (Rinternals.h, libR) is not installed in this repository's image; this file is compiled
+ * and run unchanged against the miniature R C API of tests/mini_r/ (tests/test_r_shim.py: registration table,
+ * coercion, golden vectors of the reference through .Call, R errors, PROTECT balance).  It is marshalling only;
+ * every numerical statement lives behind include/srgp.h.  Build inside the package:   PKG_LIBS = -L<dir> -lsrgp   (src/Makevars), keep R/RcppExports.R as is.
  *
  * Registered routine names and arities are those of src/RcppExports.cpp:285-304, so R/RcppExports.R loads
  * unchanged.  Error conventions: status != 0 -> Rf_error, EXCEPT unknown kernel /
@@ -163,18 +164,21 @@ SEXP _sparseRGPs_real_to_bounded(SEXP x, SEXP ub, SEXP lb)
     return out;
 }
 
+/* Rcpp's input_parameter<NumericVector> coerces integer / logical vectors to double: the registered entry points
+   (generated at the end of this section) coerce and PROTECT the vector arguments, then call impl_<name>. */
+
 /* scalar covariance functions: (x1, x2, cov_par[, lnames]) -> double */
-SEXP _sparseRGPs_cov_fun_sqrd_expC(SEXP x1, SEXP x2, SEXP cov_par)
+static SEXP impl_cov_fun_sqrd_expC(SEXP x1, SEXP x2, SEXP cov_par)
 {
     return Rf_ScalarReal(srgp_cov_fun_sqrd_exp(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"),
                                                list_get(cov_par, "l")));
 }
-SEXP _sparseRGPs_cov_fun_expC(SEXP x1, SEXP x2, SEXP cov_par)
+static SEXP impl_cov_fun_expC(SEXP x1, SEXP x2, SEXP cov_par)
 {
     return Rf_ScalarReal(srgp_cov_fun_exp(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"),
                                           list_get(cov_par, "l")));
 }
-SEXP _sparseRGPs_cov_fun_sqrd_exp_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+static SEXP impl_cov_fun_sqrd_exp_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
 {
     double l[SRGP_MAX_D];
     for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
@@ -200,7 +204,7 @@ static SEXP deriv_list(double deriv, double par)
     return out;
 }
 #define PAIR_SCALAR(NAME, FN, PARNAME)                                                                         \
-    SEXP _sparseRGPs_##NAME(SEXP x1, SEXP x2, SEXP cov_par)                                                    \
+    static SEXP impl_##NAME(SEXP x1, SEXP x2, SEXP cov_par)                                                      \
     {                                                                                                          \
         return deriv_list(FN(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), list_get(cov_par, "l")), \
                           list_get(cov_par, PARNAME));                                                         \
@@ -209,22 +213,22 @@ PAIR_SCALAR(dsqexp_dsigmaC, srgp_dsqexp_dsigma, "sigma")
 PAIR_SCALAR(dsqexp_dlC, srgp_dsqexp_dl, "l")
 PAIR_SCALAR(dexp_dsigmaC, srgp_dexp_dsigma, "sigma")
 PAIR_SCALAR(dexp_dlC, srgp_dexp_dl, "l")
-SEXP _sparseRGPs_dsqexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+static SEXP impl_dsqexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
 {
     return deriv_list(srgp_dsqexp_dtau(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "tau")), list_get(cov_par, "tau"));
 }
-SEXP _sparseRGPs_dexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+static SEXP impl_dexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
 {
     return deriv_list(srgp_dexp_dtau(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "tau")), list_get(cov_par, "tau"));
 }
-SEXP _sparseRGPs_dsqexp_dsigma_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+static SEXP impl_dsqexp_dsigma_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
 {
     double l[SRGP_MAX_D];
     for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
     return deriv_list(srgp_dsqexp_dsigma_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l),
                       list_get(cov_par, "sigma"));
 }
-SEXP _sparseRGPs_dsqexp_dl_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames, SEXP comp)
+static SEXP impl_dsqexp_dl_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames, SEXP comp)
 {
     double l[SRGP_MAX_D];
     for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
@@ -245,14 +249,14 @@ static SEXP dx2_list(SEXP x2, SEXP lb, SEXP ub, const double *deriv, const doubl
     UNPROTECT(5);
     return out;
 }
-SEXP _sparseRGPs_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
+static SEXP impl_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
 {
     double deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
     srgp_dsqexp_dx2(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), list_get(cov_par, "l"), REAL(lb),
                     REAL(ub), deriv, tp);
     return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
 }
-SEXP _sparseRGPs_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub, SEXP lnames)
+static SEXP impl_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub, SEXP lnames)
 {
     double l[SRGP_MAX_D], deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
     for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
@@ -260,7 +264,117 @@ SEXP _sparseRGPs_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP u
     return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
 }
 
-/* ---- new fused entry points (R/patches/*.R delegate to them; the R signatures stay as they are) ---------- */
+/* registered entry points of the per-pair helpers: coerce x1, x2 (and lb, ub) like Rcpp, keep them protected */
+SEXP _sparseRGPs_cov_fun_sqrd_expC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_cov_fun_sqrd_expC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_cov_fun_expC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_cov_fun_expC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_cov_fun_sqrd_exp_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_cov_fun_sqrd_exp_ardC(x1, x2, cov_par, lnames);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dsqexp_dtauC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dexp_dtauC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dsigma_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dsqexp_dsigma_ardC(x1, x2, cov_par, lnames);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dl_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames, SEXP comp)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dsqexp_dl_ardC(x1, x2, cov_par, lnames, comp);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    lb = PROTECT(Rf_coerceVector(lb, REALSXP));
+    ub = PROTECT(Rf_coerceVector(ub, REALSXP));
+    SEXP r = impl_dsqexp_dx2C(x1, x2, cov_par, lb, ub);
+    UNPROTECT(4);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub, SEXP lnames)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    lb = PROTECT(Rf_coerceVector(lb, REALSXP));
+    ub = PROTECT(Rf_coerceVector(ub, REALSXP));
+    SEXP r = impl_dsqexp_dx2_ardC(x1, x2, cov_par, lb, ub, lnames);
+    UNPROTECT(4);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dsigmaC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dsqexp_dsigmaC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dsqexp_dlC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dsqexp_dlC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dexp_dsigmaC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dexp_dsigmaC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+SEXP _sparseRGPs_dexp_dlC(SEXP x1, SEXP x2, SEXP cov_par)
+{
+    x1 = PROTECT(Rf_coerceVector(x1, REALSXP));
+    x2 = PROTECT(Rf_coerceVector(x2, REALSXP));
+    SEXP r = impl_dexp_dlC(x1, x2, cov_par);
+    UNPROTECT(2);
+    return r;
+}
+
+/* ---- new fused entry points (r/patches.R delegates to them; the R signatures stay as they are) ---------- */
 /* .Call("_sparseRGPs_gauss_obj_grad", model, cov_fun, xy, y, mu, xu, cov_par, delta, lnames)
      -> list(objective =, gradient = named numeric)  : one iteration's elbo_fun + delbo_dcov_par (model 0) or
         obj_fun_norm + dlogp_dcov_par (model 1).  A failed Cholesky raises an R error (SRGP_ERR_NOT_PD), which
