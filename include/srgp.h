@@ -46,7 +46,14 @@ enum srgp_par { SRGP_PAR_SIGMA = 0, SRGP_PAR_L = 1, SRGP_PAR_TAU = 2, SRGP_PAR_L
 enum srgp_model { SRGP_VI = 0, SRGP_FIC = 1 };
 enum srgp_family { SRGP_BERNOULLI = 0, SRGP_POISSON = 1 };
 
-#define SRGP_MAX_D 64           /* input dimension limit of the GPU kernels */
+#define SRGP_MAX_D 64           /* input dimension limit of the assembly kernels (srgp_make_cov_mat, srgp_dsig_dtheta,
+                                   trace / Omega o dK reductions) */
+#define SRGP_MAX_D_FUSED 20     /* fused objective+gradient / Laplace / predict passes: the K*M epilogue stages the
+                                   coordinates of its row tile and two knot blocks in shared memory, 3 KB per
+                                   dimension beside the 4-stage operand pipeline (227 KB per CTA) */
+#define SRGP_MAX_D_FUSED_KNOTS 12 /* the same passes with the knot-location gradient (+2 KB per dimension).
+                                   Larger d returns SRGP_ERR_ARG with the byte count in srgp_last_error(). The
+                                   reference's own examples use d <= 8 (airfoil 5, ccpp 4, copper wire 8). */
 #define SRGP_UNIQUE_ID_BYTES 128
 
 typedef struct srgp_ctx srgp_ctx;

@@ -82,3 +82,27 @@ def test_error_behaviour(ctx):
     st = fresh._lib.srgp_make_cov_mat(fresh.handle, 9, L.ptr(xu), 3, None, 0, 2, 1.0, L.ptr(l), 0.5, 0.0, L.ptr(np.zeros((3, 3), order="F")))
     assert st == L.ERR_UNKNOWN_KERNEL
     fresh.close()
+
+
+@pytest.mark.parametrize("model", ["vi", "fic"])
+def test_dimension_limits_of_the_fused_passes(ctx, model):
+    """include/srgp.h: SRGP_MAX_D_FUSED = 20 (12 with the knot gradient); beyond it SRGP_ERR_ARG, never a wrong answer."""
+    from oracle import reduced_model as red
+    from sparsergps_b200 import _lib as L
+    n, m = 700, 40
+    for d, knots, ok in [(20, False, True), (12, True, True), (21, False, False), (13, True, False)]:
+        x, y, xu, cp = _problem(n, m, d, 900 + d)
+        ctx.set_data(x, y, None)
+        args = ("ard", xu, cp["sigma"], cases.lvec(cp), cp["tau"], 1e-4)
+        if not ok:
+            with pytest.raises(RuntimeError, match="shared memory"):
+                ctx.gauss_obj_grad_knots(model, *args, red.knot_bounds(x)) if knots else ctx.gauss_obj_grad(model, *args)
+            continue
+        f = red.vi_obj_grad if model == "vi" else red.fic_obj_grad
+        ref = f(x, y, np.zeros(n), xu, cp["sigma"], cases.lvec(cp), cp["tau"], 1e-4, knots=knots)
+        if knots:
+            obj, grad, kg, _ = ctx.gauss_obj_grad_knots(model, *args, red.knot_bounds(x))
+            np.testing.assert_allclose(kg.reshape(m, d), ref[2], rtol=1e-7, atol=1e-9 * np.abs(ref[2]).max())
+        else:
+            obj, grad = ctx.gauss_obj_grad(model, *args)
+        _check(obj, grad, ref[0], ref[1], list(cp))
