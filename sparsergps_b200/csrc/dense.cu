@@ -121,6 +121,7 @@ potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *_
     double *Ls = sh;                   // NB x DLD: the factor, for the inverse phase
     double *vec = Ls + NB * DLD;       // 2 x NB double-buffered broadcast vector
     double *diag = vec + 2 * NB;       // NB pivots
+    double *rdiag = diag + NB;         // NB reciprocal pivots (no division in either column loop)
     __shared__ double red[8];
     const int tid = threadIdx.x;
     const int ti = tid & 15, tk = tid >> 4;
@@ -142,16 +143,20 @@ potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *_
             // the 16 owners of column j sit in one half-warp (tk == jt); the pivot owner is its lane ti == jt
             const double piv = __shfl_sync(0xffffffffu, a[jb][jb], (lane & 16) + jt);
             if (tk == jt) {
-                const double dj = sqrt(piv);
+                // 1/sqrt and one multiply instead of sqrt followed by a division: the pivot computation is the
+                // serial part of every column step (rsqrt is within 1 ulp; L_jj = piv / sqrt(piv) within 2)
+                const double rj = rsqrt(piv);
+                const double dj = piv * rj;
                 if (ti == jt) {
                     if (!(piv > 0.0) && *info == 0) *info = col0 + j + 1;
                     diag[j] = dj;
+                    rdiag[j] = rj;
                 }
 #pragma unroll
                 for (int ii = 0; ii < 8; ii++) {
                     const int i = ti + 16 * ii;
                     double v = 0.0;
-                    if (ii > jb || (ii == jb && ti > jt)) v = a[ii][jb] / dj;
+                    if (ii > jb || (ii == jb && ti > jt)) v = a[ii][jb] * rj;
                     else if (ii == jb && ti == jt) v = dj;
                     if (ii >= jb) a[ii][jb] = v;
                     cv[i] = (i > j) ? v : 0.0;
@@ -208,7 +213,7 @@ potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *_
             const int j = jb * 16 + jt;
             double *rv = vec + (j & 1) * NB;
             if (ti == jt) {                                      // owners of row j (16 threads, one per tk)
-                const double inv = 1.0 / diag[j];
+                const double inv = rdiag[j];
 #pragma unroll
                 for (int kk = 0; kk < 8; kk++) {
                     double v = 0.0;
@@ -261,7 +266,7 @@ __global__ void sum_parts_kernel(const double *parts, int n, double *out)
 int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, int *info, double *logdet)
 {
     static DeviceOnce once;
-    const size_t smem = sizeof(double) * (NB * DLD + 3 * NB);   // factor + 2 broadcast vectors + pivots
+    const size_t smem = sizeof(double) * (NB * DLD + 4 * NB);   // factor + 2 broadcast vectors + pivots + reciprocals
     if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nb = mp / NB;
