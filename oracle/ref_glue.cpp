@@ -9,8 +9,8 @@
 // It also binds the two R closures the reference resolves through Rcpp::Function (R/RcppExports.R:12-14,24-26)
 // to the same translation unit's C++ functions, which is what the installed package does.
 //
-// Built by oracle/ref_build.py into oracle/_ref/libsparseRGPs_ref.so (git-ignored, travels with gpurun).
-// Only tests/, tools/make_golden.py and bench.py's CPU legs load it.
+// Built by oracle/ref_native.py (build()) into oracle/_ref/libsparseRGPs_ref.so (git-ignored, travels with gpurun).
+// Only tests/ (and tests/tools/make_golden.py) load it.
 #include <Rcpp.h>
 
 #include <cstring>

@@ -12,7 +12,7 @@
  * Rcpp stand-in header (oracle/rcpp_shim/Rcpp.h -> oracle/_ref/, oracle/ref_native.py).
  * tests/test_reference_pin.py checks this restatement BIT FOR BIT against that
  * compiled reference on fresh seeded inputs and against the vectors recorded from
- * it (tests/golden/rcpp_layer.*, tools/make_golden.py), plus the analytic known
+ * it (tests/golden/rcpp_layer.*, tests/tools/make_golden.py), plus the analytic known
  * answers of tests/test_oracle.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl

@@ -9,7 +9,7 @@ R/RcppExports.R:7-127 on NumPy arrays and call the compiled reference code.
 What this pins: every per-element kernel and the four matrix builders of SURVEY.md 8(a) rows a1-a13 (the whole
 Rcpp layer). What it cannot pin: the R-level model algebra (rows a14-a25), for which no R interpreter exists here.
 
-Only tests/, tools/make_golden.py, __graft_entry__.build() and bench.py's CPU legs may import this.
+Only tests/, tests/tools/make_golden.py, __graft_entry__.build() and bench.py's CPU legs may import this.
 """
 from __future__ import annotations
 

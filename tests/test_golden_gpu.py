@@ -1,5 +1,5 @@
 """K1 / K2 against the REFERENCE's own output: the CUDA assembly kernels, called through the C ABI, reproduce the
-golden vectors recorded from the compiled reference sources (tests/golden, tools/make_golden.py) to the north-star
+golden vectors recorded from the compiled reference sources (tests/golden, tests/tools/make_golden.py) to the north-star
 tolerance: rel 1e-10 per K / dK entry; zeros, shapes and the coincidence pattern exactly."""
 import numpy as np
 import pytest

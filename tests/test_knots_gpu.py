@@ -82,7 +82,7 @@ def test_knot_gradient_all_knots_against_reduced_oracle(ctx, model, shape):
     assert obj == pytest.approx(obj_ref, rel=RTOL)
     _close(grad, [g_ref[k] for k in cp])
     # m*d = 8192 entries spanning orders of magnitude: the gradient VECTOR is held to 1e-8 of its largest entry
-    # (tools/dbg_knots.py: 6e-11 (VI) / 2e-10 (FIC) here, and closer to a long-double evaluation than this NumPy
+    # (tests/tools/dbg_knots.py: 6e-11 (VI) / 2e-10 (FIC) here, and closer to a long-double evaluation than this NumPy
     # yardstick wherever long double is affordable)
     kg = kg.reshape(m, -1)
     assert np.abs(kg - kg_ref).max() <= RTOL * np.abs(kg_ref).max()

@@ -1,7 +1,7 @@
 """Pins the oracle to the reference itself (CPU only).
 
 1. oracle/ref_kernels.c (the C restatement) reproduces, BIT FOR BIT, the committed golden vectors that
-   tools/make_golden.py recorded from the reference's own src/*.cpp compiled against oracle/rcpp_shim/Rcpp.h.
+   tests/tools/make_golden.py recorded from the reference's own src/*.cpp compiled against oracle/rcpp_shim/Rcpp.h.
 2. Where oracle/_ref is available (build container, or shipped with the gpurun snapshot) the restatement is also
    compared bit for bit with the compiled reference on fresh seeded inputs, and the golden file is re-derived.
 3. The host-side scalar helpers of the product (csrc/scalars.cpp, no GPU involved) reproduce the golden lists.

@@ -2,7 +2,7 @@
 against the extended-precision (long double) reduced oracle.  Shows which differences are conditioning (H4)."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_model as rm, reduced_model as red
 from tests import cases
 from sparsergps_b200.context import Context

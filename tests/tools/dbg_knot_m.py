@@ -1,7 +1,7 @@
 """Debug: knot-gradient error vs m / conditioning, against float64 and long-double reduced oracles."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import reduced_model as red
 from sparsergps_b200.context import Context
 

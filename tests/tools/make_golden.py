@@ -1,6 +1,6 @@
 """Generate tests/golden/rcpp_layer.{json,npz}: input/output vectors of the REFERENCE's compiled Rcpp layer.
 
-Run in the build container (needs /root/reference): `python tools/make_golden.py`. It compiles the reference's
+Run in the build container (needs /root/reference): `python tests/tools/make_golden.py`. It compiles the reference's
 src/*.cpp in place through oracle/ref_native.py (Rcpp stand-in header, see oracle/rcpp_shim/Rcpp.h), calls every
 exported function of SURVEY.md 8(b)'s routine table on seeded inputs -- configs 1 and 2 of BASELINE.json at reduced
 size, the L1/L2 `exp` kernel, coincident rows, unknown names, the unreachable exp+cross+tau branch -- and stores
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_native as rn  # noqa: E402
@@ -153,7 +153,7 @@ def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     np.savez_compressed(os.path.join(OUT_DIR, "rcpp_layer.npz"), **b.arrays)
     with open(os.path.join(OUT_DIR, "rcpp_layer.json"), "w") as f:
-        json.dump({"generator": "tools/make_golden.py",
+        json.dump({"generator": "tests/tools/make_golden.py",
                    "source": "reference src/covariance_functionsC.cpp + src/covariance_function_derivativesC.cpp, "
                              "compiled unmodified with g++ -O2 against oracle/rcpp_shim/Rcpp.h",
                    "cases": b.cases}, f, indent=1)

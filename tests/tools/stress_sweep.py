@@ -1,6 +1,6 @@
 """Randomised shape sweep of the fused VI / FIC evaluations against the reduced-form oracle (test infrastructure):
 chunk boundaries (n around multiples of the generator's 8192 / 9472-row chunks), m off the 128 tile, m up to 4096,
-d in 1..64, with and without the knot gradient.   python tools/stress_sweep.py [cases] [seed]  (GPU box)"""
+d in 1..64, with and without the knot gradient.   python tests/tools/stress_sweep.py [cases] [seed]  (GPU box)"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import reduced_model as red
 from sparsergps_b200.context import Context
 
@@ -58,7 +58,7 @@ for it in range(ncases):
         e_k = float(np.max(np.abs(np.asarray(kg).reshape(kr.shape) - kr)) / max(np.max(np.abs(kr)), 1e-300))
     worst = {"obj": max(worst["obj"], e_obj), "grad": max(worst["grad"], e_g), "knot": max(worst["knot"], e_k)}
     # the float64 NumPy oracle (explicit inverses) loses ~cond(S) * 1e-13 on the knot gradient; the CUDA path solves
-    # through triangular factors and sits 3 digits closer to the long-double yardstick (tools/dbg_knot_m.py,
+    # through triangular factors and sits 3 digits closer to the long-double yardstick (tests/tools/dbg_knot_m.py,
     # profiles/r01_stress_sweep.txt), so the knot bound scales with cond(S)
     Kuu, _ = red.kernel_matrix(xu, xu, sigma, l)
     cond = float(np.linalg.cond(Kuu + delta * np.eye(m))) if m <= 2048 else float("nan")
