@@ -40,6 +40,8 @@ def _args(pos, kw, names, defaults=None):
 
 def _num1(f, keep_dim=True):
     def g(I, pos, kw):
+        if len(pos) + len(kw) != 1:          # never drop an argument silently (plogis(log.p = TRUE) once was)
+            raise RError("unsupported extra arguments %r to a one-argument math builtin" % (list(kw),))
         x = pos[0] if pos else list(kw.values())[0]
         with np.errstate(all="ignore"):
             r = f(as_float(x))
@@ -168,6 +170,14 @@ def install(I):
             return I.eval(e.ast, env)
         return e
     reg("eval", f_eval, special=True)
+
+    def f_parse(I, pos, kw):
+        # parse(text = "..."): an expression vector; eval() of it evaluates each element and returns the last value
+        from . import rparse
+        txt = kw.get("text", pos[0] if pos else None)
+        nodes = rparse.parse("\n".join(str(s) for s in txt.v))
+        return Lang(("block", list(nodes)))
+    reg("parse", f_parse)
 
     def f_missing(I, args, env):
         nm = args[0][1][1]
@@ -314,6 +324,25 @@ def install(I):
             flat = flat.reshape((nr, nc)).reshape(-1, order="F")
         return Vec(np.ascontiguousarray(flat), dim=(nr, nc))
     reg("matrix", f_matrix)
+    def f_abind(I, pos, kw):
+        # abind::abind(a, b, along = 3) as the optimiser loops use it: stack m x d slices into an m x d x K history
+        if int(scalar(kw.get("along", dbl(3)))) != 3:
+            raise RError("abind: only along = 3 is implemented")
+        parts, base = [], None
+        for a in pos:
+            dm = tuple(a.dim) if a.dim is not None else (len(a.v), 1)
+            dm = dm + (1,) * (3 - len(dm))
+            if base is None:
+                base = dm[:2]
+            elif dm[:2] != base:
+                raise RError("abind: arg dimensions do not match")
+            parts.append((as_float(a), dm[2]))
+        return Vec(np.concatenate([p for p, _ in parts]), dim=base + (sum(k for _, k in parts),))
+    reg("abind::abind", f_abind)
+
+    # Matrix::Matrix(data = 0, nrow, ncol): the reference only uses it as a zero-initialised container whose column /
+    # entries are then assigned and which enters %*% and `*` -- a dense double matrix has the same values
+    reg("Matrix::Matrix", lambda I, pos, kw: (lambda r: Vec(r.v.astype(np.float64), dim=r.dim))(f_matrix(I, pos, kw)))
 
     def f_diag(I, pos, kw):
         a = _args(pos, kw, ["x", "nrow", "ncol"], {"nrow": None, "ncol": None})
@@ -467,7 +496,16 @@ def install(I):
         reg(nm, _num1(f))
     reg("round", lambda I, pos, kw: Vec(np.round(as_float(pos[0]), int(scalar(pos[1])) if len(pos) > 1 else
                                                  int(scalar(kw["digits"])) if "digits" in kw else 0), dim=pos[0].dim))
-    reg("plogis", _num1(lambda q: 1.0 / (1.0 + np.exp(-q))))
+    def f_plogis(I, pos, kw):
+        a = _args(pos, kw, ["q", "location", "scale", "lower.tail", "log.p"],
+                  {"location": dbl(0.0), "scale": dbl(1.0), "lower.tail": lgl(True), "log.p": lgl(False)})
+        x = (as_float(a["q"]) - scalar(a["location"])) / scalar(a["scale"])
+        if not truthy(a["lower.tail"]):
+            x = -x
+        with np.errstate(all="ignore"):
+            r = -np.logaddexp(0.0, -x) if truthy(a["log.p"]) else 1.0 / (1.0 + np.exp(-x))   # nmath/plogis.c
+        return Vec(r, dim=a["q"].dim, names=a["q"].names)
+    reg("plogis", f_plogis)
 
     def _all_values(pos):
         parts = [as_float(p) for p in pos if p is not None]
@@ -510,9 +548,14 @@ def install(I):
                 src = yes if t[k] else no
                 out[k] = src.v[k % len(src.v)]
             return Vec(out)
-        y = as_float(yes)[np.arange(n) % len(yes.v)]
-        z = as_float(no)[np.arange(n) % len(no.v)]
-        return Vec(np.where(t, y, z), dim=a["test"].dim)
+        # R only touches `yes` where test is TRUE and `no` where it is FALSE (a zero-length branch that is never
+        # selected is legal: vi_functions.R:811 reads obj_fun_vals[0] in the unused branch at iter == 1)
+        out = np.full(n, np.nan)
+        if np.any(t):
+            out[t] = as_float(yes)[np.arange(n) % len(yes.v)][t]
+        if np.any(~t):
+            out[~t] = as_float(no)[np.arange(n) % len(no.v)][~t]
+        return Vec(out, dim=a["test"].dim)
     reg("ifelse", f_ifelse)
 
     def f_duplicated(I, pos, kw):
