@@ -9,7 +9,7 @@ be split into shards whose partial sums are added (the allreduce).  tests/ use i
 It follows SURVEY.md Appendix B.2/B.3, which restate R/vi_functions.R:64-121,126-420 and
 R/laplace_approx_gradient.R:720-968; formulas are derived in DESIGN.md.
 
-PARITY UNPINNED (see oracle/ref_model.py).
+Parity: held to oracle/ref_model.py, which is pinned to the reference's own R sources (see its header).
 """
 from __future__ import annotations
 

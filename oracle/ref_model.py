@@ -7,12 +7,18 @@ Restates, statement by statement, the pure-R functions of luisdamiano/sparseRGPs
 (SURVEY.md Appendix C).  The dense covariance / derivative matrices come from the C restatement of the Rcpp
 kernels (ref_kernels.c) exactly as the R code obtains them through `.Call`.
 
-PARITY UNPINNED for the R-level algebra in this file: the reference ships no tests, golden vectors or fixtures
-for this path and no R interpreter exists here, so the model algebra below has not been compared with output of
-the reference itself. (The Rcpp layer it calls -- make_cov_mat*C, dsig_dtheta*C via oracle/ref_kernels.py -- IS
-pinned bit for bit against the reference's compiled C++ sources, tests/test_reference_pin.py.)  It is pinned
-against (i) analytic known answers, (ii) finite differences of its own Gaussian objectives, (iii) the
-independent reduced-form algebra in oracle/reduced_model.py (tests/test_oracle.py).
+PARITY PINNED to the reference's own R sources, with one stated caveat.  No R installation exists in this image and
+the reference ships no tests or fixtures, so the reference's R files (/root/reference/R/*.R) are executed, unmodified
+and where they lie, by the mini-R interpreter of oracle/mini_r with the Rcpp exports served by the reference's
+compiled C++ (oracle/ref_r.py).  tests/tools/make_golden_r.py records what those R functions return
+(tests/golden/r_level.*) and tests/test_reference_r.py holds every function below to it at 1e-10 (Gaussian rows),
+1e-9 (Laplace rows, optimiser trajectories).  Caveat: the interpreter is ours, not GNU R -- it implements the language
+subset these files use from the R Language Definition (known-answer tests: tests/test_mini_r.py) and reaches LAPACK
+through NumPy where R reaches it through its own BLAS; what is pinned is the reference's R SOURCE, statement for
+statement, not GNU R's binary.  The first run of this pin found one bug in the interpreter (plogis(log.p=)) and none in
+this file.  Further checks: analytic known answers, finite differences, and the independent reduced-form algebra
+in oracle/reduced_model.py (tests/test_oracle.py).  The Rcpp layer it calls is pinned bit for bit against the
+reference's compiled C++ (tests/test_reference_pin.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """
