@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gauss.cuh"
+#include "gauss_i8.cuh"
 #include <vector>
 #include "gemm.cuh"
 
@@ -241,6 +242,11 @@ __global__ void sum_rows_kernel(const double *__restrict__ part, int groups, int
     double s = 0.0;
     for (int g = 0; g < groups; g++) s += part[(int64_t)g * mp + j];
     out[j] = s;
+}
+
+void gram_sum_rows(cudaStream_t s, const double *part, int groups, int mp, double *out)
+{
+    sum_rows_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(part, groups, mp, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -897,6 +903,8 @@ static void launch_gen_cm(cudaStream_t s, dim3 grid, size_t smem, const double *
 int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
                 double *G, double *b1)
 {
+    // the unweighted Gram (VI pass 1, OAT border Gram) runs on the INT8 tensor cores: gauss_i8.cu
+    if (!rowweight && i8_enabled()) return gauss_pass1_i8(ctx, w, gp, rvec, G, b1);
     cudaStream_t s = ctx->stream;
     static DeviceOnce once;
     if (once.need(ctx->device)) {

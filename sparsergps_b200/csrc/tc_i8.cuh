@@ -1,0 +1,154 @@
+// tc_i8.cuh -- FP64-equivalent products on the INT8 tensor cores of sm_100a (tcgen05.mma.kind::i8, accumulators in
+// TMEM): the operand layout, the PTX wrappers and the digit splitter shared by the Gram (pass 1) and K*M (pass 2)
+// kernels of gauss_i8.cu.
+//
+// Scheme (Ozaki-style error-free splitting, fixed point): a value v in [-1, 1] is q = rint(v 2^62), and
+// q = sum_t d_t 256^t with balanced digits d_t in [-128, 127] -- NS = 8 INT8 slices, slice s = 7 - t carries weight
+// 2^(-6-8s).  A product sum_r a_r b_r is then sum_{sa,sb} 2^(-12-8(sa+sb)) (sum_r da_sa[r] db_sb[r]) where every
+// inner sum is an exact INT32 dot product; pairs with sa + sb > 7 are dropped (< 2^-58 of the operand scales per
+// term).  All pairs of one level L = sa + sb accumulate into the same TMEM accumulator (8 levels x 64 columns = the
+// whole 512-column TMEM), so a 128 x 64 output tile costs 36 INT8 MMAs per k-step instead of one FP64 MMA, on a pipe
+// that is ~120x wider than DMMA.  Overflow bound: (L + 1) <= 8 pairs x 2^14 x rows <= 2^30 for rows <= 8192.
+//
+// Operand layout: K-major, SWIZZLE_NONE ("interleaved") canonical UMMA layout -- 8 rows x 16 bytes core matrices
+// stored as 128 contiguous bytes.  The producers of the slices (generator kernels) write them to global memory
+// ALREADY in the shared-memory image,
+//     image(slice s)[blk = row / 128][kb = k / 64][c = (k % 64) / 16][r1 = (row % 128) / 8][r0 = row % 8][k % 16]
+// (8 KB per (blk, kb)), so an operand tile is one contiguous cp.async.bulk (TMA bulk copy, mbarrier complete_tx;
+// no tensor map) and its matrix descriptor has LBO = 2048 (1024 for a 64-row half tile), SBO = 128.
+#pragma once
+#include <stdint.h>
+
+namespace srgp {
+namespace i8 {
+
+constexpr int NS = 8;                 // slices per operand
+constexpr int BM = 128, BN = 64;      // output tile (BN x NS = 512 TMEM columns)
+constexpr int BK = 64;                // k extent of one stage, in INT8 elements = bytes
+constexpr int STAGES = 2;
+constexpr int A_TILE = BM * BK;       // 8 KB
+constexpr int B_TILE = BN * BK;       // 4 KB
+constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 96 KB
+constexpr int IMG_BLOCK = 128 * BK;   // bytes of one (128-row block, k-block) image
+constexpr int THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+constexpr int MAX_ROWS_PER_SPLIT = 8192;
+constexpr double FIX_SCALE = 4611686018427387904.0;   // 2^62
+// instruction descriptor: D = S32, A = B = signed INT8, both K-major, N = 64, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A protocol bug must surface as a launch error (SRGP_ERR_CUDA), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity))
+        if (++spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major SWIZZLE_NONE matrix descriptor (version 1 = Blackwell): start address, LBO = byte distance between the
+// two 16-byte k-chunks of one MMA, SBO = byte distance between 8-row groups; all in units of 16 bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+                 "l"(da), "l"(db), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc_all(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_all(uint32_t base)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread t of the warp receives row (lane base + t), columns col .. col + 31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+                 "%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Balanced base-256 digits of q = rint(v 2^62), |v| <= 1: digit t goes to slice NS - 1 - t.  `e` (0..15) is the byte
+// position inside the 16-byte k-chunk the caller is filling: w[s][e / 4] collects byte e of slice s.
+__device__ __forceinline__ void split_digits(double v, int e, uint32_t (&w)[NS][4])
+{
+    long long q = __double2ll_rn(v * FIX_SCALE);
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const long long dgt = ((q + 128) & 255) - 128;
+        q = (q - dgt) >> 8;
+        w[NS - 1 - t][e >> 2] |= (uint32_t)(dgt & 255) << (8 * (e & 3));
+    }
+}
+
+// shared-memory carve-up of the two INT8 kernels
+struct Bars {
+    uint64_t full[STAGES], empty[STAGES], tmem_full;
+    uint32_t tmem_slot, pad;
+};
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (int)sizeof(Bars);
+
+// The issue loop of one stage: 36 slice pairs x 2 k-steps; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
+// `fresh` = this is the first stage of the accumulation (the first MMA of every level overwrites).
+__device__ __forceinline__ void issue_stage(uint32_t sbase, uint32_t tmem_base, bool fresh)
+{
+#pragma unroll 1
+    for (int sb = 0; sb < NS; ++sb) {
+#pragma unroll 1
+        for (int sa = 0; sa + sb < NS; ++sa) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t da = make_desc(sbase + sa * A_TILE + kk * 2 * 2048, 2048, 128);
+                const uint64_t db = make_desc(sbase + NS * A_TILE + sb * B_TILE + kk * 2 * 1024, 1024, 128);
+                // level L is first touched by the pair (sa = L, sb = 0), k-step 0
+                mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, (!fresh || kk > 0 || sb > 0) ? 1u : 0u);
+            }
+        }
+    }
+}
+
+}  // namespace i8
+}  // namespace srgp
