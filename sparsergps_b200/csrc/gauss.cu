@@ -795,7 +795,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -1201,9 +1201,16 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
 
 // out[0 .. d] <- sum over this shard's rows (see km_reduce_kernel); out == null defers the final sum to a
 // later call that accumulates into the same per-CTA slots.
+void gram_sum_part(cudaStream_t s, const double *part, int slots, int stride, int count, double *out)
+{
+    sum_part_kernel<<<count, 32, 0, s>>>(part, slots, stride, count, out);
+}
+static_assert(PART_STRIDE == PART_STRIDE_I8, "the INT8 pass 2 shares the per-CTA slots of the DMMA pass 2");
+
 int gauss_pass2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs,
                 const double *ra, const double *beta, double *out, bool accumulate_slots)
 {
+    if (i8_pass2_supported(w)) return gauss_pass2_i8(ctx, w, gp, Mop, rs, ra, beta, out, accumulate_slots);
     return km_pass(ctx, w, gp, w->want_knots ? MODE_GRAD_KNOT : MODE_GRAD, Mop, rs, ra, beta, nullptr, out,
                    accumulate_slots, nullptr, nullptr);
 }

@@ -225,6 +225,309 @@ i8_gram_finalize_kernel(const double *__restrict__ Gpart, int nsplit, int mp, do
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pass 2 on the INT8 tensor cores:  T = K Mop^T  (T_ij' = sum_j K_ij Mop[j' + j mp]), then the fused
+// "never materialise dK" reduction of km_reduce_kernel<MODE_GRAD> (gauss.cu):
+//   Omega_ij = rs_i T_ij + ra_i beta_j ;  P_ij = Omega_ij K_ij ;  slot[0] += sum P ;  slot[1 + c] += sum P D_ijc
+// K enters the MMA as digit slices of exp(-d^2/2) (generator below); Mop as digit slices of Mop[n, :] / 2^e_n with
+// one power-of-two scale per output column n (slice_mop_kernel).  The epilogue owns one data row per thread: it
+// drains the 8 levels of 32 columns from TMEM, rebuilds K_ij and D_ijc from the row's coordinates in registers
+// and the tile's knots in shared memory (the FP64 pipe is idle while the tensor cores run INT8), and keeps the
+// 1 + d sums in registers across all column tiles of the CTA.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(128)
+gen_slices_datarows_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0, int rows_valid,
+                           const double *__restrict__ U, int m, int mp, GenParams p, int8_t *__restrict__ slices,
+                           size_t slice_stride)
+{
+    extern __shared__ double su[];   // [64][DT] scaled knots of one k-block
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const bool ivalid = i < rows_valid;
+    double xi[DT];
+#pragma unroll
+    for (int c = 0; c < DT; c++) xi[c] = ivalid ? X[r0 + i + ldx * c] * p.invl[c] : 0.0;
+    const int KBm = mp / BK;
+    for (int kb = blockIdx.y; kb < KBm; kb += gridDim.y) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < BK * DT; t += 128) {
+            const int jj = t / DT, c = t - jj * DT;
+            const int j = kb * BK + jj;
+            su[t] = (j < m) ? U[j + (int64_t)m * c] * p.invl[c] : 0.0;
+        }
+        __syncthreads();
+        int8_t *dst = slices + ((size_t)blockIdx.x * KBm + kb) * IMG_BLOCK + (size_t)threadIdx.x * 16;
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; c16++) {
+            uint32_t w[NS][4];
+#pragma unroll
+            for (int s = 0; s < NS; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+            for (int e0 = 0; e0 < 16; e0 += 4) {
+                double sq[4] = {0.0, 0.0, 0.0, 0.0};
+                const int jj = c16 * 16 + e0;
+#pragma unroll
+                for (int c = 0; c < DT; c++) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double t = xi[c] - su[(jj + q) * DT + c];
+                        sq[q] = fma(t, t, sq[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double ev = (ivalid && kb * BK + jj + q < m) ? exp(-0.5 * sq[q]) : 0.0;
+                    split_digits(ev, e0 + q, w);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; s++)
+                *reinterpret_cast<uint4 *>(dst + s * slice_stride + c16 * 2048) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        }
+    }
+}
+
+// Mop (element (n, k) at n + k mp) -> digit slices of Mop[n, :] / 2^e_n in the operand image (rows = n), and
+// colscale[n] = 2^e_n with max_k |Mop[n, k]| / 2^e_n in [0.5, 1).  grid (mp / 128, mp / 64), 128 threads.
+__global__ void __launch_bounds__(128)
+slice_mop_kernel(const double *__restrict__ Mop, int mp, int8_t *__restrict__ slices, size_t slice_stride,
+                 double *__restrict__ colscale)
+{
+    const int n = blockIdx.x * 128 + threadIdx.x, kb = blockIdx.y;
+    double mx = 0.0;
+    for (int k = 0; k < mp; k++) mx = fmax(mx, fabs(Mop[n + (int64_t)k * mp]));
+    int ex = 0;
+    if (mx > 0.0 && mx < INFINITY) ex = ilogb(mx) + 1;
+    const double inv = scalbn(1.0, -ex);
+    if (kb == 0) colscale[n] = scalbn(1.0, ex);
+    const int KBm = mp / BK;
+    int8_t *dst = slices + ((size_t)blockIdx.x * KBm + kb) * IMG_BLOCK + (size_t)threadIdx.x * 16;
+#pragma unroll 1
+    for (int c16 = 0; c16 < 4; c16++) {
+        uint32_t w[NS][4];
+#pragma unroll
+        for (int s = 0; s < NS; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            double v = Mop[n + (int64_t)(kb * BK + c16 * 16 + e) * mp] * inv;
+            v = fmin(1.0, fmax(-1.0, v));          // NaN / Inf (failed factorisation upstream) -> finite; info flags report it
+            split_digits(v, e, w);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            *reinterpret_cast<uint4 *>(dst + s * slice_stride + c16 * 2048) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+struct KmI8Args {
+    const int8_t *kslices;   // K digit slices of the chunk: blocks = 128-row blocks, k = knots
+    size_t kstride;
+    const int8_t *mslices;   // Mop digit slices: blocks = 128 output columns n, k = knots
+    size_t mstride;
+    const double *colscale;  // mp
+    int KBm, mp, m;
+    const double *X;         // resident rows (column-major, ld = ldx), chunk starts at r0
+    int64_t ldx, r0;
+    int rows_valid;
+    const double *U;         // m x d
+    const double *rs, *ra, *beta;
+    double invl[8];
+    double sigma2;
+    int tiles_per_cta;       // 64-column tiles per CTA
+    double *part;            // [gridDim.y][gridDim.x][PART_STRIDE_I8] accumulated across launches
+    int first;
+    int *coin_count, *coin_list;
+    double *coin_omega;
+    int coin_cap;
+};
+
+// Rare path of quirk Q4 (same contract as record_if_coincident in gauss.cu): decided by the reference's own test,
+// all coordinates bit-identical (src/covariance_function_derivativesC.cpp:157-163).
+__device__ __noinline__ void record_if_coincident_i8(const double *X, int64_t ldx, int64_t i_shard, const double *U, int m,
+                                                     int j, int d, int *coin_count, int *coin_list, double *coin_omega,
+                                                     int coin_cap, double omega_ij)
+{
+    for (int c = 0; c < d; c++)
+        if (X[i_shard + ldx * c] != U[j + (int64_t)m * c]) return;
+    const int slot = atomicAdd(coin_count, 1);
+    if (slot < coin_cap) {
+        coin_list[2 * slot] = (int)i_shard;
+        coin_list[2 * slot + 1] = j;
+        coin_omega[slot] = omega_ij;
+    }
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int DT>
+__global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars &bars = *reinterpret_cast<Bars *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *tmem_empty = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + sizeof(Bars));
+    double *us = reinterpret_cast<double *>(tmem_empty + 2);   // [64][DT] scaled knots of the current column tile
+    double *bt = us + BN * DT;                                  // [64] beta
+    double *cs = bt + BN;                                       // [64] sigma^2 * column scale
+    double *red = cs + BN;                                      // [4][PART_STRIDE_I8]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = blockIdx.x, jt0 = blockIdx.y * a.tiles_per_cta;
+    const int KBm = a.KBm;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bars.full[s], 1);
+            mbar_init(&bars.empty[s], 1);
+        }
+        mbar_init(&bars.tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_all(&bars.tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = 0; t < a.tiles_per_cta; ++t) {
+                const int jt = jt0 + t;
+                for (int kb = 0; kb < KBm; ++kb, ++it) {
+                    const int st = it % STAGES;
+                    if (it >= STAGES) mbar_wait(&bars.empty[st], ((it / STAGES) - 1) & 1);
+                    mbar_expect_tx(&bars.full[st], STAGE_BYTES);
+                    const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
+                    const size_t a_off = ((size_t)rb * KBm + kb) * IMG_BLOCK;
+                    const size_t b_off = ((size_t)(jt >> 1) * KBm + kb) * IMG_BLOCK + (size_t)(jt & 1) * 1024;
+                    for (int s = 0; s < NS; ++s) {
+                        bulk_g2s(sbase + s * A_TILE, a.kslices + s * a.kstride + a_off, A_TILE, &bars.full[st]);
+                        for (int c = 0; c < 4; ++c)
+                            bulk_g2s(sbase + NS * A_TILE + s * B_TILE + c * 1024, a.mslices + s * a.mstride + b_off + c * 2048,
+                                     1024, &bars.full[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = 0; t < a.tiles_per_cta; ++t) {
+                if (t > 0) {                           // the epilogue must have drained the previous tile from TMEM
+                    mbar_wait(tmem_empty, (t - 1) & 1);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < KBm; ++kb, ++it) {
+                    const int st = it % STAGES;
+                    mbar_wait(&bars.full[st], (it / STAGES) & 1);
+                    tc_fence_after();
+                    issue_stage(smem_u32(smem + st * STAGE_BYTES), tmem_base, kb == 0);
+                    mma_commit(&bars.empty[st]);
+                }
+                mma_commit(&bars.tmem_full);
+            }
+        }
+    } else {
+        // ===== epilogue: thread = one data row of the block =====
+        const int q = warp & 3, et = threadIdx.x - 64;          // epilogue thread index 0..127
+        const int row = q * 32 + lane;
+        const int i = rb * BM + row;
+        const bool iv = i < a.rows_valid;
+        const int64_t ig = a.r0 + i;
+        double xi[DT];
+#pragma unroll
+        for (int c = 0; c < DT; c++) xi[c] = iv ? a.X[ig + a.ldx * c] * a.invl[c] : 0.0;
+        const double rsi = (a.rs && iv) ? a.rs[ig] : 1.0;
+        const double rai = (a.ra && iv) ? a.ra[ig] : 0.0;
+        double s0 = 0.0, sc[DT];
+#pragma unroll
+        for (int c = 0; c < DT; c++) sc[c] = 0.0;
+        for (int t = 0; t < a.tiles_per_cta; ++t) {
+            const int j0 = (jt0 + t) * BN;
+            epi_bar();                                          // everyone is done with the previous tile's us / bt / cs
+            for (int e = et; e < BN * DT; e += 128) {
+                const int jj = e / DT, c = e - jj * DT;
+                us[e] = (j0 + jj < a.m) ? a.U[j0 + jj + (int64_t)a.m * c] * a.invl[c] : 0.0;
+            }
+            if (et < BN) {
+                bt[et] = (a.beta && j0 + et < a.m) ? a.beta[j0 + et] : 0.0;
+                cs[et] = a.sigma2 * a.colscale[j0 + et];
+            }
+            epi_bar();
+            mbar_wait(&bars.tmem_full, t & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                double T[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) T[c] = 0.0;
+#pragma unroll 1
+                for (int L = NS - 1; L >= 0; --L) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * BN + half * 32), v);
+                    const double wgt = exp2(-12.0 - 8.0 * L);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) T[c] = fma(wgt, (double)(int)v[c], T[c]);
+                }
+                if (half == 1) {                                // TMEM is free for the next tile's MMAs
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
+                if (iv) {
+#pragma unroll                                                  // T[] stays in registers only if c is a compile-time index
+                    for (int c = 0; c < 32; ++c) {
+                        const int jj = half * 32 + c;
+                        if (j0 + jj < a.m) {
+                            // same operation order as the generators: squared distance accumulated by fma
+                            double dd[DT], sqf = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DT; k++) {
+                                const double tt = xi[k] - us[jj * DT + k];
+                                dd[k] = tt * tt;
+                                sqf = fma(tt, tt, sqf);
+                            }
+                            const double ev = exp(-0.5 * sqf);
+                            const double om = fma(rsi, cs[jj] * T[c], rai * bt[jj]);
+                            const double pk = om * (a.sigma2 * ev);
+                            s0 += pk;
+#pragma unroll
+                            for (int k = 0; k < DT; k++) sc[k] = fma(pk, dd[k], sc[k]);
+                            if (ev == 1.0)
+                                record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                        a.coin_omega, a.coin_cap, om);
+                        }
+                    }
+                }
+            }
+        }
+        // CTA reduction: warp shuffles, then the 4 epilogue warps through shared memory -> this CTA's slot
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+#pragma unroll
+        for (int c = 0; c < DT; c++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sc[c] += __shfl_xor_sync(0xffffffffu, sc[c], o);
+        if (lane == 0) {
+            red[q * PART_STRIDE_I8] = s0;
+#pragma unroll
+            for (int c = 0; c < DT; c++) red[q * PART_STRIDE_I8 + 1 + c] = sc[c];
+        }
+        epi_bar();
+        if (et < 1 + DT) {
+            const double v = (red[et] + red[PART_STRIDE_I8 + et]) + (red[2 * PART_STRIDE_I8 + et] + red[3 * PART_STRIDE_I8 + et]);
+            double *slot = a.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * PART_STRIDE_I8 + et;
+            *slot = a.first ? v : (*slot + v);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_free_all(tmem_base);
+    }
+}
+
 bool i8_enabled()
 {
     static const bool on = [] {
@@ -313,6 +616,134 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         i8_gram_finalize_kernel<<<tiles, 128, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
         SRGP_LAUNCH_CHECK();
         gram_sum_rows(s, w->b1part.d(), w->gen_groups, mp, b1);
+        SRGP_LAUNCH_CHECK();
+    }
+    return SRGP_OK;
+}
+
+template <int DT>
+static void launch_gen_datarows(cudaStream_t s, dim3 grid, const double *X, int64_t ldx, int64_t r0, int rows_valid,
+                                const double *U, int m, int mp, const GenParams &p, int8_t *slices, size_t slice_stride)
+{
+    gen_slices_datarows_kernel<DT><<<grid, 128, sizeof(double) * BK * DT, s>>>(X, ldx, r0, rows_valid, U, m, mp, p, slices,
+                                                                              slice_stride);
+}
+
+template <int DT>
+static cudaError_t launch_km_i8(cudaStream_t s, dim3 grid, int device, const KmI8Args &a)
+{
+    const size_t smem = STAGES * STAGE_BYTES + sizeof(Bars) + 16 + sizeof(double) * (BN * DT + 2 * BN + 4 * PART_STRIDE_I8);
+    static DeviceOnce once;
+    if (once.need(device)) {
+        cudaError_t e = cudaFuncSetAttribute(i8_km_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    i8_km_kernel<DT><<<grid, THREADS, smem, s>>>(a);
+    return cudaSuccess;
+}
+
+bool i8_pass2_supported(const GaussWS *w) { return i8_enabled() && !w->want_knots && w->d >= 1 && w->d <= 8; }
+
+// Pass 2 (gradient sums) on the INT8 tensor cores; same contract and the same per-CTA slots as gauss_pass2.
+int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
+                   const double *beta, double *out, bool accumulate_slots)
+{
+    cudaStream_t s = ctx->stream;
+    const int mp = w->mp, m = w->m, d = w->d;
+    const int KBm = mp / BK;
+    const int slots = w->rblocks * w->cgroups;
+    const size_t mstride = (size_t)mp * mp;
+    SRGP_TRY(w->i8buf.reserve(mstride * NS + (size_t)mp * 8));
+    int8_t *mslices = reinterpret_cast<int8_t *>(w->i8buf.p);
+    double *colscale = reinterpret_cast<double *>(mslices + mstride * NS);
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        slice_mop_kernel<<<dim3(mp / 128, KBm), 128, 0, s>>>(Mop, mp, mslices, mstride, colscale);
+        SRGP_LAUNCH_CHECK();
+    }
+    int first = accumulate_slots ? 0 : 1;
+    if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE_I8 * 8, s));
+    cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
+    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    int cidx = 0;
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2, cidx++) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
+        const int b = cidx & 1;
+        int8_t *kslices = reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
+        const size_t kstride = (size_t)w->rows2 * mp;
+        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
+        {
+            KernelScope ks(ctx, SRGP_PROF_GEN, sg);
+            dim3 grid(w->rblocks, std::min(KBm, 16));
+#define CALL(D) launch_gen_datarows<D>(sg, grid, ctx->Xp, ctx->n, r0, rows_valid, w->U.d(), m, mp, gp, kslices, kstride)
+            switch (d) {
+            case 1: CALL(1); break;
+            case 2: CALL(2); break;
+            case 3: CALL(3); break;
+            case 4: CALL(4); break;
+            case 5: CALL(5); break;
+            case 6: CALL(6); break;
+            case 7: CALL(7); break;
+            default: CALL(8); break;
+            }
+#undef CALL
+            SRGP_LAUNCH_CHECK();
+        }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
+        SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
+        {
+            KernelScope ks(ctx, SRGP_PROF_KM, s);
+            KmI8Args a;
+            a.kslices = kslices;
+            a.kstride = kstride;
+            a.mslices = mslices;
+            a.mstride = mstride;
+            a.colscale = colscale;
+            a.KBm = KBm;
+            a.mp = mp;
+            a.m = m;
+            a.X = ctx->Xp;
+            a.ldx = ctx->n;
+            a.r0 = r0;
+            a.rows_valid = rows_valid;
+            a.U = w->U.d();
+            a.rs = rs;
+            a.ra = ra;
+            a.beta = beta;
+            for (int c = 0; c < 8; c++) a.invl[c] = gp.invl[c];
+            a.sigma2 = gp.sigma2;
+            a.tiles_per_cta = (mp / BN) / w->cgroups;
+            a.part = w->part2.d();
+            a.first = first;
+            a.coin_count = reinterpret_cast<int *>(w->coin.p);
+            a.coin_list = reinterpret_cast<int *>(w->coin.p) + 16;
+            a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
+                                                      (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
+            a.coin_cap = GaussWS::COIN_CAP;
+            dim3 grid(w->rblocks, w->cgroups);
+            cudaError_t e = cudaSuccess;
+#define CALL(D) e = launch_km_i8<D>(s, grid, ctx->device, a)
+            switch (d) {
+            case 1: CALL(1); break;
+            case 2: CALL(2); break;
+            case 3: CALL(3); break;
+            case 4: CALL(4); break;
+            case 5: CALL(5); break;
+            case 6: CALL(6); break;
+            case 7: CALL(7); break;
+            default: CALL(8); break;
+            }
+#undef CALL
+            SRGP_CUDA(e);
+            SRGP_LAUNCH_CHECK();
+        }
+        SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
+        first = 0;
+    }
+    if (out) {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        gram_sum_part(s, w->part2.d(), slots, PART_STRIDE_I8, d + 1, out);
         SRGP_LAUNCH_CHECK();
     }
     return SRGP_OK;

@@ -8,6 +8,12 @@ namespace srgp {
 bool i8_enabled();
 // unweighted pass 1: G = K^T K (mp x mp, both triangles), b1 = K^T rvec over the resident shard
 int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rvec, double *G, double *b1);
+// pass 2 (MODE_GRAD of gauss.cu: sum P, sum P o D_c, coincident pairs) on the INT8 tensor cores; same per-CTA slots
+constexpr int PART_STRIDE_I8 = SRGP_MAX_D + 8;
+bool i8_pass2_supported(const GaussWS *w);
+int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
+                   const double *beta, double *out, bool accumulate_slots);
+void gram_sum_part(cudaStream_t s, const double *part, int slots, int stride, int count, double *out);
 // out[j] = sum_g part[g][j] (gauss.cu)
 void gram_sum_rows(cudaStream_t s, const double *part, int groups, int mp, double *out);
 
