@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(lambda so: _compile(so[0], so[1], verbose), jobs))
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-Xlinker", "-z", "-Xlinker", "defs"]   # undefined symbols fail the link, not the dlopen
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -357,10 +357,15 @@ __device__ __noinline__ void record_if_coincident_i8(const double *X, int64_t ld
     }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// pass-2 CTA: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue.  Two epilogue warps share a TMEM lane
+// quadrant (32 rows) and take 32 of the tile's 64 columns each, so every thread drains its 8 levels x 32 columns at
+// once, releases TMEM, and only then does the FP64 work -- which overlaps the next tile's MMAs.
+constexpr int KM_THREADS = 320;
+constexpr int KM_EPI_THREADS = 256;
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int DT>
-__global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
+__global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars &bars = *reinterpret_cast<Bars *>(smem + STAGES * STAGE_BYTES);
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
     double *us = reinterpret_cast<double *>(tmem_empty + 2);   // [64][DT] scaled knots of the current column tile
     double *bt = us + BN * DT;                                  // [64] beta
     double *cs = bt + BN;                                       // [64] sigma^2 * column scale
-    double *red = cs + BN;                                      // [4][PART_STRIDE_I8]
+    double *red = cs + BN;                                      // [8][PART_STRIDE_I8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x, jt0 = blockIdx.y * a.tiles_per_cta;
     const int KBm = a.KBm;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
             mbar_init(&bars.empty[s], 1);
         }
         mbar_init(&bars.tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, 8);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc_all(&bars.tmem_slot);
@@ -428,8 +433,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
             }
         }
     } else {
-        // ===== epilogue: thread = one data row of the block =====
-        const int q = warp & 3, et = threadIdx.x - 64;          // epilogue thread index 0..127
+        // ===== epilogue: thread = one data row of the block x 32 columns of the tile =====
+        const int ew = warp - 2, q = warp & 3, half = ew >> 2, et = threadIdx.x - 64;
         const int row = q * 32 + lane;
         const int i = rb * BM + row;
         const bool iv = i < a.rows_valid;
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
         for (int t = 0; t < a.tiles_per_cta; ++t) {
             const int j0 = (jt0 + t) * BN;
             epi_bar();                                          // everyone is done with the previous tile's us / bt / cs
-            for (int e = et; e < BN * DT; e += 128) {
+            for (int e = et; e < BN * DT; e += KM_EPI_THREADS) {
                 const int jj = e / DT, c = e - jj * DT;
                 us[e] = (j0 + jj < a.m) ? a.U[j0 + jj + (int64_t)a.m * c] * a.invl[c] : 0.0;
             }
@@ -456,52 +461,47 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
             epi_bar();
             mbar_wait(&bars.tmem_full, t & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                double T[32];
+            double T[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) T[c] = 0.0;
+            for (int c = 0; c < 32; ++c) T[c] = 0.0;
 #pragma unroll 1
-                for (int L = NS - 1; L >= 0; --L) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * BN + half * 32), v);
-                    const double wgt = exp2(-12.0 - 8.0 * L);
+            for (int L = NS - 1; L >= 0; --L) {                 // least significant level first
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * BN + half * 32), v);
+                const double wgt = exp2(-12.0 - 8.0 * L);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) T[c] = fma(wgt, (double)(int)v[c], T[c]);
-                }
-                if (half == 1) {                                // TMEM is free for the next tile's MMAs
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
-                if (iv) {
+                for (int c = 0; c < 32; ++c) T[c] = fma(wgt, (double)(int)v[c], T[c]);
+            }
+            tc_fence_before();                                  // TMEM is free for the next tile's MMAs
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            if (iv) {
 #pragma unroll                                                  // T[] stays in registers only if c is a compile-time index
-                    for (int c = 0; c < 32; ++c) {
-                        const int jj = half * 32 + c;
-                        if (j0 + jj < a.m) {
-                            // same operation order as the generators: squared distance accumulated by fma
-                            double dd[DT], sqf = 0.0;
+                for (int c = 0; c < 32; ++c) {
+                    const int jj = half * 32 + c;
+                    if (j0 + jj < a.m) {
+                        // same operation order as the generators: squared distance accumulated by fma
+                        double dd[DT], sqf = 0.0;
 #pragma unroll
-                            for (int k = 0; k < DT; k++) {
-                                const double tt = xi[k] - us[jj * DT + k];
-                                dd[k] = tt * tt;
-                                sqf = fma(tt, tt, sqf);
-                            }
-                            const double ev = exp(-0.5 * sqf);
-                            const double om = fma(rsi, cs[jj] * T[c], rai * bt[jj]);
-                            const double pk = om * (a.sigma2 * ev);
-                            s0 += pk;
-#pragma unroll
-                            for (int k = 0; k < DT; k++) sc[k] = fma(pk, dd[k], sc[k]);
-                            if (ev == 1.0)
-                                record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
-                                                        a.coin_omega, a.coin_cap, om);
+                        for (int k = 0; k < DT; k++) {
+                            const double tt = xi[k] - us[jj * DT + k];
+                            dd[k] = tt * tt;
+                            sqf = fma(tt, tt, sqf);
                         }
+                        const double ev = exp(-0.5 * sqf);
+                        const double om = fma(rsi, cs[jj] * T[c], rai * bt[jj]);
+                        const double pk = om * (a.sigma2 * ev);
+                        s0 += pk;
+#pragma unroll
+                        for (int k = 0; k < DT; k++) sc[k] = fma(pk, dd[k], sc[k]);
+                        if (ev == 1.0)
+                            record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                    a.coin_omega, a.coin_cap, om);
                     }
                 }
             }
         }
-        // CTA reduction: warp shuffles, then the 4 epilogue warps through shared memory -> this CTA's slot
+        // CTA reduction: warp shuffles, then the 8 epilogue warps through shared memory -> this CTA's slot
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
 #pragma unroll
@@ -509,13 +509,14 @@ __global__ void __launch_bounds__(THREADS, 1) i8_km_kernel(KmI8Args a)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sc[c] += __shfl_xor_sync(0xffffffffu, sc[c], o);
         if (lane == 0) {
-            red[q * PART_STRIDE_I8] = s0;
+            red[ew * PART_STRIDE_I8] = s0;
 #pragma unroll
-            for (int c = 0; c < DT; c++) red[q * PART_STRIDE_I8 + 1 + c] = sc[c];
+            for (int c = 0; c < DT; c++) red[ew * PART_STRIDE_I8 + 1 + c] = sc[c];
         }
         epi_bar();
         if (et < 1 + DT) {
-            const double v = (red[et] + red[PART_STRIDE_I8 + et]) + (red[2 * PART_STRIDE_I8 + et] + red[3 * PART_STRIDE_I8 + et]);
+            double v = 0.0;
+            for (int k = 0; k < 8; k++) v += red[k * PART_STRIDE_I8 + et];
             double *slot = a.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * PART_STRIDE_I8 + et;
             *slot = a.first ? v : (*slot + v);
         }
@@ -632,13 +633,13 @@ static void launch_gen_datarows(cudaStream_t s, dim3 grid, const double *X, int6
 template <int DT>
 static cudaError_t launch_km_i8(cudaStream_t s, dim3 grid, int device, const KmI8Args &a)
 {
-    const size_t smem = STAGES * STAGE_BYTES + sizeof(Bars) + 16 + sizeof(double) * (BN * DT + 2 * BN + 4 * PART_STRIDE_I8);
+    const size_t smem = STAGES * STAGE_BYTES + sizeof(Bars) + 16 + sizeof(double) * (BN * DT + 2 * BN + 8 * PART_STRIDE_I8);
     static DeviceOnce once;
     if (once.need(device)) {
         cudaError_t e = cudaFuncSetAttribute(i8_km_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    i8_km_kernel<DT><<<grid, THREADS, smem, s>>>(a);
+    i8_km_kernel<DT><<<grid, KM_THREADS, smem, s>>>(a);
     return cudaSuccess;
 }
 

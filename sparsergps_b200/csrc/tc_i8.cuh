@@ -131,20 +131,29 @@ struct Bars {
 };
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (int)sizeof(Bars);
 
-// The issue loop of one stage: 36 slice pairs x 2 k-steps; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
+// The issue sequence of one stage: 36 slice pairs x 2 k-steps; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
 // `fresh` = this is the first stage of the accumulation (the first MMA of every level overwrites).
+// One thread issues all 72 MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
+// descriptor plus a compile-time constant (the start-address field is the low 14 bits, in 16-byte units; the sums
+// stay below 2^14): 2 integer adds per MMA.  With descriptors rebuilt per MMA the issuing thread, not the tensor
+// pipe, was the limit (85 instead of ~45 cycles per MMA, profiles/r01_ozaki_proto.json).
 __device__ __forceinline__ void issue_stage(uint32_t sbase, uint32_t tmem_base, bool fresh)
 {
-#pragma unroll 1
-    for (int sb = 0; sb < NS; ++sb) {
-#pragma unroll 1
-        for (int sa = 0; sa + sb < NS; ++sa) {
+    const uint64_t da0 = make_desc(sbase, 2048, 128);
+    const uint64_t db0 = make_desc(sbase + NS * A_TILE, 1024, 128);
+    const uint32_t keep = fresh ? 0u : 1u;
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t da = make_desc(sbase + sa * A_TILE + kk * 2 * 2048, 2048, 128);
-                const uint64_t db = make_desc(sbase + NS * A_TILE + sb * B_TILE + kk * 2 * 1024, 1024, 128);
-                // level L is first touched by the pair (sa = L, sb = 0), k-step 0
-                mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, (!fresh || kk > 0 || sb > 0) ? 1u : 0u);
+    for (int sb = 0; sb < NS; ++sb) {
+#pragma unroll
+        for (int sa = 0; sa < NS; ++sa) {
+            if (sa + sb < NS) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t da = da0 + (uint64_t)((sa * A_TILE + kk * 2 * 2048) >> 4);
+                    const uint64_t db = db0 + (uint64_t)((sb * B_TILE + kk * 2 * 1024) >> 4);
+                    // level L is first touched by the pair (sa = L, sb = 0), k-step 0
+                    mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, (sb == 0 && kk == 0) ? keep : 1u);
+                }
             }
         }
     }

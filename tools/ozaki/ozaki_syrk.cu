@@ -29,62 +29,8 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
-constexpr int NS = 8;            // slices
-constexpr int BM = 128, BN = 64; // output tile
-constexpr int BK = 64;           // bytes (= int8 elements) of K per stage
-constexpr int STAGES = 2;
-constexpr int A_TILE = BM * BK;  // 8 KB
-constexpr int B_TILE = BN * BK;  // 4 KB
-constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 96 KB
-constexpr int THREADS = 192;     // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t spins = 0;
-    while (!mbar_try(bar, parity))
-        if (++spins > (1u << 26)) __trap();          // a protocol bug must end in an error, not in a hung GPU
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor: 8 x 16 B core matrices (128 B contiguous), LBO = byte
-// distance between the two 16 B K-chunks of one MMA, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
-{
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+#include "../../sparsergps_b200/csrc/tc_i8.cuh"      // the product's INT8 engine: layout constants, PTX wrappers, issue_stage
+using namespace srgp::i8;
 
 // ---- splitter: doubles in (0, 1] (column j of K contiguous over rows) -> 8 INT8 slices in the smem image --------
 // image of slice s: [jblk = j/128][kb = r/64][c = (r%64)/16][r1 = (j%128)/8][r0 = j%8][r%16]   (8 KB per (jblk, kb))
@@ -120,7 +66,7 @@ struct Tile { int I, J; };       // output rows 128 I .., columns 64 J ..  (J <=
 
 __global__ void __launch_bounds__(THREADS, 1)
 ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int rows, int nsplit, const Tile *__restrict__ tiles,
-                  double *__restrict__ Gpart, int *__restrict__ dbg_levels)
+                  double *__restrict__ Gpart, int *__restrict__ dbg_levels, int mode)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -137,11 +83,10 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc_all(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
@@ -154,8 +99,13 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
             for (int it = 0; it < kb_per; ++it) {
                 const int st = it % STAGES;
                 if (it >= STAGES) mbar_wait(&empty[st], ((it / STAGES) - 1) & 1);
-                mbar_expect_tx(&full[st], STAGE_BYTES);
                 const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
+                if (mode == 1 && it >= STAGES) {            // diagnostic: no operand traffic (stale smem), MMA-bound rate
+                    mbar_expect_tx(&full[st], 16);
+                    bulk_g2s(sbase, slices, 16, &full[st]);
+                    continue;
+                }
+                mbar_expect_tx(&full[st], STAGE_BYTES);
                 const size_t a_off = ((size_t)tile.I * KB + kb0 + it) * (size_t)(128 * BK);
                 const size_t b_off = ((size_t)(tile.J >> 1) * KB + kb0 + it) * (size_t)(128 * BK) + (size_t)(tile.J & 1) * 1024;
                 for (int s = 0; s < NS; ++s) {
@@ -173,18 +123,12 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
                 mbar_wait(&full[st], (it / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
-#pragma unroll 1
-                for (int sb = 0; sb < NS; ++sb) {
-#pragma unroll 1
-                    for (int sa = 0; sa + sb < NS; ++sa) {
-#pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint64_t da = make_desc(sbase + sa * A_TILE + kk * 2 * 2048, 2048, 128);
-                            const uint64_t db = make_desc(sbase + NS * A_TILE + sb * B_TILE + kk * 2 * 1024, 1024, 128);
-                            mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, (it > 0 || kk > 0 || sb > 0) ? 1u : 0u);
-                        }
-                    }
+                if (mode == 2) {                            // diagnostic: no MMAs, load-bound rate
+                    if (it == 0) mma_i8(tmem_base, make_desc(sbase, 2048, 128), make_desc(sbase + NS * A_TILE, 1024, 128), 0u);
+                    mma_commit(&empty[st]);
+                    continue;
                 }
+                issue_stage(sbase, tmem_base, it == 0);
                 mma_commit(&empty[st]);               // frees the stage when these MMAs have read it
             }
             mma_commit(tmem_full);                     // all levels complete
@@ -222,7 +166,7 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        tmem_free_all(tmem_base);
     }
 }
 
@@ -286,7 +230,7 @@ int main(int argc, char **argv)
     const size_t ngroups = (size_t)(rows / 16) * m;
     split_kernel<<<(unsigned)((ngroups + 255) / 256), 256>>>(dK, rows, m, dS, slice_stride);
     CK(cudaGetLastError());
-    ozaki_syrk_kernel<<<grid, THREADS, smem_bytes>>>(dS, slice_stride, rows, nsplit, dT, dG, dDbg);
+    ozaki_syrk_kernel<<<grid, THREADS, smem_bytes>>>(dS, slice_stride, rows, nsplit, dT, dG, dDbg, 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
 
@@ -322,15 +266,23 @@ int main(int argc, char **argv)
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms_split; CK(cudaEventElapsedTime(&ms_split, e0, e1)); ms_split /= reps;
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) ozaki_syrk_kernel<<<grid, THREADS, smem_bytes>>>(dS, slice_stride, rows, nsplit, dT, dG, nullptr);
+    for (int r = 0; r < reps; ++r) ozaki_syrk_kernel<<<grid, THREADS, smem_bytes>>>(dS, slice_stride, rows, nsplit, dT, dG, nullptr, 0);
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
+    float ms_mode[3] = {ms, 0.f, 0.f};
+    for (int mode = 1; mode <= 2; ++mode) {
+        CK(cudaEventRecord(e0));
+        for (int r = 0; r < reps; ++r) ozaki_syrk_kernel<<<grid, THREADS, smem_bytes>>>(dS, slice_stride, rows, nsplit, dT, dG, nullptr, mode);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms_mode[mode], e0, e1)); ms_mode[mode] /= reps;
+    }
     const double int8_ops = 36.0 * 2.0 * (double)rows * BM * BN * ntiles;            // executed INT8 multiply-adds x 2
     const double f64_flops = (double)rows * m * (m + 1);                                // the SYRK count bench.py uses
     printf("{\"gpu\": \"%s\", \"rows\": %d, \"m\": %d, \"ctas\": %d, \"ms_gram\": %.4f, \"ms_split\": %.4f, \"int8_tops\": %.1f, "
-           "\"fp64_equiv_tflops\": %.2f, \"fp64_equiv_tflops_with_split\": %.2f, \"level_mismatches\": %lld, \"max_rel_err_vs_double_double\": %.3e}\n",
+           "\"fp64_equiv_tflops\": %.2f, \"fp64_equiv_tflops_with_split\": %.2f, \"ms_mma_only\": %.4f, \"ms_load_only\": %.4f, \"l2_to_sm_TBps\": %.2f, \"level_mismatches\": %lld, \"max_rel_err_vs_double_double\": %.3e}\n",
            prop.name, rows, m, grid, ms, ms_split, int8_ops / ms * 1e-9, f64_flops / ms * 1e-9, f64_flops / (ms + ms_split) * 1e-9,
-           level_mismatch, max_rel);
+           ms_mode[1], ms_mode[2], (double)grid * (rows / BK / nsplit) * STAGE_BYTES / ms * 1e-9, level_mismatch, max_rel);
     return (level_mismatch == 0 && max_rel < 1e-14) ? 0 : 1;
 }
