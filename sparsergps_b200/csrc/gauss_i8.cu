@@ -333,7 +333,8 @@ struct KmI8Args {
     const double *rs, *ra, *beta;
     double invl[8];
     double sigma2;
-    int tiles_per_cta;       // 64-column tiles per CTA
+    int tiles_per_cta;       // 64-column tiles per CTA and row block
+    int nsub;                // row blocks per CTA (processed one after the other): rb = sub * gridDim.x + blockIdx.x
     double *part;            // [gridDim.y][gridDim.x][PART_STRIDE_I8] accumulated across launches
     int first;
     int *coin_count, *coin_list;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
     double *cs = bt + BN;                                       // [64] sigma^2 * column scale
     double *red = cs + BN;                                      // [8][PART_STRIDE_I8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rb = blockIdx.x, jt0 = blockIdx.y * a.tiles_per_cta;
+    const int jt0 = blockIdx.y * a.tiles_per_cta;
     const int KBm = a.KBm;
 
     if (threadIdx.x == 0) {
@@ -396,8 +397,9 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int t = 0; t < a.tiles_per_cta; ++t) {
-                const int jt = jt0 + t;
+            for (int tt = 0; tt < a.nsub * a.tiles_per_cta; ++tt) {
+                const int jt = jt0 + tt % a.tiles_per_cta;
+                const int rb = (tt / a.tiles_per_cta) * gridDim.x + blockIdx.x;
                 for (int kb = 0; kb < KBm; ++kb, ++it) {
                     const int st = it % STAGES;
                     if (it >= STAGES) mbar_wait(&bars.empty[st], ((it / STAGES) - 1) & 1);
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
     } else if (warp == 1) {
         if (lane == 0) {
             int it = 0;
-            for (int t = 0; t < a.tiles_per_cta; ++t) {
+            for (int t = 0; t < a.nsub * a.tiles_per_cta; ++t) {
                 if (t > 0) {                           // the epilogue must have drained the previous tile from TMEM
                     mbar_wait(tmem_empty, (t - 1) & 1);
                     tc_fence_after();
@@ -436,19 +438,24 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
         // ===== epilogue: thread = one data row of the block x 32 columns of the tile =====
         const int ew = warp - 2, q = warp & 3, half = ew >> 2, et = threadIdx.x - 64;
         const int row = q * 32 + lane;
-        const int i = rb * BM + row;
-        const bool iv = i < a.rows_valid;
-        const int64_t ig = a.r0 + i;
-        double xi[DT];
-#pragma unroll
-        for (int c = 0; c < DT; c++) xi[c] = iv ? a.X[ig + a.ldx * c] * a.invl[c] : 0.0;
-        const double rsi = (a.rs && iv) ? a.rs[ig] : 1.0;
-        const double rai = (a.ra && iv) ? a.ra[ig] : 0.0;
         double s0 = 0.0, sc[DT];
 #pragma unroll
         for (int c = 0; c < DT; c++) sc[c] = 0.0;
-        for (int t = 0; t < a.tiles_per_cta; ++t) {
-            const int j0 = (jt0 + t) * BN;
+        int i = 0;
+        bool iv = false;
+        int64_t ig = 0;
+        double xi[DT], rsi = 1.0, rai = 0.0;
+        for (int t = 0; t < a.nsub * a.tiles_per_cta; ++t) {
+            if (t % a.tiles_per_cta == 0) {                     // next row block of this CTA
+                i = ((t / a.tiles_per_cta) * gridDim.x + blockIdx.x) * BM + row;
+                iv = i < a.rows_valid;
+                ig = a.r0 + i;
+#pragma unroll
+                for (int c = 0; c < DT; c++) xi[c] = iv ? a.X[ig + a.ldx * c] * a.invl[c] : 0.0;
+                rsi = (a.rs && iv) ? a.rs[ig] : 1.0;
+                rai = (a.ra && iv) ? a.ra[ig] : 0.0;
+            }
+            const int j0 = (jt0 + t % a.tiles_per_cta) * BN;
             epi_bar();                                          // everyone is done with the previous tile's us / bt / cs
             for (int e = et; e < BN * DT; e += KM_EPI_THREADS) {
                 const int jj = e / DT, c = e - jj * DT;
@@ -714,7 +721,14 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             a.beta = beta;
             for (int c = 0; c < 8; c++) a.invl[c] = gp.invl[c];
             a.sigma2 = gp.sigma2;
-            a.tiles_per_cta = (mp / BN) / w->cgroups;
+            // Two row blocks per CTA, one after the other, and twice the column groups: all CTAs sweep the first half
+            // of the chunk's row blocks before the second, so the K slices a CTA re-reads for every column tile
+            // (37 MB per half at m = 1024) stay L2-resident between the sweeps.  With one row block per CTA the
+            // 74 MB re-read distance thrashed the L2 and every sweep came from HBM (ncu: 600 MB DRAM reads per launch).
+            const int col_tiles = mp / BN;
+            const int nsub = (w->rblocks % 2 == 0 && col_tiles % (w->cgroups * 2) == 0) ? 2 : 1;
+            a.nsub = nsub;
+            a.tiles_per_cta = col_tiles / (w->cgroups * nsub);
             a.part = w->part2.d();
             a.first = first;
             a.coin_count = reinterpret_cast<int *>(w->coin.p);
@@ -722,7 +736,7 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
                                                       (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
             a.coin_cap = GaussWS::COIN_CAP;
-            dim3 grid(w->rblocks, w->cgroups);
+            dim3 grid(w->rblocks / nsub, w->cgroups * nsub);
             cudaError_t e = cudaSuccess;
 #define CALL(D) e = launch_km_i8<D>(s, grid, ctx->device, a)
             switch (d) {
