@@ -470,40 +470,49 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
             tc_fence_after();
             double T[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) T[c] = 0.0;
-#pragma unroll 1
-            for (int L = NS - 1; L >= 0; --L) {                 // least significant level first
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L * BN + half * 32), v);
-                const double wgt = exp2(-12.0 - 8.0 * L);
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + g * 16);
+                long long acc[16];
+                drain16x4(tcol + 4 * BN, acc);                  // levels 4..7
 #pragma unroll
-                for (int c = 0; c < 32; ++c) T[c] = fma(wgt, (double)(int)v[c], T[c]);
+                for (int c = 0; c < 16; ++c) T[g * 16 + c] = W_LEVELS_LO * (double)acc[c];
+                drain16x4(tcol, acc);                           // levels 0..3
+#pragma unroll
+                for (int c = 0; c < 16; ++c) T[g * 16 + c] = fma(W_LEVELS_HI, (double)acc[c], T[g * 16 + c]);
             }
             tc_fence_before();                                  // TMEM is free for the next tile's MMAs
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
             if (iv) {
+                // K_ij / sigma^2 comes back from the generator's digit slices (exact to 2^-62; 8 coalesced 16-byte loads
+                // per 16 columns) instead of being recomputed: exp and the distance chain are ~33 FP64 instructions per
+                // entry, and FP64 work is what competes with the tensor pipe (profiles/r01_ncu_i8_km.txt).
+                const int8_t *kimg = a.kslices + ((size_t)(i / BM) * KBm) * IMG_BLOCK + (size_t)row * 16;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int jg = j0 + half * 32 + g * 16;     // first column of this 16-column group
+                    uint4 w[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        w[s] = __ldg(reinterpret_cast<const uint4 *>(kimg + s * a.kstride + (size_t)(jg / BK) * IMG_BLOCK +
+                                                                     (size_t)((jg % BK) / 16) * 2048));
 #pragma unroll                                                  // T[] stays in registers only if c is a compile-time index
-                for (int c = 0; c < 32; ++c) {
-                    const int jj = half * 32 + c;
-                    if (j0 + jj < a.m) {
-                        // same operation order as the generators: squared distance accumulated by fma
-                        double dd[DT], sqf = 0.0;
+                    for (int e = 0; e < 16; ++e) {
+                        const int jj = half * 32 + g * 16 + e;
+                        if (j0 + jj < a.m) {
+                            const long long qd = join_digits(w, e);
+                            const double om = fma(rsi, cs[jj] * T[g * 16 + e], rai * bt[jj]);
+                            const double pk = om * (a.sigma2 * FIX_INV * (double)qd);
+                            s0 += pk;
 #pragma unroll
-                        for (int k = 0; k < DT; k++) {
-                            const double tt = xi[k] - us[jj * DT + k];
-                            dd[k] = tt * tt;
-                            sqf = fma(tt, tt, sqf);
+                            for (int k = 0; k < DT; k++) {
+                                const double tt = xi[k] - us[jj * DT + k];
+                                sc[k] = fma(pk, tt * tt, sc[k]);
+                            }
+                            if (qd == (1ll << 62))              // exp(0) = 1: candidate for the bit-identical test
+                                record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                        a.coin_omega, a.coin_cap, om);
                         }
-                        const double ev = exp(-0.5 * sqf);
-                        const double om = fma(rsi, cs[jj] * T[c], rai * bt[jj]);
-                        const double pk = om * (a.sigma2 * ev);
-                        s0 += pk;
-#pragma unroll
-                        for (int k = 0; k < DT; k++) sc[k] = fma(pk, dd[k], sc[k]);
-                        if (ev == 1.0)
-                            record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
-                                                    a.coin_omega, a.coin_cap, om);
                     }
                 }
             }
@@ -721,12 +730,11 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             a.beta = beta;
             for (int c = 0; c < 8; c++) a.invl[c] = gp.invl[c];
             a.sigma2 = gp.sigma2;
-            // Two row blocks per CTA, one after the other, and twice the column groups: all CTAs sweep the first half
-            // of the chunk's row blocks before the second, so the K slices a CTA re-reads for every column tile
-            // (37 MB per half at m = 1024) stay L2-resident between the sweeps.  With one row block per CTA the
-            // 74 MB re-read distance thrashed the L2 and every sweep came from HBM (ncu: 600 MB DRAM reads per launch).
-            const int col_tiles = mp / BN;
-            const int nsub = (w->rblocks % 2 == 0 && col_tiles % (w->cgroups * 2) == 0) ? 2 : 1;
+            // The kernel can take several row blocks per CTA one after the other (all CTAs then sweep a fraction of the
+            // chunk's row blocks at a time, which shortens the re-read distance of the K slices in L2).  Measured: no
+            // change in kernel time (the pass is bound by the shared-memory port and the FP64 pipe, not by HBM), so one
+            // row block per CTA it stays.
+            const int nsub = 1;
             a.nsub = nsub;
             a.tiles_per_cta = col_tiles / (w->cgroups * nsub);
             a.part = w->part2.d();

@@ -111,6 +111,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 16 columns of 4 consecutive level accumulators (columns col + k * BN, k = 0..3) -> exact 64-bit integers
+// sum_k lev_k 256^(3-k)  (|lev| < 2^30, so the sum stays below 2^55): the INT32 -> FP64 conversions and the
+// weighting of the levels cost 3 FP64 instructions per entry instead of 16 (the FP64 pipe is the contended one).
+__device__ __forceinline__ void drain16x4(uint32_t taddr, long long (&acc)[16])
+{
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = (long long)(int)v[c];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        tmem_ld16(taddr + (uint32_t)(k * BN), v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = acc[c] * 256 + (long long)(int)v[c];
+    }
+}
+constexpr double W_LEVELS_HI = 1.4551915228366852e-11;   // 2^-36: levels 0..3 as one integer
+constexpr double W_LEVELS_LO = 3.3881317890172014e-21;   // 2^-68: levels 4..7 as one integer
+constexpr double FIX_INV = 2.168404344971009e-19;        // 2^-62
+
+// The inverse of split_digits for byte position e of a 16-byte k-chunk: q = sum_s digit_s 256^(7-s), exact.
+__device__ __forceinline__ long long join_digits(const uint4 (&w)[NS], int e)
+{
+    long long q = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const uint32_t word = (e >> 2) == 0 ? w[s].x : (e >> 2) == 1 ? w[s].y : (e >> 2) == 2 ? w[s].z : w[s].w;
+        q = q * 256 + (long long)(int)(signed char)(word >> (8 * (e & 3)));
+    }
+    return q;
+}
+
 // Balanced base-256 digits of q = rint(v 2^62), |v| <= 1: digit t goes to slice NS - 1 - t.  `e` (0..15) is the byte
 // position inside the 16-byte k-chunk the caller is filling: w[s][e / 4] collects byte e of slice s.
 __device__ __forceinline__ void split_digits(double v, int e, uint32_t (&w)[NS][4])
