@@ -736,7 +736,7 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             // row block per CTA it stays.
             const int nsub = 1;
             a.nsub = nsub;
-            a.tiles_per_cta = col_tiles / (w->cgroups * nsub);
+            a.tiles_per_cta = (mp / BN) / (w->cgroups * nsub);
             a.part = w->part2.d();
             a.first = first;
             a.coin_count = reinterpret_cast<int *>(w->coin.p);
