@@ -123,18 +123,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
 // 16 columns of 4 consecutive level accumulators (columns col + k * BN, k = 0..3) -> exact 64-bit integers
 // sum_k lev_k 256^(3-k)  (|lev| < 2^30, so the sum stays below 2^55): the INT32 -> FP64 conversions and the
 // weighting of the levels cost 3 FP64 instructions per entry instead of 16 (the FP64 pipe is the contended one).
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void drain16x4(uint32_t taddr, long long (&acc)[16])
 {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
+    // the four loads are in flight together: one TMEM round trip per 16 x 4 block instead of four
+    uint32_t v0[16], v1[16], v2[16], v3[16];
+    tmem_ld16_nowait(taddr, v0);
+    tmem_ld16_nowait(taddr + (uint32_t)BN, v1);
+    tmem_ld16_nowait(taddr + (uint32_t)(2 * BN), v2);
+    tmem_ld16_nowait(taddr + (uint32_t)(3 * BN), v3);
+    tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = (long long)(int)v[c];
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        tmem_ld16(taddr + (uint32_t)(k * BN), v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = acc[c] * 256 + (long long)(int)v[c];
-    }
+    for (int c = 0; c < 16; ++c)
+        acc[c] = (((long long)(int)v0[c] * 256 + (long long)(int)v1[c]) * 256 + (long long)(int)v2[c]) * 256 + (long long)(int)v3[c];
 }
 constexpr double W_LEVELS_HI = 1.4551915228366852e-11;   // 2^-36: levels 0..3 as one integer
 constexpr double W_LEVELS_LO = 3.3881317890172014e-21;   // 2^-68: levels 4..7 as one integer
