@@ -147,24 +147,17 @@ i8_gram_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int KB, i
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < kb_per; ++it) {
+            for (int it = 0; it < 2 * kb_per; ++it) {
                 const int st = it % STAGES;
                 if (it >= STAGES) mbar_wait(&bars.empty[st], ((it / STAGES) - 1) & 1);
-                mbar_expect_tx(&bars.full[st], STAGE_BYTES);
-                const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
-                const size_t a_off = ((size_t)I * KB + kb0 + it) * IMG_BLOCK;
-                const size_t b_off = ((size_t)(J >> 1) * KB + kb0 + it) * IMG_BLOCK + (size_t)(J & 1) * 1024;
-                for (int s = 0; s < NS; ++s) {
-                    bulk_g2s(sbase + s * A_TILE, slices + s * slice_stride + a_off, A_TILE, &bars.full[st]);
-                    for (int c = 0; c < 4; ++c)
-                        bulk_g2s(sbase + NS * A_TILE + s * B_TILE + c * 1024, slices + s * slice_stride + b_off + c * 2048,
-                                 1024, &bars.full[st]);
-                }
+                load_stage(smem_u32(smem + st * STAGE_BYTES), &bars.full[st], slices, slice_stride,
+                           ((size_t)I * KB + kb0) * IMG_BLOCK, slices, slice_stride, ((size_t)(J >> 1) * KB + kb0) * IMG_BLOCK,
+                           J & 1, it);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int it = 0; it < kb_per; ++it) {
+            for (int it = 0; it < 2 * kb_per; ++it) {
                 const int st = it % STAGES;
                 mbar_wait(&bars.full[st], (it / STAGES) & 1);
                 tc_fence_after();
@@ -400,19 +393,11 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
             for (int tt = 0; tt < a.nsub * a.tiles_per_cta; ++tt) {
                 const int jt = jt0 + tt % a.tiles_per_cta;
                 const int rb = (tt / a.tiles_per_cta) * gridDim.x + blockIdx.x;
-                for (int kb = 0; kb < KBm; ++kb, ++it) {
+                for (int ks = 0; ks < 2 * KBm; ++ks, ++it) {
                     const int st = it % STAGES;
                     if (it >= STAGES) mbar_wait(&bars.empty[st], ((it / STAGES) - 1) & 1);
-                    mbar_expect_tx(&bars.full[st], STAGE_BYTES);
-                    const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
-                    const size_t a_off = ((size_t)rb * KBm + kb) * IMG_BLOCK;
-                    const size_t b_off = ((size_t)(jt >> 1) * KBm + kb) * IMG_BLOCK + (size_t)(jt & 1) * 1024;
-                    for (int s = 0; s < NS; ++s) {
-                        bulk_g2s(sbase + s * A_TILE, a.kslices + s * a.kstride + a_off, A_TILE, &bars.full[st]);
-                        for (int c = 0; c < 4; ++c)
-                            bulk_g2s(sbase + NS * A_TILE + s * B_TILE + c * 1024, a.mslices + s * a.mstride + b_off + c * 2048,
-                                     1024, &bars.full[st]);
-                    }
+                    load_stage(smem_u32(smem + st * STAGE_BYTES), &bars.full[st], a.kslices, a.kstride,
+                               (size_t)rb * KBm * IMG_BLOCK, a.mslices, a.mstride, (size_t)(jt >> 1) * KBm * IMG_BLOCK, jt & 1, ks);
                 }
             }
         }
@@ -424,11 +409,11 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                     mbar_wait(tmem_empty, (t - 1) & 1);
                     tc_fence_after();
                 }
-                for (int kb = 0; kb < KBm; ++kb, ++it) {
+                for (int ks = 0; ks < 2 * KBm; ++ks, ++it) {
                     const int st = it % STAGES;
                     mbar_wait(&bars.full[st], (it / STAGES) & 1);
                     tc_fence_after();
-                    issue_stage(smem_u32(smem + st * STAGE_BYTES), tmem_base, kb == 0);
+                    issue_stage(smem_u32(smem + st * STAGE_BYTES), tmem_base, ks == 0);
                     mma_commit(&bars.empty[st]);
                 }
                 mma_commit(&bars.tmem_full);

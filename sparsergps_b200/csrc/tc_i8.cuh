@@ -24,11 +24,14 @@ namespace i8 {
 
 constexpr int NS = 8;                 // slices per operand
 constexpr int BM = 128, BN = 64;      // output tile (BN x NS = 512 TMEM columns)
-constexpr int BK = 64;                // k extent of one stage, in INT8 elements = bytes
-constexpr int STAGES = 2;
-constexpr int A_TILE = BM * BK;       // 8 KB
-constexpr int B_TILE = BN * BK;       // 4 KB
-constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 96 KB
+constexpr int BK = 64;                // k extent of one block of the operand image, in INT8 elements = bytes
+constexpr int KS = 32;                // k extent of one pipeline stage = one MMA k-step (half an image block)
+constexpr int STAGES = 4;             // 4 x 48 KB: three stages (144 KB) in flight while one is consumed.  With 2 x 96 KB
+                                      // only one stage was ever in flight and the K*M pass, whose K slices come from
+                                      // HBM rather than L2, ran at 2.66 us per 64-byte block instead of 2.17
+constexpr int A_TILE = BM * KS;       // 4 KB
+constexpr int B_TILE = BN * KS;       // 2 KB
+constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 48 KB
 constexpr int IMG_BLOCK = 128 * BK;   // bytes of one (128-row block, k-block) image
 constexpr int THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 constexpr int MAX_ROWS_PER_SPLIT = 8192;
@@ -180,9 +183,9 @@ struct Bars {
 };
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (int)sizeof(Bars);
 
-// The issue sequence of one stage: 36 slice pairs x 2 k-steps; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
+// The issue sequence of one stage (one 32-byte k-step): 36 slice pairs; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
 // `fresh` = this is the first stage of the accumulation (the first MMA of every level overwrites).
-// One thread issues all 72 MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
+// One thread issues all 36 MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
 // descriptor plus a compile-time constant (the start-address field is the low 14 bits, in 16-byte units; the sums
 // stay below 2^14): 2 integer adds per MMA.  With descriptors rebuilt per MMA the issuing thread, not the tensor
 // pipe, was the limit (85 instead of ~45 cycles per MMA, profiles/r01_ozaki_proto.json).
@@ -196,15 +199,28 @@ __device__ __forceinline__ void issue_stage(uint32_t sbase, uint32_t tmem_base, 
 #pragma unroll
         for (int sa = 0; sa < NS; ++sa) {
             if (sa + sb < NS) {
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const uint64_t da = da0 + (uint64_t)((sa * A_TILE + kk * 2 * 2048) >> 4);
-                    const uint64_t db = db0 + (uint64_t)((sb * B_TILE + kk * 2 * 1024) >> 4);
-                    // level L is first touched by the pair (sa = L, sb = 0), k-step 0
-                    mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, (sb == 0 && kk == 0) ? keep : 1u);
-                }
+                const uint64_t da = da0 + (uint64_t)((sa * A_TILE) >> 4);
+                const uint64_t db = db0 + (uint64_t)((sb * B_TILE) >> 4);
+                // level L is first touched by the pair (sa = L, sb = 0)
+                mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, sb == 0 ? keep : 1u);
             }
         }
+    }
+}
+
+// Producer side of one stage (k-step ks of the operand images, 32 bytes): 8 A slice tiles (128 rows: the two 16-byte
+// k-chunks of a 128-row block image are 4 KB contiguous) and 8 B slice tiles (64 rows = one half of a 128-row block:
+// 1 KB per k-chunk).  a_blk / b_blk: byte offsets of the operands' (block, k-block 0) images inside a slice.
+__device__ __forceinline__ void load_stage(uint32_t sbase, uint64_t *full, const int8_t *a_slices, size_t a_stride, size_t a_blk,
+                                           const int8_t *b_slices, size_t b_stride, size_t b_blk, int b_half, int ks)
+{
+    mbar_expect_tx(full, STAGE_BYTES);
+    const size_t a_off = a_blk + (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * A_TILE;
+    const size_t b_off = b_blk + (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * 4096 + (size_t)b_half * 1024;
+    for (int s = 0; s < NS; ++s) {
+        bulk_g2s(sbase + s * A_TILE, a_slices + s * a_stride + a_off, A_TILE, full);
+        bulk_g2s(sbase + NS * A_TILE + s * B_TILE, b_slices + s * b_stride + b_off, 1024, full);
+        bulk_g2s(sbase + NS * A_TILE + s * B_TILE + 1024, b_slices + s * b_stride + b_off + 2048, 1024, full);
     }
 }
 

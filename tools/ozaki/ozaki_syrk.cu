@@ -96,7 +96,7 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
     if (warp == 0) {
         if (lane == 0) {
             // ===== producer: 8 A slice tiles (8 KB each) + 8 B slice tiles (4 x 1 KB each) per stage =====
-            for (int it = 0; it < kb_per; ++it) {
+            for (int it = 0; it < 2 * kb_per; ++it) {
                 const int st = it % STAGES;
                 if (it >= STAGES) mbar_wait(&empty[st], ((it / STAGES) - 1) & 1);
                 const uint32_t sbase = smem_u32(smem + st * STAGE_BYTES);
@@ -105,20 +105,14 @@ ozaki_syrk_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int ro
                     bulk_g2s(sbase, slices, 16, &full[st]);
                     continue;
                 }
-                mbar_expect_tx(&full[st], STAGE_BYTES);
-                const size_t a_off = ((size_t)tile.I * KB + kb0 + it) * (size_t)(128 * BK);
-                const size_t b_off = ((size_t)(tile.J >> 1) * KB + kb0 + it) * (size_t)(128 * BK) + (size_t)(tile.J & 1) * 1024;
-                for (int s = 0; s < NS; ++s) {
-                    bulk_g2s(sbase + s * A_TILE, slices + s * slice_stride + a_off, A_TILE, &full[st]);
-                    for (int c = 0; c < 4; ++c)
-                        bulk_g2s(sbase + NS * A_TILE + s * B_TILE + c * 1024, slices + s * slice_stride + b_off + c * 2048, 1024, &full[st]);
-                }
+                load_stage(sbase, &full[st], slices, slice_stride, ((size_t)tile.I * KB + kb0) * IMG_BLOCK, slices, slice_stride,
+                           ((size_t)(tile.J >> 1) * KB + kb0) * IMG_BLOCK, tile.J & 1, it);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer: 36 slice pairs x 2 k-steps per stage, level L = sa + sb -> TMEM columns [64 L, 64 L + 64) =====
-            for (int it = 0; it < kb_per; ++it) {
+            for (int it = 0; it < 2 * kb_per; ++it) {
                 const int st = it % STAGES;
                 mbar_wait(&full[st], (it / STAGES) & 1);
                 tc_fence_after();
@@ -283,6 +277,6 @@ int main(int argc, char **argv)
     printf("{\"gpu\": \"%s\", \"rows\": %d, \"m\": %d, \"ctas\": %d, \"ms_gram\": %.4f, \"ms_split\": %.4f, \"int8_tops\": %.1f, "
            "\"fp64_equiv_tflops\": %.2f, \"fp64_equiv_tflops_with_split\": %.2f, \"ms_mma_only\": %.4f, \"ms_load_only\": %.4f, \"l2_to_sm_TBps\": %.2f, \"level_mismatches\": %lld, \"max_rel_err_vs_double_double\": %.3e}\n",
            prop.name, rows, m, grid, ms, ms_split, int8_ops / ms * 1e-9, f64_flops / ms * 1e-9, f64_flops / (ms + ms_split) * 1e-9,
-           ms_mode[1], ms_mode[2], (double)grid * (rows / BK / nsplit) * STAGE_BYTES / ms * 1e-9, level_mismatch, max_rel);
+           ms_mode[1], ms_mode[2], (double)grid * (2 * rows / BK / nsplit) * STAGE_BYTES / ms * 1e-9, level_mismatch, max_rel);
     return (level_mismatch == 0 && max_rel < 1e-14) ? 0 : 1;
 }
