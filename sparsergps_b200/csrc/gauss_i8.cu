@@ -87,15 +87,16 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                         }
                     }
                 }
+                double ev[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    double ev = 0.0;
+                    ev[q] = 0.0;
                     if (jvalid && it0 + ii + q < rows_valid) {
-                        ev = exp(-0.5 * sq[q]);
-                        bacc = fma(p.sigma2 * ev, sr[ii + q], bacc);
+                        ev[q] = exp(-0.5 * sq[q]);
+                        bacc = fma(p.sigma2 * ev[q], sr[ii + q], bacc);
                     }
-                    split_digits(ev, e0 + q, w);
                 }
+                split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
             }
 #pragma unroll
             for (int s = 0; s < NS; s++)
@@ -267,11 +268,10 @@ gen_slices_datarows_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0
                         sq[q] = fma(t, t, sq[q]);
                     }
                 }
+                double ev[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double ev = (ivalid && kb * BK + jj + q < m) ? exp(-0.5 * sq[q]) : 0.0;
-                    split_digits(ev, e0 + q, w);
-                }
+                for (int q = 0; q < 4; q++) ev[q] = (ivalid && kb * BK + jj + q < m) ? exp(-0.5 * sq[q]) : 0.0;
+                split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
             }
 #pragma unroll
             for (int s = 0; s < NS; s++)
@@ -301,10 +301,12 @@ slice_mop_kernel(const double *__restrict__ Mop, int mp, int8_t *__restrict__ sl
 #pragma unroll
         for (int s = 0; s < NS; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            double v = Mop[n + (int64_t)(kb * BK + c16 * 16 + e) * mp] * inv;
-            v = fmin(1.0, fmax(-1.0, v));          // NaN / Inf (failed factorisation upstream) -> finite; info flags report it
-            split_digits(v, e, w);
+        for (int e = 0; e < 16; e += 4) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)               // NaN / Inf (failed factorisation upstream) -> finite; info flags report it
+                v[k] = fmin(1.0, fmax(-1.0, Mop[n + (int64_t)(kb * BK + c16 * 16 + e + k) * mp] * inv));
+            split_quad(v[0], v[1], v[2], v[3], e >> 2, w);
         }
 #pragma unroll
         for (int s = 0; s < NS; s++)
@@ -484,8 +486,10 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
 #pragma unroll                                                  // T[] stays in registers only if c is a compile-time index
                     for (int e = 0; e < 16; ++e) {
                         const int jj = half * 32 + g * 16 + e;
+                        long long q4[4];
+                        if ((e & 3) == 0) join_quad(w, e >> 2, q4);
                         if (j0 + jj < a.m) {
-                            const long long qd = join_digits(w, e);
+                            const long long qd = q4[e & 3];
                             const double om = fma(rsi, cs[jj] * T[g * 16 + e], rai * bt[jj]);
                             const double pk = om * (a.sigma2 * FIX_INV * (double)qd);
                             s0 += pk;

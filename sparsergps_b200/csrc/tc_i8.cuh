@@ -151,28 +151,53 @@ constexpr double W_LEVELS_HI = 1.4551915228366852e-11;   // 2^-36: levels 0..3 a
 constexpr double W_LEVELS_LO = 3.3881317890172014e-21;   // 2^-68: levels 4..7 as one integer
 constexpr double FIX_INV = 2.168404344971009e-19;        // 2^-62
 
-// The inverse of split_digits for byte position e of a 16-byte k-chunk: q = sum_s digit_s 256^(7-s), exact.
-__device__ __forceinline__ long long join_digits(const uint4 (&w)[NS], int e)
+// 4 x 4 byte transpose: out[t] = (a.byte_t, b.byte_t, c.byte_t, d.byte_t), a's byte in bits 0..7  (8 PRMT)
+__device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&out)[4])
 {
-    long long q = 0;
+    const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(a, b, 0x7362);
+    const uint32_t t2 = __byte_perm(c, d, 0x5140), t3 = __byte_perm(c, d, 0x7362);
+    out[0] = __byte_perm(t0, t2, 0x5410);
+    out[1] = __byte_perm(t0, t2, 0x7632);
+    out[2] = __byte_perm(t1, t3, 0x5410);
+    out[3] = __byte_perm(t1, t3, 0x7632);
+}
+constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull;
+
+// The inverse of split_quad for the 4 entries of word `wi` (0..3) of a 16-byte k-chunk: exact q of each entry.
+__device__ __forceinline__ void join_quad(const uint4 (&w)[NS], int wi, long long (&q)[4])
+{
+    uint32_t in[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const uint32_t word = (e >> 2) == 0 ? w[s].x : (e >> 2) == 1 ? w[s].y : (e >> 2) == 2 ? w[s].z : w[s].w;
-        q = q * 256 + (long long)(int)(signed char)(word >> (8 * (e & 3)));
+    for (int s = 0; s < NS; ++s) in[s] = wi == 0 ? w[s].x : wi == 1 ? w[s].y : wi == 2 ? w[s].z : w[s].w;
+    uint32_t lo[4], hi[4];
+    transpose4x4(in[7], in[6], in[5], in[4], lo);     // digits 0..3 live in slices 7..4
+    transpose4x4(in[3], in[2], in[1], in[0], hi);     // digits 4..7 in slices 3..0
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned long long y = ((unsigned long long)hi[k] << 32) | lo[k];
+        q[k] = (long long)((y ^ DIGIT_BIAS) - DIGIT_BIAS);
     }
-    return q;
 }
 
-// Balanced base-256 digits of q = rint(v 2^62), |v| <= 1: digit t goes to slice NS - 1 - t.  `e` (0..15) is the byte
-// position inside the 16-byte k-chunk the caller is filling: w[s][e / 4] collects byte e of slice s.
-__device__ __forceinline__ void split_digits(double v, int e, uint32_t (&w)[NS][4])
+// Balanced base-256 digits of q = rint(v 2^62), |v| <= 1, for 4 consecutive entries (word `wi` of a 16-byte k-chunk).
+// q = sum_t d_t 256^t with d_t in [-128, 127]  <=>  q + B = sum_t (d_t + 128) 256^t with B = 0x8080...80, i.e. the
+// plain bytes of q + B; and d_t as a two's-complement INT8 is (d_t + 128) ^ 0x80.  So all 8 digits of an entry are
+// the bytes of (q + B) ^ B: two 64-bit integer operations instead of a carry chain, then two 4 x 4 byte transposes
+// put digit t of the 4 entries into one 32-bit word of slice NS - 1 - t.
+__device__ __forceinline__ void split_quad(double v0, double v1, double v2, double v3, int wi, uint32_t (&w)[NS][4])
 {
-    long long q = __double2ll_rn(v * FIX_SCALE);
+    unsigned long long y[4];
+    const double v[4] = {v0, v1, v2, v3};
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        const long long dgt = ((q + 128) & 255) - 128;
-        q = (q - dgt) >> 8;
-        w[NS - 1 - t][e >> 2] |= (uint32_t)(dgt & 255) << (8 * (e & 3));
+    for (int k = 0; k < 4; ++k)
+        y[k] = ((unsigned long long)__double2ll_rn(v[k] * FIX_SCALE) + DIGIT_BIAS) ^ DIGIT_BIAS;
+    uint32_t lo[4], hi[4];
+    transpose4x4((uint32_t)y[0], (uint32_t)y[1], (uint32_t)y[2], (uint32_t)y[3], lo);
+    transpose4x4((uint32_t)(y[0] >> 32), (uint32_t)(y[1] >> 32), (uint32_t)(y[2] >> 32), (uint32_t)(y[3] >> 32), hi);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        w[NS - 1 - t][wi] = lo[t];
+        w[3 - t][wi] = hi[t];
     }
 }
 

@@ -45,15 +45,7 @@ __global__ void split_kernel(const double *__restrict__ Kcm, int rows, int m, in
 #pragma unroll
     for (int s = 0; s < NS; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        long long q = __double2ll_rn(src[e] * 4611686018427387904.0);      // k 2^62, exact for k >= 2^-9
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            const long long d = ((q + 128) & 255) - 128;                     // balanced digit in [-128, 127]
-            q = (q - d) >> 8;
-            w[NS - 1 - t][e >> 2] |= (uint32_t)(d & 255) << (8 * (e & 3));
-        }
-    }
+    for (int e = 0; e < 16; e += 4) split_quad(src[e], src[e + 1], src[e + 2], src[e + 3], e >> 2, w);   // the product's splitter
     const int KB = rows / BK;
     const size_t off = ((size_t)(j / 128) * KB + r / BK) * (size_t)(128 * BK) + (size_t)((r % BK) / 16) * 2048 + (size_t)((j % 128) / 8) * 128 + (size_t)(j % 8) * 16;
 #pragma unroll
