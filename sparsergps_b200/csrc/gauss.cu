@@ -795,7 +795,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -903,8 +903,9 @@ static void launch_gen_cm(cudaStream_t s, dim3 grid, size_t smem, const double *
 int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
                 double *G, double *b1)
 {
-    // the unweighted Gram (VI pass 1, OAT border Gram) runs on the INT8 tensor cores: gauss_i8.cu
-    if (!rowweight && i8_enabled()) return gauss_pass1_i8(ctx, w, gp, rvec, G, b1);
+    // the Grams over generated K (VI / FIC pass 1, FIC's K^T diag(rho) K, OAT border Gram) run on the INT8 tensor
+    // cores: gauss_i8.cu.  (The Laplace Newton loop keeps K materialised in FP64: gram_materialised below.)
+    if (i8_enabled()) return gauss_pass1_i8(ctx, w, gp, rowweight, rvec, G, b1);
     cudaStream_t s = ctx->stream;
     static DeviceOnce once;
     if (once.need(ctx->device)) {

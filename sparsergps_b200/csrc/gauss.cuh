@@ -40,6 +40,7 @@ struct GaussWS {
     // knot-gradient request of the current call (set by the entry point, read by gauss_pass2 / knot_finish)
     bool want_knots = false, knot_transform = false;
     double knot_lb[SRGP_MAX_D], knot_ub[SRGP_MAX_D];
+    DevBuf i8scal;   // INT8 weighted Gram: max |w| over the shard (device scalar)
     DevBuf i8buf;    // INT8 tensor-core passes: digit slices of Mop (8 x mp x mp bytes) + per-column scales
     DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal

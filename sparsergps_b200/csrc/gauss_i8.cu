@@ -23,16 +23,27 @@ using namespace i8;
 // ------------------------------------------------------------------------------------------------
 // generator for pass 1: operand rows = knots (block = 128 knots), k index = data rows of the chunk
 // ------------------------------------------------------------------------------------------------
-template <int DT>
+// power of two >= |x| (1 for x = 0 or a non-finite x): the scale of a weighted operand
+__device__ __forceinline__ double pow2_ceil(double x)
+{
+    return (x > 0.0 && x < INFINITY) ? scalbn(1.0, ilogb(x) + 1) : 1.0;
+}
+
+// WEIGHTED: a second slice set holds w_i e_ij / 2^ew (2^ew >= max_i |w_i|, *wmax on the device) for the weighted Grams
+// K^T diag(w) K = (diag(w) K)^T K of the FIC model; w may have either sign.
+template <int DT, bool WEIGHTED>
 __global__ void __launch_bounds__(128)
 gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const double *__restrict__ r, int64_t r0,
                            int rows_valid, int rows_padded, const double *__restrict__ U, int m, int mp, int d_rt,
                            GenParams p, int8_t *__restrict__ slices, size_t slice_stride, double *__restrict__ b1part,
-                           int first)
+                           int first, const double *__restrict__ rw, const double *__restrict__ wmax,
+                           int8_t *__restrict__ slices_w)
 {
-    extern __shared__ double sx[];   // [64][d] scaled rows, then [64] residuals
+    extern __shared__ double sx[];   // [64][d] scaled rows, then [64] residuals, then [64] scaled row weights
     const int d = DT > 0 ? DT : d_rt;
     double *sr = sx + 64 * d;
+    double *sw = sr + 64;
+    const double winv = WEIGHTED ? 1.0 / pow2_ceil(*wmax) : 0.0;
     const int j = blockIdx.x * 128 + threadIdx.x;
     const bool jvalid = j < m;
     double uj[DT > 0 ? DT : 1];
@@ -55,14 +66,14 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
         if (threadIdx.x < BK) {
             const int i = it0 + threadIdx.x;
             sr[threadIdx.x] = (i < rows_valid) ? r[r0 + i] : 0.0;
+            if (WEIGHTED) sw[threadIdx.x] = (i < rows_valid) ? rw[r0 + i] * winv : 0.0;
         }
         __syncthreads();
-        int8_t *dst = slices + ((size_t)blockIdx.x * KB + kb) * IMG_BLOCK + (size_t)threadIdx.x * 16;
+        const size_t img = ((size_t)blockIdx.x * KB + kb) * IMG_BLOCK + (size_t)threadIdx.x * 16;
+        int8_t *dst = slices + img;
 #pragma unroll 1
         for (int c16 = 0; c16 < 4; c16++) {
-            uint32_t w[NS][4];
-#pragma unroll
-            for (int s = 0; s < NS; s++) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
+            uint32_t w[NS][4], ww[WEIGHTED ? NS : 1][4];
 #pragma unroll
             for (int e0 = 0; e0 < 16; e0 += 4) {
                 // 4 rows in flight per thread: independent distance / exp chains hide the FP64 latency
@@ -97,10 +108,17 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                     }
                 }
                 split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
+                if (WEIGHTED)
+                    split_quad(ev[0] * sw[ii], ev[1] * sw[ii + 1], ev[2] * sw[ii + 2], ev[3] * sw[ii + 3], e0 >> 2,
+                               reinterpret_cast<uint32_t (&)[NS][4]>(ww));
             }
 #pragma unroll
-            for (int s = 0; s < NS; s++)
+            for (int s = 0; s < NS; s++) {
                 *reinterpret_cast<uint4 *>(dst + s * slice_stride + c16 * 2048) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+                if (WEIGHTED)
+                    *reinterpret_cast<uint4 *>(slices_w + img + s * slice_stride + c16 * 2048) =
+                        make_uint4(ww[s][0], ww[s][1], ww[s][2], ww[s][3]);
+            }
         }
     }
     double *slot = b1part + (int64_t)blockIdx.y * mp + j;
@@ -121,9 +139,9 @@ __device__ __forceinline__ void tile_to_ij(int t, int &I, int &J)
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-i8_gram_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int KB, int nsplit, double scale,
-               double *__restrict__ Gpart, int first)
-{
+i8_gram_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ slices, size_t slice_stride, int KB,
+               int nsplit, double scale, const double *__restrict__ wmax, double *__restrict__ Gpart, int first)
+{   // slices_a: A operand (rows 128 I ..): the weighted slice set, or `slices` itself; slices: B operand (columns 64 J ..)
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars &bars = *reinterpret_cast<Bars *>(smem + STAGES * STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,7 +169,7 @@ i8_gram_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int KB, i
             for (int it = 0; it < 2 * kb_per; ++it) {
                 const int st = it % STAGES;
                 if (it >= STAGES) mbar_wait(&bars.empty[st], ((it / STAGES) - 1) & 1);
-                load_stage(smem_u32(smem + st * STAGE_BYTES), &bars.full[st], slices, slice_stride,
+                load_stage(smem_u32(smem + st * STAGE_BYTES), &bars.full[st], slices_a, slice_stride,
                            ((size_t)I * KB + kb0) * IMG_BLOCK, slices, slice_stride, ((size_t)(J >> 1) * KB + kb0) * IMG_BLOCK,
                            J & 1, it);
             }
@@ -172,6 +190,7 @@ i8_gram_kernel(const int8_t *__restrict__ slices, size_t slice_stride, int KB, i
         mbar_wait(&bars.tmem_full, 0);
         tc_fence_after();
         const int row = q * 32 + lane;
+        if (wmax) scale *= pow2_ceil(*wmax);
         double *out = Gpart + ((size_t)blockIdx.x * BM + row) * BN;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -546,10 +565,34 @@ bool i8_enabled()
 template <int DT>
 static void launch_gen_knotrows(cudaStream_t s, dim3 grid, size_t smem, const double *X, int64_t ldx, const double *r,
                                 int64_t r0, int rows_valid, int rows_padded, const double *U, int m, int mp, int d,
-                                const GenParams &p, int8_t *slices, size_t slice_stride, double *b1part, int first)
+                                const GenParams &p, int8_t *slices, size_t slice_stride, double *b1part, int first,
+                                const double *rw, const double *wmax, int8_t *slices_w)
 {
-    gen_slices_knotrows_kernel<DT><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p, slices,
-                                                         slice_stride, b1part, first);
+    if (rw)
+        gen_slices_knotrows_kernel<DT, true><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                                   slices, slice_stride, b1part, first, rw, wmax, slices_w);
+    else
+        gen_slices_knotrows_kernel<DT, false><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                                    slices, slice_stride, b1part, first, nullptr, nullptr,
+                                                                    nullptr);
+}
+
+// *out = max_i |w_i| over the shard (one block; n is at most a few million)
+__global__ void __launch_bounds__(1024) absmax_kernel(const double *__restrict__ w, int64_t n, double *__restrict__ out)
+{
+    __shared__ double red[32];
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) mx = fmax(mx, fabs(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mx = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (threadIdx.x == 0) *out = mx;
+    }
 }
 
 #define SRGP_D_SWITCH_I8(d, CALL)                    \
@@ -565,8 +608,10 @@ static void launch_gen_knotrows(cudaStream_t s, dim3 grid, size_t smem, const do
     default: CALL(0); break;                         \
     }
 
-// Unweighted pass 1 on the INT8 tensor cores: G = K^T K (mp x mp, both triangles), b1 = K^T rvec.
-int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rvec, double *G, double *b1)
+// Pass 1 on the INT8 tensor cores: G = K^T diag(rowweight) K (mp x mp, both triangles; rowweight may be null = 1),
+// b1 = K^T rvec.  With weights the chunk holds two slice sets (e and w e / 2^ew), so it covers half the rows.
+int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec, double *G,
+                   double *b1)
 {
     cudaStream_t s = ctx->stream;
     static DeviceOnce once;
@@ -576,11 +621,20 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     const int tiles = w->nt * (w->nt + 1);
     const int nsplit = std::max(1, std::min(16, ctx->sm_count / tiles));
     const int quantum = BK * nsplit;
-    // rows per launch: the chunk buffer holds 8 slices x rows x mp bytes (= the FP64 chunk it replaces), and one
-    // INT32 accumulator may sum at most MAX_ROWS_PER_SPLIT rows
-    int64_t rows1 = std::min<int64_t>((int64_t)w->chunk_elems / mp, (int64_t)MAX_ROWS_PER_SPLIT * nsplit);
+    const int sets = rowweight ? 2 : 1;
+    // rows per launch: the chunk buffer holds sets x 8 slices x rows x mp bytes, and one INT32 accumulator may sum at
+    // most MAX_ROWS_PER_SPLIT rows
+    int64_t rows1 = std::min<int64_t>((int64_t)w->chunk_elems / mp / sets, (int64_t)MAX_ROWS_PER_SPLIT * nsplit);
     rows1 = std::max<int64_t>(quantum, rows1 / quantum * quantum);
     SRGP_TRY(w->Gpart.reserve((size_t)tiles * nsplit * BM * BN * 8));
+    double *wmax = nullptr;
+    if (rowweight) {
+        SRGP_TRY(w->i8scal.reserve(64));
+        wmax = w->i8scal.d();
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        absmax_kernel<<<1, 1024, 0, s>>>(rowweight, ctx->n, wmax);
+        SRGP_LAUNCH_CHECK();
+    }
     int first = 1;
     if (ctx->n == 0) {
         SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)tiles * nsplit * BM * BN * 8, s));
@@ -596,12 +650,13 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         const int b = cidx & 1;
         int8_t *slices = reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
         const size_t slice_stride = (size_t)rows_padded * mp;
+        int8_t *slices_w = rowweight ? slices + slice_stride * NS : slices;
         if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(mp / 128, w->gen_groups);
-            const size_t smem = sizeof(double) * BK * (d + 1);
-#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, slice_stride, w->b1part.d(), first)
+            const size_t smem = sizeof(double) * BK * (d + 2);
+#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, slice_stride, w->b1part.d(), first, rowweight, wmax, slices_w)
             SRGP_D_SWITCH_I8(d, CALL)
 #undef CALL
             SRGP_LAUNCH_CHECK();
@@ -610,8 +665,8 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GRAM, s);
-            i8_gram_kernel<<<tiles * nsplit, THREADS, SMEM_BYTES, s>>>(slices, slice_stride, rows_padded / BK, nsplit,
-                                                                      gp.sigma2 * gp.sigma2, w->Gpart.d(), first);
+            i8_gram_kernel<<<tiles * nsplit, THREADS, SMEM_BYTES, s>>>(slices_w, slices, slice_stride, rows_padded / BK, nsplit,
+                                                                      gp.sigma2 * gp.sigma2, wmax, w->Gpart.d(), first);
             SRGP_LAUNCH_CHECK();
         }
         SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));

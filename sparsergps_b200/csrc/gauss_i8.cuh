@@ -6,8 +6,9 @@ namespace srgp {
 
 // true unless SRGP_TENSOR=dmma (diagnostic switch that keeps the FP64 DMMA kernels for the unweighted Gram)
 bool i8_enabled();
-// unweighted pass 1: G = K^T K (mp x mp, both triangles), b1 = K^T rvec over the resident shard
-int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rvec, double *G, double *b1);
+// pass 1: G = K^T diag(rowweight) K (mp x mp, both triangles; rowweight null = 1), b1 = K^T rvec over the resident shard
+int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec, double *G,
+                   double *b1);
 // pass 2 (MODE_GRAD of gauss.cu: sum P, sum P o D_c, coincident pairs) on the INT8 tensor cores; same per-CTA slots
 constexpr int PART_STRIDE_I8 = SRGP_MAX_D + 8;
 bool i8_pass2_supported(const GaussWS *w);
