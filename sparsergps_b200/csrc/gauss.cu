@@ -1259,9 +1259,16 @@ int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *
 // Per-row, per-dimension sums over the shard (FIC): out[slot * stride + i], slots as in KmArgs::rowd_part --
 // T = K Mop (Mop symmetric): sum_j T_ij K_ij D_ijc (c = 0..d, D_ij0 = 1); with beta: sum_j beta_j K_ij D_ijc;
 // with vvec: sum_j K_ij v_j.  Bit-identical (row, knot) pairs are appended to w->coin together with T_ij.
+void gram_combine_rowd(cudaStream_t s, const double *part, int groups, int nslots, int64_t ld, int rows, double *out,
+                       int64_t out_stride)
+{
+    combine_rowd_kernel<<<dim3((unsigned)ceil_div(rows, 256), nslots), 256, 0, s>>>(part, groups, nslots, ld, rows, out, out_stride);
+}
+
 int gauss_rowd(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta,
                const double *vvec, double *out, int64_t stride)
 {
+    if (i8_pass2_supported(w)) return gauss_rowd_i8(ctx, w, gp, Mop, beta, vvec, out, stride);
     return km_pass(ctx, w, gp, MODE_ROWD, Mop, nullptr, nullptr, beta, vvec, nullptr, false, nullptr, nullptr, out,
                    stride);
 }

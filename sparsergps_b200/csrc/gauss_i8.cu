@@ -354,6 +354,14 @@ struct KmI8Args {
     int *coin_count, *coin_list;
     double *coin_omega;
     int coin_cap;
+    // ROWD mode (per-row, per-dimension sums of the FIC model, see KmArgs::rowd_part in gauss.cu):
+    //   rowd_part[((group * nslots + slot) * ld + row], group = blockIdx.y * 2 + column half of the epilogue thread
+    //   slot c (0..d): sum_j T_ij K_ij D_ijc (D_ij0 = 1); slot d+1+c (beta given): sum_j beta_j K_ij D_ijc;
+    //   last slot (vvec given): sum_j K_ij v_j.  Coincident pairs are recorded with T_ij.
+    const double *vvec;
+    double *rowd_part;
+    int nslots;
+    int64_t ld;
 };
 
 // Rare path of quirk Q4 (same contract as record_if_coincident in gauss.cu): decided by the reference's own test,
@@ -379,7 +387,7 @@ constexpr int KM_THREADS = 320;
 constexpr int KM_EPI_THREADS = 256;
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int DT>
+template <int DT, bool ROWD>
 __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -388,7 +396,8 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
     double *us = reinterpret_cast<double *>(tmem_empty + 2);   // [64][DT] scaled knots of the current column tile
     double *bt = us + BN * DT;                                  // [64] beta
     double *cs = bt + BN;                                       // [64] sigma^2 * column scale
-    double *red = cs + BN;                                      // [8][PART_STRIDE_I8]
+    double *vv = cs + BN;                                       // [64] v (ROWD)
+    double *red = vv + BN;                                      // [8][PART_STRIDE_I8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int jt0 = blockIdx.y * a.tiles_per_cta;
     const int KBm = a.KBm;
@@ -447,6 +456,9 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
         double s0 = 0.0, sc[DT];
 #pragma unroll
         for (int c = 0; c < DT; c++) sc[c] = 0.0;
+        double rt[ROWD ? DT + 1 : 1], rbt[ROWD ? DT + 1 : 1], rkv = 0.0;   // ROWD: this thread's row sums over its columns
+#pragma unroll
+        for (int c = 0; c < (ROWD ? DT + 1 : 1); c++) rt[c] = rbt[c] = 0.0;
         int i = 0;
         bool iv = false;
         int64_t ig = 0;
@@ -470,6 +482,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
             if (et < BN) {
                 bt[et] = (a.beta && j0 + et < a.m) ? a.beta[j0 + et] : 0.0;
                 cs[et] = a.sigma2 * a.colscale[j0 + et];
+                if (ROWD) vv[et] = (a.vvec && j0 + et < a.m) ? a.vvec[j0 + et] : 0.0;
             }
             epi_bar();
             mbar_wait(&bars.tmem_full, t & 1);
@@ -507,7 +520,25 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                         const int jj = half * 32 + g * 16 + e;
                         long long q4[4];
                         if ((e & 3) == 0) join_quad(w, e >> 2, q4);
-                        if (j0 + jj < a.m) {
+                        if (ROWD) {
+                            if (j0 + jj < a.m) {
+                                const long long qd = q4[e & 3];
+                                const double kij = a.sigma2 * FIX_INV * (double)qd, tij = cs[jj] * T[g * 16 + e];
+                                const double tk = tij * kij, bk = bt[jj] * kij;
+                                rt[0] += tk;
+                                rbt[0] += bk;
+                                rkv = fma(kij, vv[jj], rkv);
+#pragma unroll
+                                for (int k = 0; k < DT; k++) {
+                                    const double tt = xi[k] - us[jj * DT + k], d2 = tt * tt;
+                                    rt[(ROWD ? 1 + k : 0)] = fma(tk, d2, rt[(ROWD ? 1 + k : 0)]);
+                                    rbt[(ROWD ? 1 + k : 0)] = fma(bk, d2, rbt[(ROWD ? 1 + k : 0)]);
+                                }
+                                if (qd == (1ll << 62))
+                                    record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                            a.coin_omega, a.coin_cap, tij);
+                            }
+                        } else if (j0 + jj < a.m) {
                             const long long qd = q4[e & 3];
                             const double om = fma(rsi, cs[jj] * T[g * 16 + e], rai * bt[jj]);
                             const double pk = om * (a.sigma2 * FIX_INV * (double)qd);
@@ -525,6 +556,16 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                 }
             }
         }
+        if (ROWD) {
+            // one partial per (column group, column half): nothing to reduce across threads, stores only
+            double *part = a.rowd_part + ((int64_t)(blockIdx.y * 2 + half) * a.nslots) * a.ld + i;
+#pragma unroll
+            for (int c = 0; c < DT + 1; c++) {
+                part[(int64_t)c * a.ld] = rt[ROWD ? c : 0];
+                if (a.beta) part[(int64_t)(DT + 1 + c) * a.ld] = rbt[ROWD ? c : 0];
+            }
+            if (a.vvec) part[(int64_t)(a.nslots - 1) * a.ld] = rkv;
+        }
         // CTA reduction: warp shuffles, then the 8 epilogue warps through shared memory -> this CTA's slot
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -538,7 +579,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
             for (int c = 0; c < DT; c++) red[ew * PART_STRIDE_I8 + 1 + c] = sc[c];
         }
         epi_bar();
-        if (et < 1 + DT) {
+        if (!ROWD && et < 1 + DT) {
             double v = 0.0;
             for (int k = 0; k < 8; k++) v += red[k * PART_STRIDE_I8 + et];
             double *slot = a.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * PART_STRIDE_I8 + et;
@@ -690,24 +731,42 @@ static void launch_gen_datarows(cudaStream_t s, dim3 grid, const double *X, int6
                                                                               slice_stride);
 }
 
-template <int DT>
+template <int DT, bool ROWD>
 static cudaError_t launch_km_i8(cudaStream_t s, dim3 grid, int device, const KmI8Args &a)
 {
-    const size_t smem = STAGES * STAGE_BYTES + sizeof(Bars) + 16 + sizeof(double) * (BN * DT + 2 * BN + 8 * PART_STRIDE_I8);
+    const size_t smem = STAGES * STAGE_BYTES + sizeof(Bars) + 16 + sizeof(double) * (BN * DT + 3 * BN + 8 * PART_STRIDE_I8);
     static DeviceOnce once;
     if (once.need(device)) {
-        cudaError_t e = cudaFuncSetAttribute(i8_km_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(i8_km_kernel<DT, ROWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    i8_km_kernel<DT><<<grid, KM_THREADS, smem, s>>>(a);
+    i8_km_kernel<DT, ROWD><<<grid, KM_THREADS, smem, s>>>(a);
     return cudaSuccess;
 }
 
 bool i8_pass2_supported(const GaussWS *w) { return i8_enabled() && !w->want_knots && w->d >= 1 && w->d <= 8; }
 
+static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
+                      const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,
+                      int64_t rowd_stride);
+
 // Pass 2 (gradient sums) on the INT8 tensor cores; same contract and the same per-CTA slots as gauss_pass2.
 int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                    const double *beta, double *out, bool accumulate_slots)
+{
+    return km_pass_i8(ctx, w, gp, Mop, rs, ra, beta, out, accumulate_slots, false, nullptr, nullptr, 0);
+}
+
+// Per-row, per-dimension sums (gauss_rowd of gauss.cu) on the INT8 tensor cores: out[slot * stride + i].
+int gauss_rowd_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta, const double *vvec,
+                  double *out, int64_t stride)
+{
+    return km_pass_i8(ctx, w, gp, Mop, nullptr, nullptr, beta, nullptr, false, true, vvec, out, stride);
+}
+
+static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
+                      const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,
+                      int64_t rowd_stride)
 {
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
@@ -723,7 +782,9 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         SRGP_LAUNCH_CHECK();
     }
     int first = accumulate_slots ? 0 : 1;
-    if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE_I8 * 8, s));
+    if (!rowd && ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE_I8 * 8, s));
+    const int nslots = (d + 1) * (beta ? 2 : 1) + (vvec ? 1 : 0), groups = w->cgroups * 2;
+    if (rowd) SRGP_TRY(w->rowdpart.reserve((size_t)groups * nslots * w->rows2 * 8));
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
     SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
@@ -788,9 +849,13 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
                                                       (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
             a.coin_cap = GaussWS::COIN_CAP;
+            a.vvec = vvec;
+            a.rowd_part = rowd ? w->rowdpart.d() : nullptr;
+            a.nslots = nslots;
+            a.ld = w->rows2;
             dim3 grid(w->rblocks / nsub, w->cgroups * nsub);
             cudaError_t e = cudaSuccess;
-#define CALL(D) e = launch_km_i8<D>(s, grid, ctx->device, a)
+#define CALL(D) e = rowd ? launch_km_i8<D, true>(s, grid, ctx->device, a) : launch_km_i8<D, false>(s, grid, ctx->device, a)
             switch (d) {
             case 1: CALL(1); break;
             case 2: CALL(2); break;
@@ -806,6 +871,11 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             SRGP_LAUNCH_CHECK();
         }
         SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
+        if (rowd) {
+            KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+            gram_combine_rowd(s, w->rowdpart.d(), groups, nslots, w->rows2, rows_valid, rowd_out + r0, rowd_stride);
+            SRGP_LAUNCH_CHECK();
+        }
         first = 0;
     }
     if (out) {

@@ -14,6 +14,10 @@ constexpr int PART_STRIDE_I8 = SRGP_MAX_D + 8;
 bool i8_pass2_supported(const GaussWS *w);
 int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                    const double *beta, double *out, bool accumulate_slots);
+int gauss_rowd_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta, const double *vvec,
+                  double *out, int64_t stride);
+void gram_combine_rowd(cudaStream_t s, const double *part, int groups, int nslots, int64_t ld, int rows, double *out,
+                       int64_t out_stride);
 void gram_sum_part(cudaStream_t s, const double *part, int slots, int stride, int count, double *out);
 // out[j] = sum_g part[g][j] (gauss.cu)
 void gram_sum_rows(cudaStream_t s, const double *part, int groups, int mp, double *out);
