@@ -1252,6 +1252,7 @@ int rowform_chunk(srgp_ctx *ctx, GaussWS *w, const double *Mop, int rows_valid, 
 int gauss_rowform(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec,
                   double *rowq, double *rowkv)
 {
+    if (i8_pass2_supported(w)) return gauss_rowform_i8(ctx, w, gp, Mop, vvec, rowq, vvec ? rowkv : nullptr);
     return km_pass(ctx, w, gp, MODE_ROWFORM, Mop, nullptr, nullptr, nullptr, vvec, nullptr, false, rowq,
                    vvec ? rowkv : nullptr);
 }

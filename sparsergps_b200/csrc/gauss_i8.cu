@@ -362,6 +362,7 @@ struct KmI8Args {
     double *rowd_part;
     int nslots;
     int64_t ld;
+    int nodims;              // ROWD without the per-dimension slots (gauss_rowform): slot 0 = sum_j T_ij K_ij, slot 1 = K v
 };
 
 // Rare path of quirk Q4 (same contract as record_if_coincident in gauss.cu): decided by the reference's own test,
@@ -528,13 +529,15 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                                 rt[0] += tk;
                                 rbt[0] += bk;
                                 rkv = fma(kij, vv[jj], rkv);
+                                if (!a.nodims) {
 #pragma unroll
-                                for (int k = 0; k < DT; k++) {
-                                    const double tt = xi[k] - us[jj * DT + k], d2 = tt * tt;
-                                    rt[(ROWD ? 1 + k : 0)] = fma(tk, d2, rt[(ROWD ? 1 + k : 0)]);
-                                    rbt[(ROWD ? 1 + k : 0)] = fma(bk, d2, rbt[(ROWD ? 1 + k : 0)]);
+                                    for (int k = 0; k < DT; k++) {
+                                        const double tt = xi[k] - us[jj * DT + k], d2 = tt * tt;
+                                        rt[(ROWD ? 1 + k : 0)] = fma(tk, d2, rt[(ROWD ? 1 + k : 0)]);
+                                        rbt[(ROWD ? 1 + k : 0)] = fma(bk, d2, rbt[(ROWD ? 1 + k : 0)]);
+                                    }
                                 }
-                                if (qd == (1ll << 62))
+                                if (qd == (1ll << 62) && !a.nodims)   // the row forms (gauss_rowform) record no pairs
                                     record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
                                                             a.coin_omega, a.coin_cap, tij);
                             }
@@ -559,10 +562,14 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
         if (ROWD) {
             // one partial per (column group, column half): nothing to reduce across threads, stores only
             double *part = a.rowd_part + ((int64_t)(blockIdx.y * 2 + half) * a.nslots) * a.ld + i;
+            if (a.nodims) {
+                part[0] = rt[0];
+            } else {
 #pragma unroll
-            for (int c = 0; c < DT + 1; c++) {
-                part[(int64_t)c * a.ld] = rt[ROWD ? c : 0];
-                if (a.beta) part[(int64_t)(DT + 1 + c) * a.ld] = rbt[ROWD ? c : 0];
+                for (int c = 0; c < DT + 1; c++) {
+                    part[(int64_t)c * a.ld] = rt[ROWD ? c : 0];
+                    if (a.beta) part[(int64_t)(DT + 1 + c) * a.ld] = rbt[ROWD ? c : 0];
+                }
             }
             if (a.vvec) part[(int64_t)(a.nslots - 1) * a.ld] = rkv;
         }
@@ -748,7 +755,7 @@ bool i8_pass2_supported(const GaussWS *w) { return i8_enabled() && !w->want_knot
 
 static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                       const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,
-                      int64_t rowd_stride);
+                      int64_t rowd_stride, bool nodims = false);
 
 // Pass 2 (gradient sums) on the INT8 tensor cores; same contract and the same per-CTA slots as gauss_pass2.
 int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
@@ -764,9 +771,17 @@ int gauss_rowd_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *
     return km_pass_i8(ctx, w, gp, Mop, nullptr, nullptr, beta, nullptr, false, true, vvec, out, stride);
 }
 
+// Row quadratic forms (gauss_rowform of gauss.cu): rowq_i = K_i Mop K_i^T, rowkv_i = K_i v (v may be null).
+int gauss_rowform_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec, double *rowq,
+                     double *rowkv)
+{
+    // slot 0 -> rowq, slot 1 -> rowkv: the two outputs are addressed as out[slot * stride + i] with stride = rowkv - rowq
+    return km_pass_i8(ctx, w, gp, Mop, nullptr, nullptr, nullptr, nullptr, false, true, vvec, rowq, vvec ? rowkv - rowq : 0, true);
+}
+
 static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                       const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,
-                      int64_t rowd_stride)
+                      int64_t rowd_stride, bool nodims)
 {
     cudaStream_t s = ctx->stream;
     const int mp = w->mp, m = w->m, d = w->d;
@@ -783,7 +798,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
     }
     int first = accumulate_slots ? 0 : 1;
     if (!rowd && ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE_I8 * 8, s));
-    const int nslots = (d + 1) * (beta ? 2 : 1) + (vvec ? 1 : 0), groups = w->cgroups * 2;
+    const int nslots = nodims ? (vvec ? 2 : 1) : (d + 1) * (beta ? 2 : 1) + (vvec ? 1 : 0), groups = w->cgroups * 2;
     if (rowd) SRGP_TRY(w->rowdpart.reserve((size_t)groups * nslots * w->rows2 * 8));
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
@@ -853,6 +868,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.rowd_part = rowd ? w->rowdpart.d() : nullptr;
             a.nslots = nslots;
             a.ld = w->rows2;
+            a.nodims = nodims ? 1 : 0;
             dim3 grid(w->rblocks / nsub, w->cgroups * nsub);
             cudaError_t e = cudaSuccess;
 #define CALL(D) e = rowd ? launch_km_i8<D, true>(s, grid, ctx->device, a) : launch_km_i8<D, false>(s, grid, ctx->device, a)

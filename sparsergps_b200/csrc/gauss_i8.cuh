@@ -16,6 +16,8 @@ int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
                    const double *beta, double *out, bool accumulate_slots);
 int gauss_rowd_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta, const double *vvec,
                   double *out, int64_t stride);
+int gauss_rowform_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *vvec, double *rowq,
+                     double *rowkv);
 void gram_combine_rowd(cudaStream_t s, const double *part, int groups, int nslots, int64_t ld, int rows, double *out,
                        int64_t out_stride);
 void gram_sum_part(cudaStream_t s, const double *part, int slots, int stride, int count, double *out);
