@@ -323,7 +323,8 @@ def main():
         def frac(x, ms_, pk):
             return rate(x, ms_) / pk if ms_ > 0 else None
 
-        rows2 = 74 * 128                                         # pass-2 chunk (row blocks x 128), rows are padded to it
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        rows2 = (sms // 2) * 128                                 # pass-2 chunk: (SMs / 2 column groups) row blocks x 128, rows are padded to it
         km_rows = -(-nloc // rows2) * rows2
         km_ops8 = 36 * 2.0 * km_rows * mp * mp * steps           # 36 slice pairs, every 64-column tile of every row block
         gram_quant = 128

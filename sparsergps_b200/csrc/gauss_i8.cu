@@ -1,11 +1,18 @@
-// gauss_i8.cu -- the row passes of the fused Gaussian pipeline on the INT8 tensor cores (tcgen05 + TMEM).
+// gauss_i8.cu -- the row passes of the fused Gaussian / Laplace pipelines on the INT8 tensor cores (tcgen05 + TMEM).
+// Reference functions served: the n x m products inside elbo_fun / delbo_dcov_par (R/vi_functions.R:64-121, 126-420),
+// obj_fun_norm / dlogp_dcov_par (R/laplace_approx_obj_funs.R:6-52, R/laplace_approx_gradient.R:720-968) and
+// dlogq_dcov_par (R/laplace_approx_gradient.R:25-339); the algebra is in gauss_vi.cu / gauss_fic.cu / laplace.cu,
+// the scheme and its error bound in tc_i8.cuh and DESIGN.md section 3a.
 //
-// Pass 1 (this file, first half): G1 = K^T K and b1 = K^T r.  The generator emits k_ij / sigma^2 = exp(-d_ij^2 / 2)
-// in (0, 1] as 8 INT8 digit slices, already in the shared-memory operand image of tc_i8.cuh; the Gram kernel runs
-// one CTA per (128 x 64 tile of the lower block triangle, row split), keeps all 8 significance levels of the tile
-// in TMEM over its row range, converts INT32 -> FP64 once per launch and adds into its own slot (deterministic).
-// Everything is exact except the final FP64 summation of levels, splits and chunks (see tc_i8.cuh for the bound),
-// so the result is at least as accurate as the DMMA SYRK it replaces (profiles/r01_ozaki_*.json).
+// Pass 1: G = K^T diag(w) K (w optional) and b1 = K^T r.  The generator emits k_ij / sigma^2 = exp(-d_ij^2 / 2) in
+// (0, 1] as 8 INT8 digit slices, already in the shared-memory operand image of tc_i8.cuh (plus a second slice set
+// w_i k_ij / (sigma^2 2^ew) for a weighted Gram); the Gram kernel runs one CTA per (128 x 64 tile of the lower block
+// triangle, row split), keeps all 8 significance levels of the tile in TMEM over its row range, converts
+// INT32 -> FP64 once per launch and adds into its own slot (deterministic).  Everything is exact except the final
+// FP64 summation of levels, splits and chunks, so the result is at least as accurate as the DMMA SYRK it replaces
+// (profiles/r01_ozaki_*.json).
+// Pass 2 and the row forms: T = K Mop^T with Mop sliced per output column; one epilogue thread per data row forms the
+// gradient sums (gauss_pass2), the per-row / per-dimension sums (gauss_rowd) or the row quadratic forms (gauss_rowform).
 #include <math.h>
 #include <stdlib.h>
 
