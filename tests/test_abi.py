@@ -56,3 +56,31 @@ def test_scalar_exports_known_answers():
     # exp kernel: L1 distance in the covariance, L2 in the derivatives (quirk Q8)
     assert R.cov_fun_expC([0.0, 0.0], [3.0, 4.0], {"sigma": 1, "l": 1}) == pytest.approx(np.exp(-7.0))
     assert R.dexp_dsigmaC([0.0, 0.0], [3.0, 4.0], {"sigma": 1, "l": 1})["derivative"] == pytest.approx(2 * np.exp(-5.0))
+
+
+def test_library_sass_is_blackwell_native():
+    """The built library must contain the sm_100a tensor-core path, not a recompiled legacy one: tcgen05.mma (SASS
+    UTCIMMA) with TMEM loads (LDTM) and TMA bulk copies (UBLKCP) in the INT8 row-pass kernels."""
+    import re
+    import shutil
+    import subprocess
+    from sparsergps_b200 import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", build.LIB], capture_output=True, text=True).stdout
+    cur, per = None, {}
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = {"UTCIMMA": 0, "LDTM": 0, "UBLKCP": 0}
+        elif cur:
+            for k in per[cur]:
+                if k in line:
+                    per[cur][k] += 1
+    gram = [v for f, v in per.items() if "i8_gram_kernel" in f]
+    km = [v for f, v in per.items() if "i8_km_kernel" in f]
+    assert gram and km, "INT8 tensor-core kernels missing from libsrgp.so"
+    for v in gram + km:
+        assert v["UTCIMMA"] == 36 and v["LDTM"] >= 1 and v["UBLKCP"] >= 1, v      # 36 slice pairs per k-step
