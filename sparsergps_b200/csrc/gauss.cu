@@ -11,9 +11,14 @@
 //   m x m    chol(S), S^-1, chol(S + G), C, v, beta, M, N, log-dets                  (replicated)
 //   pass 2   T = K Mop (DMMA), Omega = T + a beta^T, sum_ij Omega_ij dK_ij(theta)    -> one allreduce
 //
-// K is generated in row chunks that stay L2-resident between the generator and the DMMA kernel (the FP64
-// pipe is shared by DFMA and DMMA on sm_100 -- profiles/r01_microbench.json -- so each K entry is generated
-// exactly once per pass instead of once per output tile); K never exists as an n x m matrix.
+// K is generated in row chunks that stay L2-resident between the generator and the tensor-core kernel (each K entry
+// is generated exactly once per pass instead of once per output tile); K never exists as an n x m matrix.
+//
+// Two tensor-core engines serve the passes.  The default is the INT8 engine of gauss_i8.cu / tc_i8.cuh
+// (tcgen05.mma.kind::i8 with TMEM accumulators, error-free digit splitting: DESIGN.md section 3a); gauss_pass1,
+// gauss_pass2, gauss_rowd and gauss_rowform below route to it whenever it supports the request.  The FP64 DMMA engine
+// of this file (gemm.cuh) remains for the knot-gradient epilogue, d > 8, the Gram over the materialised K of the
+// Laplace Newton loop, and as the SRGP_TENSOR=dmma diagnostic.
 #include <math.h>
 #include <stdlib.h>
 
