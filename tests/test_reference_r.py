@@ -3,8 +3,9 @@
 tests/golden/r_level.* holds what /root/reference/R/*.R returns -- executed unmodified by oracle/mini_r with the Rcpp
 exports bound to the reference's compiled C++ (tests/tools/make_golden_r.py) -- for rows a14-a25 and f1, f2, f4 of
 SURVEY.md section 8: trace_term_fun, dtrace_term_dtau, elbo_fun, obj_fun_norm, delbo_dcov_par, dlogp_dcov_par (theta
-and knot gradients), newtrap_sparseGP, dlogq_dcov_par, predict_vi / predict_laplace, and FIT_IT iterations of
-norm_grad_ascent_vi / norm_grad_ascent / laplace_grad_ascent.  The transcription must reproduce them to 1e-10
+and knot gradients), newtrap_sparseGP, dlogq_dcov_par, predict_vi / predict_laplace, FIT_IT iterations of
+norm_grad_ascent_vi / norm_grad_ascent / laplace_grad_ascent, and the OAT candidate selection of
+knot_prop_random_norm_vi / knot_prop_random_norm (row f3).  The transcription must reproduce them to 1e-10
 (different BLAS call grouping is the only licence); in the build container the R code is re-run on two cases to
 prove the committed file is what the reference computes today."""
 import numpy as np
@@ -105,6 +106,23 @@ def test_optimiser_loops_match_reference_r(name):
         pm, pv = rm.predict_laplace(o["u_mean"], o["u_var"], o["xu_final"], o["x_pred"], cf, cpf, mu_p, i["muu"], family=fam, delta=delta)
     _close(pm, o["pred_mean"], 1e-9, "pred_mean")
     _close(pv, o["pred_var"], 1e-8, "pred_var")
+
+
+@pytest.mark.parametrize("name", _cases("o_"))
+def test_oat_candidate_selection_matches_reference_r(name):
+    """knot_prop_random_norm_vi / knot_prop_random_norm run unmodified (only sample.int is a fixed draw): the scores of
+    the candidate loop and the chosen knot, including "no candidate beats the current objective -> first knot"."""
+    c = G[name]
+    meta, i, o = c["meta"], c["in"], c["out"]
+    cp, cf, delta, vi = meta["cov_par"], meta["cov_fun"], meta["delta"], meta["model"] == "vi"
+    pp = i["xy"][i["draw"].astype(int) - 1]
+    np.testing.assert_array_equal(pp, o["pseudo_prop"])
+    sc = rm.oat_candidate_scores(cp, cf, i["xu"], i["xy"], i["y"], i["mu"], pp, delta, vi=vi)
+    _close(sc, o["scores"], what="candidate scores")
+    chosen = rm.knot_prop_choice(i["xu"], pp, float(i["obj_current"]), sc)
+    np.testing.assert_array_equal(chosen, o["chosen"])
+    if name.endswith("none_better"):
+        np.testing.assert_array_equal(chosen[0], i["xu"][0])
 
 
 @pytest.mark.skipif(not rr.available(), reason="/root/reference is only present in the build container")

@@ -47,6 +47,11 @@ R_GLUE = r'''
   list("sigma" = dsqexp_dsigma_ard, "tau" = dsqexp_dtau)
 }
 .srgp_dknot <- function(cov_fun) { if(cov_fun == "sqexp") dsqexp_dx2 else dsqexp_dx2_ard }
+.srgp_scores <- numeric()
+.srgp_rec_elbo <- function(...) { v <- elbo_fun(...); .srgp_scores <<- c(.srgp_scores, as.numeric(v)); v }
+.srgp_rec_norm <- function(...) { v <- obj_fun_norm(...); .srgp_scores <<- c(.srgp_scores, as.numeric(v)); v }
+.srgp_reset_scores <- function() { .srgp_scores <<- numeric(); 0 }
+.srgp_get_scores <- function() .srgp_scores
 '''
 
 
@@ -249,12 +254,52 @@ def fit_cases():
     return out
 
 
+def run_oat(c):
+    """The reference's candidate-selection functions knot_prop_random_norm_vi (R/vi_functions.R:2108-2304) and
+    knot_prop_random_norm (R/knot_proposal_functions.R:1176-1357), run unmodified; their only random input --
+    sample.int() choosing TTmax candidate rows of xy -- is replaced by the fixed draw c["draw"] (1-based), and the
+    objective function handed in through `...` is a recording wrapper around the reference's own elbo_fun /
+    obj_fun_norm, so the per-candidate scores of the loop come back besides the chosen knot."""
+    from oracle.mini_r import interp as RI
+    I = rr.session()
+    I.run(R_GLUE)
+    draw = np.asarray(c["draw"], dtype=np.int64)
+    I.globalenv.vars["sample.int"] = RI.Builtin("sample.int", lambda I_, pos, kw: RI.Vec(draw.copy()))
+    rr.call(".srgp_reset_scores")
+    vi = c["model"] == "vi"
+    norm_opt = {"xu": c["xu"], "cov_par": c["cov_par"], "xy": c["xy"], "mu": c["mu"], "cov_fun": c["cov_fun"],
+                "obj_fun": np.array([c["obj_current"] - 1.0, c["obj_current"]])}
+    out = rr.call("knot_prop_random_norm_vi" if vi else "knot_prop_random_norm", norm_opt=norm_opt,
+                  opt={"TTmax": len(draw), "delta": c["delta"]}, y=c["y"],
+                  obj_fun=rr.rfun(".srgp_rec_elbo" if vi else ".srgp_rec_norm"), cov_fun=c["cov_fun"])
+    scores = np.asarray(rr.call(".srgp_get_scores")).reshape(-1)
+    del I.globalenv.vars["sample.int"]
+    return {"chosen": np.asarray(out).reshape(1, -1), "scores": scores, "pseudo_prop": c["xy"][draw - 1]}
+
+
+def oat_cases():
+    from oracle import ref_model as rm
+    g = gauss_cases()
+    out = {}
+    for nm, src, model, draw, shift in (("o_vi_ard_d5", g["g_ard_d5"], "vi", [5, 17, 33, 60, 2, 48], 0.0),
+                                        ("o_fic_ard_d5", g["g_ard_d5"], "fic", [5, 17, 33, 60, 2, 48], 0.0),
+                                        ("o_vi_sqexp_2d", g["g_sqexp_2d_mu"], "vi", [1, 9, 30, 44], 0.0),
+                                        ("o_vi_none_better", g["g_sqexp_2d_mu"], "vi", [1, 9, 30, 44], 1e6)):
+        c = dict(src, model=model, draw=np.array(draw, dtype=np.float64))
+        f = rm.vi_obj_grad if model == "vi" else rm.fic_obj_grad
+        # the last objective value of the fit the OAT step starts from (shift > 0: no candidate can beat it, the reference
+        # then returns the FIRST existing knot)
+        c["obj_current"] = float(f(c["cov_par"], c["cov_fun"], c["xu"], c["xy"], c["y"], c["mu"], c["delta"])[0]) + shift
+        out[nm] = c
+    return out
+
+
 def flatten(cases, results):
     arrays, index = {}, {}
     for nm, c in cases.items():
         index[nm] = {"cov_par": c["cov_par"], "cov_fun": c["cov_fun"], "delta": c["delta"], "knots": c["knots"],
                      "family": c.get("family", "gaussian"), "model": c.get("model"), "outputs": sorted(results[nm])}
-        for k in ("xy", "y", "mu", "xu", "muu"):
+        for k in ("xy", "y", "mu", "xu", "muu", "draw", "obj_current"):
             if k in c:
                 arrays["%s/in/%s" % (nm, k)] = np.asarray(c[k], dtype=np.float64)
         for k, v in c.get("extra", {}).items():
@@ -278,6 +323,10 @@ def generate(verbose=False):
             print("%-22s %.1f s (%d Newton iterations)" % (nm, time.time() - t0, len(results[nm]["objective_function_values"]) - 1))
     for nm, c in fit_cases().items():
         cases[nm], results[nm] = c, run_fit(c)
+        if verbose:
+            print("%-22s %.1f s" % (nm, time.time() - t0))
+    for nm, c in oat_cases().items():
+        cases[nm], results[nm] = c, run_oat(c)
         if verbose:
             print("%-22s %.1f s" % (nm, time.time() - t0))
     return flatten(cases, results)
