@@ -125,6 +125,21 @@ def test_oat_candidate_selection_matches_reference_r(name):
         np.testing.assert_array_equal(chosen[0], i["xu"][0])
 
 
+@pytest.mark.parametrize("name", _cases("p_"))
+def test_laplace_candidate_selection_matches_reference_r(name):
+    """knot_prop_random (sparse Laplace models) run unmodified with a fixed draw: the chosen knot."""
+    c = G[name]
+    meta, i, o = c["meta"], c["in"], c["out"]
+    cp, cf, delta, fam = meta["cov_par"], meta["cov_fun"], meta["delta"], meta["family"]
+    pp = i["xy"][i["draw"].astype(int) - 1]
+    np.testing.assert_array_equal(pp, o["pseudo_prop"])
+    sc = rm.laplace_oat_candidate_scores(cp, cf, i["xu"], i["xy"], i["y"], o["fmax"], fam, i["mu"], i["muu"], pp, delta,
+                                         **gu.r_case_extra(c))
+    assert np.all(np.isfinite(sc))
+    chosen = rm.knot_prop_choice(i["xu"], pp, float(o["obj_current"][0]), sc)
+    np.testing.assert_array_equal(chosen, o["chosen"])
+
+
 @pytest.mark.skipif(not rr.available(), reason="/root/reference is only present in the build container")
 def test_golden_file_is_what_the_reference_r_computes_now():
     import importlib.util

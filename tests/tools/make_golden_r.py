@@ -277,6 +277,26 @@ def run_oat(c):
     return {"chosen": np.asarray(out).reshape(1, -1), "scores": scores, "pseudo_prop": c["xy"][draw - 1]}
 
 
+def run_oat_laplace(c, nr):
+    """knot_prop_random (R/knot_proposal_functions.R:1001-1175) run unmodified with a fixed sample.int draw: one
+    warm-started newtrap_sparseGP per candidate; returns the chosen knot.  nr = the Newton result the step starts from."""
+    from oracle.mini_r import interp as RI
+    I = rr.session()
+    I.run(R_GLUE)
+    sfx = {"bernoulli": "bern", "poisson": "pois"}[c["family"]]
+    draw = np.asarray(c["draw"], dtype=np.int64)
+    I.globalenv.vars["sample.int"] = RI.Builtin("sample.int", lambda I_, pos, kw: RI.Vec(draw.copy()))
+    lo = {"xu": c["xu"], "cov_par": c["cov_par"], "xy": c["xy"], "mu": c["mu"], "muu": c["muu"], "cov_fun": c["cov_fun"],
+          "fmax": nr["gp"], "obj_fun": nr["objective_function_values"]}
+    out = rr.call("knot_prop_random", laplace_opt=lo, opt={"TTmax": len(draw), "delta": c["delta"]}, cov_fun=c["cov_fun"], y=c["y"],
+                  obj_fun=rr.rfun("obj_fun_" + sfx), grad_loglik_fn=rr.rfun("grad_loglik_fn_" + sfx),
+                  dlog_py_dff=rr.rfun("dlog_py_dff_" + sfx), d2log_py_dff=rr.rfun("d2log_py_dff_" + sfx), maxit=1000, tol=1e-6,
+                  **c["extra"])
+    del I.globalenv.vars["sample.int"]
+    return {"chosen": np.asarray(out).reshape(1, -1), "pseudo_prop": c["xy"][draw - 1], "fmax": nr["gp"],
+            "obj_current": np.asarray(nr["objective_function_values"]).reshape(-1)[-1:]}
+
+
 def oat_cases():
     from oracle import ref_model as rm
     g = gauss_cases()
@@ -327,6 +347,11 @@ def generate(verbose=False):
             print("%-22s %.1f s" % (nm, time.time() - t0))
     for nm, c in oat_cases().items():
         cases[nm], results[nm] = c, run_oat(c)
+        if verbose:
+            print("%-22s %.1f s" % (nm, time.time() - t0))
+    for nm, src, draw in (("p_lap_bern_d3", "l_bern_ard_d3", [3, 21, 40, 55]), ("p_lap_pois_1d", "l_pois_sqexp_1d", [4, 18, 33])):
+        c = dict(cases[src], draw=np.array(draw, dtype=np.float64), model="laplace")
+        cases[nm], results[nm] = c, run_oat_laplace(c, results[src])
         if verbose:
             print("%-22s %.1f s" % (nm, time.time() - t0))
     return flatten(cases, results)
