@@ -21,6 +21,20 @@ import sys
 import threading
 import time
 
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    # The reference arm owns all host cores whatever the launcher exported: torch.distributed.run sets
+    # OMP_NUM_THREADS=1 for its workers, which silently made the r01 arm single-threaded at N >= 2.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(host_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -120,11 +134,9 @@ def fp64_peak_tflops():
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    """DRAM bytes per launch (and tensor-pipe activity) of a kernel from the committed ncu --set full capture (profiles/)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
-        return {"bytes_per_launch": t["bytes_per_launch"], "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_launch"],
-                "source": t["source"]}
+        return dict(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel])
     except Exception:
         return None
 
@@ -143,52 +155,164 @@ def cpu_reference_time(n_sample, m, d, threads=None):
     return time.perf_counter() - t0, obj
 
 
+def blas_threads(n=None):
+    """Pin (n given) and report the BLAS thread count actually in use (threadpoolctl), not os.cpu_count()."""
+    try:
+        import threadpoolctl
+        if n is not None:
+            threadpoolctl.threadpool_limits(limits=int(n), user_api="blas")
+        info = [p for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
+        if info:
+            return int(info[0]["num_threads"]), "%s %s" % (info[0].get("internal_api", "blas"), info[0].get("version", "?"))
+    except Exception:
+        pass
+    return None, "BLAS (threadpoolctl unavailable)"
+
+
+def affine(n1, t1, n2, t2, n_full):
+    """t(n) = a + b n through two samples: the reference's cost at fixed m is a fixed part (m x m factorisations and
+    per-parameter m^3 products) plus a part linear in n, so a proportional extrapolation t(n2) n_full / n2 would charge
+    the reference its fixed cost n_full / n2 times over."""
+    b = max((t2 - t1) / (n2 - n1), 0.05 * t2 / n2)     # guard: timing noise must not produce a ~zero slope
+    a = max(t2 - b * n2, 0.0)
+    return a, b, a + b * n_full
+
+
 def cpu_reference_estimate(n_sample, m, d, n_full):
-    """Seconds per evaluation of the CPU port at n_full rows from TWO bounded samples (n_sample / 4 and n_sample rows):
-    the reference's cost is a + b n at fixed m (m x m factorisations and per-parameter m^3 products do not depend on n,
-    every other term is linear in n), so the estimate is the affine fit, not t(n_sample) * n_full / n_sample, which
-    would charge the reference n_full / n_sample times its fixed cost."""
+    """Seconds per evaluation of the CPU port at n_full rows from TWO bounded samples (n_sample / 4 and n_sample rows)."""
     n1, n2 = max(256, n_sample // 4), n_sample
     t1, _ = cpu_reference_time(n1, m, d)
     t2, _ = cpu_reference_time(n2, m, d)
-    b = max((t2 - t1) / (n2 - n1), 0.05 * t2 / n2)     # guard: timing noise must not produce a ~zero slope
-    a = max(t2 - b * n2, 0.0)
-    sec = a + b * n_full
+    a, b, sec = affine(n1, t1, n2, t2, n_full)
     return sec, ("%d rows %.2f s, %d rows %.2f s -> %.2f s + %.3g s/row, affine extrapolation to %d rows = %.0f s per "
                  "evaluation" % (n1, t1, n2, t2, a, b, n_full, sec))
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  R is not installed on this image
-    (SURVEY.md 8c), so the timed code is the oracle port; n = 1e6 is out of reach for the literal algebra
-    (>= 12 live 8.2 GB matrices, ~286 TFLOP), so each step evaluates two bounded row samples and the value is
-    the affine extrapolation a + b n (see cpu_reference_estimate)."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.  R is not installed on
+    this image, so the timed code is the oracle port (kind "port"); n = 1e6 is out of reach for the literal
+    algebra (>= 12 live 8.2 GB matrices, ~286 TFLOP), so the value is an affine EXTRAPOLATION a + b n:
+      * once, before the steps: 16384 and 65536 rows on all cores, plus 512 and 2048 rows on ONE
+        BLAS thread (the stand-in for R's default single-threaded reference BLAS, BASELINE.md section 3.2);
+      * every step: a bounded 2048-row sample; the step's value is the line through (2048, this step) and (65536, calibration)
+        evaluated at n; the 16384-row calibration point is the linearity check (its residual from that line is printed).
+    The thread count is pinned explicitly and reported from threadpoolctl, so the arm is the same at every --gpus N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, m, d = args.n, args.m, args.d
-    n_sample = args.ref_sample
-    cores = os.cpu_count() or 1
-    times, notes = [], []
+    cores = host_cores()
+    threads, blas = blas_threads(cores)
+    n_small, n_mid, n_big = args.ref_sample, 8 * args.ref_sample, 32 * args.ref_sample
+    cpu_reference_time(1024, m, d)                                   # page in BLAS / build the C assembly
+    t_mid, _ = cpu_reference_time(n_mid, m, d)
+    t_big, _ = cpu_reference_time(n_big, m, d)
+    one_thread = None
+    if not args.no_one_thread:
+        blas_threads(1)
+        t1a, _ = cpu_reference_time(n_small // 4, m, d)
+        t1b, _ = cpu_reference_time(n_small, m, d)
+        a1, b1, sec1 = affine(n_small // 4, t1a, n_small, t1b, n)
+        one_thread = {"value": 1.0 / sec1, "unit": UNIT, "cores": 1,
+                      "sample": "%d rows %.2f s, %d rows %.2f s on 1 BLAS thread -> %.2f s + %.3g s/row = %.0f s per evaluation "
+                                "(extrapolated)" % (n_small // 4, t1a, n_small, t1b, a1, b1, sec1)}
+        threads, blas = blas_threads(cores)
+    times, notes, resid = [], [], []
     for i in range(args.warmup + args.steps):
-        t, note = cpu_reference_estimate(n_sample, m, d, n)
+        t_small, _ = cpu_reference_time(n_small, m, d)
+        a, b, sec = affine(n_small, t_small, n_big, t_big, n)
         if i >= args.warmup:
-            times.append(t)
-            notes.append(note)
+            times.append(sec)
+            resid.append((t_mid - (a + b * n_mid)) / t_mid)
+            notes.append("%d rows %.2f s (this step), %d rows %.2f s and %d rows %.2f s (calibration) -> %.2f s + %.3g s/row, "
+                         "linearity residual at %d rows %+.1f %%, affine extrapolation to %d rows = %.0f s per evaluation"
+                         % (n_small, t_small, n_mid, t_mid, n_big, t_big, a, b, n_mid, 100 * resid[-1], n, sec))
     sec_per_eval_full = float(np.mean(times))
     value = 1.0 / sec_per_eval_full
-    blas = "OpenBLAS (numpy scipy-openblas), %d threads" % cores
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_eval_full * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n, m, d)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "oracle (NumPy literal transcription + single-threaded C assembly, %s); each step "
-                                   "times two row samples; last step: %s" % (blas, notes[-1])},
+        "config": {"workload": workload_name(n, m, d), "extrapolated": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads or cores, "kind": "port", "host_cores": cores,
+                         "blas": blas, "extrapolated": True, "linearity_residual": float(np.mean(resid)),
+                         "one_thread": one_thread,
+                         "sample": "oracle (NumPy literal transcription of elbo_fun + delbo_dcov_par on %s with %s threads "
+                                   "[threadpoolctl] + single-threaded C assembly as Rcpp is); last step: %s"
+                                   % (blas, threads, notes[-1])},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "stated_sizes.json")
+
+
+def load_golden():
+    try:
+        with open(GOLDEN) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def rel_errs(obj, grad, ref_obj, ref_grad):
+    ref_grad = np.asarray(ref_grad, dtype=np.float64)
+    grad = np.asarray(grad, dtype=np.float64)
+    return {"obj_rel": float(abs(obj - ref_obj) / abs(ref_obj)),
+            "grad_rel": float(np.max(np.abs(grad - ref_grad) / np.abs(ref_grad))),
+            "grad_rel_to_max": float(np.max(np.abs(grad - ref_grad)) / np.max(np.abs(ref_grad)))}
+
+
+def knot_errs(kg, summ):
+    kg = np.asarray(kg, dtype=np.float64).reshape(summ["shape"])
+    probe = np.array([kg[k, c] for k, c in summ["probe_idx"]])
+    return float(max(abs(np.linalg.norm(kg) - summ["fro"]) / summ["fro"],
+                     abs(np.abs(kg).sum() - summ["abs_sum"]) / summ["abs_sum"],
+                     np.max(np.abs(probe - np.asarray(summ["probe"]))) / np.max(np.abs(summ["probe"]))))
+
+
+def parity_checks(ctx, world, rank, golden):
+    """Sharded (world ranks) evaluations of the secondary paths against the committed CPU-oracle goldens, before the
+    timed region: FIC objective + gradient + knot gradient (n = 250k, m = 1024), the sparse-Laplace Newton search and
+    gradient of BASELINE configs[3] (Bernoulli, n = 100k, m = 512).  Every multi-GPU driver run is thereby a parity
+    check of the NCCL paths of gauss_fic.cu, laplace.cu and the knot-gradient allreduce."""
+    from sparsergps_b200.vi_functions import knot_bounds
+    out = {}
+    if "cfg5_fic" in golden:
+        g = golden["cfg5_fic"]
+        x, y, xu, th = workload(g["n"], g["m"], g["d"])
+        lo, hi = shard_bounds(g["n"], world, rank)
+        ctx.set_data(np.asfortranarray(x[lo:hi]), np.ascontiguousarray(y[lo:hi]), None)
+        ctx.timer_start()
+        obj, grad, kg, _ = ctx.gauss_obj_grad_knots("fic", "ard", xu, th["sigma"], th["l"], th["tau"], th["delta"], knot_bounds(x))
+        ms = ctx.timer_stop_ms()
+        out["fic_n250k_m1024"] = dict(rel_errs(obj, grad, g["obj"], g["grad"]), knot_rel=knot_errs(kg, g["knot"]), ms=ms)
+    if "cfg4" in golden:
+        from sparsergps_b200 import laplace as Lp
+        from tests import cases
+        g = golden["cfg4"]
+        c = cases.config4(n=g["n"], d=g["d"], m=g["m"])
+        cp = c["cov_par"]
+        lo, hi = shard_bounds(g["n"], world, rank)
+        xs, ys = np.asfortranarray(c["x"][lo:hi]), np.ascontiguousarray(c["y"][lo:hi])
+        t0 = time.perf_counter()
+        fit = Lp.newtrap_sparseGP(np.zeros(hi - lo), "bernoulli", cp, "ard", xs, c["xu"], ys, np.zeros(hi - lo),
+                                  np.zeros(g["m"]), maxit=g["maxit"], tol=g["tol"], delta=c["delta"], ctx=ctx)
+        sec = time.perf_counter() - t0
+        h = fit["objective_function_values"]
+        ff = (1.5 * np.sin(c["x"][:, 0]) + c["x"][:, 1] - 0.5 * c["x"][:, 2])[lo:hi]        # tests/tools/make_golden_sizes.py
+        t0 = time.perf_counter()
+        got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], xs, ys, ff, "bernoulli", np.zeros(hi - lo), c["delta"], ctx=ctx)["gradient"]
+        gsec = time.perf_counter() - t0
+        gerr = rel_errs(0.0, [got[k] for k in g["names"]], 1.0, g["grad_at_closed_form_ff"])
+        out["laplace_n100k_m512"] = {
+            "newton_iterations": int(len(h)), "newton_iterations_golden": g["iterations"],
+            "hist_rel": float(np.max(np.abs(h - np.asarray(g["hist"])[:len(h)]) / np.abs(np.asarray(g["hist"])[:len(h)])))
+            if len(h) <= len(g["hist"]) else None,
+            "u_mean_rel_to_max": float(np.max(np.abs(fit["u_posterior_mean"] - np.asarray(g["u_mean"]))) / np.max(np.abs(g["u_mean"]))),
+            "grad_rel": gerr["grad_rel"], "newton_it_per_s": (len(h) - 1) / sec, "grad_ms": gsec * 1e3}
+    return out
 
 
 def main():
@@ -200,8 +324,10 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--m", type=int, default=1024)
     ap.add_argument("--d", type=int, default=8)
-    ap.add_argument("--ref-sample", type=int, default=4096, help="rows per CPU-baseline evaluation")
+    ap.add_argument("--ref-sample", type=int, default=2048, help="reference arm: rows of the per-step CPU sample (calibration: 8x and 32x)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-one-thread", action="store_true", help="reference arm: skip the 1-BLAS-thread figure")
+    ap.add_argument("--no-check", action="store_true", help="skip the sharded parity checks before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -252,6 +378,11 @@ def main():
         return ctx.gauss_obj_grad_host("vi", "ard", xs_host, ys_host, None, xu, th["sigma"], th["l"], th["tau"],
                                        th["delta"])
 
+    golden = load_golden()
+    checks = None
+    if not args.no_check and (n, m, d) == (1_000_000, 1024, 8):
+        checks = parity_checks(ctx, world, rank, golden)
+
     # ---------------- device-resident arm (value) ----------------
     ctx.set_data(xs, ys, None)
     for _ in range(max(3, args.warmup)):
@@ -293,29 +424,43 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e_max = float(t.item())
 
+    parity = None
+    g5 = golden.get("cfg5_vi")
+    if g5 and (n, m, d) == (g5["n"], g5["m"], g5["d"]):
+        parity = dict(rel_errs(obj, grad, g5["obj"], g5["grad"]), e2e=rel_errs(obj_e, grad_e, g5["obj"], g5["grad"]),
+                      golden="tests/golden/stated_sizes.json cfg5_vi: oracle/reduced_model.vi_obj_grad on the CPU, 100 row shards, "
+                             "float64 (tests/tools/make_golden_sizes.py)", tolerance=1e-8)
+        if checks is not None:
+            from sparsergps_b200.vi_functions import knot_bounds
+            ctx.set_data(xs, ys, None)
+            ctx.timer_start()
+            _, _, kg, _ = ctx.gauss_obj_grad_knots("vi", "ard", xu, th["sigma"], th["l"], th["tau"], th["delta"], knot_bounds(x))
+            checks["vi_knot_gradient_n1M_m1024"] = {"knot_rel": knot_errs(kg, g5["knot"]), "ms": ctx.timer_stop_ms()}
+
     if rank == 0:
         steps = args.steps
         value = steps / (ms_max * 1e-3)
         e2e_value = steps / (ms_e_max * 1e-3)
         nloc = hi - lo
         # Roofline of the dominant kernel.  Both row passes run on the INT8 tensor cores (tcgen05.mma.kind::i8, Ozaki
-        # splitting: 36 exact INT8 slice-pair products per FP64 product), so the pipe that bounds
-        # them is the INT8 tensor pipe: achieved = EXECUTED INT8 operations / kernel time, peak = 2 x the measured dense
-        # bf16 rate of MEASURED_PEAKS.json (sustained figure: the kernels are timed inside a long step; INT8 : bf16 is
-        # 2 : 1 on B200, 4.5 vs 2.25 POP/s nominal).  The algorithmic FP64 rate (2 n m^2 flop / kernel time) is given
-        # beside it against the cuBLAS DGEMM rate measured in this run -- it exceeds 1 because no FP64 unit is used.
+        # splitting: NS (NS + 1) / 2 exact INT8 slice-pair products per FP64 product), so the pipe
+        # that bounds them is the INT8 tensor pipe: achieved = EXECUTED INT8 operations / kernel time against the INT8
+        # peak measured in this run.  The algorithmic FP64 rate (2 n m^2 flop / kernel time) is given beside it against
+        # the cuBLAS DGEMM rate measured in this run -- it exceeds 1 because no FP64 unit is used.
         peak64 = fp64_peak_tflops()
         km_launches, km_ms = prof["km"]
         gram_launches, gram_ms = prof["gram"]
         mp = (m + 127) // 128 * 128
         km_flops = 2.0 * nloc * m * m * steps
         gram_flops = 1.0 * nloc * m * (m + 1) * steps          # SYRK count: lower triangle incl. diagonal
-        dmma = os.environ.get("SRGP_TENSOR", "").lower().startswith("d")
-        try:
-            mpk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak8, peak8_src = 2.0 * float(mpk["bf16_tflops_sustained"]), "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (measured)"
-        except Exception:
-            peak8, peak8_src = 2.0 * 1400.0, "2 x 1.4 PFLOP/s sustained bf16 (fallback of B200_PROFILING.md)"
+        # INT8 peak: measured in this run by the resident-operand issue-rate probe of the library (csrc/probe.cu,
+        # tcgen05.mma.kind::i8 128x128x32 on every SM; MEASURED_PEAKS.json has no INT8 entry).  It is a burst figure at
+        # the clocks the probe ran at; the row-pass kernels run inside a long step at the lower clocks in `clocks`.
+        slices = ctx.i8_slices()
+        pairs = slices * (slices + 1) // 2
+        peak8, cyc_mma = ctx.probe_i8_peak()
+        peak8_src = ("measured in this run: csrc/probe.cu, resident-operand tcgen05.mma.kind::i8 128x128x32 on all SMs, "
+                     "%.1f clk per MMA (64 = 8192 MAC/clk/SM), burst clocks" % cyc_mma)
 
         def rate(x, ms_):
             return x / (ms_ * 1e-3) / 1e12 if ms_ > 0 else None
@@ -326,41 +471,35 @@ def main():
         sms = torch.cuda.get_device_properties(0).multi_processor_count
         rows2 = (sms // 2) * 128                                 # pass-2 chunk: (SMs / 2 column groups) row blocks x 128, rows are padded to it
         km_rows = -(-nloc // rows2) * rows2
-        km_ops8 = 36 * 2.0 * km_rows * mp * mp * steps           # 36 slice pairs, every 64-column tile of every row block
+        km_ops8 = pairs * 2.0 * km_rows * mp * mp * steps        # slice pairs x every 64-column tile of every row block
         gram_quant = 128
         gram_rows = -(-nloc // gram_quant) * gram_quant
-        gram_ops8 = 36 * 2.0 * gram_rows * (mp * (mp + 128) / 2.0) * steps   # 128 x 64 tiles of the lower block triangle
-        if dmma:
-            roof = {"bound": "tensor", "kernel": "km_reduce_kernel (K*M on DMMA + fused dK reductions)",
-                    "achieved": rate(km_flops, km_ms), "peak": peak64, "unit": "TFLOP/s", "frac": frac(km_flops, km_ms, peak64),
-                    "traffic": (ncu_traffic("km_reduce_kernel") or {}).get("bytes_per_launch"),
-                    "traffic_detail": ncu_traffic("km_reduce_kernel"),
-                    "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (no FP64 entry in MEASURED_PEAKS.json)"}
-            roof_gram = {"kernel": "syrk_chunk_kernel (K^T K on DMMA, SYRK flop count n m (m+1))",
-                         "achieved": rate(gram_flops, gram_ms), "peak": peak64, "unit": "TFLOP/s",
-                         "frac": frac(gram_flops, gram_ms, peak64)}
-        else:
-            roof = {"bound": "tensor", "kernel": "i8_km_kernel (K*Mop^T on tcgen05 kind::i8, 8 x 8 digit slices, fused dK reductions)",
-                    "achieved": rate(km_ops8, km_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)", "frac": frac(km_ops8, km_ms, peak8),
-                    "peak_source": peak8_src,
-                    "fp64_equivalent": {"achieved": rate(km_flops, km_ms), "unit": "TFLOP/s", "algorithmic_flops": "2 n m^2",
-                                        "vs_cublas_dgemm": frac(km_flops, km_ms, peak64), "cublas_dgemm_tflops": peak64},
-                    "traffic": (ncu_traffic("i8_km_kernel") or {}).get("bytes_per_launch"),
-                    "traffic_detail": ncu_traffic("i8_km_kernel")}
-            roof_gram = {"kernel": "i8_gram_kernel (K^T K on tcgen05 kind::i8, lower block triangle)",
-                         "achieved": rate(gram_ops8, gram_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)",
-                         "frac": frac(gram_ops8, gram_ms, peak8),
-                         "fp64_equivalent": {"achieved": rate(gram_flops, gram_ms), "unit": "TFLOP/s",
-                                             "algorithmic_flops": "n m (m+1)", "vs_cublas_dgemm": frac(gram_flops, gram_ms, peak64)}}
+        gram_ops8 = pairs * 2.0 * gram_rows * (mp * (mp + 128) / 2.0) * steps   # 128 x 64 tiles of the lower block triangle
+        ncu = ncu_traffic("i8_km_kernel") or {}
+        roof = {"bound": "tensor", "kernel": "i8_km_kernel (K*Mop^T on tcgen05 kind::i8, %d x %d digit slices = %d exact INT8 "
+                "products per FP64 product, fused dK reductions)" % (slices, slices, pairs),
+                "achieved": rate(km_ops8, km_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)", "frac": frac(km_ops8, km_ms, peak8),
+                "peak_source": peak8_src,
+                "fp64_equivalent": {"achieved": rate(km_flops, km_ms), "unit": "TFLOP/s", "algorithmic_flops": "2 n m^2",
+                                    "vs_cublas_dgemm": frac(km_flops, km_ms, peak64), "cublas_dgemm_tflops": peak64},
+                "tensor_pipe_active_ncu": ncu.get("tensor_pipe_active"),
+                "traffic": ncu.get("bytes_per_launch"), "traffic_detail": ncu or None}
+        roof_gram = {"kernel": "i8_gram_kernel (K^T K on tcgen05 kind::i8, lower block triangle)",
+                     "achieved": rate(gram_ops8, gram_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)",
+                     "frac": frac(gram_ops8, gram_ms, peak8),
+                     "tensor_pipe_active_ncu": (ncu_traffic("i8_gram_kernel") or {}).get("tensor_pipe_active"),
+                     "fp64_equivalent": {"achieved": rate(gram_flops, gram_ms), "unit": "TFLOP/s",
+                                         "algorithmic_flops": "n m (m+1)", "vs_cublas_dgemm": frac(gram_flops, gram_ms, peak64)}}
         roof.update({"launches_per_step": km_launches / steps, "avg_launch_ms": km_ms / max(1, km_launches),
                      "share_of_step": km_ms / ms_max})
         roof_gram.update({"launches_per_step": gram_launches / steps, "share_of_step": gram_ms / ms_max})
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            tsec, note = cpu_reference_estimate(args.ref_sample, m, d, n)
-            cpu = {"value": 1.0 / tsec, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle (NumPy/OpenBLAS %d threads + single-threaded C assembly): %s" % (cores, note)}
+            threads, blas = blas_threads(host_cores())
+            tsec, note = cpu_reference_estimate(16384, m, d, n)
+            cpu = {"value": 1.0 / tsec, "unit": UNIT, "cores": threads or host_cores(), "kind": "port", "extrapolated": True,
+                   "sample": "oracle (NumPy literal transcription on %s, %s threads [threadpoolctl] + single-threaded C assembly): %s"
+                             % (blas, threads, note)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -373,6 +512,7 @@ def main():
             "roofline": roof, "roofline_gram": roof_gram, "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v[1] / steps for k, v in prof.items()},
             "objective": obj, "grad_norm": float(np.linalg.norm(grad)),
+            "parity": parity, "parity_checks": checks,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -295,6 +295,13 @@ int srgp_prof_get(srgp_ctx *ctx, int id, int64_t *launches, double *ms);
 int64_t srgp_launch_count(srgp_ctx *ctx);
 /* Flush L2 by writing a scratch buffer larger than the 126 MB L2 (timing hygiene between iterations). */
 int srgp_flush_l2(srgp_ctx *ctx);
+/* Measured INT8 tensor-pipe peak (bench.py's roofline denominator; MEASURED_PEAKS.json has no INT8 entry): every SM
+   issues `iters` x 32 resident tcgen05.mma.kind::i8 128x128x32.  tops = 1e-12 INT8 op/s from CUDA-event time,
+   cycles_per_mma = SM cycles per MMA on SM 0 (64 = 8192 MAC/clk/SM).  No reference counterpart. */
+int srgp_probe_i8_peak(srgp_ctx *ctx, int iters, double *tops, double *cycles_per_mma);
+/* Digit slices per operand of the INT8 row passes (compile-time SRGP_I8_NS of csrc/tc_i8.cuh: 7, or 8 in the validation
+   build): NS (NS + 1) / 2 exact INT8 MMAs stand for one FP64 MMA.  Returns the count, not a status. */
+int srgp_i8_slices(void);
 
 #ifdef __cplusplus
 }

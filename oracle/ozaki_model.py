@@ -4,10 +4,10 @@ Restates, with plain integer arithmetic, what csrc/tc_i8.cuh / csrc/gauss_i8.cu 
 (DESIGN.md section 3a), so that the scheme itself -- digit extraction, level sums, overflow bound, dropped pairs,
 level weights -- is checked on the CPU, independently of any kernel:
 
-    q = rint(v 2^62)                 62-bit fixed point of v in [-1, 1]
-    q = sum_t d_t 256^t              balanced digits d_t in [-128, 127]; slice s = 7 - t
-    bytes of (q + B) ^ B, B = 0x80..80   are exactly those digits (two's complement INT8)
-    sum_r a_r b_r ~= sum_{sa+sb<=7} 2^(-12-8(sa+sb)) sum_r da_sa[r] db_sb[r]
+    q = rint(v 2^(8 NS - 2))         fixed point of v in [-1, 1]: NS = 7 slices (54 bits, the product's default) or 8 (62)
+    q = sum_t d_t 256^t              balanced digits d_t in [-128, 127]; slice s = NS - 1 - t
+    bytes of (q + B) ^ B, B = 0x80..80 (NS bytes)   are exactly those digits (two's complement INT8)
+    sum_r a_r b_r ~= sum_{sa+sb<NS} 2^(-12-8(sa+sb)) sum_r da_sa[r] db_sb[r]
 
 There is no reference-file citation here: the reference computes these products in FP64 (R's %*%); this module is
 the checker of OUR replacement for that arithmetic.  Only tests/ import it.
@@ -16,18 +16,25 @@ from __future__ import annotations
 
 import numpy as np
 
-NS = 8
-BIAS = np.uint64(0x8080808080808080)
+NS = 7                                  # SRGP_I8_NS of csrc/tc_i8.cuh; set_slices(8) models the validation build
+BIAS = np.uint64(0x0080808080808080)
+
+
+def set_slices(ns):
+    global NS, BIAS
+    assert ns in (7, 8)
+    NS = ns
+    BIAS = np.uint64(0x8080808080808080 if ns == 8 else 0x0080808080808080)
 
 
 def fixed_point(v):
     v = np.asarray(v, dtype=np.float64)
     assert np.all(np.abs(v) <= 1.0)
-    return np.rint(v * 2.0 ** 62).astype(np.int64)
+    return np.rint(v * 2.0 ** (8 * NS - 2)).astype(np.int64)
 
 
 def digits_carry_chain(q):
-    """Balanced base-256 digits by the textbook carry chain: out[..., s], slice s = 7 - t."""
+    """Balanced base-256 digits by the textbook carry chain: out[..., s], slice s = NS - 1 - t."""
     q = np.array(q, dtype=np.int64, copy=True)
     out = np.zeros(q.shape + (NS,), dtype=np.int8)
     for t in range(NS):
@@ -42,7 +49,7 @@ def digits_bias_trick(q):
     """The same digits as the bytes of (q + B) ^ B (what split_quad does on the GPU)."""
     y = (np.asarray(q, dtype=np.int64).astype(np.uint64) + BIAS) ^ BIAS
     by = y[..., None] >> (np.arange(NS, dtype=np.uint64) * np.uint64(8)) & np.uint64(255)      # byte t
-    return by.astype(np.uint8).view(np.int8)[..., ::-1].copy()                                   # slice s = 7 - t
+    return by.astype(np.uint8).view(np.int8)[..., ::-1].copy()                                   # slice s = NS - 1 - t
 
 
 def join(digits):
@@ -67,11 +74,13 @@ def level_sums(da, db):
 
 
 def combine(lev, scale=1.0):
-    """FP64 value of the levels as the kernels form it: two exact 64-bit integers (levels 0..3, 4..7), then
-    2^-68 lo + 2^-36 hi, least significant first."""
+    """FP64 value of the levels as the kernels form it: two exact 64-bit integers (levels 0..3, 4..NS-1), then
+    2^(-12-8(NS-1)) lo + 2^-36 hi, least significant first."""
     hi = ((lev[0] * 256 + lev[1]) * 256 + lev[2]) * 256 + lev[3]
-    lo = ((lev[4] * 256 + lev[5]) * 256 + lev[6]) * 256 + lev[7]
-    return scale * (2.0 ** -68 * lo.astype(np.float64) + 2.0 ** -36 * hi.astype(np.float64))
+    lo = lev[4]
+    for L in range(5, NS):
+        lo = lo * 256 + lev[L]
+    return scale * (2.0 ** (-12 - 8 * (NS - 1)) * lo.astype(np.float64) + 2.0 ** -36 * hi.astype(np.float64))
 
 
 def matmul_nt(a, b):

@@ -96,6 +96,8 @@ SIGNATURES = {
     "srgp_prof_get": (ci, [vp, ci, C.POINTER(i64), dp]),
     "srgp_launch_count": (i64, [vp]),
     "srgp_flush_l2": (ci, [vp]),
+    "srgp_probe_i8_peak": (ci, [vp, ci, dp, dp]),
+    "srgp_i8_slices": (ci, []),
 }
 
 

@@ -201,6 +201,15 @@ class Context:
     def flush_l2(self):
         L.check(self._lib.srgp_flush_l2(self.handle))
 
+    def i8_slices(self) -> int:
+        return int(self._lib.srgp_i8_slices())
+
+    def probe_i8_peak(self, iters=4000):
+        """(INT8 TOP/s, cycles per 128x128x32 MMA) of the resident-operand issue-rate probe (csrc/probe.cu)."""
+        tops, cyc = C.c_double(), C.c_double()
+        L.check(self._lib.srgp_probe_i8_peak(self.handle, int(iters), C.byref(tops), C.byref(cyc)))
+        return tops.value, cyc.value
+
     # ---- raw device memory (bench / tests) --------------------------------------------------
     def dev_alloc(self, nbytes: int):
         p = L.vp()

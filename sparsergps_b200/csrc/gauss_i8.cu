@@ -500,10 +500,10 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
             for (int g = 0; g < 2; ++g) {
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + g * 16);
                 long long acc[16];
-                drain16x4(tcol + 4 * BN, acc);                  // levels 4..7
+                drain16<NS - 4>(tcol + 4 * BN, acc);            // levels 4..NS-1
 #pragma unroll
                 for (int c = 0; c < 16; ++c) T[g * 16 + c] = W_LEVELS_LO * (double)acc[c];
-                drain16x4(tcol, acc);                           // levels 0..3
+                drain16<4>(tcol, acc);                          // levels 0..3
 #pragma unroll
                 for (int c = 0; c < 16; ++c) T[g * 16 + c] = fma(W_LEVELS_HI, (double)acc[c], T[g * 16 + c]);
             }
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                                         rbt[(ROWD ? 1 + k : 0)] = fma(bk, d2, rbt[(ROWD ? 1 + k : 0)]);
                                     }
                                 }
-                                if (qd == (1ll << 62) && !a.nodims)   // the row forms (gauss_rowform) record no pairs
+                                if (qd == FIX_ONE && !a.nodims)   // the row forms (gauss_rowform) record no pairs
                                     record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
                                                             a.coin_omega, a.coin_cap, tij);
                             }
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
                                 const double tt = xi[k] - us[jj * DT + k];
                                 sc[k] = fma(pk, tt * tt, sc[k]);
                             }
-                            if (qd == (1ll << 62))              // exp(0) = 1: candidate for the bit-identical test
+                            if (qd == FIX_ONE)                  // exp(0) = 1: candidate for the bit-identical test
                                 record_if_coincident_i8(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
                                                         a.coin_omega, a.coin_cap, om);
                         }
@@ -758,7 +758,11 @@ static cudaError_t launch_km_i8(cudaStream_t s, dim3 grid, int device, const KmI
     return cudaSuccess;
 }
 
-bool i8_pass2_supported(const GaussWS *w) { return i8_enabled() && !w->want_knots && w->d >= 1 && w->d <= 8; }
+// mp <= 16384: one INT32 level accumulator sums up to NS pairs x 2^14 x mp over the knots (tc_i8.cuh)
+bool i8_pass2_supported(const GaussWS *w)
+{
+    return i8_enabled() && !w->want_knots && w->d >= 1 && w->d <= 8 && w->mp <= 16384;
+}
 
 static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                       const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,

@@ -8,7 +8,8 @@
 // inner sum is an exact INT32 dot product; pairs with sa + sb > 7 are dropped (< 2^-58 of the operand scales per
 // term).  All pairs of one level L = sa + sb accumulate into the same TMEM accumulator (8 levels x 64 columns = the
 // whole 512-column TMEM), so a 128 x 64 output tile costs 36 INT8 MMAs per k-step instead of one FP64 MMA, on a pipe
-// that is ~120x wider than DMMA.  Overflow bound: (L + 1) <= 8 pairs x 2^14 x rows <= 2^30 for rows <= 8192.
+// that is ~120x wider than DMMA.  Overflow bound: (L + 1) <= 8 pairs x 2^14 x rows <= 2^30 for rows <= 8192
+// (the K*M pass sums over the mp knots: mp <= 16384, checked by i8_pass2_supported).
 //
 // Operand layout: K-major, SWIZZLE_NONE ("interleaved") canonical UMMA layout -- 8 rows x 16 bytes core matrices
 // stored as 128 contiguous bytes.  The producers of the slices (generator kernels) write them to global memory
@@ -22,11 +23,22 @@
 namespace srgp {
 namespace i8 {
 
-constexpr int NS = 8;                 // slices per operand
-constexpr int BM = 128, BN = 64;      // output tile (BN x NS = 512 TMEM columns)
+// Slices per operand: a compile-time choice.  7 (default): q = rint(v 2^54), absolute 2^-55 on |v| <= 1 -- at or below
+// half an ulp of the double itself for |v| >= 1/4 -- and 28 slice pairs (levels 0..6; the dropped pairs weigh
+// < 2^-51 of the operand scales per term, typically 2^-54: one FP64 product rounding).  8: q = rint(v 2^62), 36 pairs
+// (dropped < 2^-58): the validation build, `-DSRGP_I8_NS=8`; tests/test_i8_gpu.py holds the 7-slice default to the
+// long-double yardstick.
+#ifndef SRGP_I8_NS
+#define SRGP_I8_NS 7
+#endif
+constexpr int NS = SRGP_I8_NS;
+static_assert(NS == 7 || NS == 8, "digit slices per operand");
+constexpr int NPAIRS = NS * (NS + 1) / 2;   // MMAs per k-step
+constexpr int FIX_BITS = 8 * NS - 2;  // fixed-point fraction bits: 54 / 62
+constexpr int BM = 128, BN = 64;      // output tile (BN x NS <= 512 TMEM columns)
 constexpr int BK = 64;                // k extent of one block of the operand image, in INT8 elements = bytes
 constexpr int KS = 32;                // k extent of one pipeline stage = one MMA k-step (half an image block)
-constexpr int STAGES = 4;             // 4 x 48 KB: three stages (144 KB) in flight while one is consumed.  With 2 x 96 KB
+constexpr int STAGES = NS == 8 ? 4 : 5;   // 4 x 48 KB / 5 x 42 KB: all but one stage in flight while one is consumed.  With 2 x 96 KB
                                       // only one stage was ever in flight and the K*M pass, whose K slices come from
                                       // HBM rather than L2, ran at 2.66 us per 64-byte block instead of 2.17
 constexpr int A_TILE = BM * KS;       // 4 KB
@@ -35,7 +47,8 @@ constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 48 KB
 constexpr int IMG_BLOCK = 128 * BK;   // bytes of one (128-row block, k-block) image
 constexpr int THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 constexpr int MAX_ROWS_PER_SPLIT = 8192;
-constexpr double FIX_SCALE = 4611686018427387904.0;   // 2^62
+constexpr double FIX_SCALE = (double)(1ull << FIX_BITS);   // 2^54 / 2^62
+constexpr long long FIX_ONE = 1ll << FIX_BITS;             // the image of exp(0) = 1: candidate for quirk Q4
 // instruction descriptor: D = S32, A = B = signed INT8, both K-major, N = 64, M = 128
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -123,9 +136,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// 16 columns of 4 consecutive level accumulators (columns col + k * BN, k = 0..3) -> exact 64-bit integers
-// sum_k lev_k 256^(3-k)  (|lev| < 2^30, so the sum stays below 2^55): the INT32 -> FP64 conversions and the
-// weighting of the levels cost 3 FP64 instructions per entry instead of 16 (the FP64 pipe is the contended one).
+// 16 columns of the NS level accumulators (columns col + L * BN) -> two exact 64-bit integers per entry:
+// hi = sum_{k<4} lev_k 256^(3-k) (levels 0..3, weight 2^-36) and lo = sum_{k<NS-4} lev_{4+k} 256^(NS-5-k) (levels 4..NS-1,
+// weight 2^(-12-8(NS-1))); |lev| < 2^30, so both stay below 2^55.  The INT32 -> FP64 conversions and the weighting of
+// the levels cost 3 FP64 instructions per entry instead of 2 NS (the FP64 pipe is the contended one).
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -134,22 +148,27 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v)
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void drain16x4(uint32_t taddr, long long (&acc)[16])
+// NL consecutive levels starting at taddr: acc = sum_k lev_k 256^(NL-1-k); the NL loads are in flight together (one
+// TMEM round trip per 16 x NL block)
+template <int NL>
+__device__ __forceinline__ void drain16(uint32_t taddr, long long (&acc)[16])
 {
-    // the four loads are in flight together: one TMEM round trip per 16 x 4 block instead of four
-    uint32_t v0[16], v1[16], v2[16], v3[16];
-    tmem_ld16_nowait(taddr, v0);
-    tmem_ld16_nowait(taddr + (uint32_t)BN, v1);
-    tmem_ld16_nowait(taddr + (uint32_t)(2 * BN), v2);
-    tmem_ld16_nowait(taddr + (uint32_t)(3 * BN), v3);
+    static_assert(NL == 3 || NL == 4, "levels per exact 64-bit group");
+    uint32_t v[NL][16];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) tmem_ld16_nowait(taddr + (uint32_t)(k * BN), v[k]);
     tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 16; ++c)
-        acc[c] = (((long long)(int)v0[c] * 256 + (long long)(int)v1[c]) * 256 + (long long)(int)v2[c]) * 256 + (long long)(int)v3[c];
+    for (int c = 0; c < 16; ++c) {
+        long long a = (long long)(int)v[0][c];
+#pragma unroll
+        for (int k = 1; k < NL; ++k) a = a * 256 + (long long)(int)v[k][c];
+        acc[c] = a;
+    }
 }
-constexpr double W_LEVELS_HI = 1.4551915228366852e-11;   // 2^-36: levels 0..3 as one integer
-constexpr double W_LEVELS_LO = 3.3881317890172014e-21;   // 2^-68: levels 4..7 as one integer
-constexpr double FIX_INV = 2.168404344971009e-19;        // 2^-62
+constexpr double W_LEVELS_HI = 1.4551915228366852e-11;                           // 2^-36: levels 0..3 as one integer
+constexpr double W_LEVELS_LO = NS == 8 ? 3.3881317890172014e-21 : 8.673617379884035e-19;   // 2^-68 / 2^-60: levels 4..NS-1
+constexpr double FIX_INV = 1.0 / FIX_SCALE;                                      // 2^-54 / 2^-62
 
 // 4 x 4 byte transpose: out[t] = (a.byte_t, b.byte_t, c.byte_t, d.byte_t), a's byte in bits 0..7  (8 PRMT)
 __device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&out)[4])
@@ -161,7 +180,7 @@ __device__ __forceinline__ void transpose4x4(uint32_t a, uint32_t b, uint32_t c,
     out[2] = __byte_perm(t1, t3, 0x5410);
     out[3] = __byte_perm(t1, t3, 0x7632);
 }
-constexpr unsigned long long DIGIT_BIAS = 0x8080808080808080ull;
+constexpr unsigned long long DIGIT_BIAS = NS == 8 ? 0x8080808080808080ull : 0x0080808080808080ull;   // 128 in each of the NS digit bytes
 
 // The inverse of split_quad for the 4 entries of word `wi` (0..3) of a 16-byte k-chunk: exact q of each entry.
 __device__ __forceinline__ void join_quad(const uint4 (&w)[NS], int wi, long long (&q)[4])
@@ -170,8 +189,8 @@ __device__ __forceinline__ void join_quad(const uint4 (&w)[NS], int wi, long lon
 #pragma unroll
     for (int s = 0; s < NS; ++s) in[s] = wi == 0 ? w[s].x : wi == 1 ? w[s].y : wi == 2 ? w[s].z : w[s].w;
     uint32_t lo[4], hi[4];
-    transpose4x4(in[7], in[6], in[5], in[4], lo);     // digits 0..3 live in slices 7..4
-    transpose4x4(in[3], in[2], in[1], in[0], hi);     // digits 4..7 in slices 3..0
+    transpose4x4(in[NS - 1], in[NS - 2], in[NS - 3], in[NS - 4], lo);            // digits 0..3 live in slices NS-1..NS-4
+    transpose4x4(in[NS - 5], in[NS - 6], in[NS - 7], NS == 8 ? in[0] : 0u, hi);  // digits 4..NS-1 in slices NS-5..0
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const unsigned long long y = ((unsigned long long)hi[k] << 32) | lo[k];
@@ -179,9 +198,9 @@ __device__ __forceinline__ void join_quad(const uint4 (&w)[NS], int wi, long lon
     }
 }
 
-// Balanced base-256 digits of q = rint(v 2^62), |v| <= 1, for 4 consecutive entries (word `wi` of a 16-byte k-chunk).
-// q = sum_t d_t 256^t with d_t in [-128, 127]  <=>  q + B = sum_t (d_t + 128) 256^t with B = 0x8080...80, i.e. the
-// plain bytes of q + B; and d_t as a two's-complement INT8 is (d_t + 128) ^ 0x80.  So all 8 digits of an entry are
+// Balanced base-256 digits of q = rint(v 2^FIX_BITS), |v| <= 1, for 4 consecutive entries (word `wi` of a 16-byte k-chunk).
+// q = sum_t d_t 256^t with d_t in [-128, 127]  <=>  q + B = sum_t (d_t + 128) 256^t with B = 0x80...80 (NS bytes), i.e. the
+// plain bytes of q + B (< 2^(8 NS), the bytes above stay 0); and d_t as a two's-complement INT8 is (d_t + 128) ^ 0x80.  So all NS digits of an entry are
 // the bytes of (q + B) ^ B: two 64-bit integer operations instead of a carry chain, then two 4 x 4 byte transposes
 // put digit t of the 4 entries into one 32-bit word of slice NS - 1 - t.
 __device__ __forceinline__ void split_quad(double v0, double v1, double v2, double v3, int wi, uint32_t (&w)[NS][4])
@@ -197,7 +216,7 @@ __device__ __forceinline__ void split_quad(double v0, double v1, double v2, doub
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         w[NS - 1 - t][wi] = lo[t];
-        w[3 - t][wi] = hi[t];
+        if (t + 4 < NS) w[NS - 5 - t][wi] = hi[t];
     }
 }
 
@@ -208,9 +227,9 @@ struct Bars {
 };
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (int)sizeof(Bars);
 
-// The issue sequence of one stage (one 32-byte k-step): 36 slice pairs; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
+// The issue sequence of one stage (one 32-byte k-step): NPAIRS slice pairs; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
 // `fresh` = this is the first stage of the accumulation (the first MMA of every level overwrites).
-// One thread issues all 36 MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
+// One thread issues all NPAIRS MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
 // descriptor plus a compile-time constant (the start-address field is the low 14 bits, in 16-byte units; the sums
 // stay below 2^14): 2 integer adds per MMA.  With descriptors rebuilt per MMA the issuing thread, not the tensor
 // pipe, was the limit (85 instead of ~45 cycles per MMA, profiles/r01_ozaki_proto.json).

@@ -83,4 +83,4 @@ def test_library_sass_is_blackwell_native():
     km = [v for f, v in per.items() if "i8_km_kernel" in f]
     assert gram and km, "INT8 tensor-core kernels missing from libsrgp.so"
     for v in gram + km:
-        assert v["UTCIMMA"] == 36 and v["LDTM"] >= 1 and v["UBLKCP"] >= 1, v      # 36 slice pairs per k-step
+        assert v["UTCIMMA"] == 28 and v["LDTM"] >= 1 and v["UBLKCP"] >= 1, v      # 28 slice pairs per k-step (7 slices)

@@ -8,35 +8,45 @@ import pytest
 from oracle import ozaki_model as oz
 
 
+@pytest.fixture(autouse=True, params=[7, 8], ids=["ns7", "ns8"])
+def slices(request):
+    """7 = the product's default (csrc/tc_i8.cuh SRGP_I8_NS), 8 = the validation build."""
+    oz.set_slices(request.param)
+    yield request.param
+    oz.set_slices(7)
+
+
 def test_bias_trick_digits_equal_the_carry_chain_and_invert():
     rng = np.random.default_rng(1)
-    v = np.concatenate([rng.uniform(-1, 1, 5000), np.exp(-rng.uniform(0, 40, 5000)), [0.0, 1.0, -1.0, 2.0 ** -62, -2.0 ** -62,
+    v = np.concatenate([rng.uniform(-1, 1, 5000), np.exp(-rng.uniform(0, 40, 5000)), [0.0, 1.0, -1.0, 2.0 ** -(8 * oz.NS - 2), -2.0 ** -(8 * oz.NS - 2),
                         0.5, 127 / 256, 128 / 256, -128 / 256]])
     q = oz.fixed_point(v)
     a, b = oz.digits_carry_chain(q), oz.digits_bias_trick(q)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(oz.join(b), q)
     assert b.min() >= -128 and b.max() <= 127 and abs(int(b[..., 0].max())) <= 64      # top slice: |d| <= 64
-    assert oz.join(oz.digits_bias_trick(oz.fixed_point(np.array([1.0]))))[0] == 1 << 62   # the coincidence marker of pass 2
+    assert oz.join(oz.digits_bias_trick(oz.fixed_point(np.array([1.0]))))[0] == 1 << (8 * oz.NS - 2)   # the coincidence marker of pass 2
 
 
-def test_fixed_point_is_at_least_double_precision_above_2_to_minus_9():
+def test_fixed_point_is_at_least_double_precision_for_large_entries():
+    """Exact (the double itself) for v >= 2^-9 with 8 slices, v >= 2^-1 ... 2^-2 with 7; absolute 2^-(bits+1) below."""
     rng = np.random.default_rng(2)
-    v = np.exp(-rng.uniform(0, 6, 10000))                       # >= 2^-9
+    bits = 8 * oz.NS - 2
+    v = np.exp(-rng.uniform(0, 6 if oz.NS == 8 else 1.38, 10000))                     # >= 2^-9 / >= 2^-2
     q = oz.fixed_point(v)
-    np.testing.assert_array_equal(q.astype(np.float64) * 2.0 ** -62, v)               # exact: 53 bits fit below 2^62
-    tiny = np.exp(-rng.uniform(30, 60, 1000))
-    assert np.max(np.abs(oz.fixed_point(tiny).astype(np.float64) * 2.0 ** -62 - tiny)) <= 2.0 ** -63
+    np.testing.assert_array_equal(q.astype(np.float64) * 2.0 ** -bits, v)             # exact: 53 bits fit below 2^bits
+    tiny = np.exp(-rng.uniform(2, 60, 1000))
+    assert np.max(np.abs(oz.fixed_point(tiny).astype(np.float64) * 2.0 ** -bits - tiny)) <= 2.0 ** -(bits + 1)
 
 
 def test_accumulators_stay_below_2_to_31_at_the_row_limit():
-    # worst case: every digit at its extreme, 8192 rows, 8 pairs on level 7
+    # worst case: every digit at its extreme, 8192 rows, NS pairs on the last level
     K = 8192
     da = np.full((1, K, oz.NS), -128, dtype=np.int8)
     da[:, :, 0] = 64
     lev = oz.level_sums(da, da)
     assert np.max(np.abs(lev)) < 2 ** 31
-    assert int(lev[7, 0, 0]) == 2 * 64 * -128 * K + 6 * 128 * 128 * K
+    assert int(lev[oz.NS - 1, 0, 0]) == 2 * 64 * -128 * K + (oz.NS - 2) * 128 * 128 * K
 
 
 @pytest.mark.parametrize("shape", [(16, 8192, 24), (33, 1024, 17)])
