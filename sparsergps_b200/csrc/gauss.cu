@@ -800,7 +800,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &coinrow, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -857,7 +857,6 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     SRGP_TRY(w->vecs.reserve((size_t)GaussWS::NVECS * mp * 8 + (size_t)dense::GEMV_SCRATCH * mp * 8));
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
     SRGP_TRY(w->part2.reserve(std::max((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE, (size_t)128 * mp) * 8));
-    SRGP_TRY(w->coin.reserve((size_t)GaussWS::COIN_CAP * (2 * sizeof(int) + sizeof(double)) + 64));
     SRGP_TRY(w->rowpart.reserve((size_t)2 * w->cgroups * w->rows2 * 8));
     SRGP_TRY(w->nspart.reserve((size_t)NS_BLOCKS * PART_STRIDE * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
@@ -1148,11 +1147,10 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
             a.vvec = vvec;
             a.rowq_part = rowpart;
             a.rowkv_part = rowkv ? rowpart + (size_t)w->cgroups * w->rows2 : nullptr;
-            a.coin_count = reinterpret_cast<int *>(w->coin.p);
-            a.coin_list = reinterpret_cast<int *>(w->coin.p) + 16;
-            a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
-                                                      (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
-            a.coin_cap = GaussWS::COIN_CAP;
+            a.coin_count = w->coin_count();
+            a.coin_list = w->coin_list();
+            a.coin_omega = w->coin_omega();
+            a.coin_cap = w->coin_cap;
             a.knot_part = mode == MODE_GRAD_KNOT ? w->knotpart.d() : nullptr;
             a.rowd_part = mode == MODE_ROWD ? w->rowdpart.d() : nullptr;
             a.nslots = nslots;
@@ -1383,62 +1381,97 @@ int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, c
     return SRGP_OK;
 }
 
-// one warp per recorded pair: val_p = omega_p - coef * sum_k K(x_i, u_k) Sinv[k, j]
+// Quirk Q4 bookkeeping.  The row passes append every bit-identical (row, knot) pair to w->coin; the kernels below turn
+// each pair into its contribution to the tau gradient and add it to a PER-ROW slot (a row holds more than one pair only
+// when knots are duplicated, and two addends commute exactly), which coin_sum_kernel then sums over the rows in a fixed
+// order: the result does not depend on the order in which the atomics filled the list.
+int coin_reset(srgp_ctx *ctx, GaussWS *w)
+{
+    cudaStream_t s = ctx->stream;
+    const int64_t want = std::min<int64_t>(ctx->n + GaussWS::COIN_SLACK, 0x7fff0000ll);
+    if (want > w->coin_cap) {
+        SRGP_TRY(w->coin.reserve((size_t)want * (2 * sizeof(int) + sizeof(double)) + 64));
+        w->coin_cap = (int)want;
+    }
+    if (ctx->n > w->coinrow_n) {
+        SRGP_TRY(w->coinrow.reserve((size_t)ctx->n * 8));
+        SRGP_CUDA(cudaMemsetAsync(w->coinrow.p, 0, w->coinrow.cap, s));
+        w->coinrow_n = (int64_t)(w->coinrow.cap / 8);
+    }
+    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+    SRGP_CUDA(cudaMemsetAsync(w->sc(GaussWS::S_P2 + w->d + 3), 0, 8, s));
+    return SRGP_OK;
+}
+
+// one warp per recorded pair: rowq[i] += omega_p - coef * sum_k K(x_i, u_k) Sinv[k, j]
 __global__ void __launch_bounds__(256)
 coin_fix_kernel(const int *__restrict__ count, const int *__restrict__ list, const double *__restrict__ omega, int cap,
                 const double *__restrict__ X, int64_t ldx, const double *__restrict__ U, int m, int mp, int d,
-                GenParams p, const double *__restrict__ Sinv, double coef, double *__restrict__ vals)
+                GenParams p, const double *__restrict__ Sinv, double coef, double *__restrict__ rowq)
 {
     const int lane = threadIdx.x & 31;
     const int npairs = min(*count, cap);
     for (int pr = blockIdx.x * 8 + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8) {
         const int i = list[2 * pr], j = list[2 * pr + 1];
         double acc = 0.0;
-        for (int k = lane; k < m; k += 32) {
-            double sq = 0.0;
-            for (int c = 0; c < d; c++) {
-                const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
-                sq = fma(t, t, sq);
+        if (coef != 0.0) {
+            for (int k = lane; k < m; k += 32) {
+                double sq = 0.0;
+                for (int c = 0; c < d; c++) {
+                    const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
+                    sq = fma(t, t, sq);
+                }
+                acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
             }
-            acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) vals[pr] = omega[pr] - coef * acc;
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) atomicAdd(&rowq[i], omega[pr] - coef * acc);
     }
 }
 
-__global__ void coin_sum_kernel(const int *__restrict__ count, int cap, const double *__restrict__ vals,
-                                double *__restrict__ out)
+// *out = sum_i rowq[i] in a fixed order (rowq is re-zeroed on the way); *ovf = 1 if the list overflowed
+__global__ void __launch_bounds__(1024)
+coin_sum_kernel(const int *__restrict__ count, int cap, double *__restrict__ rowq, int64_t n, double *__restrict__ out,
+                double *__restrict__ ovf)
 {
-    __shared__ double red[8];
-    const int npairs = min(*count, cap);
+    __shared__ double red[32];
+    const int cnt = *count;
+    if (cnt == 0) {
+        if (threadIdx.x == 0) {
+            *out = 0.0;
+            *ovf = 0.0;
+        }
+        return;
+    }
     double acc = 0.0;
-    for (int i = threadIdx.x; i < npairs; i += blockDim.x) acc += vals[i];
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const double v = rowq[i];
+        if (v != 0.0) {
+            acc += v;
+            rowq[i] = 0.0;
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         double v = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w];
+        for (int w = 0; w < 32; w++) v += red[w];
         *out = v;
+        *ovf = cnt > cap ? 1.0 : 0.0;
     }
 }
 
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out)
 {
     cudaStream_t s = ctx->stream;
-    int *count = reinterpret_cast<int *>(w->coin.p);
-    int *list = count + 16;
-    double *omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
-                                               (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
-    // per-pair values overwrite the omega array in place
     KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-    coin_fix_kernel<<<64, 256, 0, s>>>(count, list, omega, GaussWS::COIN_CAP, ctx->Xp, ctx->n, w->U.d(), w->m, w->mp,
-                                       w->d, gp, Sinv, coef, omega);
+    coin_fix_kernel<<<64, 256, 0, s>>>(w->coin_count(), w->coin_list(), w->coin_omega(), w->coin_cap, ctx->Xp, ctx->n,
+                                       w->U.d(), w->m, w->mp, w->d, gp, Sinv, coef, w->coinrow.d());
     SRGP_LAUNCH_CHECK();
-    coin_sum_kernel<<<1, 256, 0, s>>>(count, GaussWS::COIN_CAP, omega, out);
+    coin_sum_kernel<<<1, 1024, 0, s>>>(w->coin_count(), w->coin_cap, w->coinrow.d(), ctx->n, out, out + 2);
     SRGP_LAUNCH_CHECK();
     return SRGP_OK;
 }
@@ -1450,7 +1483,7 @@ coin_fix_fic_kernel(const int *__restrict__ count, const int *__restrict__ list,
                     const double *__restrict__ X, int64_t ldx, const double *__restrict__ U, int m, int mp, int d,
                     GenParams p, const double *__restrict__ Sinv, const double *__restrict__ B,
                     const double *__restrict__ rho, const double *__restrict__ alpha, const double *__restrict__ beta,
-                    double *__restrict__ vals)
+                    double *__restrict__ rowq)
 {
     const int lane = threadIdx.x & 31;
     const int npairs = min(*count, cap);
@@ -1467,7 +1500,7 @@ coin_fix_fic_kernel(const int *__restrict__ count, const int *__restrict__ list,
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) vals[pr] = -2.0 * rho[i] * acc - B[i] * kc[pr] + alpha[i] * beta[j];
+        if (lane == 0) atomicAdd(&rowq[i], -2.0 * rho[i] * acc - B[i] * kc[pr] + alpha[i] * beta[j]);
     }
 }
 
@@ -1475,15 +1508,11 @@ int coin_fix_fic(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *S
                  const double *alpha, const double *beta, double *out)
 {
     cudaStream_t s = ctx->stream;
-    int *count = reinterpret_cast<int *>(w->coin.p);
-    int *list = count + 16;
-    double *omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
-                                               (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
     KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-    coin_fix_fic_kernel<<<64, 256, 0, s>>>(count, list, omega, GaussWS::COIN_CAP, ctx->Xp, ctx->n, w->U.d(), w->m,
-                                           w->mp, w->d, gp, Sinv, B, rho, alpha, beta, omega);
+    coin_fix_fic_kernel<<<64, 256, 0, s>>>(w->coin_count(), w->coin_list(), w->coin_omega(), w->coin_cap, ctx->Xp, ctx->n,
+                                           w->U.d(), w->m, w->mp, w->d, gp, Sinv, B, rho, alpha, beta, w->coinrow.d());
     SRGP_LAUNCH_CHECK();
-    coin_sum_kernel<<<1, 256, 0, s>>>(count, GaussWS::COIN_CAP, omega, out);
+    coin_sum_kernel<<<1, 1024, 0, s>>>(w->coin_count(), w->coin_cap, w->coinrow.d(), ctx->n, out, out + 2);
     SRGP_LAUNCH_CHECK();
     return SRGP_OK;
 }

@@ -30,7 +30,10 @@ struct GaussWS {
     DevBuf vecs;     // NVECS m-vectors + gemv scratch
     DevBuf scal;     // device scalars
     DevBuf part2;    // pass-2 per-CTA partial sums
-    DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4)
+    DevBuf coin;     // bit-identical (row, knot) pairs found in pass 2 (quirk Q4): [64 B header | cap x (i, j) | cap x omega]
+    DevBuf coinrow;  // per-row sums of the pair values (all zero between evaluations): the deterministic summation order
+    int coin_cap = 0;      // pairs the list can hold = rows of the largest shard seen + 65536 (coin_reset)
+    int64_t coinrow_n = 0;
     DevBuf rowpart;  // per-column-group row sums of one chunk (row-form passes)
     DevBuf nspart;   // scratch of ns_reduce (runs on the side stream)
     DevBuf rowdpart; // per-(column group, warp column) partials of one chunk in the per-row / per-dimension mode
@@ -45,13 +48,14 @@ struct GaussWS {
     DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal
 
-    enum { NMATS = 24, NVECS = 16, NROWV = 20, NSCAL = 256, COIN_CAP = 65536 };
+    enum { NMATS = 24, NVECS = 16, NROWV = 20, NSCAL = 256, COIN_SLACK = 65536 };
     enum Mat { M_S = 0, M_SINV, M_A, M_C, M_LINV, M_TMP, M_CG, M_CGS, M_SG, M_SGS, M_N, M_MOP, M_T1, M_T2, M_X1, M_X2,
                M_GZ, M_CZ, M_GWP, M_L1, M_L2, M_L3, M_L4, M_L5 };
     enum Vec { V_B = 0, V_V, V_GV, V_TMP, V_BETA, V_T1, V_T2, V_T3, V_T4, V_T5, V_T6, V_T7 };
     enum Scal {
         S_S0 = 0, S_LOGDET_S, S_LOGDET_A, S_SUMQ, S_TRCG1, S_BV, S_B1V, S_VGV, S_INFO, S_INFO_HI, S_NTOT, S_S0TOT, S_Q4,
-        S_P2 = 32,      // pass-2 sums: 1 + d entries, + q4 at S_P2 + 1 + d  (allreduced together)
+        S_P2 = 32,      // pass-2 sums: 1 + d entries, + q4 at S_P2 + 1 + d, sum rho at + 2 + d, pair-list overflow flag at
+                        // + 3 + d  (allreduced together: P2_LEN(d) entries)
         S_NS = 128,     // N o dS sums: 2 + d entries
         S_X = 224       // model-specific extras
     };
@@ -66,6 +70,13 @@ struct GaussWS {
     double *rowv(int i, int64_t n) const { return rowa.d() + (size_t)i * row_stride(n); }
     double *sc(int i) const { return scal.d() + i; }
     int *info(int which) const { return reinterpret_cast<int *>(scal.d() + S_INFO) + which; }
+    static int p2_len(int d) { return d + 4; }
+    int *coin_count() const { return reinterpret_cast<int *>(coin.p); }
+    int *coin_list() const { return reinterpret_cast<int *>(coin.p) + 16; }
+    double *coin_omega() const
+    {
+        return reinterpret_cast<double *>(reinterpret_cast<char *>(coin.p) + 64 + (size_t)coin_cap * 2 * sizeof(int));
+    }
     void release();
 };
 
@@ -97,6 +108,10 @@ int gram_materialised(srgp_ctx *ctx, GaussWS *w, const double *rowweight, double
 int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, const double *S, double nugget,
               double *out, cudaStream_t s);
 // quirk Q4: *out = sum over recorded pairs of (omega_p - coef * (K S^-1)_{i_p j_p})
+// Empties the pair list before a pass that records pairs (grows it to the shard's row count + slack; clears the
+// overflow flag p2[d + 3]).  A list that still overflows (many rows coinciding with SEVERAL duplicated knots) is an error
+// reported by fetch_scalars on every rank, never a silently truncated tau gradient.
+int coin_reset(srgp_ctx *ctx, GaussWS *w);
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
 // FIC variant: pairs recorded by gauss_rowd(C, ...) carry (K C)_ij; *out = sum of Omega_ij over the pairs
 int coin_fix_fic(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, const double *B, const double *rho,

@@ -138,7 +138,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
 
     double *GB = w->red1.d(), *b = GB + mm, *tail = b + mp;   // allreduce buffer of pass 1
     SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
-    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+    SRGP_TRY(coin_reset(ctx, w));
 
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
     double *Linv = w->mat(W::M_LINV), *LinvT = w->mat(W::M_X1), *tmp = w->mat(W::M_TMP);
@@ -213,7 +213,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         double *p2 = w->sc(W::S_P2);
         if (rowd_path) {
             // pairs recorded by pass 1a carry (K S^-1)_ij; restart the list so that it holds (K C)_ij only
-            SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+            SRGP_TRY(coin_reset(ctx, w));
             SRGP_TRY(gauss_rowd(ctx, w, gp, C, beta, v, Ud, rstride));
             cq = Ud;
             kv = Ed + (int64_t)(d + 1) * rstride;
@@ -246,11 +246,11 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
             SRGP_TRY(coin_fix(ctx, w, gp, Sinv, 0.0, p2 + 1 + d));
         }
         // ---- G_rho ----------------------------------------------------------------------------------------------
-        double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho | p2 (d + 3)]
+        double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho | p2 (d + 4)]
         SRGP_TRY(gauss_pass1(ctx, w, gp, rho, rho, red2, tv));
-        SRGP_TRY(copy_scalar(ctx, red2 + mm, p2, d + 3));
-        SRGP_TRY(comm_allreduce(ctx, red2, mm + d + 3, s));
-        SRGP_TRY(copy_scalar(ctx, p2, red2 + mm, d + 3));
+        SRGP_TRY(copy_scalar(ctx, red2 + mm, p2, W::p2_len(d)));
+        SRGP_TRY(comm_allreduce(ctx, red2, mm + W::p2_len(d), s));
+        SRGP_TRY(copy_scalar(ctx, p2, red2 + mm, W::p2_len(d)));
         SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
 
         // ---- N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1; with M2 = S^-1 - C and

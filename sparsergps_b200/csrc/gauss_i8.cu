@@ -870,11 +870,10 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.tiles_per_cta = (mp / BN) / (w->cgroups * nsub);
             a.part = w->part2.d();
             a.first = first;
-            a.coin_count = reinterpret_cast<int *>(w->coin.p);
-            a.coin_list = reinterpret_cast<int *>(w->coin.p) + 16;
-            a.coin_omega = reinterpret_cast<double *>(reinterpret_cast<char *>(w->coin.p) + 64 +
-                                                      (size_t)GaussWS::COIN_CAP * 2 * sizeof(int));
-            a.coin_cap = GaussWS::COIN_CAP;
+            a.coin_count = w->coin_count();
+            a.coin_list = w->coin_list();
+            a.coin_omega = w->coin_omega();
+            a.coin_cap = w->coin_cap;
             a.vvec = vvec;
             a.rowd_part = rowd ? w->rowdpart.d() : nullptr;
             a.nslots = nslots;

@@ -44,6 +44,11 @@ int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
         set_error("device execution failed: %s", cudaGetErrorString(e));
         return SRGP_ERR_CUDA;
     }
+    if (w->h_scal[W::S_P2 + w->d + 3] > 0.0) {      // summed over the ranks: every rank fails together
+        set_error("more than %d bit-identical (data row, knot) pairs on one shard (duplicated knots on gridded inputs?): "
+                  "the tau gradient of quirk Q4 would be truncated", w->coin_cap);
+        return SRGP_ERR_STATE;
+    }
     const int *info = reinterpret_cast<const int *>(w->h_scal + W::S_INFO);
     for (int k = 0; k < 4; k++)
         if (info[k] != 0) {
@@ -66,7 +71,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
 
     double *G1 = w->red1.d(), *b1 = G1 + mm, *tail = b1 + mp;
     SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
-    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+    SRGP_TRY(coin_reset(ctx, w));
 
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
     double *Linv = w->mat(W::M_LINV), *tmp = w->mat(W::M_TMP);
@@ -142,7 +147,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
         // quirk Q4: d K_ij / d log tau = 2 tau^2 on bit-identical (row, knot) pairs; the tau-gradient picks up
         // sum (Omega_ij - (K S^-1)_ij / tau^2) there (the trace-term part of Omega does not apply to tau)
         SRGP_TRY(coin_fix(ctx, w, gp, Sinv, itau2, p2 + 1 + d));
-        SRGP_TRY(comm_allreduce(ctx, p2, d + 2, s));
+        SRGP_TRY(comm_allreduce(ctx, p2, W::p2_len(d), s));
     }
     SRGP_TRY(stream_join(ctx));
     if (grad && w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));

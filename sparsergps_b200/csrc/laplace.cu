@@ -333,7 +333,7 @@ static int lap_setup(Lap &L, srgp_ctx *ctx, int family, int kernel, const double
     const int mp = L.mp;
     const size_t mm = (size_t)mp * mp;
     SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W_::S_INFO, 0, 16, s));
-    SRGP_CUDA(cudaMemsetAsync(w->coin.p, 0, 64, s));
+    SRGP_TRY(coin_reset(ctx, w));
     SRGP_TRY(materialise_k(ctx, w, L.gp));
     // S keeps tau^2 + delta on its diagonal in the Laplace models (R/newtrap_sparseGP.R:51-60)
     SRGP_TRY(assemble_dev_ld(ctx, s, kernel, w->U.d(), m, L.d, sigma, l, tau * tau + delta, L.S, mp));
@@ -586,13 +586,13 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     SRGP_TRY(coin_fix(ctx, w, L.gp, L.Sinv, 0.0, p2 + 1 + d));
     // G_rho, K^T t -> one allreduce with the gradient partials
     double *red2 = w->mat(W_::M_T2);   // [G_rho (mm)] then M_X1.. is LinvT: use a separate tail buffer
-    double *tail2 = w->vec(W_::V_T2);  // [K^T t (mp) | p2 (d + 3)]  (V_T2, V_T3 adjacent: 2 mp >= mp + d + 3)
+    double *tail2 = w->vec(W_::V_T2);  // [K^T t (mp) | p2 (d + 4)]  (V_T2, V_T3 adjacent: 2 mp >= mp + d + 4)
     SRGP_TRY(gram_materialised(ctx, w, rho, red2));
     SRGP_TRY(L.ktv(tt, tail2));
-    SRGP_TRY(copy_scalar(ctx, tail2 + mp, p2, d + 3));
+    SRGP_TRY(copy_scalar(ctx, tail2 + mp, p2, W_::p2_len(d)));
     SRGP_TRY(comm_allreduce(ctx, red2, mm, s));
-    SRGP_TRY(comm_allreduce(ctx, tail2, mp + d + 3, s));
-    SRGP_TRY(copy_scalar(ctx, p2, tail2 + mp, d + 3));
+    SRGP_TRY(comm_allreduce(ctx, tail2, mp + W_::p2_len(d), s));
+    SRGP_TRY(copy_scalar(ctx, p2, tail2 + mp, W_::p2_len(d)));
     SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, L.Sinv, tail2, 0.0, nullptr, skt, L.gsc));
     // N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1 + (S^-1 K^T t) GG^T/2, and

@@ -106,3 +106,45 @@ def test_dimension_limits_of_the_fused_passes(ctx, model):
         else:
             obj, grad = ctx.gauss_obj_grad(model, *args)
         _check(obj, grad, ref[0], ref[1], list(cp))
+
+
+def _gridded(n, n_knots, repeat=1, seed=41):
+    """d = 1 integer-valued inputs with knots ON the grid: every data row is bit-identical to `repeat` knots."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, n_knots, size=n).astype(np.float64).reshape(-1, 1)
+    y = np.sin(0.7 * x[:, 0]) + 0.3 * rng.normal(size=n)
+    xu = np.tile(np.arange(n_knots, dtype=np.float64), repeat).reshape(-1, 1)
+    return x, y, xu, {"sigma": 1.3, "l": 1.1, "tau": 0.4}
+
+
+@pytest.mark.parametrize("model", ["vi", "fic"])
+def test_more_coincident_pairs_than_the_old_fixed_list(ctx, model):
+    """Quirk Q4 on gridded inputs: 200,000 bit-identical (row, knot) pairs -- three times the 65,536 the
+    round-1 list silently truncated at -- must all enter the tau gradient, and the sum must not depend on the order in
+    which the atomics filled the list (two evaluations agree bit for bit)."""
+    from oracle import reduced_model as red
+    n = 200_000
+    x, y, xu, cp = _gridded(n, 48)
+    ctx.set_data(x, y, None)
+    obj, grad = ctx.gauss_obj_grad(model, "sqexp", xu, cp["sigma"], [cp["l"]], cp["tau"], 1e-3)
+    f = red.vi_obj_grad if model == "vi" else red.fic_obj_grad
+    obj_ref, g_ref = f(x, y, np.zeros(n), xu, cp["sigma"], [cp["l"]], cp["tau"], 1e-3, cov_fun="sqexp")
+    _check(obj, grad, obj_ref, g_ref, ["sigma", "l", "tau"])
+    obj2, grad2 = ctx.gauss_obj_grad(model, "sqexp", xu, cp["sigma"], [cp["l"]], cp["tau"], 1e-3)
+    assert obj2 == obj and np.array_equal(grad2, grad)
+
+
+def test_pair_list_overflow_is_an_error_not_a_truncation(ctx):
+    """Each row coincides with THREE duplicated knots: 3 n pairs > n + 65,536 list entries -> SRGP_ERR_STATE."""
+    from sparsergps_b200 import _lib as L
+    n = 100_000
+    x, y, xu, cp = _gridded(n, 16, repeat=3)
+    ctx.set_data(x, y, None)
+    with pytest.raises(L.SrgpError, match="bit-identical") as e:
+        ctx.gauss_obj_grad("vi", "sqexp", xu, cp["sigma"], [cp["l"]], cp["tau"], 1e-2)
+    assert e.value.status == L.ERR_STATE
+    # the context stays usable and the next evaluation is clean
+    x2, y2, xu2, _ = _gridded(5000, 16)
+    ctx.set_data(x2, y2, None)
+    obj, grad = ctx.gauss_obj_grad("vi", "sqexp", xu2, cp["sigma"], [cp["l"]], cp["tau"], 1e-2)
+    assert np.isfinite(obj) and np.all(np.isfinite(grad))
