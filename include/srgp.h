@@ -272,6 +272,16 @@ int srgp_comm_unique_id(char id[SRGP_UNIQUE_ID_BYTES]);
 int srgp_comm_init(srgp_ctx *ctx, int world, int rank, const char id[SRGP_UNIQUE_ID_BYTES]);
 int srgp_comm_destroy(srgp_ctx *ctx);
 
+/* ---------------------------------------------------------------- objectives from materialised matrices ---- */
+/* Bodies of obj_fun_norm(ff, mu, Z, Sigma12, Sigma22, y, ...) (R/laplace_approx_obj_funs.R:6-52) and of elbo_fun
+   (R/vi_functions.R:64-121) WITHOUT its trace term (elbo_fun adds trace_term_fun(...), see r/patches.R):
+     -1/2 r' Z^-1 r + 1/2 b' (S22 + G)^-1 b - 1/2 (sum log Z - log|S22| + log|S22 + G|) - n/2 log 2 pi
+   with G = S12' diag(1/Z) S12, b = S12' (r / Z), r = y - mu.  Sigma12 is n x m, Sigma22 m x m (column-major, as the R
+   callers built them with make_cov_mat*C); Z has length nz = 1 or n, mu length nmu = 0 (zero mean), 1 or n (R's
+   recycling).  Drops the resident data shard of the context (call srgp_set_data again before a fused evaluation). */
+int srgp_gauss_obj_mats(srgp_ctx *ctx, const double *Sigma12, int64_t n, int64_t m, const double *Sigma22,
+                        const double *Z, int64_t nz, const double *y, const double *mu, int64_t nmu, double *obj);
+
 /* ---------------------------------------------------------------- instrumentation ------------ */
 /* Device memory helpers for callers without a CUDA binding (bench.py, tests). */
 int srgp_dev_alloc(srgp_ctx *ctx, int64_t bytes, void **out_dev);

@@ -185,9 +185,28 @@ def install(I):
         return lgl(v is MISSING)
     reg("missing", f_missing, special=True)
 
-    def f_function_exists(I, pos, kw):
-        return lgl(False)
-    reg("exists", f_function_exists)
+    # exists / get / assign on the global environment (where the sourced files and the builtins live); the reference's
+    # R code uses none of them -- r/patches.R does, to keep the reference bodies as <name>_R
+    def _name_arg(pos, kw):
+        return str((pos[0] if pos else kw.get("x", kw.get("name"))).v[0])
+
+    def f_exists(I, pos, kw):
+        return lgl(_name_arg(pos, kw) in I.globalenv.vars)
+    reg("exists", f_exists)
+
+    def f_get(I, pos, kw):
+        nm = _name_arg(pos, kw)
+        if nm not in I.globalenv.vars:
+            raise RError("object '%s' not found" % nm)
+        return I.force(I.globalenv.vars[nm])
+    reg("get", f_get)
+
+    def f_assign(I, pos, kw):
+        value = pos[1] if len(pos) > 1 else kw["value"]
+        I.globalenv.vars[_name_arg(pos, kw)] = value
+        return value
+    reg("assign", f_assign)
+    reg("globalenv", lambda I, pos, kw: I.globalenv)
 
     def f_stop(I, pos, kw):
         raise RError(" ".join(str(p.v[0]) if isinstance(p, Vec) and len(p.v) else "" for p in pos))
@@ -588,7 +607,8 @@ def install(I):
     reg("paste", f_paste)
     reg("paste0", lambda I, pos, kw: f_paste(I, pos, kw, ""))
     reg("nchar", lambda I, pos, kw: Vec(np.array([len(s) for s in pos[0].v], dtype=np.int64)))
-    reg("identical", lambda I, pos, kw: lgl(isinstance(pos[0], Vec) and isinstance(pos[1], Vec) and
+    reg("identical", lambda I, pos, kw: lgl(pos[0] is pos[1] if isinstance(pos[0], (Closure, Builtin)) else
+                                            isinstance(pos[0], Vec) and isinstance(pos[1], Vec) and
                                             len(pos[0].v) == len(pos[1].v) and bool(np.all(pos[0].v == pos[1].v))))
 
     # ---------------------------------------------------------------- linear algebra

@@ -58,8 +58,64 @@ static SEXP empty_matrix(const char *msg)
     return Rf_allocMatrix(REALSXP, 0, 0);
 }
 
-/* x_pred = matrix() arrives as a 1 x 1 logical NA (src/covariance_functionsC.cpp:81) */
-static int is_empty(SEXP x_pred) { return ISNA(REAL(x_pred)[0]) || ISNAN(REAL(x_pred)[0]); }
+/* x_pred = matrix() arrives as a 1 x 1 logical NA (src/covariance_functionsC.cpp:81); a zero-length x_pred has no
+   element 0 to look at and is a cross-covariance with zero columns */
+static int is_empty(SEXP x_pred) { return Rf_xlength(x_pred) > 0 && (ISNA(REAL(x_pred)[0]) || ISNAN(REAL(x_pred)[0])); }
+
+/* length-scale array of the kernel from the named list; d is checked BEFORE the fixed-size array is filled */
+static void get_l(SEXP cov_par, int kernel, int d, SEXP lnames, double *l)
+{
+    if (kernel == SRGP_ARD) {
+        if (d > SRGP_MAX_D) Rf_error("sparseRGPs: d = %d exceeds %d", d, SRGP_MAX_D);
+        if (Rf_length(lnames) < d) Rf_error("sparseRGPs: lnames has %d entries for d = %d", Rf_length(lnames), d);
+        for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    } else {
+        l[0] = list_get(cov_par, "l");
+    }
+}
+
+/* R recycles a mean of length 1 (`y - mu`); length n passes through, length 0 is the zero mean, anything else is the
+   R error a length mismatch deserves.  v must already be a REALSXP. */
+static const double *recycled(SEXP v, int n, const char *what)
+{
+    const int len = Rf_length(v);
+    if (len == n) return REAL(v);
+    if (len == 0) return NULL;
+    if (len == 1) {
+        double *out = (double *)R_alloc(n > 0 ? n : 1, sizeof(double));
+        for (int i = 0; i < n; i++) out[i] = REAL(v)[0];
+        return out;
+    }
+    Rf_error("sparseRGPs: %s has length %d, expected 1 or %d", what, len, n);
+    return NULL;
+}
+
+/* gradient in the library's canonical order with its names: c(sigma, l | l1..ld, tau).  The R side reorders it to
+   names(cov_par) (the reference fills its gradient by name, R/vi_functions.R:163,259-261,416). */
+static SEXP named_gradient(const double *g, int kernel, int d, SEXP lnames)
+{
+    const int p = (kernel == SRGP_ARD) ? d + 2 : 3;
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, p)), nm = PROTECT(Rf_allocVector(STRSXP, p));
+    for (int k = 0; k < p; k++) REAL(out)[k] = g[k];
+    SET_STRING_ELT(nm, 0, Rf_mkChar("sigma"));
+    if (kernel == SRGP_ARD) for (int c = 0; c < d; c++) SET_STRING_ELT(nm, 1 + c, STRING_ELT(lnames, c));
+    else SET_STRING_ELT(nm, 1, Rf_mkChar("l"));
+    SET_STRING_ELT(nm, p - 1, Rf_mkChar("tau"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+
+static SEXP named_list(int n, const char **names, SEXP *vals)
+{
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, n)), nm = PROTECT(Rf_allocVector(STRSXP, n));
+    for (int i = 0; i < n; i++) { SET_VECTOR_ELT(out, i, vals[i]); SET_STRING_ELT(nm, i, Rf_mkChar(names[i])); }
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+
+static int family_id(SEXP family) { return strcmp(CHAR(STRING_ELT(family, 0)), "poisson") ? SRGP_BERNOULLI : SRGP_POISSON; }
 
 static SEXP assemble(SEXP x, SEXP x_pred, SEXP cov_par, int kernel, double delta, SEXP lnames, int par, int comp0,
                      int derivative)
@@ -70,12 +126,7 @@ static SEXP assemble(SEXP x, SEXP x_pred, SEXP cov_par, int kernel, double delta
     const int self = is_empty(x_pred);
     const int n2 = self ? n1 : Rf_nrows(x_pred);
     double l[SRGP_MAX_D];
-    if (kernel == SRGP_ARD) {
-        if (d > SRGP_MAX_D) Rf_error("sparseRGPs: d = %d exceeds %d", d, SRGP_MAX_D);
-        for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    } else {
-        l[0] = list_get(cov_par, "l");
-    }
+    get_l(cov_par, kernel, d, lnames, l);
     SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n1, n2));
     int st;
     if (!derivative)
@@ -181,7 +232,7 @@ static SEXP impl_cov_fun_expC(SEXP x1, SEXP x2, SEXP cov_par)
 static SEXP impl_cov_fun_sqrd_exp_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
 {
     double l[SRGP_MAX_D];
-    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    get_l(cov_par, SRGP_ARD, Rf_length(x1), lnames, l);
     return Rf_ScalarReal(srgp_cov_fun_sqrd_exp_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l));
 }
 
@@ -224,14 +275,14 @@ static SEXP impl_dexp_dtauC(SEXP x1, SEXP x2, SEXP cov_par)
 static SEXP impl_dsqexp_dsigma_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames)
 {
     double l[SRGP_MAX_D];
-    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    get_l(cov_par, SRGP_ARD, Rf_length(x1), lnames, l);
     return deriv_list(srgp_dsqexp_dsigma_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l),
                       list_get(cov_par, "sigma"));
 }
 static SEXP impl_dsqexp_dl_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lnames, SEXP comp)
 {
     double l[SRGP_MAX_D];
-    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    get_l(cov_par, SRGP_ARD, Rf_length(x1), lnames, l);
     const int c0 = (int)Rf_asReal(comp) - 1;   /* 1-based in R (covariance_function_derivativesC.cpp:121) */
     return deriv_list(srgp_dsqexp_dl_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l, c0), l[c0]);
 }
@@ -252,6 +303,7 @@ static SEXP dx2_list(SEXP x2, SEXP lb, SEXP ub, const double *deriv, const doubl
 static SEXP impl_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
 {
     double deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
+    if (Rf_length(x1) > SRGP_MAX_D) Rf_error("sparseRGPs: d = %d exceeds %d", Rf_length(x1), SRGP_MAX_D);
     srgp_dsqexp_dx2(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), list_get(cov_par, "l"), REAL(lb),
                     REAL(ub), deriv, tp);
     return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
@@ -259,7 +311,7 @@ static SEXP impl_dsqexp_dx2C(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub)
 static SEXP impl_dsqexp_dx2_ardC(SEXP x1, SEXP x2, SEXP cov_par, SEXP lb, SEXP ub, SEXP lnames)
 {
     double l[SRGP_MAX_D], deriv[SRGP_MAX_D], tp[SRGP_MAX_D];
-    for (int c = 0; c < Rf_length(x1); c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
+    get_l(cov_par, SRGP_ARD, Rf_length(x1), lnames, l);
     srgp_dsqexp_dx2_ard(REAL(x1), REAL(x2), Rf_length(x1), list_get(cov_par, "sigma"), l, REAL(lb), REAL(ub), deriv, tp);
     return dx2_list(x2, lb, ub, deriv, tp, Rf_length(x1));
 }
@@ -388,16 +440,15 @@ SEXP _sparseRGPs_gauss_obj_grad(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP 
     mu = PROTECT(Rf_coerceVector(mu, REALSXP));
     const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
     double l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
-    const int p = (k == SRGP_ARD) ? d + 2 : 3;
-    SEXP grad = PROTECT(Rf_allocVector(REALSXP, p));
+    get_l(cov_par, k, d, lnames, l);
+    double gbuf[SRGP_MAX_D + 2];
     double obj = NA_REAL;
     const int st = srgp_gauss_obj_grad_host(ctx(), Rf_asInteger(model), k, REAL(xy), n, d, REAL(y),
-                                            Rf_length(mu) == n ? REAL(mu) : NULL, REAL(xu), m,
+                                            recycled(mu, n, "mu"), REAL(xu), m,
                                             list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta),
-                                            &obj, REAL(grad));
-    if (st != SRGP_OK) { UNPROTECT(5); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+                                            &obj, gbuf);
+    if (st != SRGP_OK) { UNPROTECT(4); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP grad = PROTECT(named_gradient(gbuf, k, d, lnames));
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
     SET_VECTOR_ELT(out, 0, Rf_ScalarReal(obj));
     SET_VECTOR_ELT(out, 1, grad);
@@ -425,22 +476,21 @@ SEXP _sparseRGPs_gauss_obj_grad_knots(SEXP model, SEXP cov_fun, SEXP xy, SEXP y,
     const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
     const int tr = Rf_asLogical(transform), n_opt = Rf_length(knot_opt);
     double l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
+    get_l(cov_par, k, d, lnames, l);
     int *opt0 = (int *)R_alloc(n_opt > 0 ? n_opt : 1, sizeof(int));
     for (int t = 0; t < n_opt; t++) opt0[t] = INTEGER(knot_opt)[t] - 1;
-    const int p = (k == SRGP_ARD) ? d + 2 : 3;
-    SEXP grad = PROTECT(Rf_allocVector(REALSXP, p));
+    double gbuf[SRGP_MAX_D + 2];
     SEXP kgrad = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)m * d));
     SEXP tknot = PROTECT(Rf_allocMatrix(REALSXP, m, d));
     double obj = NA_REAL;
-    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
     if (st == SRGP_OK)
         st = srgp_gauss_obj_grad_knots(ctx(), Rf_asInteger(model), k, REAL(xu), m, list_get(cov_par, "sigma"), l,
                                        list_get(cov_par, "tau"), Rf_asReal(delta),
                                        tr ? REAL(knot_bounds) : NULL, tr ? REAL(knot_bounds) + d : NULL,  /* cbind(lb, ub) */
-                                       opt0, n_opt, &obj, REAL(grad), REAL(kgrad), REAL(tknot));
-    if (st != SRGP_OK) { UNPROTECT(9); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+                                       opt0, n_opt, &obj, gbuf, REAL(kgrad), REAL(tknot));
+    if (st != SRGP_OK) { UNPROTECT(8); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP grad = PROTECT(named_gradient(gbuf, k, d, lnames));
     const char *names[] = {"objective", "gradient", "knot_gradient", "trans_knot"};
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 4)), nm = PROTECT(Rf_allocVector(STRSXP, 4));
     SET_VECTOR_ELT(out, 0, Rf_ScalarReal(obj));
@@ -468,11 +518,10 @@ SEXP _sparseRGPs_oat_scores(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, 
     pseudo_prop = PROTECT(Rf_coerceVector(pseudo_prop, REALSXP));
     const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu), T = Rf_nrows(pseudo_prop);
     double l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
+    get_l(cov_par, k, d, lnames, l);
     SEXP scores = PROTECT(Rf_allocVector(REALSXP, T));
     double obj0 = NA_REAL;
-    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
     if (st == SRGP_OK)
         st = srgp_oat_scores(ctx(), Rf_asInteger(model), k, REAL(xu), m, REAL(pseudo_prop), T,
                              list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta), &obj0,
@@ -505,8 +554,7 @@ SEXP _sparseRGPs_gauss_fit(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, S
     const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu_out);
     const int nl = (k == SRGP_ARD) ? d : 1, p = nl + 2, mi = Rf_asInteger(maxit), n_opt = Rf_length(knot_opt);
     double sigma = list_get(cov_par, "sigma"), tau = list_get(cov_par, "tau"), l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
+    get_l(cov_par, k, d, lnames, l);
     srgp_fit_opt o;
     o.optim_method = strcmp(CHAR(STRING_ELT(optim_method, 0)), "ga") ? SRGP_OPT_ADADELTA : SRGP_OPT_GA;
     o.decay = REAL(optim_par)[0]; o.epsilon = REAL(optim_par)[1]; o.eta = REAL(optim_par)[2];
@@ -518,7 +566,7 @@ SEXP _sparseRGPs_gauss_fit(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, S
     double *obj_h = (double *)R_alloc(mi, sizeof(double));
     double *par_h = (double *)R_alloc((size_t)mi * p, sizeof(double)), *grad_h = (double *)R_alloc((size_t)mi * p, sizeof(double));
     int iter = 0;
-    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL);
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
     if (st == SRGP_OK)
         st = srgp_gauss_fit(ctx(), Rf_asInteger(model), k, REAL(xu_out), m, &sigma, l, &tau, Rf_asReal(delta), &o,
                             o.opt_knots ? REAL(knot_bounds) : NULL, o.opt_knots ? REAL(knot_bounds) + d : NULL,
@@ -556,9 +604,12 @@ SEXP _sparseRGPs_gauss_fit(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, S
 SEXP _sparseRGPs_trace_term(SEXP sigma, SEXP tau, SEXP delta, SEXP Sigma12, SEXP Sigma22)
 {
     double out = NA_REAL;
-    if (srgp_trace_term(ctx(), Rf_asReal(sigma), Rf_asReal(tau), Rf_asReal(delta), REAL(Sigma12), Rf_nrows(Sigma12),
-                        Rf_ncols(Sigma12), REAL(Sigma22), &out) != SRGP_OK)
-        Rf_error("sparseRGPs: %s", srgp_last_error());
+    Sigma12 = PROTECT(Rf_coerceVector(Sigma12, REALSXP));
+    Sigma22 = PROTECT(Rf_coerceVector(Sigma22, REALSXP));
+    const int st = srgp_trace_term(ctx(), Rf_asReal(sigma), Rf_asReal(tau), Rf_asReal(delta), REAL(Sigma12),
+                                   Rf_nrows(Sigma12), Rf_ncols(Sigma12), REAL(Sigma22), &out);
+    UNPROTECT(2);
+    if (st != SRGP_OK) Rf_error("sparseRGPs: %s", srgp_last_error());
     return Rf_ScalarReal(out);
 }
 
@@ -574,16 +625,15 @@ SEXP _sparseRGPs_laplace_newton(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP
     muu = PROTECT(Rf_coerceVector(muu, REALSXP));
     const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu), mi = Rf_asInteger(maxit);
     double l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
-    if (srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), Rf_length(mu) == n ? REAL(mu) : NULL) != SRGP_OK)
+    get_l(cov_par, k, d, lnames, l);
+    if (srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu")) != SRGP_OK)
         Rf_error("sparseRGPs: %s", srgp_last_error());
     SEXP ff = PROTECT(Rf_duplicate(Rf_coerceVector(start_vals, REALSXP)));
     SEXP hist = PROTECT(Rf_allocVector(REALSXP, mi + 1)), gpsi = PROTECT(Rf_allocVector(REALSXP, n));
     SEXP um = PROTECT(Rf_allocVector(REALSXP, m)), uv = PROTECT(Rf_allocMatrix(REALSXP, m, m));
     int nit = 0;
     const int fam = strcmp(CHAR(STRING_ELT(family, 0)), "poisson") ? SRGP_BERNOULLI : SRGP_POISSON;
-    const int st = srgp_laplace_newton(ctx(), fam, k, REAL(xu), m, Rf_length(muu) == m ? REAL(muu) : NULL,
+    const int st = srgp_laplace_newton(ctx(), fam, k, REAL(xu), m, recycled(muu, m, "muu"),
                                        list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta),
                                        Rf_asReal(pois_m), mi, Rf_asReal(tol), REAL(ff), REAL(hist), &nit, REAL(gpsi),
                                        REAL(um), REAL(uv));
@@ -605,22 +655,239 @@ SEXP _sparseRGPs_predict(SEXP cov_fun, SEXP x_pred, SEXP mu_pred, SEXP xu, SEXP 
 {
     x_pred = PROTECT(Rf_coerceVector(x_pred, REALSXP));
     xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    mu_pred = PROTECT(Rf_coerceVector(mu_pred, REALSXP));
+    muu = PROTECT(Rf_coerceVector(muu, REALSXP));
+    u_mean = PROTECT(Rf_coerceVector(u_mean, REALSXP));
+    u_var = PROTECT(Rf_coerceVector(u_var, REALSXP));
     const int k = kernel_id(cov_fun), n = Rf_nrows(x_pred), d = Rf_ncols(x_pred), m = Rf_nrows(xu);
+    if (Rf_length(u_mean) != m || Rf_xlength(u_var) != (R_xlen_t)m * m)
+        Rf_error("sparseRGPs: u_mean / u_var do not match the %d knots", m);
     double l[SRGP_MAX_D];
-    if (k == SRGP_ARD) for (int c = 0; c < d; c++) l[c] = list_get(cov_par, CHAR(STRING_ELT(lnames, c)));
-    else l[0] = list_get(cov_par, "l");
+    get_l(cov_par, k, d, lnames, l);
     SEXP pm = PROTECT(Rf_allocVector(REALSXP, n)), pv = PROTECT(Rf_allocVector(REALSXP, n));
-    const int st = srgp_predict(ctx(), k, REAL(x_pred), n, d, Rf_length(mu_pred) == n ? REAL(mu_pred) : NULL, REAL(xu),
-                                m, Rf_length(muu) == m ? REAL(muu) : NULL, REAL(u_mean), REAL(u_var),
+    const int st = srgp_predict(ctx(), k, REAL(x_pred), n, d, recycled(mu_pred, n, "mu_pred"), REAL(xu),
+                                m, recycled(muu, m, "muu"), REAL(u_mean), REAL(u_var),
                                 list_get(cov_par, "sigma"), l, Rf_asReal(s22_nugget), Rf_asReal(var_const), REAL(pm),
                                 REAL(pv));
-    if (st != SRGP_OK) { UNPROTECT(4); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    if (st != SRGP_OK) { UNPROTECT(8); Rf_error("sparseRGPs: %s", srgp_last_error()); }
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)), nm = PROTECT(Rf_allocVector(STRSXP, 2));
     SET_VECTOR_ELT(out, 0, pm); SET_VECTOR_ELT(out, 1, pv);
     SET_STRING_ELT(nm, 0, Rf_mkChar("pred_mean")); SET_STRING_ELT(nm, 1, Rf_mkChar("pred_var"));
     Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(10);
+    return out;
+}
+
+/* ---- sparse Laplace gradient, optimiser loop, OAT scores; posterior at the knots; objectives from matrices ------ */
+/* .Call("_sparseRGPs_laplace_grad", family, cov_fun, xy, y, mu, xu, cov_par, delta, lnames, ff, pois_m)
+     -> list(gradient = named numeric): dlogq_dcov_par with dcov_fun_dknot = NA (R/laplace_approx_gradient.R:25-339) */
+SEXP _sparseRGPs_laplace_grad(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP cov_par, SEXP delta,
+                              SEXP lnames, SEXP ff, SEXP pois_m)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    ff = PROTECT(Rf_coerceVector(ff, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
+    double l[SRGP_MAX_D], gbuf[SRGP_MAX_D + 2];
+    get_l(cov_par, k, d, lnames, l);
+    if (Rf_length(ff) != n) Rf_error("sparseRGPs: ff has length %d, expected %d", Rf_length(ff), n);
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
+    if (st == SRGP_OK)
+        st = srgp_laplace_grad(ctx(), family_id(family), k, REAL(xu), m, list_get(cov_par, "sigma"), l,
+                               list_get(cov_par, "tau"), Rf_asReal(delta), Rf_asReal(pois_m), REAL(ff), gbuf);
+    if (st != SRGP_OK) { UNPROTECT(5); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP grad = PROTECT(named_gradient(gbuf, k, d, lnames));
+    const char *nms[] = {"gradient"};
+    SEXP out = named_list(1, nms, &grad);
     UNPROTECT(6);
     return out;
+}
+
+/* .Call("_sparseRGPs_laplace_grad_knots", family, cov_fun, xy, y, mu, xu, cov_par, delta, lnames, ff, pois_m,
+         knot_bounds, knot_opt, transform) -> list(gradient, knot_gradient, trans_knot): dlogq_dcov_par with a
+   dcov_fun_dknot (R/laplace_approx_gradient.R:345-705) */
+SEXP _sparseRGPs_laplace_grad_knots(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP cov_par,
+                                    SEXP delta, SEXP lnames, SEXP ff, SEXP pois_m, SEXP knot_bounds, SEXP knot_opt,
+                                    SEXP transform)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    ff = PROTECT(Rf_coerceVector(ff, REALSXP));
+    knot_bounds = PROTECT(Rf_coerceVector(knot_bounds, REALSXP));
+    knot_opt = PROTECT(Rf_coerceVector(knot_opt, INTSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
+    const int tr = Rf_asLogical(transform), n_opt = Rf_length(knot_opt);
+    double l[SRGP_MAX_D], gbuf[SRGP_MAX_D + 2];
+    get_l(cov_par, k, d, lnames, l);
+    if (Rf_length(ff) != n) Rf_error("sparseRGPs: ff has length %d, expected %d", Rf_length(ff), n);
+    int *opt0 = (int *)R_alloc(n_opt > 0 ? n_opt : 1, sizeof(int));
+    for (int t = 0; t < n_opt; t++) opt0[t] = INTEGER(knot_opt)[t] - 1;
+    SEXP kgrad = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)m * d));
+    SEXP tknot = PROTECT(Rf_allocMatrix(REALSXP, m, d));
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
+    if (st == SRGP_OK)
+        st = srgp_laplace_grad_knots(ctx(), family_id(family), k, REAL(xu), m, list_get(cov_par, "sigma"), l,
+                                     list_get(cov_par, "tau"), Rf_asReal(delta), Rf_asReal(pois_m), REAL(ff),
+                                     tr ? REAL(knot_bounds) : NULL, tr ? REAL(knot_bounds) + d : NULL, opt0, n_opt, gbuf,
+                                     REAL(kgrad), REAL(tknot));
+    if (st != SRGP_OK) { UNPROTECT(9); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP grad = PROTECT(named_gradient(gbuf, k, d, lnames));
+    const char *nms[] = {"gradient", "knot_gradient", "trans_knot"};
+    SEXP vals[] = {grad, kgrad, tknot};
+    SEXP out = named_list(3, nms, vals);
+    UNPROTECT(10);
+    return out;
+}
+
+/* .Call("_sparseRGPs_laplace_fit", family, cov_fun, xy, y, mu, xu, muu, cov_par_start, delta, lnames, ff, pois_m,
+         optim_method, optim_par = c(decay, epsilon, eta, learn_rate), maxit, obj_tol, grad_tol, maxit_nr, tol_nr,
+         opt_theta, opt_knots, knot_bounds, knot_opt)
+     -> list(cov_par, xu, iter, obj_fun, grad, cov_par_history, nr_iter, fmax, u_mean, u_var): the loop of
+   laplace_grad_ascent (R/laplace_gradient_ascent.R:10-628) */
+SEXP _sparseRGPs_laplace_fit(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP muu, SEXP cov_par,
+                             SEXP delta, SEXP lnames, SEXP ff, SEXP pois_m, SEXP optim_method, SEXP optim_par, SEXP maxit,
+                             SEXP obj_tol, SEXP grad_tol, SEXP maxit_nr, SEXP tol_nr, SEXP opt_theta, SEXP opt_knots,
+                             SEXP knot_bounds, SEXP knot_opt)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    muu = PROTECT(Rf_coerceVector(muu, REALSXP));
+    optim_par = PROTECT(Rf_coerceVector(optim_par, REALSXP));
+    knot_bounds = PROTECT(Rf_coerceVector(knot_bounds, REALSXP));
+    knot_opt = PROTECT(Rf_coerceVector(knot_opt, INTSXP));
+    SEXP xu_out = PROTECT(Rf_duplicate(Rf_coerceVector(xu, REALSXP)));          /* in/out */
+    SEXP ff_out = PROTECT(Rf_duplicate(Rf_coerceVector(ff, REALSXP)));          /* in/out */
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu_out);
+    const int nl = (k == SRGP_ARD) ? d : 1, p = nl + 2, mi = Rf_asInteger(maxit), n_opt = Rf_length(knot_opt);
+    double sigma = list_get(cov_par, "sigma"), tau = list_get(cov_par, "tau"), l[SRGP_MAX_D];
+    get_l(cov_par, k, d, lnames, l);
+    if (Rf_length(ff_out) != n) Rf_error("sparseRGPs: ff has length %d, expected %d", Rf_length(ff_out), n);
+    if (Rf_length(optim_par) < 4) Rf_error("sparseRGPs: optim_par needs c(decay, epsilon, eta, learn_rate)");
+    srgp_fit_opt o;
+    o.optim_method = strcmp(CHAR(STRING_ELT(optim_method, 0)), "ga") ? SRGP_OPT_ADADELTA : SRGP_OPT_GA;
+    o.decay = REAL(optim_par)[0]; o.epsilon = REAL(optim_par)[1]; o.eta = REAL(optim_par)[2];
+    o.learn_rate = REAL(optim_par)[3];
+    o.maxit = mi; o.obj_tol = Rf_asReal(obj_tol); o.grad_tol = Rf_asReal(grad_tol);
+    o.opt_theta = Rf_asLogical(opt_theta); o.opt_knots = Rf_asLogical(opt_knots);
+    int *opt0 = (int *)R_alloc(n_opt > 0 ? n_opt : 1, sizeof(int));
+    for (int t = 0; t < n_opt; t++) opt0[t] = INTEGER(knot_opt)[t] - 1;
+    double *obj_h = (double *)R_alloc(mi > 0 ? mi : 1, sizeof(double));
+    double *par_h = (double *)R_alloc((size_t)(mi > 0 ? mi : 1) * p, sizeof(double));
+    double *grad_h = (double *)R_alloc((size_t)(mi > 0 ? mi : 1) * p, sizeof(double));
+    int *nr_h = (int *)R_alloc(mi > 0 ? mi : 1, sizeof(int));
+    SEXP um = PROTECT(Rf_allocVector(REALSXP, m)), uv = PROTECT(Rf_allocMatrix(REALSXP, m, m));
+    int iter = 0;
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
+    if (st == SRGP_OK)
+        st = srgp_laplace_fit(ctx(), family_id(family), k, REAL(xu_out), m, recycled(muu, m, "muu"), &sigma, l, &tau,
+                              Rf_asReal(delta), Rf_asReal(pois_m), Rf_asInteger(maxit_nr), Rf_asReal(tol_nr), &o,
+                              o.opt_knots ? REAL(knot_bounds) : NULL, o.opt_knots ? REAL(knot_bounds) + d : NULL, opt0,
+                              n_opt, REAL(ff_out), &iter, obj_h, par_h, grad_h, nr_h, REAL(um), REAL(uv));
+    if (st != SRGP_OK) { UNPROTECT(11); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    SEXP cp = PROTECT(Rf_duplicate(cov_par));      /* same names and order as cov_par_start */
+    set_list(cp, "sigma", sigma); set_list(cp, "tau", tau);
+    if (k == SRGP_ARD) for (int c = 0; c < d; c++) set_list(cp, CHAR(STRING_ELT(lnames, c)), l[c]);
+    else set_list(cp, "l", l[0]);
+    SEXP objv = PROTECT(Rf_allocVector(REALSXP, iter)), nrv = PROTECT(Rf_allocVector(INTSXP, iter));
+    SEXP gh = PROTECT(Rf_allocMatrix(REALSXP, iter, p)), ph = PROTECT(Rf_allocMatrix(REALSXP, iter, p));
+    for (int i = 0; i < iter; i++) {
+        REAL(objv)[i] = obj_h[i];
+        INTEGER(nrv)[i] = nr_h[i];
+        for (int j = 0; j < p; j++) {               /* row-major history -> R's column-major matrix */
+            REAL(gh)[i + (size_t)iter * j] = grad_h[(size_t)i * p + j];
+            REAL(ph)[i + (size_t)iter * j] = par_h[(size_t)i * p + j];
+        }
+    }
+    const char *nms[] = {"cov_par", "xu", "iter", "obj_fun", "grad", "cov_par_history", "nr_iter", "fmax", "u_mean", "u_var"};
+    SEXP it = PROTECT(Rf_ScalarInteger(iter));
+    SEXP vals[] = {cp, xu_out, it, objv, gh, ph, nrv, ff_out, um, uv};
+    SEXP out = named_list(10, nms, vals);
+    UNPROTECT(17);
+    return out;
+}
+
+/* .Call("_sparseRGPs_laplace_oat_scores", family, cov_fun, xy, y, mu, xu, pseudo_prop, cov_par, delta, lnames, fmax,
+         pois_m, maxit_nr, tol_nr) -> list(scores): the candidate loop of knot_prop_random
+   (R/knot_proposal_functions.R:1096-1120); NaN marks a candidate whose chol() would have raised */
+SEXP _sparseRGPs_laplace_oat_scores(SEXP family, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP pseudo_prop,
+                                    SEXP cov_par, SEXP delta, SEXP lnames, SEXP fmax, SEXP pois_m, SEXP maxit_nr,
+                                    SEXP tol_nr)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    pseudo_prop = PROTECT(Rf_coerceVector(pseudo_prop, REALSXP));
+    fmax = PROTECT(Rf_coerceVector(fmax, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu), T = Rf_nrows(pseudo_prop);
+    double l[SRGP_MAX_D];
+    get_l(cov_par, k, d, lnames, l);
+    if (Rf_length(fmax) != n) Rf_error("sparseRGPs: fmax has length %d, expected %d", Rf_length(fmax), n);
+    SEXP scores = PROTECT(Rf_allocVector(REALSXP, T));
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
+    if (st == SRGP_OK)
+        st = srgp_laplace_oat_scores(ctx(), family_id(family), k, REAL(xu), m, REAL(pseudo_prop), T,
+                                     list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta),
+                                     Rf_asReal(pois_m), Rf_asInteger(maxit_nr), Rf_asReal(tol_nr), REAL(fmax), REAL(scores));
+    if (st != SRGP_OK) { UNPROTECT(7); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    const char *nms[] = {"scores"};
+    SEXP out = named_list(1, nms, &scores);
+    UNPROTECT(7);
+    return out;
+}
+
+/* .Call("_sparseRGPs_gauss_posterior_u", model, cov_fun, xy, y, mu, xu, muu, cov_par, delta, lnames)
+     -> list(u_mean, u_var): the tail of norm_grad_ascent_vi (R/vi_functions.R:1160-1180, model 0) / norm_grad_ascent
+   (R/laplace_gradient_ascent.R:1637-1656, model 1) */
+SEXP _sparseRGPs_gauss_posterior_u(SEXP model, SEXP cov_fun, SEXP xy, SEXP y, SEXP mu, SEXP xu, SEXP muu, SEXP cov_par,
+                                   SEXP delta, SEXP lnames)
+{
+    xy = PROTECT(Rf_coerceVector(xy, REALSXP));
+    xu = PROTECT(Rf_coerceVector(xu, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    muu = PROTECT(Rf_coerceVector(muu, REALSXP));
+    const int k = kernel_id(cov_fun), n = Rf_nrows(xy), d = Rf_ncols(xy), m = Rf_nrows(xu);
+    double l[SRGP_MAX_D];
+    get_l(cov_par, k, d, lnames, l);
+    SEXP um = PROTECT(Rf_allocVector(REALSXP, m)), uv = PROTECT(Rf_allocMatrix(REALSXP, m, m));
+    int st = srgp_set_data(ctx(), REAL(xy), n, d, REAL(y), recycled(mu, n, "mu"));
+    if (st == SRGP_OK)
+        st = srgp_gauss_posterior_u(ctx(), Rf_asInteger(model), k, REAL(xu), m, recycled(muu, m, "muu"),
+                                    list_get(cov_par, "sigma"), l, list_get(cov_par, "tau"), Rf_asReal(delta), REAL(um),
+                                    REAL(uv));
+    if (st != SRGP_OK) { UNPROTECT(7); Rf_error("sparseRGPs: %s", srgp_last_error()); }
+    const char *nms[] = {"u_mean", "u_var"};
+    SEXP vals[] = {um, uv};
+    SEXP out = named_list(2, nms, vals);
+    UNPROTECT(7);
+    return out;
+}
+
+/* .Call("_sparseRGPs_gauss_obj_mats", Sigma12, Sigma22, Z, y, mu) -> double: the body of obj_fun_norm
+   (R/laplace_approx_obj_funs.R:6-52) = elbo_fun without its trace term (R/vi_functions.R:64-121) */
+SEXP _sparseRGPs_gauss_obj_mats(SEXP Sigma12, SEXP Sigma22, SEXP Z, SEXP y, SEXP mu)
+{
+    Sigma12 = PROTECT(Rf_coerceVector(Sigma12, REALSXP));
+    Sigma22 = PROTECT(Rf_coerceVector(Sigma22, REALSXP));
+    Z = PROTECT(Rf_coerceVector(Z, REALSXP));
+    y = PROTECT(Rf_coerceVector(y, REALSXP));
+    mu = PROTECT(Rf_coerceVector(mu, REALSXP));
+    const int n = Rf_nrows(Sigma12), m = Rf_ncols(Sigma12);
+    if (Rf_length(y) != n) Rf_error("sparseRGPs: y has length %d, expected %d", Rf_length(y), n);
+    if (Rf_length(Z) != 1 && Rf_length(Z) != n) Rf_error("sparseRGPs: Z has length %d, expected 1 or %d", Rf_length(Z), n);
+    if (Rf_length(mu) > 1 && Rf_length(mu) != n) Rf_error("sparseRGPs: mu has length %d, expected 1 or %d", Rf_length(mu), n);
+    double obj = NA_REAL;
+    const int st = srgp_gauss_obj_mats(ctx(), REAL(Sigma12), n, m, REAL(Sigma22), REAL(Z), Rf_length(Z), REAL(y),
+                                       Rf_length(mu) ? REAL(mu) : NULL, Rf_length(mu), &obj);
+    UNPROTECT(5);
+    if (st != SRGP_OK) Rf_error("sparseRGPs: %s", srgp_last_error());
+    return Rf_ScalarReal(obj);
 }
 
 static const R_CallMethodDef CallEntries[] = {
@@ -651,6 +918,12 @@ static const R_CallMethodDef CallEntries[] = {
     {"_sparseRGPs_trace_term", (DL_FUNC)&_sparseRGPs_trace_term, 5},
     {"_sparseRGPs_laplace_newton", (DL_FUNC)&_sparseRGPs_laplace_newton, 14},
     {"_sparseRGPs_predict", (DL_FUNC)&_sparseRGPs_predict, 11},
+    {"_sparseRGPs_laplace_grad", (DL_FUNC)&_sparseRGPs_laplace_grad, 11},
+    {"_sparseRGPs_laplace_grad_knots", (DL_FUNC)&_sparseRGPs_laplace_grad_knots, 14},
+    {"_sparseRGPs_laplace_fit", (DL_FUNC)&_sparseRGPs_laplace_fit, 23},
+    {"_sparseRGPs_laplace_oat_scores", (DL_FUNC)&_sparseRGPs_laplace_oat_scores, 14},
+    {"_sparseRGPs_gauss_posterior_u", (DL_FUNC)&_sparseRGPs_gauss_posterior_u, 10},
+    {"_sparseRGPs_gauss_obj_mats", (DL_FUNC)&_sparseRGPs_gauss_obj_mats, 5},
     {NULL, NULL, 0}};
 
 void R_init_sparseRGPs(DllInfo *dll)

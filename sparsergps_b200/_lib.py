@@ -81,6 +81,7 @@ SIGNATURES = {
     "srgp_laplace_fit": (ci, [vp, ci, ci, dp, i64, dp, dp, dp, dp, cd, cd, ci, cd, C.POINTER(FitOpt), dp, dp,
                               C.POINTER(ci), i64, dp, C.POINTER(ci), dp, dp, dp, C.POINTER(ci), dp, dp]),
     "srgp_laplace_oat_scores": (ci, [vp, ci, ci, dp, i64, dp, i64, cd, dp, cd, cd, cd, ci, cd, dp, dp]),
+    "srgp_gauss_obj_mats": (ci, [vp, dp, i64, i64, dp, dp, i64, dp, dp, i64, dp]),
     "srgp_comm_unique_id": (ci, [C.c_char_p]),
     "srgp_comm_init": (ci, [vp, ci, ci, C.c_char_p]),
     "srgp_comm_destroy": (ci, [vp]),

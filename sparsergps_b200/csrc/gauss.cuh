@@ -112,6 +112,7 @@ int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, c
 // overflow flag p2[d + 3]).  A list that still overflows (many rows coinciding with SEVERAL duplicated knots) is an error
 // reported by fetch_scalars on every rank, never a silently truncated tau gradient.
 int coin_reset(srgp_ctx *ctx, GaussWS *w);
+int coin_check(const GaussWS *w);
 int coin_fix(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, double coef, double *out);
 // FIC variant: pairs recorded by gauss_rowd(C, ...) carry (K C)_ij; *out = sum of Omega_ij over the pairs
 int coin_fix_fic(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Sinv, const double *B, const double *rho,

@@ -263,6 +263,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         if (w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));
     }
     SRGP_TRY(fetch_scalars(ctx, w));
+    if (grad) SRGP_TRY(coin_check(w));
 
     const double *h = w->h_scal;
     const double s0 = h[W::S_X], s1 = h[W::S_X + 1], ntot = h[W::S_X + 2];

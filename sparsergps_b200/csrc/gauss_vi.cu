@@ -44,11 +44,6 @@ int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
         set_error("device execution failed: %s", cudaGetErrorString(e));
         return SRGP_ERR_CUDA;
     }
-    if (w->h_scal[W::S_P2 + w->d + 3] > 0.0) {      // summed over the ranks: every rank fails together
-        set_error("more than %d bit-identical (data row, knot) pairs on one shard (duplicated knots on gridded inputs?): "
-                  "the tau gradient of quirk Q4 would be truncated", w->coin_cap);
-        return SRGP_ERR_STATE;
-    }
     const int *info = reinterpret_cast<const int *>(w->h_scal + W::S_INFO);
     for (int k = 0; k < 4; k++)
         if (info[k] != 0) {
@@ -56,6 +51,18 @@ int fetch_scalars(srgp_ctx *ctx, GaussWS *w)
                       info[k], k);
             return SRGP_ERR_NOT_PD;
         }
+    return SRGP_OK;
+}
+
+// After fetch_scalars of an evaluation that recorded quirk-Q4 pairs: the overflow flag travelled in the pass-2 allreduce,
+// so it is the sum over the ranks and every rank fails together.
+int coin_check(const GaussWS *w)
+{
+    if (w->h_scal[W::S_P2 + w->d + 3] > 0.0) {
+        set_error("more than %d bit-identical (data row, knot) pairs on one shard (duplicated knots on gridded inputs?): "
+                  "the tau gradient of quirk Q4 would be truncated", w->coin_cap);
+        return SRGP_ERR_STATE;
+    }
     return SRGP_OK;
 }
 
@@ -152,6 +159,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(stream_join(ctx));
     if (grad && w->want_knots) SRGP_TRY(knot_finish(ctx, w, gp, N, S));
     SRGP_TRY(fetch_scalars(ctx, w));
+    if (grad) SRGP_TRY(coin_check(w));
 
     // ---- host: a handful of scalars ---------------------------------------------------------------------
     const double *h = w->h_scal;

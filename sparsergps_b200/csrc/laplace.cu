@@ -18,6 +18,7 @@
 
 #include "dense.cuh"
 #include "gauss.cuh"
+#include "gemm.cuh"
 
 namespace srgp {
 
@@ -605,6 +606,7 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     SRGP_TRY(ns_reduce(ctx, w, L.gp, N, L.S, tau * tau + delta, w->sc(W_::S_NS), s));
     if (knot_grad) SRGP_TRY(knot_finish(ctx, w, L.gp, N, L.S));
     SRGP_TRY(fetch_scalars(ctx, w));
+    SRGP_TRY(coin_check(w));
     if (knot_grad) {
         SRGP_CUDA(cudaMemcpyAsync(knot_grad, w->knotsum.d() + (int64_t)d * mp, (size_t)m * d * 8, cudaMemcpyDeviceToHost, s));
         SRGP_CUDA(cudaStreamSynchronize(s));
@@ -665,5 +667,143 @@ extern "C" int srgp_laplace_grad_knots(srgp_ctx *ctx, int family, int kernel, co
                 const double u = xu[k + m * c];
                 trans_knot[k + m * c] = knot_lb ? log((u - knot_lb[c]) + 1e-4) - log((knot_ub[c] - u) + 1e-4) : u;
             }
+    return SRGP_OK;
+}
+
+// ====================================================================================================
+// Objective from MATERIALISED matrices: the bodies of obj_fun_norm (R/laplace_approx_obj_funs.R:6-52) and of elbo_fun
+// without its trace term (R/vi_functions.R:64-121; the R patch adds trace_term_fun's value, r/patches.R):
+//   -1/2 r^T Z^-1 r + 1/2 b^T (S22 + G)^-1 b - 1/2 (sum log Z - log|S22| + log|S22 + G|) - n/2 log 2 pi,
+//   G = S12^T diag(1/Z) S12, b = S12^T (r / Z), r = y - mu.
+// The callers that stay in R (norm_grad_ascent_vi :755,910,1114, the knot proposal loops) hand over the matrices they
+// built with make_cov_mat*C; here they are uploaded, S12 is laid out row-major [n][mp] like the Laplace path's K, and
+// the Gram runs on the same DMMA kernel.  log|S22| comes from the Cholesky factor (the reference's log(det()) is the
+// same number until det() under/overflows, quirk Q6).  The resident data shard of the context is dropped.
+// ====================================================================================================
+namespace srgp {
+
+// Kr[(r0 + i) * mp + j] = S12c[i + j * rows]  (one chunk of rows; columns j >= m stay zero)
+__global__ void __launch_bounds__(256)
+transpose_chunk_kernel(const double *__restrict__ src, int rows, int m, int mp, double *__restrict__ dst)
+{
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int i = i0 + threadIdx.x, j = j0 + jj;
+        tile[jj][threadIdx.x] = (i < rows && j < m) ? src[i + (int64_t)j * rows] : 0.0;
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += 8) {
+        const int i = i0 + ii, j = j0 + threadIdx.x;
+        if (i < rows && j < mp) dst[(int64_t)i * mp + j] = tile[threadIdx.x][ii];
+    }
+}
+
+// invZ, rz = (y - mu) / Z (Z, mu recycled like R vectors of length 1 or n); part[2 b + {0, 1}] = sum r^2 / Z, sum log Z
+__global__ void __launch_bounds__(256)
+mats_rows_kernel(const double *__restrict__ y, const double *__restrict__ mu, int64_t nmu, const double *__restrict__ Z,
+                 int64_t nz, int64_t n, double *__restrict__ invZ, double *__restrict__ rz, double *__restrict__ part)
+{
+    __shared__ double red[8];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double z = Z[nz == 1 ? 0 : i], r = y[i] - (nmu == 0 ? 0.0 : mu[nmu == 1 ? 0 : i]);
+        invZ[i] = 1.0 / z;
+        rz[i] = r / z;
+        s0 = fma(r, r / z, s0);
+        s1 += log(z);
+    }
+    s0 = block_sum_256(s0, red);
+    s1 = block_sum_256(s1, red);
+    if (threadIdx.x == 0) {
+        part[2 * blockIdx.x] = s0;
+        part[2 * blockIdx.x + 1] = s1;
+    }
+}
+
+}  // namespace srgp
+
+extern "C" int srgp_gauss_obj_mats(srgp_ctx *ctx, const double *Sigma12, int64_t n, int64_t m, const double *Sigma22,
+                                   const double *Z, int64_t nz, const double *y, const double *mu, int64_t nmu,
+                                   double *obj)
+{
+    if (!ctx || !Sigma12 || !Sigma22 || !Z || !y || !obj || n <= 0 || m <= 0 || m > 32768 || (nz != 1 && nz != n) ||
+        (nmu != 0 && nmu != 1 && nmu != n) || (nmu > 0 && !mu)) {
+        set_error("bad argument (Z must have length 1 or n, mu length 0, 1 or n)");
+        return SRGP_ERR_ARG;
+    }
+    SRGP_TRY(use_device(ctx));
+    cudaStream_t s = ctx->stream;
+    GaussWS *w = gauss_ws(ctx);
+    SRGP_TRY(plan(ctx, w, (int)m, 1));
+    ctx->have_data = false;                        // the row buffers below replace the resident shard
+    ctx->n = n;
+    const int mp = w->mp;
+    const size_t mm = (size_t)mp * mp;
+    SRGP_TRY(w->rowa.reserve(GaussWS::row_stride(n) * 8 * GaussWS::NROWV));
+    SRGP_CUDA(cudaMemsetAsync(w->rowa.p, 0, GaussWS::row_stride(n) * 8 * GaussWS::NROWV, s));
+    SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
+    SRGP_TRY(w->part2.reserve((size_t)std::max(256, KTV_GROUPS * mp) * 8));
+    SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W_::S_INFO, 0, 16, s));
+    double *invZ = w->rowv(0, n), *rz = w->rowv(1, n);
+    // y, mu, Z -> device
+    SRGP_TRY(ctx->y.reserve((size_t)n * 8));
+    SRGP_TRY(ctx->mu.reserve((size_t)std::max<int64_t>(nmu, 1) * 8));
+    SRGP_TRY(ctx->tmp1.reserve((size_t)nz * 8));
+    SRGP_CUDA(cudaMemcpyAsync(ctx->y.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (nmu > 0) SRGP_CUDA(cudaMemcpyAsync(ctx->mu.p, mu, (size_t)nmu * 8, cudaMemcpyHostToDevice, s));
+    SRGP_CUDA(cudaMemcpyAsync(ctx->tmp1.p, Z, (size_t)nz * 8, cudaMemcpyHostToDevice, s));
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 3);
+        mats_rows_kernel<<<LROW_BLOCKS, 256, 0, s>>>(ctx->y.d(), ctx->mu.d(), nmu, ctx->tmp1.d(), nz, n, invZ, rz, w->part2.d());
+        SRGP_LAUNCH_CHECK();
+        sum_strided2_kernel<<<1, 256, 0, s>>>(w->part2.d(), LROW_BLOCKS, 2, 0, w->sc(W_::S_X));
+        SRGP_LAUNCH_CHECK();
+        sum_strided2_kernel<<<1, 256, 0, s>>>(w->part2.d(), LROW_BLOCKS, 2, 1, w->sc(W_::S_X + 1));
+        SRGP_LAUNCH_CHECK();
+    }
+    // Sigma22 -> S (identity on the padding), log|S| from its Cholesky factor
+    double *S = w->mat(W_::M_S), *A = w->mat(W_::M_A), *T1 = w->mat(W_::M_T1);
+    SRGP_CUDA(cudaMemsetAsync(S, 0, mm * 8, s));
+    SRGP_CUDA(cudaMemcpy2DAsync(S, (size_t)mp * 8, Sigma22, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice, s));
+    SRGP_TRY(dense::pad_identity(ctx, s, S, mp, (int)m, 1.0));
+    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s));
+    SRGP_TRY(dense::potrf(ctx, s, T1, mp, (int)m, w->dinv(0), w->info(0), w->sc(W_::S_LOGDET_S)));
+    // Sigma12 (column-major n x m on the host) -> K row-major [rows][mp], zero rows up to the Gram kernel's quantum
+    const int quantum = gemm::BK * w->splits;
+    const int64_t rows_alloc = round_up(n, quantum);
+    SRGP_TRY(w->Kmat.reserve((size_t)rows_alloc * mp * 8));
+    SRGP_CUDA(cudaMemsetAsync(w->Kmat.p, 0, (size_t)rows_alloc * mp * 8, s));
+    const int crows = 16384;
+    SRGP_TRY(ctx->out_mat.reserve((size_t)crows * m * 8));
+    for (int64_t r0 = 0; r0 < n; r0 += crows) {
+        const int rows = (int)std::min<int64_t>(crows, n - r0);
+        SRGP_CUDA(cudaMemcpy2DAsync(ctx->out_mat.p, (size_t)rows * 8, Sigma12 + r0, (size_t)n * 8, (size_t)rows * 8, m,
+                                    cudaMemcpyHostToDevice, s));
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
+        transpose_chunk_kernel<<<dim3(ceil_div(rows, 32), ceil_div(mp, 32)), dim3(32, 8), 0, s>>>(
+            ctx->out_mat.d(), rows, (int)m, mp, w->Kmat.d() + (size_t)r0 * mp);
+        SRGP_LAUNCH_CHECK();
+    }
+    // G = K^T diag(1/Z) K, b = K^T (r / Z); A = S + G; b^T A^-1 b = |L^-1 b|^2; log|A|
+    double *buf = w->red1.d(), *bv = w->vec(W_::V_B), *t1 = w->vec(W_::V_T1);
+    SRGP_TRY(gram_materialised(ctx, w, invZ, buf));
+    {
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+        kt_v_kernel<<<dim3(mp / 128, KTV_GROUPS), 128, 0, s>>>(w->Kmat.d(), mp, n, rz, w->part2.d());
+        SRGP_LAUNCH_CHECK();
+        sum_groups_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->part2.d(), KTV_GROUPS, mp, bv);
+        SRGP_LAUNCH_CHECK();
+    }
+    SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, S, 1.0, buf, 0.0, A));
+    SRGP_TRY(dense::chol_inverse(ctx, s, A, mp, (int)m, w->dinv(1), w->mat(W_::M_LINV), w->mat(W_::M_X1), w->mat(W_::M_TMP),
+                                 w->mat(W_::M_C), w->info(1), w->sc(W_::S_LOGDET_A)));
+    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W_::M_LINV), bv, 0.0, nullptr, t1, w->gemv_scratch()));
+    SRGP_TRY(dense::dot_v(ctx, s, (int)m, t1, t1, w->sc(W_::S_BV)));
+    SRGP_TRY(fetch_scalars(ctx, w));
+    const double *h = w->h_scal;
+    *obj = -0.5 * h[W_::S_X] + 0.5 * h[W_::S_BV] - 0.5 * (h[W_::S_X + 1] - h[W_::S_LOGDET_S] + h[W_::S_LOGDET_A]) -
+           0.5 * (double)n * log(2.0 * M_PI);
+    ctx->n = 0;
     return SRGP_OK;
 }

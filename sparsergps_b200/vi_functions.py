@@ -114,6 +114,28 @@ def elbo_xy(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None):
     return _fused("vi", cov_par, cov_fun, xu, xy, y, mu, delta, False, ctx)["objective"]
 
 
+def obj_fun_norm(mu, Z, Sigma12, Sigma22, y, ff=None, ctx=None, **_ignored):
+    """obj_fun_norm(ff = NA, mu, Z, Sigma12, Sigma22, y, ...) (R/laplace_approx_obj_funs.R:6-52) from the matrices the R
+    callers materialise; Z and mu recycle like R vectors (length 1 or n)."""
+    ctx = ctx or default_context()
+    S12, S22 = L.fmat(Sigma12), L.fmat(Sigma22)
+    n, m = S12.shape
+    Zv, yv = L.fvec(np.atleast_1d(Z)), L.fvec(y)
+    muv = L.fvec(np.atleast_1d(mu)) if mu is not None else None
+    obj = L.cd()
+    L.check(ctx._lib.srgp_gauss_obj_mats(ctx.handle, L.ptr(S12), n, m, L.ptr(S22), L.ptr(Zv), Zv.size, L.ptr(yv),
+                                         L.ptr(muv) if muv is not None else None, muv.size if muv is not None else 0,
+                                         C.byref(obj)))
+    return obj.value
+
+
+def elbo_fun(mu, Z, Sigma12, Sigma22, y, cov_par, delta, trace_term_fun=None, ff=None, ctx=None, **_ignored):
+    """elbo_fun(ff = NA, mu, Z, Sigma12, Sigma22, y, trace_term_fun, cov_par, ...) (R/vi_functions.R:64-121): the
+    obj_fun_norm expression plus trace_term_fun(cov_par, Sigma12, Sigma22, delta) (delta arrives through `...`)."""
+    tt = (trace_term_fun or globals()["trace_term_fun"])(cov_par, Sigma12, Sigma22, delta, ctx=ctx)
+    return obj_fun_norm(mu, Z, Sigma12, Sigma22, y, ctx=ctx) + tt
+
+
 def dlogp_dcov_par(cov_par, cov_fun, xu, xy, y, mu, delta=1e-6, ctx=None, dcov_fun_dknot=None, knot_opt=None,
                    transform=True, **_ignored):
     """R/laplace_approx_gradient.R:720-1126 (FIC Gaussian) + obj_fun_norm (R/laplace_approx_obj_funs.R:6-52); knot

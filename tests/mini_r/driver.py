@@ -106,6 +106,11 @@ def to_sexp(v):
     return L.mr_real(a.ctypes.data_as(C.POINTER(C.c_double)), a.size, nr, nc)
 
 
+class NamedArray(np.ndarray):
+    """An atomic vector that came back with a names attribute (e.g. the gradients of the fused entry points)."""
+    names = None
+
+
 def from_sexp(s):
     L = lib()
     t, n = L.mr_type(s), L.mr_len(s)
@@ -122,6 +127,9 @@ def from_sexp(s):
     a = np.ctypeslib.as_array(C.cast(L.mr_data(s), C.POINTER(ctype)), shape=(max(n, 1),))[:n].astype(dt).copy() if n else np.zeros(0, dt)
     if L.mr_has_dim(s):
         return a.reshape((L.mr_dim(s, 0), L.mr_dim(s, 1)), order="F")
+    if L.mr_has_names(s):
+        a = a.view(NamedArray)
+        a.names = [L.mr_name(s, i).decode() for i in range(n)]
     return a
 
 
