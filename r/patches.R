@@ -73,11 +73,12 @@ elbo_fun <- function(ff = NA, mu, Z, Sigma12, Sigma22, y, trace_term_fun = NULL,
 
 ## Shared body of the two Gaussian gradients: dcov_fun_dknot = NA -> fused objective + gradient; a function -> the same
 ## evaluation plus the knot-location gradient (R/vi_functions.R:425-592 / R/laplace_approx_gradient.R:965-1126).
+## `fallback` is the NAME of the reference body (looked up only when it is needed).
 .srgp_gauss_grad <- function(model, fallback, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y,
                              ff, mu, transform, delta, ...)
 {
   if(!is.list(dcov_fun_dtheta) || !transform)
-    return(fallback(cov_par = cov_par, cov_fun = cov_fun, dcov_fun_dtheta = dcov_fun_dtheta,
+    return(get(fallback)(cov_par = cov_par, cov_fun = cov_fun, dcov_fun_dtheta = dcov_fun_dtheta,
                     dcov_fun_dknot = dcov_fun_dknot, knot_opt = knot_opt, xu = xu, xy = xy, y = y, ff = ff, mu = mu,
                     transform = transform, delta = delta, ...))
   lnames <- .srgp_lnames(cov_fun, ncol(xy))
@@ -99,13 +100,13 @@ elbo_fun <- function(ff = NA, mu, Z, Sigma12, Sigma22, y, trace_term_fun = NULL,
 ## R/vi_functions.R:126 -- signature unchanged
 delbo_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = NA, knot_opt, xu, xy, y, ff = NA,
                            mu, transform = TRUE, delta = 1e-6, ...)
-  .srgp_gauss_grad(0L, delbo_dcov_par_R, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
+  .srgp_gauss_grad(0L, "delbo_dcov_par_R", cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
                    mu, transform, delta, ...)
 
 ## R/laplace_approx_gradient.R:720 -- same for the FIC gradient (model 1)
 dlogp_dcov_par <- function(cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot = NA, knot_opt, xu, xy, y, ff = NA,
                            mu, transform = TRUE, delta = 1e-6, ...)
-  .srgp_gauss_grad(1L, dlogp_dcov_par_R, cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
+  .srgp_gauss_grad(1L, "dlogp_dcov_par_R", cov_par, cov_fun, dcov_fun_dtheta, dcov_fun_dknot, knot_opt, xu, xy, y, ff,
                    mu, transform, delta, ...)
 
 ## R/newtrap_sparseGP.R:6 -- signature unchanged.  The family is read off the likelihood derivative the caller passes.
