@@ -8,6 +8,7 @@
 // threads write consecutive rows of a column => 256-byte coalesced streaming stores.  The kernel is bound by
 // the HBM write of 8*n1*n2 bytes (plus the FP64 pipe for exp); nothing is read twice.
 #include "common.cuh"
+#include "fastexp.cuh"
 #include "gauss.cuh"
 
 namespace srgp {
@@ -33,6 +34,8 @@ assemble_kernel(const double *__restrict__ x, int64_t n1, const double *__restri
                 AsmParams p, int self, double *__restrict__ out, int64_t ldo)
 {
     extern __shared__ double su[];  // [ASM_COLS][d]
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, ASM_ROWS);
     const int d = DT > 0 ? DT : d_rt;
     const int64_t i = (int64_t)blockIdx.x * ASM_ROWS + threadIdx.x;
     double xi[DT > 0 ? DT : 1];
@@ -96,17 +99,17 @@ assemble_kernel(const double *__restrict__ x, int64_t n1, const double *__restri
             } else if (MODE == MODE_ZERO) {
                 v = 0.0;
             } else if (KT == SRGP_ARD) {
-                double k = p.sigma2 * exp(-0.5 * acc);
+                double k = p.sigma2 * exp_tab(-0.5 * acc, etab);
                 v = (MODE == MODE_COV) ? k : (MODE == MODE_DSIGMA) ? 2.0 * k : k * dc2;
             } else if (KT == SRGP_SQEXP) {
-                double k = p.sigma2 * exp(p.c_exp * acc);
+                double k = p.sigma2 * exp_tab(p.c_exp * acc, etab);
                 v = (MODE == MODE_COV) ? k : (MODE == MODE_DSIGMA) ? 2.0 * k : k * (acc * p.inv_l2);
             } else {  // SRGP_EXP: covariance uses the L1 distance, derivatives the L2 distance (quirk Q8)
                 if (MODE == MODE_COV) {
-                    v = p.sigma2 * exp(p.c_exp * acc);
+                    v = p.sigma2 * exp_tab(p.c_exp * acc, etab);
                 } else {
                     double r = sqrt(acc);
-                    double k = p.sigma2 * exp(p.c_exp * r);
+                    double k = p.sigma2 * exp_tab(p.c_exp * r, etab);
                     v = (MODE == MODE_DSIGMA) ? 2.0 * k : k * (r * p.inv_l2);
                 }
             }

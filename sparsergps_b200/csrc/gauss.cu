@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "dense.cuh"
+#include "fastexp.cuh"
 #include "gauss.cuh"
 #include "gauss_i8.cuh"
 #include <vector>
@@ -48,6 +49,8 @@ gen_rowmajor_kernel(const double *__restrict__ X, int64_t ldx, const double *__r
                     GenParams p, double *__restrict__ Kr, double *__restrict__ b1part, int first)
 {
     extern __shared__ double sx[];   // [GEN_ROWS_TILE][d] scaled rows, then [GEN_ROWS_TILE] residuals
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, 128);
     const int d = DT > 0 ? DT : d_rt;
     double *sr = sx + GEN_ROWS_TILE * d;
     const int j = blockIdx.x * 128 + threadIdx.x;
@@ -102,7 +105,7 @@ gen_rowmajor_kernel(const double *__restrict__ X, int64_t ldx, const double *__r
                 if (ii + q < nt) {
                     double k = 0.0;
                     if (jvalid && i < rows_valid) {
-                        k = p.sigma2 * exp(-0.5 * sq[q]);
+                        k = p.sigma2 * exp_tab(-0.5 * sq[q], etab);
                         bacc = fma(k, sr[ii + q], bacc);
                     }
                     Kr[(int64_t)i * mp + j] = k;
@@ -125,6 +128,8 @@ gen_colmajor_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0, int r
                     int64_t ldc)
 {
     extern __shared__ double su[];   // [GENC_COLS][d] scaled knots
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, GENC_ROWS);
     const int d = DT > 0 ? DT : d_rt;
     const int i = blockIdx.x * GENC_ROWS + threadIdx.x;
     const bool ivalid = i < rows_valid;
@@ -160,7 +165,7 @@ gen_colmajor_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0, int r
                         s = fma(t, t, s);
                     }
                 }
-                k = p.sigma2 * exp(-0.5 * s);
+                k = p.sigma2 * exp_tab(-0.5 * s, etab);
             }
             Kc[i + (int64_t)(j0 + jj) * ldc] = k;
         }

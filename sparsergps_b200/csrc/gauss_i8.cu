@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "fastexp.cuh"
 #include "gauss.cuh"
 #include "gauss_i8.cuh"
 #include "tc_i8.cuh"
@@ -47,6 +48,8 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                            int8_t *__restrict__ slices_w)
 {
     extern __shared__ double sx[];   // [64][d] scaled rows, then [64] residuals, then [64] scaled row weights
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, 128);
     const int d = DT > 0 ? DT : d_rt;
     double *sr = sx + 64 * d;
     double *sw = sr + 64;
@@ -110,7 +113,7 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                 for (int q = 0; q < 4; q++) {
                     ev[q] = 0.0;
                     if (jvalid && it0 + ii + q < rows_valid) {
-                        ev[q] = exp(-0.5 * sq[q]);
+                        ev[q] = exp_tab(-0.5 * sq[q], etab);
                         bacc = fma(p.sigma2 * ev[q], sr[ii + q], bacc);
                     }
                 }
@@ -262,6 +265,8 @@ gen_slices_datarows_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0
                            size_t slice_stride)
 {
     extern __shared__ double su[];   // [64][DT] scaled knots of one k-block
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, 128);
     const int i = blockIdx.x * 128 + threadIdx.x;
     const bool ivalid = i < rows_valid;
     double xi[DT];
@@ -296,7 +301,7 @@ gen_slices_datarows_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0
                 }
                 double ev[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) ev[q] = (ivalid && kb * BK + jj + q < m) ? exp(-0.5 * sq[q]) : 0.0;
+                for (int q = 0; q < 4; q++) ev[q] = (ivalid && kb * BK + jj + q < m) ? exp_tab(-0.5 * sq[q], etab) : 0.0;
                 split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
             }
 #pragma unroll
@@ -306,15 +311,27 @@ gen_slices_datarows_kernel(const double *__restrict__ X, int64_t ldx, int64_t r0
     }
 }
 
-// Mop (element (n, k) at n + k mp) -> digit slices of Mop[n, :] / 2^e_n in the operand image (rows = n), and
-// colscale[n] = 2^e_n with max_k |Mop[n, k]| / 2^e_n in [0.5, 1).  grid (mp / 128, mp / 64), 128 threads.
+// colscale[n] = 2^e_n with max_k |Mop[n, k]| / 2^e_n in [0.5, 1): one pass over Mop (element (n, k) at n + k mp), the k
+// range split over blockIdx.y and merged with an integer atomicMax on the bit patterns (non-negative doubles order like
+// their bits).  colbits must be zeroed before the launch.  grid (mp / 128, 16), 128 threads.
+__global__ void __launch_bounds__(128)
+mop_rowmax_kernel(const double *__restrict__ Mop, int mp, unsigned long long *__restrict__ colbits)
+{
+    const int n = blockIdx.x * 128 + threadIdx.x;
+    const int per = mp / gridDim.y, k0 = blockIdx.y * per;
+    double mx = 0.0;
+    for (int k = k0; k < k0 + per; k++) mx = fmax(mx, fabs(Mop[n + (int64_t)k * mp]));     // fmax drops NaN
+    atomicMax(colbits + n, (unsigned long long)__double_as_longlong(mx));
+}
+
+// Mop -> digit slices of Mop[n, :] / 2^e_n in the operand image (rows = n); colscale[n] = 2^e_n replaces the max bits.
+// grid (mp / 128, mp / 64), 128 threads.
 __global__ void __launch_bounds__(128)
 slice_mop_kernel(const double *__restrict__ Mop, int mp, int8_t *__restrict__ slices, size_t slice_stride,
-                 double *__restrict__ colscale)
+                 const unsigned long long *__restrict__ colbits, double *__restrict__ colscale)
 {
     const int n = blockIdx.x * 128 + threadIdx.x, kb = blockIdx.y;
-    double mx = 0.0;
-    for (int k = 0; k < mp; k++) mx = fmax(mx, fabs(Mop[n + (int64_t)k * mp]));
+    const double mx = __longlong_as_double((long long)colbits[n]);
     int ex = 0;
     if (mx > 0.0 && mx < INFINITY) ex = ilogb(mx) + 1;
     const double inv = scalbn(1.0, -ex);
@@ -799,12 +816,16 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
     const int KBm = mp / BK;
     const int slots = w->rblocks * w->cgroups;
     const size_t mstride = (size_t)mp * mp;
-    SRGP_TRY(w->i8buf.reserve(mstride * NS + (size_t)mp * 8));
+    SRGP_TRY(w->i8buf.reserve(mstride * NS + (size_t)mp * 16));
     int8_t *mslices = reinterpret_cast<int8_t *>(w->i8buf.p);
     double *colscale = reinterpret_cast<double *>(mslices + mstride * NS);
+    unsigned long long *colbits = reinterpret_cast<unsigned long long *>(colscale + mp);
     {
-        KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
-        slice_mop_kernel<<<dim3(mp / 128, KBm), 128, 0, s>>>(Mop, mp, mslices, mstride, colscale);
+        SRGP_CUDA(cudaMemsetAsync(colbits, 0, (size_t)mp * 8, s));
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
+        mop_rowmax_kernel<<<dim3(mp / 128, 16), 128, 0, s>>>(Mop, mp, colbits);
+        SRGP_LAUNCH_CHECK();
+        slice_mop_kernel<<<dim3(mp / 128, KBm), 128, 0, s>>>(Mop, mp, mslices, mstride, colbits, colscale);
         SRGP_LAUNCH_CHECK();
     }
     int first = accumulate_slots ? 0 : 1;

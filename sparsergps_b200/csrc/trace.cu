@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "dense.cuh"
+#include "fastexp.cuh"
 #include "gauss.cuh"
 
 namespace srgp {
@@ -61,8 +62,8 @@ constexpr int OD_ROWS = OD_THREADS * OD_RPT;    // rows per CTA
 constexpr int OD_COLS = 32;
 constexpr int OD_STRIDE = SRGP_MAX_D + 8;
 
-// FP64-pipe budget per entry (d = 8): 8 DADD + 8 DFMA (distance) + 17 (libdevice exp) + 8 DMUL + 8 DFMA
-// (per-dimension sums) + 5 = 54 instructions for 8 bytes of Omega: on B200 (37 TF/s FP64 vs 6.5 TB/s HBM, ridge
+// FP64-pipe budget per entry (d = 8): 8 DADD + 8 DFMA (distance) + 10 (exp_tab, fastexp.cuh) + 8 DMUL + 8 DFMA
+// (per-dimension sums) + 5 = 47 instructions for 8 bytes of Omega: on B200 (37 TF/s FP64 vs 6.5 TB/s HBM, ridge
 // = 22 instructions per 8-byte entry) this kernel is bound by the FP64 pipe, not by HBM.
 template <int DT>
 __global__ void __launch_bounds__(OD_THREADS)
@@ -72,6 +73,8 @@ omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__r
 {
     extern __shared__ double su[];   // [OD_COLS][d] scaled knots
     __shared__ double red[OD_THREADS / 32][OD_STRIDE];
+    __shared__ double etab[EXP_TAB_DOUBLES];
+    exp_tab_load(etab, threadIdx.x, OD_THREADS);
     const int d = DT > 0 ? DT : d_rt;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = lane; t < OD_STRIDE; t += 32) red[warp][t] = 0.0;
@@ -115,7 +118,7 @@ omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__r
                         t[c] = xi[q][c] - uj[c];
                         sq = fma(t[c], t[c], sq);
                     }
-                    const double pk = om * exp(fma(-0.5, sq, logs2));
+                    const double pk = om * exp_tab(fma(-0.5, sq, logs2), etab);
                     g0 += pk;
                     // identical scaled coordinates <=> sq == 0 (exact differences): quirk Q4 pairs
                     if (sq == 0.0) gt += om;
@@ -132,7 +135,7 @@ omega_dk_kernel(const double *__restrict__ Omega, int64_t ldo, const double *__r
                         const double t = __dmul_rn(X[irow[q] + ldx * c], p.invl[c]) - su[jj * d + c];
                         sq = fma(t, t, sq);
                     }
-                    const double pk = om * exp(fma(-0.5, sq, logs2));
+                    const double pk = om * exp_tab(fma(-0.5, sq, logs2), etab);
                     g0 += pk;
                     if (sq == 0.0) gt += om;
                     for (int c = 0; c < d; c++) {
