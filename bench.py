@@ -308,8 +308,10 @@ def parity_checks(ctx, world, rank, golden):
         gerr = rel_errs(0.0, [got[k] for k in g["names"]], 1.0, g["grad_at_closed_form_ff"])
         out["laplace_n100k_m512"] = {
             "newton_iterations": int(len(h)), "newton_iterations_golden": g["iterations"],
-            "hist_rel": float(np.max(np.abs(h - np.asarray(g["hist"])[:len(h)]) / np.abs(np.asarray(g["hist"])[:len(h)])))
-            if len(h) <= len(g["hist"]) else None,
+            # the stopping test compares |grad_psi| with tol row by row, so the iteration count may move by a few with
+            # the summation order of a different sharding; the histories must agree on their common prefix
+            "hist_rel": float(np.max(np.abs(h[:min(len(h), len(g["hist"]))] - np.asarray(g["hist"])[:min(len(h), len(g["hist"]))])
+                                     / np.abs(np.asarray(g["hist"])[:min(len(h), len(g["hist"]))]))),
             "u_mean_rel_to_max": float(np.max(np.abs(fit["u_posterior_mean"] - np.asarray(g["u_mean"]))) / np.max(np.abs(g["u_mean"]))),
             "grad_rel": gerr["grad_rel"], "newton_it_per_s": (len(h) - 1) / sec, "grad_ms": gsec * 1e3}
     return out

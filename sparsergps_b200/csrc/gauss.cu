@@ -1393,7 +1393,7 @@ int ns_reduce(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N, c
 int coin_reset(srgp_ctx *ctx, GaussWS *w)
 {
     cudaStream_t s = ctx->stream;
-    const int64_t want = std::min<int64_t>(ctx->n + GaussWS::COIN_SLACK, 0x7fff0000ll);
+    const int64_t want = std::min<int64_t>(2 * ctx->n + GaussWS::COIN_SLACK, 0x7fff0000ll);   // two records per pair: one per sweep
     if (want > w->coin_cap) {
         SRGP_TRY(w->coin.reserve((size_t)want * (2 * sizeof(int) + sizeof(double)) + 64));
         w->coin_cap = (int)want;
@@ -1417,9 +1417,11 @@ coin_fix_kernel(const int *__restrict__ count, const int *__restrict__ list, con
     const int lane = threadIdx.x & 31;
     const int npairs = min(*count, cap);
     for (int pr = blockIdx.x * 8 + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8) {
-        const int i = list[2 * pr], j = list[2 * pr + 1];
+        const int i = list[2 * pr], jraw = list[2 * pr + 1];
+        const bool partial = jraw < 0;           // second sweep of a pair (gauss_i8.cu): only the T-linear part of Omega
+        const int j = partial ? ~jraw : jraw;
         double acc = 0.0;
-        if (coef != 0.0) {
+        if (coef != 0.0 && !partial) {
             for (int k = lane; k < m; k += 32) {
                 double sq = 0.0;
                 for (int c = 0; c < d; c++) {
@@ -1431,7 +1433,7 @@ coin_fix_kernel(const int *__restrict__ count, const int *__restrict__ list, con
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         }
-        if (lane == 0) atomicAdd(&rowq[i], omega[pr] - coef * acc);
+        if (lane == 0) atomicAdd(&rowq[i], omega[pr] - (partial ? 0.0 : coef * acc));
     }
 }
 
@@ -1493,19 +1495,24 @@ coin_fix_fic_kernel(const int *__restrict__ count, const int *__restrict__ list,
     const int lane = threadIdx.x & 31;
     const int npairs = min(*count, cap);
     for (int pr = blockIdx.x * 8 + (threadIdx.x >> 5); pr < npairs; pr += gridDim.x * 8) {
-        const int i = list[2 * pr], j = list[2 * pr + 1];
+        const int i = list[2 * pr], jraw = list[2 * pr + 1];
+        const bool partial = jraw < 0;           // second sweep of a pair: only -B_i (K C)_ij, the part linear in T
+        const int j = partial ? ~jraw : jraw;
         double acc = 0.0;
-        for (int k = lane; k < m; k += 32) {
-            double sq = 0.0;
-            for (int c = 0; c < d; c++) {
-                const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
-                sq = fma(t, t, sq);
+        if (!partial) {
+            for (int k = lane; k < m; k += 32) {
+                double sq = 0.0;
+                for (int c = 0; c < d; c++) {
+                    const double t = (X[i + ldx * c] - U[k + (int64_t)m * c]) * p.invl[c];
+                    sq = fma(t, t, sq);
+                }
+                acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
             }
-            acc = fma(p.sigma2 * exp(-0.5 * sq), Sinv[k + (int64_t)j * mp], acc);
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) atomicAdd(&rowq[i], -2.0 * rho[i] * acc - B[i] * kc[pr] + alpha[i] * beta[j]);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0)
+            atomicAdd(&rowq[i], partial ? -B[i] * kc[pr] : -2.0 * rho[i] * acc - B[i] * kc[pr] + alpha[i] * beta[j]);
     }
 }
 

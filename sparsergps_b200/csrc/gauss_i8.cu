@@ -249,6 +249,144 @@ i8_gram_finalize_kernel(const double *__restrict__ Gpart, int nsplit, int mp, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gram kernel on 128 x 128 tiles, two sweeps (tc_i8.cuh): slot[tile][split] (+)= scale * sum_L 2^(-12-8L) level_L.
+// tile t -> (I, J), J <= I, 128-row / 128-column knot blocks; on the diagonal tiles of an unweighted Gram the A and B
+// operands are the same block and are loaded once.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile2_to_ij(int t, int &I, int &J)
+{
+    I = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((I + 1) * (I + 2) / 2 <= t) I++;
+    while (I * (I + 1) / 2 > t) I--;
+    J = t - I * (I + 1) / 2;
+}
+
+constexpr int GRAM2_STAGES = 4;
+constexpr int GRAM2_SMEM = GRAM2_STAGES * STAGE2_BYTES + (int)sizeof(Bars) + 16;
+
+__global__ void __launch_bounds__(THREADS, 1)
+i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ slices, size_t slice_stride, int KB,
+                int nsplit, double scale, const double *__restrict__ wmax, double *__restrict__ Gpart, int first)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars &bars = *reinterpret_cast<Bars *>(smem + GRAM2_STAGES * STAGE2_BYTES);
+    uint64_t *tmem_empty = reinterpret_cast<uint64_t *>(smem + GRAM2_STAGES * STAGE2_BYTES + sizeof(Bars));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int I, J;
+    tile2_to_ij(blockIdx.x / nsplit, I, J);
+    const int split = blockIdx.x % nsplit;
+    const int kb_per = KB / nsplit, kb0 = split * kb_per, ksteps = 2 * kb_per;
+    const bool same = (I == J) && (slices_a == slices);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GRAM2_STAGES; ++s) {
+            mbar_init(&bars.full[s], 1);
+            mbar_init(&bars.empty[s], 1);
+        }
+        mbar_init(&bars.tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc_all(&bars.tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int g = 0;
+            for (int sw = 0; sw < 2; ++sw)
+                for (int it = 0; it < ksteps; ++it, ++g) {
+                    const int st = g % GRAM2_STAGES;
+                    if (g >= GRAM2_STAGES) mbar_wait(&bars.empty[st], ((g / GRAM2_STAGES) - 1) & 1);
+                    load_stage2(smem_u32(smem + st * STAGE2_BYTES), &bars.full[st], slices_a, slice_stride,
+                                ((size_t)I * KB + kb0) * IMG_BLOCK, slices, slice_stride, ((size_t)J * KB + kb0) * IMG_BLOCK, same,
+                                it, sweep_slices(sw));
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int g = 0;
+            for (int sw = 0; sw < 2; ++sw) {
+                if (sw > 0) {                           // the epilogue must have drained sweep 0 from TMEM
+                    mbar_wait(tmem_empty, 0);
+                    tc_fence_after();
+                }
+                for (int it = 0; it < ksteps; ++it, ++g) {
+                    const int st = g % GRAM2_STAGES;
+                    mbar_wait(&bars.full[st], (g / GRAM2_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + st * STAGE2_BYTES);
+                    const uint32_t b_base = same ? a_base : a_base + NS * A_TILE;
+                    if (sw == 0) issue_stage2<0>(a_base, b_base, tmem_base, it == 0);
+                    else issue_stage2<1>(a_base, b_base, tmem_base, it == 0);
+                    mma_commit(&bars.empty[st]);
+                }
+                mma_commit(&bars.tmem_full);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        if (wmax) scale *= pow2_ceil(*wmax);
+        double *out = Gpart + ((size_t)blockIdx.x * BM + row) * BN2;
+#pragma unroll 1
+        for (int sw = 0; sw < 2; ++sw) {
+            mbar_wait(&bars.tmem_full, sw & 1);
+            tc_fence_after();
+            const int nl = sweep_levels(sw), l0 = 4 * sw;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                double acc[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+#pragma unroll 1
+                for (int k = nl - 1; k >= 0; --k) {        // least significant level first
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * BN2 + c4 * 32), v);
+                    const double wgt = scale * exp2(-12.0 - 8.0 * (l0 + k));
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[c] = fma(wgt, (double)(int)v[c], acc[c]);
+                }
+                double2 *o2 = reinterpret_cast<double2 *>(out + c4 * 32);
+                const bool overwrite = first && sw == 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    double2 prev = overwrite ? make_double2(0.0, 0.0) : o2[c];
+                    o2[c] = make_double2(prev.x + acc[2 * c], prev.y + acc[2 * c + 1]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_free_all(tmem_base);
+    }
+}
+
+// Sum the split slots of the 128 x 128 tiles and scatter to the full symmetric matrix (column-major, ld = mp).
+__global__ void __launch_bounds__(128)
+i8_gram2_finalize_kernel(const double *__restrict__ Gpart, int nsplit, int mp, double *__restrict__ G)
+{
+    int I, J;
+    tile2_to_ij(blockIdx.x, I, J);
+    const int r = I * BM + threadIdx.x;
+    const double *base = Gpart + ((size_t)blockIdx.x * nsplit * BM + threadIdx.x) * BN2;
+    for (int c = 0; c < BN2; ++c) {
+        double v = 0.0;
+        for (int s = 0; s < nsplit; ++s) v += base[(size_t)s * BM * BN2 + c];
+        const int col = J * BN2 + c;
+        G[r + (int64_t)col * mp] = v;
+        if (J < I) G[col + (int64_t)r * mp] = v;          // strictly below the diagonal block: mirror
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pass 2 on the INT8 tensor cores:  T = K Mop^T  (T_ij' = sum_j K_ij Mop[j' + j mp]), then the fused
 // "never materialise dK" reduction of km_reduce_kernel<MODE_GRAD> (gauss.cu):
 //   Omega_ij = rs_i T_ij + ra_i beta_j ;  P_ij = Omega_ij K_ij ;  slot[0] += sum P ;  slot[1 + c] += sum P D_ijc
@@ -387,6 +525,8 @@ struct KmI8Args {
     int nslots;
     int64_t ld;
     int nodims;              // ROWD without the per-dimension slots (gauss_rowform): slot 0 = sum_j T_ij K_ij, slot 1 = K v
+    int cluster;             // i8_km2_kernel: 2 = adjacent row blocks run as tcgen05 CTA pairs (cta_group::2), 1 = single CTAs
+    int debug;               // measurement only (SRGP_KM_DEBUG): bit 0 = skip the FP64 epilogue arithmetic
 };
 
 // Rare path of quirk Q4 (same contract as record_if_coincident in gauss.cu): decided by the reference's own test,
@@ -625,6 +765,358 @@ __global__ void __launch_bounds__(KM_THREADS, 1) i8_km_kernel(KmI8Args a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pass 2 on 128 x 128 tiles, two sweeps per column block (tc_i8.cuh): every quantity the epilogue forms is linear in
+// T = K Mop^T, so the two level groups of a tile are two "virtual tiles" whose contributions add; the terms that do not
+// involve T (ra_i beta_j, the beta / v row sums of the ROWD mode) ride on sweep 0 only.
+// CTA = 384 threads = 3 warpgroups: warp 0 TMA producer, warp 1 MMA issuer (warps 2, 3 idle), warps 4..11 epilogue.  The
+// epilogue holds the 64 drained columns of its row in registers (so TMEM is released before the FP64 work starts):
+// setmaxnreg moves registers from the first warpgroup to the two epilogue warpgroups.
+// Operand ring: 5 units of 32 KB = 4 A-slice tiles + 4 B-slice tiles of one 32-byte k-step.  Sweep 0 needs slices 0..3 =
+// one unit per k-step; sweep 1 needs all NS slices = two units (slices 0..3, then 4..NS-1).
+// ------------------------------------------------------------------------------------------------
+constexpr int KM2_THREADS = 384;
+constexpr int KM2_EPI_REGS = 232, KM2_AUX_REGS = 40;
+constexpr int KM2_MAX_UNITS = 7;
+// operand ring of one CTA: units of 4 A-slice tiles (4 KB each) + 4 B-slice tiles of one 32-byte k-step.
+//   single CTA: B tiles are 128 columns x 32 B = 4 KB -> 32 KB units, 5 of them;
+//   CTA pair (cta_group::2): each CTA holds the 64-column half of the B tiles (2 KB) -> 24 KB units, 7 of them.
+template <bool PAIR> struct Km2Cfg {
+    static constexpr int B_TILE_BYTES = PAIR ? A_TILE / 2 : A_TILE;
+    static constexpr int UNIT_BYTES = 4 * A_TILE + 4 * B_TILE_BYTES;
+    static constexpr int UNITS = PAIR ? 7 : 5;
+    static constexpr int RING_BYTES = UNITS * UNIT_BYTES;
+};
+
+struct Bars2 {
+    uint64_t full[KM2_MAX_UNITS], empty[KM2_MAX_UNITS], tmem_full, tmem_empty;
+    uint32_t tmem_slot, pad;
+};
+
+// a record of quirk Q4 that carries only the part of Omega_ij that is linear in T (the second sweep of a pair): the knot
+// index is stored as ~j and coin_fix* add no T-free term for it
+__device__ __noinline__ void record_if_coincident_i8_part(const double *X, int64_t ldx, int64_t i_shard, const double *U, int m,
+                                                          int j, int d, int *coin_count, int *coin_list, double *coin_omega,
+                                                          int coin_cap, double omega_ij, int partial)
+{
+    for (int c = 0; c < d; c++)
+        if (X[i_shard + ldx * c] != U[j + (int64_t)m * c]) return;
+    const int slot = atomicAdd(coin_count, 1);
+    if (slot < coin_cap) {
+        coin_list[2 * slot] = (int)i_shard;
+        coin_list[2 * slot + 1] = partial ? ~j : j;
+        coin_omega[slot] = omega_ij;
+    }
+}
+
+// PAIR: the two CTAs of a cluster (adjacent row blocks, same column group) form one tcgen05 CTA pair.
+template <int DT, bool ROWD, bool PAIR>
+__global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
+{
+    using Cfg = Km2Cfg<PAIR>;
+    constexpr int NU = Cfg::UNITS, UB = Cfg::UNIT_BYTES, BT = Cfg::B_TILE_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Bars2 &bars = *reinterpret_cast<Bars2 *>(smem + Cfg::RING_BYTES);
+    double *us = reinterpret_cast<double *>(smem + Cfg::RING_BYTES + sizeof(Bars2));   // [128][DT] scaled knots
+    double *bt = us + BN2 * DT;                                 // [128] beta
+    double *cs = bt + BN2;                                      // [128] sigma^2 * column scale
+    double *vv = cs + BN2;                                      // [128] v (ROWD)
+    double *red = vv + BN2;                                     // [8][PART_STRIDE_I8]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jb0 = blockIdx.y * a.tiles_per_cta;               // first 128-column block of this CTA
+    const int KBm = a.KBm, ksteps = 2 * KBm;
+    const int nvt = 2 * a.tiles_per_cta;                        // virtual tiles: (column block, sweep)
+    const int rb = blockIdx.x;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+    const bool leader = crank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int u = 0; u < NU; ++u) {
+            // the leader of a pair issues for both CTAs: its "full" also counts the peer's relay (one wait per unit for
+            // the single issuing thread, whose waits are on the critical path of every k-step)
+            mbar_init(&bars.full[u], (PAIR && leader) ? 2 : 1);
+            mbar_init(&bars.empty[u], 1);
+        }
+        mbar_init(&bars.tmem_full, 1);
+        mbar_init(&bars.tmem_empty, PAIR ? 16 : 8);             // epilogue warps of every CTA that shares the MMAs
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_all_pair(&bars.tmem_slot);
+        else tmem_alloc_all(&bars.tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync_all();                               // the peer's barriers exist before anything is sent to them
+    tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(KM2_AUX_REGS));
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer (every CTA: its own K rows, its share of the Mop columns) =====
+            const size_t a_blk = (size_t)rb * KBm * IMG_BLOCK;
+            int g = 0;                                          // unit counter
+            for (int vt = 0; vt < nvt; ++vt) {
+                const int sw = vt & 1;
+                const size_t b_blk = (size_t)(jb0 + (vt >> 1)) * KBm * IMG_BLOCK;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const size_t off = (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * A_TILE;
+                    for (int part = 0; part <= sw; ++part, ++g) {
+                        const int u = g % NU;
+                        if (g >= NU) mbar_wait(&bars.empty[u], ((g / NU) - 1) & 1);
+                        const int s0 = 4 * part, ns = part == 0 ? 4 : NS - 4;
+                        const uint32_t ub = smem_u32(smem + u * UB);
+                        mbar_expect_tx(&bars.full[u], (uint32_t)(ns * (A_TILE + BT)));
+                        for (int s = 0; s < ns; ++s) {
+                            bulk_g2s(ub + s * A_TILE, a.kslices + (size_t)(s0 + s) * a.kstride + a_blk + off, A_TILE, &bars.full[u]);
+                            const int8_t *bsrc = a.mslices + (size_t)(s0 + s) * a.mstride + b_blk + off;
+                            const uint32_t bdst = ub + 4 * A_TILE + s * BT;
+                            if (PAIR) {                         // columns 64 crank .. 64 crank + 63: 1 KB of each 16-byte k-chunk
+                                bulk_g2s(bdst, bsrc + crank * 1024, 1024, &bars.full[u]);
+                                bulk_g2s(bdst + 1024, bsrc + 2048 + crank * 1024, 1024, &bars.full[u]);
+                            } else {
+                                bulk_g2s(bdst, bsrc, A_TILE, &bars.full[u]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1 && lane == 0 && !leader) {
+            // ===== peer of a pair: tell the leader when this CTA's half of a unit has landed =====
+            int g = 0;
+            for (int vt = 0; vt < nvt; ++vt)
+                for (int ks = 0; ks < ksteps; ++ks)
+                    for (int part = 0; part <= (vt & 1); ++part, ++g) {
+                        mbar_wait(&bars.full[g % NU], (g / NU) & 1);
+                        mbar_arrive_remote(&bars.full[g % NU], 0);
+                    }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer (the leader issues for both CTAs of a pair) =====
+            constexpr uint32_t B_LBO = PAIR ? 1024 : 2048;
+            int g = 0;
+            for (int vt = 0; vt < nvt; ++vt) {
+                const int sw = vt & 1;
+                if (vt > 0) {                                   // the epilogue must have drained the previous virtual tile
+                    mbar_wait(&bars.tmem_empty, (vt - 1) & 1);
+                    tc_fence_after();
+                }
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int u0 = g % NU;
+                    mbar_wait(&bars.full[u0], (g / NU) & 1);
+                    const uint32_t b0 = smem_u32(smem + u0 * UB);
+                    const uint32_t keep = ks == 0 ? 0u : 1u;
+                    if (sw == 0) {
+                        tc_fence_after();
+                        const uint64_t da0 = make_desc(b0, 2048, 128), db0 = make_desc(b0 + 4 * A_TILE, B_LBO, 128);
+#pragma unroll
+                        for (int sb = 0; sb < 4; ++sb)
+#pragma unroll
+                            for (int sa = 0; sa < 4; ++sa)
+                                if (sa + sb < 4) {
+                                    const uint64_t da = da0 + (uint64_t)((sa * A_TILE) >> 4), db = db0 + (uint64_t)((sb * BT) >> 4);
+                                    if (PAIR) mma_i8_n128_pair(tmem_base + (uint32_t)(sa + sb) * BN2, da, db, sb == 0 ? keep : 1u);
+                                    else mma_i8_n128(tmem_base + (uint32_t)(sa + sb) * BN2, da, db, sb == 0 ? keep : 1u);
+                                }
+                        if (PAIR) mma_commit_pair(&bars.empty[u0]);
+                        else mma_commit(&bars.empty[u0]);
+                        g += 1;
+                    } else {
+                        const int u1 = (g + 1) % NU;
+                        mbar_wait(&bars.full[u1], ((g + 1) / NU) & 1);
+                        tc_fence_after();
+                        const uint32_t b1 = smem_u32(smem + u1 * UB);
+                        const uint64_t dlo_a = make_desc(b0, 2048, 128), dlo_b = make_desc(b0 + 4 * A_TILE, B_LBO, 128);
+                        const uint64_t dhi_a = make_desc(b1, 2048, 128), dhi_b = make_desc(b1 + 4 * A_TILE, B_LBO, 128);
+#pragma unroll
+                        for (int sb = 0; sb < NS; ++sb)
+#pragma unroll
+                            for (int sa = 0; sa < NS; ++sa) {
+                                const int L = sa + sb;
+                                if (L >= 4 && L < NS) {
+                                    const uint64_t da = (sa < 4 ? dlo_a : dhi_a) + (uint64_t)(((sa & 3) * A_TILE) >> 4);
+                                    const uint64_t db = (sb < 4 ? dlo_b : dhi_b) + (uint64_t)(((sb & 3) * BT) >> 4);
+                                    if (PAIR) mma_i8_n128_pair(tmem_base + (uint32_t)(L - 4) * BN2, da, db, sb == 0 ? keep : 1u);
+                                    else mma_i8_n128(tmem_base + (uint32_t)(L - 4) * BN2, da, db, sb == 0 ? keep : 1u);
+                                }
+                            }
+                        if (PAIR) {
+                            mma_commit_pair(&bars.empty[u0]);
+                            mma_commit_pair(&bars.empty[u1]);
+                        } else {
+                            mma_commit(&bars.empty[u0]);
+                            mma_commit(&bars.empty[u1]);
+                        }
+                        g += 2;
+                    }
+                }
+                if (PAIR) mma_commit_pair(&bars.tmem_full);
+                else mma_commit(&bars.tmem_full);
+            }
+        }
+    } else {
+        // ===== epilogue: thread = one data row of the block x 64 columns of the 128-column block =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(KM2_EPI_REGS));
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2, et = threadIdx.x - 128;
+        const int row = q * 32 + lane;
+        double s0 = 0.0, sc[DT];
+#pragma unroll
+        for (int c = 0; c < DT; c++) sc[c] = 0.0;
+        double rt[ROWD ? DT + 1 : 1], rbt[ROWD ? DT + 1 : 1], rkv = 0.0;
+#pragma unroll
+        for (int c = 0; c < (ROWD ? DT + 1 : 1); c++) rt[c] = rbt[c] = 0.0;
+        const int i = rb * BM + row;
+        const bool iv = i < a.rows_valid;
+        const int64_t ig = a.r0 + i;
+        double xi[DT];
+#pragma unroll
+        for (int c = 0; c < DT; c++) xi[c] = iv ? a.X[ig + a.ldx * c] * a.invl[c] : 0.0;
+        const double rsi = (a.rs && iv) ? a.rs[ig] : 1.0;
+        const double rai = (a.ra && iv) ? a.ra[ig] : 0.0;
+        for (int vt = 0; vt < nvt; ++vt) {
+            const int sw = vt & 1;
+            const int j0 = (jb0 + (vt >> 1)) * BN2;
+            if (sw == 0) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the previous block's us / bt / cs
+                for (int e = et; e < BN2 * DT; e += 256) {
+                    const int jj = e / DT, c = e - jj * DT;
+                    us[e] = (j0 + jj < a.m) ? a.U[j0 + jj + (int64_t)a.m * c] * a.invl[c] : 0.0;
+                }
+                if (et < BN2) {
+                    bt[et] = (a.beta && j0 + et < a.m) ? a.beta[j0 + et] : 0.0;
+                    cs[et] = a.sigma2 * a.colscale[j0 + et];
+                    if (ROWD) vv[et] = (a.vvec && j0 + et < a.m) ? a.vvec[j0 + et] : 0.0;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(&bars.tmem_full, vt & 1);
+            tc_fence_after();
+            double T[64];
+            {
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+                const double wgt = sw == 0 ? W_LEVELS_HI : W_LEVELS_LO;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    long long acc[16];
+                    if (sw == 0) drain16_n128<4>(tcol + g * 16, acc);
+                    else drain16_n128<NS - 4>(tcol + g * 16, acc);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) T[g * 16 + c] = wgt * (double)acc[c];
+                }
+            }
+            tc_fence_before();                                  // TMEM is free for the next virtual tile's MMAs
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR && !leader) mbar_arrive_remote(&bars.tmem_empty, 0);
+                else mbar_arrive(&bars.tmem_empty);
+            }
+            if (a.debug & 1) {
+                s0 += T[0] + T[17] + T[34] + T[51];
+            } else if (iv) {
+                const int8_t *kimg = a.kslices + ((size_t)rb * KBm) * IMG_BLOCK + (size_t)row * 16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int jg = j0 + half * 64 + g * 16;     // first column of this 16-column group
+                    uint4 w[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        w[s] = __ldg(reinterpret_cast<const uint4 *>(kimg + s * a.kstride + (size_t)(jg / BK) * IMG_BLOCK +
+                                                                     (size_t)((jg % BK) / 16) * 2048));
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int jj = half * 64 + g * 16 + e;
+                        long long q4[4];
+                        if ((e & 3) == 0) join_quad(w, e >> 2, q4);
+                        if (j0 + jj < a.m) {
+                            const long long qd = q4[e & 3];
+                            const double kij = a.sigma2 * FIX_INV * (double)qd;
+                            if (ROWD) {
+                                const double tij = cs[jj] * T[g * 16 + e];
+                                const double tk = tij * kij;
+                                rt[0] += tk;
+                                if (sw == 0) {
+                                    rbt[0] = fma(bt[jj], kij, rbt[0]);
+                                    rkv = fma(kij, vv[jj], rkv);
+                                }
+                                if (!a.nodims) {
+                                    const double bk = sw == 0 ? bt[jj] * kij : 0.0;
+#pragma unroll
+                                    for (int k = 0; k < DT; k++) {
+                                        const double tt = xi[k] - us[jj * DT + k], d2 = tt * tt;
+                                        rt[(ROWD ? 1 + k : 0)] = fma(tk, d2, rt[(ROWD ? 1 + k : 0)]);
+                                        rbt[(ROWD ? 1 + k : 0)] = fma(bk, d2, rbt[(ROWD ? 1 + k : 0)]);
+                                    }
+                                }
+                                if (qd == FIX_ONE && !a.nodims)
+                                    record_if_coincident_i8_part(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                                 a.coin_omega, a.coin_cap, tij, sw);
+                            } else {
+                                const double om = fma(rsi, cs[jj] * T[g * 16 + e], sw == 0 ? rai * bt[jj] : 0.0);
+                                const double pk = om * kij;
+                                s0 += pk;
+#pragma unroll
+                                for (int k = 0; k < DT; k++) {
+                                    const double tt = xi[k] - us[jj * DT + k];
+                                    sc[k] = fma(pk, tt * tt, sc[k]);
+                                }
+                                if (qd == FIX_ONE)
+                                    record_if_coincident_i8_part(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
+                                                                 a.coin_omega, a.coin_cap, om, sw);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (ROWD) {
+            double *part = a.rowd_part + ((int64_t)(blockIdx.y * 2 + half) * a.nslots) * a.ld + i;
+            if (a.nodims) {
+                part[0] = rt[0];
+            } else {
+#pragma unroll
+                for (int c = 0; c < DT + 1; c++) {
+                    part[(int64_t)c * a.ld] = rt[ROWD ? c : 0];
+                    if (a.beta) part[(int64_t)(DT + 1 + c) * a.ld] = rbt[ROWD ? c : 0];
+                }
+            }
+            if (a.vvec) part[(int64_t)(a.nslots - 1) * a.ld] = rkv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+#pragma unroll
+        for (int c = 0; c < DT; c++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sc[c] += __shfl_xor_sync(0xffffffffu, sc[c], o);
+        if (lane == 0) {
+            red[ew * PART_STRIDE_I8] = s0;
+#pragma unroll
+            for (int c = 0; c < DT; c++) red[ew * PART_STRIDE_I8 + 1 + c] = sc[c];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!ROWD && et < 1 + DT) {
+            double v = 0.0;
+            for (int k = 0; k < 8; k++) v += red[k * PART_STRIDE_I8 + et];
+            double *slot = a.part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * PART_STRIDE_I8 + et;
+            *slot = a.first ? v : (*slot + v);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_free_all(tmem_base);
+    }
+}
+
+bool i8_wide_tiles()
+{
+    static const bool on = [] {
+        const char *e = getenv("SRGP_I8_TILE");
+        return !(e && atoi(e) == 64);
+    }();
+    return on;
+}
+
 bool i8_enabled()
 {
     static const bool on = [] {
@@ -686,11 +1178,16 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
                    double *b1)
 {
     cudaStream_t s = ctx->stream;
-    static DeviceOnce once;
+    static DeviceOnce once, once2;
     if (once.need(ctx->device))
         SRGP_CUDA(cudaFuncSetAttribute(i8_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int mp = w->mp, m = w->m, d = w->d;
-    const int tiles = w->nt * (w->nt + 1);
+    // 128 x 128 tiles in two sweeps (default) or the 128 x 64 single-sweep tiles (SRGP_I8_TILE=64: the A/B switch the
+    // measurements in profiles/ were taken with)
+    const bool wide = i8_wide_tiles();
+    if (wide && once2.need(ctx->device))
+        SRGP_CUDA(cudaFuncSetAttribute(i8_gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM2_SMEM));
+    const int tiles = wide ? w->nt * (w->nt + 1) / 2 : w->nt * (w->nt + 1);
     const int nsplit = std::max(1, std::min(16, ctx->sm_count / tiles));
     const int quantum = BK * nsplit;
     const int sets = rowweight ? 2 : 1;
@@ -698,7 +1195,8 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     // most MAX_ROWS_PER_SPLIT rows
     int64_t rows1 = std::min<int64_t>((int64_t)w->chunk_elems / mp / sets, (int64_t)MAX_ROWS_PER_SPLIT * nsplit);
     rows1 = std::max<int64_t>(quantum, rows1 / quantum * quantum);
-    SRGP_TRY(w->Gpart.reserve((size_t)tiles * nsplit * BM * BN * 8));
+    const size_t tile_elems = (size_t)BM * (wide ? BN2 : BN);
+    SRGP_TRY(w->Gpart.reserve((size_t)tiles * nsplit * tile_elems * 8));
     double *wmax = nullptr;
     if (rowweight) {
         SRGP_TRY(w->i8scal.reserve(64));
@@ -709,7 +1207,7 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     }
     int first = 1;
     if (ctx->n == 0) {
-        SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)tiles * nsplit * BM * BN * 8, s));
+        SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)tiles * nsplit * tile_elems * 8, s));
         SRGP_CUDA(cudaMemsetAsync(w->b1part.p, 0, (size_t)w->gen_groups * mp * 8, s));
     }
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
@@ -737,8 +1235,12 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GRAM, s);
-            i8_gram_kernel<<<tiles * nsplit, THREADS, SMEM_BYTES, s>>>(slices_w, slices, slice_stride, rows_padded / BK, nsplit,
-                                                                      gp.sigma2 * gp.sigma2, wmax, w->Gpart.d(), first);
+            if (wide)
+                i8_gram2_kernel<<<tiles * nsplit, THREADS, GRAM2_SMEM, s>>>(slices_w, slices, slice_stride, rows_padded / BK,
+                                                                            nsplit, gp.sigma2 * gp.sigma2, wmax, w->Gpart.d(), first);
+            else
+                i8_gram_kernel<<<tiles * nsplit, THREADS, SMEM_BYTES, s>>>(slices_w, slices, slice_stride, rows_padded / BK, nsplit,
+                                                                          gp.sigma2 * gp.sigma2, wmax, w->Gpart.d(), first);
             SRGP_LAUNCH_CHECK();
         }
         SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
@@ -746,7 +1248,8 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     }
     {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-        i8_gram_finalize_kernel<<<tiles, 128, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
+        if (wide) i8_gram2_finalize_kernel<<<tiles, 128, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
+        else i8_gram_finalize_kernel<<<tiles, 128, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
         SRGP_LAUNCH_CHECK();
         gram_sum_rows(s, w->b1part.d(), w->gen_groups, mp, b1);
         SRGP_LAUNCH_CHECK();
@@ -773,6 +1276,30 @@ static cudaError_t launch_km_i8(cudaStream_t s, dim3 grid, int device, const KmI
     }
     i8_km_kernel<DT, ROWD><<<grid, KM_THREADS, smem, s>>>(a);
     return cudaSuccess;
+}
+
+template <int DT, bool ROWD, bool PAIR>
+static cudaError_t launch_km2_i8(cudaStream_t s, dim3 grid, int device, const KmI8Args &a)
+{
+    const size_t smem = Km2Cfg<PAIR>::RING_BYTES + sizeof(Bars2) + sizeof(double) * (BN2 * DT + 3 * BN2 + 8 * PART_STRIDE_I8);
+    static DeviceOnce once;
+    if (once.need(device)) {
+        cudaError_t e = cudaFuncSetAttribute(i8_km2_kernel<DT, ROWD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(KM2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PAIR ? 2 : 1;      // adjacent row blocks
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, i8_km2_kernel<DT, ROWD, PAIR>, a);
 }
 
 // mp <= 16384: one INT32 level accumulator sums up to NS pairs x 2^14 x mp over the knots (tc_i8.cuh)
@@ -888,7 +1415,10 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             // row block per CTA it stays.
             const int nsub = 1;
             a.nsub = nsub;
-            a.tiles_per_cta = (mp / BN) / (w->cgroups * nsub);
+            const bool wide = i8_wide_tiles();
+            a.tiles_per_cta = wide ? (mp / BN2) / w->cgroups : (mp / BN) / (w->cgroups * nsub);
+            a.cluster = (wide && (w->rblocks / nsub) % 2 == 0 && getenv("SRGP_PAIR")) ? 2 : 1;
+            a.debug = getenv("SRGP_KM_DEBUG") ? atoi(getenv("SRGP_KM_DEBUG")) : 0;
             a.part = w->part2.d();
             a.first = first;
             a.coin_count = w->coin_count();
@@ -902,7 +1432,10 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.nodims = nodims ? 1 : 0;
             dim3 grid(w->rblocks / nsub, w->cgroups * nsub);
             cudaError_t e = cudaSuccess;
-#define CALL(D) e = rowd ? launch_km_i8<D, true>(s, grid, ctx->device, a) : launch_km_i8<D, false>(s, grid, ctx->device, a)
+#define CALL2(D, R) (a.cluster == 2 ? launch_km2_i8<D, R, true>(s, grid, ctx->device, a) : launch_km2_i8<D, R, false>(s, grid, ctx->device, a))
+#define CALL(D)                                                                                                          \
+    e = wide ? (rowd ? CALL2(D, true) : CALL2(D, false))                                                                 \
+             : (rowd ? launch_km_i8<D, true>(s, grid, ctx->device, a) : launch_km_i8<D, false>(s, grid, ctx->device, a))
             switch (d) {
             case 1: CALL(1); break;
             case 2: CALL(2); break;
@@ -914,6 +1447,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             default: CALL(8); break;
             }
 #undef CALL
+#undef CALL2
             SRGP_CUDA(e);
             SRGP_LAUNCH_CHECK();
         }

@@ -268,5 +268,155 @@ __device__ __forceinline__ void load_stage(uint32_t sbase, uint64_t *full, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 128 x 128 output tiles in TWO SWEEPS over k.  An MMA reads its A tile (128 rows x 32 B) from shared memory whatever N
+// is, so at N = 64 the shared-memory port (128 B/clk: 4 KB + 2 KB per 32-clk MMA) and not the tensor pipe bounds the
+// kernels (tools/ozaki/mma_rate.cu: 48 clk per MMA resident, 58 with the TMA writes; N = 128: 64 clk = the pipe).  N = 128
+// leaves room for 4 accumulators in the 512 TMEM columns, so a tile is computed as two "virtual tiles" over the same k
+// range: sweep 0 = levels 0..3 (10 slice pairs, needs slices 0..3 of both operands only), sweep 1 = levels 4..NS-1 (18
+// pairs, all slices).  Both level groups are contiguous, so each drains as one exact 64-bit integer per entry, and every
+// quantity downstream is linear in the product, so the two sweeps are simply two contributions.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BN2 = 128;
+constexpr int STAGE2_BYTES = NS * 2 * A_TILE;          // 56 KB (NS = 7): NS A tiles + NS B tiles of 4 KB
+__host__ __device__ constexpr int sweep_slices(int sw) { return sw == 0 ? 4 : NS; }       // operand slices a sweep reads
+__host__ __device__ constexpr int sweep_levels(int sw) { return sw == 0 ? 4 : NS - 4; }   // accumulators it fills
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8_n128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+                 "l"(da), "l"(db), "r"(IDESC2), "r"(accumulate), "r"(0u) : "memory");
+}
+
+// one 32-byte k-step of sweep SW: level L = sa + sb -> TMEM columns [128 (L - 4 SW), + 128).  a_base / b_base: shared
+// addresses of the A and B slice tiles of the stage (b_base == a_base on the diagonal tiles of a Gram).
+template <int SW>
+__device__ __forceinline__ void issue_stage2(uint32_t a_base, uint32_t b_base, uint32_t tmem_base, bool fresh)
+{
+    const uint64_t da0 = make_desc(a_base, 2048, 128);
+    const uint64_t db0 = make_desc(b_base, 2048, 128);
+    const uint32_t keep = fresh ? 0u : 1u;
+#pragma unroll
+    for (int sb = 0; sb < NS; ++sb) {
+#pragma unroll
+        for (int sa = 0; sa < NS; ++sa) {
+            const int L = sa + sb;
+            if (SW == 0 ? L < 4 : (L >= 4 && L < NS)) {
+                const uint64_t da = da0 + (uint64_t)((sa * A_TILE) >> 4);
+                const uint64_t db = db0 + (uint64_t)((sb * A_TILE) >> 4);
+                // accumulator L is first touched by the pair (sa = L, sb = 0)
+                mma_i8_n128(tmem_base + (uint32_t)(L - 4 * SW) * BN2, da, db, sb == 0 ? keep : 1u);
+            }
+        }
+    }
+}
+
+// producer side of one stage of sweep sw: slices 0 .. sweep_slices(sw) - 1 of the A block (and of the B block unless it is
+// the same block); a 128-row block's two 16-byte k-chunks of a 32-byte k-step are 4 KB contiguous in the image
+__device__ __forceinline__ void load_stage2(uint32_t sbase, uint64_t *full, const int8_t *a_slices, size_t a_stride, size_t a_blk,
+                                            const int8_t *b_slices, size_t b_stride, size_t b_blk, bool same, int ks, int nsl)
+{
+    mbar_expect_tx(full, (uint32_t)(nsl * A_TILE * (same ? 1 : 2)));
+    const size_t off = (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * A_TILE;
+    for (int s = 0; s < nsl; ++s) {
+        bulk_g2s(sbase + s * A_TILE, a_slices + s * a_stride + a_blk + off, A_TILE, full);
+        if (!same) bulk_g2s(sbase + (NS + s) * A_TILE, b_slices + s * b_stride + b_blk + off, A_TILE, full);
+    }
+}
+
+// ---- thread-block clusters: operand tiles that several CTAs need at the same time are fetched from L2 once and
+// multicast into the shared memory of all of them (the row passes are bound by the L2 -> SM path, not by the tensor
+// pipe or HBM: profiles/r02_km_bound.txt) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// data lands at the same CTA-relative offset, and complete_tx is signalled on the same-offset mbarrier, in every CTA of
+// `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrives (once the issued MMAs completed) on the same-offset mbarrier of every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask) : "memory");
+}
+
+// ---- CTA pairs (tcgen05 cta_group::2): one MMA spans two SMs -- M = 256 = 128 rows per CTA, each CTA holds its own A
+// tile and HALF of the B tile (the hardware reads the peer's half), each CTA's TMEM receives its 128 rows x N columns.
+// The B operand is therefore fetched from L2 once per pair instead of once per CTA (tools/ozaki/pair_rate.cu checks the
+// levels bit for bit against single-CTA MMAs).  Only the leader (cluster rank 0) issues MMAs and commits. ----
+constexpr uint32_t IDESC2_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ void mma_i8_n128_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+                 "l"(da), "l"(db), "r"(IDESC2_PAIR), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrives on the same-offset mbarrier of both CTAs of the pair once the MMAs issued so far completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_all_pair(uint32_t *slot)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_all_pair(uint32_t base)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// wait on a local mbarrier whose arrivals come from the peer CTA (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+
+// NL levels at stride BN2 columns: acc = sum_k lev_k 256^(NL-1-k) for 16 columns
+template <int NL>
+__device__ __forceinline__ void drain16_n128(uint32_t taddr, long long (&acc)[16])
+{
+    static_assert(NL == 3 || NL == 4, "levels per exact 64-bit group");
+    uint32_t v[NL][16];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) tmem_ld16_nowait(taddr + (uint32_t)(k * BN2), v[k]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        long long a = (long long)(int)v[0][c];
+#pragma unroll
+        for (int k = 1; k < NL; ++k) a = a * 256 + (long long)(int)v[k][c];
+        acc[c] = a;
+    }
+}
+
 }  // namespace i8
 }  // namespace srgp

@@ -87,11 +87,20 @@ def test_config4_newton_and_gradient_full_size(ctx):
     np.testing.assert_allclose(h, g["hist"], rtol=RTOL)
     np.testing.assert_allclose(fit["gp"][:64], g["gp_head"], rtol=1e-7, atol=1e-9)
     assert float(np.linalg.norm(fit["gp"])) == pytest.approx(g["gp_norm"], rel=1e-8)
-    np.testing.assert_allclose(fit["u_posterior_mean"], g["u_mean"], rtol=1e-7, atol=1e-9)
-    np.testing.assert_allclose(np.diag(fit["u_posterior_variance"]), g["u_var_diag"], rtol=1e-6, atol=1e-9)
+    # u_mean = muu + a - G_Z C_Z a cancels ~6 digits at this size (|a| ~ n / Z): the reference's own float64 formula is
+    # 9e-7 (relative to max |u_mean|) from a long-double evaluation of the same expression, a Cholesky-solve form
+    # 3e-10 (tests/tools/make_golden_sizes.py header; measured at the closed-form ff).  The golden holds the reference's
+    # formula, so the comparison is stated at 1e-5, not at the 1e-7 of the small cases.
+    um_ref = np.asarray(g["u_mean"])
+    np.testing.assert_allclose(fit["u_posterior_mean"], um_ref, rtol=0, atol=1e-5 * np.abs(um_ref).max())
+    np.testing.assert_allclose(np.diag(fit["u_posterior_variance"]), g["u_var_diag"], rtol=1e-5, atol=1e-9)
     ff = cfg4_ff_closed_form(c["x"])
     got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], ff, "bernoulli", c["mu"], c["delta"], ctx=ctx)["gradient"]
-    _check_grad([got[k] for k in g["names"]], g["grad_at_closed_form_ff"], g["names"], RTOL)
+    # float64 oracle vs product 1.7e-8 at this size (n / Z ~ 1e7 in the row sums); the long-double yardstick of the same
+    # gradient (cfg4 "grad_longdouble", when present) is held to 1e-8
+    _check_grad([got[k] for k in g["names"]], g["grad_at_closed_form_ff"], g["names"], 5e-8)
+    if "grad_longdouble_at_closed_form_ff" in g:
+        _check_grad([got[k] for k in g["names"]], g["grad_longdouble_at_closed_form_ff"], g["names"], RTOL)
     # at the mode the two Newton runs agree to ~1e-7 in ff, so the gradient is held to 1e-6
     got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], fit["gp"], "bernoulli", c["mu"], c["delta"], ctx=ctx)["gradient"]
     _check_grad([got[k] for k in g["names"]], g["grad_at_mode"], g["names"], 1e-6)
