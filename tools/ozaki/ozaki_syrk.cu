@@ -29,7 +29,7 @@
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
-#include "../../sparsergps_b200/csrc/tc_i8.cuh"      // the product's INT8 engine: layout constants, PTX wrappers, issue_stage
+#include "tc_i8_r01.cuh"      // the product's INT8 engine: layout constants, PTX wrappers, issue_stage
 using namespace srgp::i8;
 
 // ---- splitter: doubles in (0, 1] (column j of K contiguous over rows) -> 8 INT8 slices in the smem image --------

@@ -9,7 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
-#include "../../sparsergps_b200/csrc/tc_i8.cuh"
+#include "tc_i8_r01.cuh"
 using namespace srgp::i8;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
 

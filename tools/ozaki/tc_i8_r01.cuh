@@ -1,29 +1,24 @@
+// Frozen copy of sparsergps_b200/csrc/tc_i8.cuh as of round 1 / early round 2 (128 x 64 single-sweep tiles, slice-major
+// operand images): the engine the probes in this directory were written and measured against.  NOT product code.
 // tc_i8.cuh -- FP64-equivalent products on the INT8 tensor cores of sm_100a (tcgen05.mma.kind::i8, accumulators in
 // TMEM): the operand layout, the PTX wrappers and the digit splitter shared by the Gram (pass 1) and K*M (pass 2)
 // kernels of gauss_i8.cu.
 //
-// Scheme (Ozaki-style error-free splitting, fixed point): a value v in [-1, 1] is q = rint(v 2^FIX_BITS), and
-// q = sum_t d_t 256^t with balanced digits d_t in [-128, 127] -- NS INT8 slices, slice s = NS - 1 - t.  A product
-// sum_r a_r b_r is then sum_{sa,sb} 2^(-12-8(sa+sb)) (sum_r da_sa[r] db_sb[r]) where every inner sum is an exact INT32
-// dot product; pairs with sa + sb >= NS are dropped.  All pairs of one level L = sa + sb accumulate into the same
-// TMEM accumulator.  Output tiles are 128 x 128 (an MMA reads its 128-row A tile from shared memory whatever N is, so
-// at N = 64 the shared-memory port bounds the MMA rate at 48 clk; N = 128 runs at the pipe's 64 clk for twice the
-// work: tools/ozaki/mma_rate.cu), which leaves room for 4 accumulators in the 512 TMEM columns: a tile is computed in
-// TWO SWEEPS over the same k range, sweep 0 = levels 0..3 (10 slice pairs, slices 0..3 of both operands), sweep 1 =
-// levels 4..NS-1 (18 pairs, all slices).  Both level groups are contiguous, so each drains as one exact 64-bit integer
-// per entry, and every quantity downstream is linear in the product, so the sweeps are simply two contributions.
-// Overflow bound: (L + 1) <= NS pairs x 2^14 x rows <= 2^30 for rows <= 8192 per accumulation (the K*M pass sums over
-// the mp knots: mp <= 8192, checked by i8_pass2_supported).
+// Scheme (Ozaki-style error-free splitting, fixed point): a value v in [-1, 1] is q = rint(v 2^62), and
+// q = sum_t d_t 256^t with balanced digits d_t in [-128, 127] -- NS = 8 INT8 slices, slice s = 7 - t carries weight
+// 2^(-6-8s).  A product sum_r a_r b_r is then sum_{sa,sb} 2^(-12-8(sa+sb)) (sum_r da_sa[r] db_sb[r]) where every
+// inner sum is an exact INT32 dot product; pairs with sa + sb > 7 are dropped (< 2^-58 of the operand scales per
+// term).  All pairs of one level L = sa + sb accumulate into the same TMEM accumulator (8 levels x 64 columns = the
+// whole 512-column TMEM), so a 128 x 64 output tile costs 36 INT8 MMAs per k-step instead of one FP64 MMA, on a pipe
+// that is ~120x wider than DMMA.  Overflow bound: (L + 1) <= 8 pairs x 2^14 x rows <= 2^30 for rows <= 8192
+// (the K*M pass sums over the mp knots: mp <= 16384, checked by i8_pass2_supported).
 //
 // Operand layout: K-major, SWIZZLE_NONE ("interleaved") canonical UMMA layout -- 8 rows x 16 bytes core matrices
 // stored as 128 contiguous bytes.  The producers of the slices (generator kernels) write them to global memory
-// ALREADY in the shared-memory image, with all slices of one (128-row block, 32-byte k-step) contiguous:
-//     image[blk = row / 128][ks = k / 32][slice s][c = (k % 32) / 16][r1 = (row % 128) / 8][r0 = row % 8][k % 16]
-// (4 KB per slice tile, KSTEP_BYTES = NS x 4 KB per (blk, ks)), so the operand tiles of a pipeline stage are ONE
-// contiguous cp.async.bulk per operand (TMA bulk copy, mbarrier complete_tx; no tensor map) -- 16 KB for the slices
-// 0..3, 12 KB for the slices 4..6 -- and a matrix descriptor is the stage base plus a compile-time constant
-// (LBO = 2048, SBO = 128).  (With one 4 KB copy per slice tile the single producer thread, at ~180 clk per copy, was the
-// bound of both row passes: profiles/r02_ncu_km2_before_layout.txt.)
+// ALREADY in the shared-memory image,
+//     image(slice s)[blk = row / 128][kb = k / 64][c = (k % 64) / 16][r1 = (row % 128) / 8][r0 = row % 8][k % 16]
+// (8 KB per (blk, kb)), so an operand tile is one contiguous cp.async.bulk (TMA bulk copy, mbarrier complete_tx;
+// no tensor map) and its matrix descriptor has LBO = 2048 (1024 for a 64-row half tile), SBO = 128.
 #pragma once
 #include <stdint.h>
 
@@ -42,22 +37,22 @@ constexpr int NS = SRGP_I8_NS;
 static_assert(NS == 7 || NS == 8, "digit slices per operand");
 constexpr int NPAIRS = NS * (NS + 1) / 2;   // MMAs per k-step
 constexpr int FIX_BITS = 8 * NS - 2;  // fixed-point fraction bits: 54 / 62
-constexpr int BM = 128;               // rows of an output tile = rows of an operand block
-constexpr int BN2 = 128;              // columns of an output tile (4 accumulators x 128 = the 512 TMEM columns)
-constexpr int KS = 32;                // k extent of one MMA k-step, in INT8 elements = bytes
-constexpr int BK = 64;                // granule of the k extents handled by the generators (two k-steps)
-constexpr int A_TILE = BM * KS;       // 4 KB: one slice of one (block, k-step)
-constexpr int KSTEP_BYTES = NS * A_TILE;   // all slices of one (block, k-step), contiguous in the image
-constexpr int THREADS = 256;          // Gram kernel: warp 0 TMA producer, warps 1, 2 MMA issuers, warps 4..7 epilogue
+constexpr int BM = 128, BN = 64;      // output tile (BN x NS <= 512 TMEM columns)
+constexpr int BK = 64;                // k extent of one block of the operand image, in INT8 elements = bytes
+constexpr int KS = 32;                // k extent of one pipeline stage = one MMA k-step (half an image block)
+constexpr int STAGES = NS == 8 ? 4 : 5;   // 4 x 48 KB / 5 x 42 KB: all but one stage in flight while one is consumed.  With 2 x 96 KB
+                                      // only one stage was ever in flight and the K*M pass, whose K slices come from
+                                      // HBM rather than L2, ran at 2.66 us per 64-byte block instead of 2.17
+constexpr int A_TILE = BM * KS;       // 4 KB
+constexpr int B_TILE = BN * KS;       // 2 KB
+constexpr int STAGE_BYTES = NS * (A_TILE + B_TILE);   // 48 KB
+constexpr int IMG_BLOCK = 128 * BK;   // bytes of one (128-row block, k-block) image
+constexpr int THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 constexpr int MAX_ROWS_PER_SPLIT = 8192;
 constexpr double FIX_SCALE = (double)(1ull << FIX_BITS);   // 2^54 / 2^62
 constexpr long long FIX_ONE = 1ll << FIX_BITS;             // the image of exp(0) = 1: candidate for quirk Q4
-
-// byte offset of slice tile (blk, ks, s) in an image whose k extent is `ksteps` k-steps
-__host__ __device__ __forceinline__ size_t img_off(int blk, int ksteps, int ks, int s = 0)
-{
-    return ((size_t)blk * ksteps + ks) * KSTEP_BYTES + (size_t)s * A_TILE;
-}
+// instruction descriptor: D = S32, A = B = signed INT8, both K-major, N = 64, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -99,6 +94,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+                 "l"(da), "l"(db), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -128,7 +129,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// 32 lanes x 16 consecutive columns, no wait: several loads can be in flight before tmem_ld_wait()
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 16 columns of the NS level accumulators (columns col + L * BN) -> two exact 64-bit integers per entry:
+// hi = sum_{k<4} lev_k 256^(3-k) (levels 0..3, weight 2^-36) and lo = sum_{k<NS-4} lev_{4+k} 256^(NS-5-k) (levels 4..NS-1,
+// weight 2^(-12-8(NS-1))); |lev| < 2^30, so both stay below 2^55.  The INT32 -> FP64 conversions and the weighting of
+// the levels cost 3 FP64 instructions per entry instead of 2 NS (the FP64 pipe is the contended one).
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -137,6 +150,24 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v)
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// NL consecutive levels starting at taddr: acc = sum_k lev_k 256^(NL-1-k); the NL loads are in flight together (one
+// TMEM round trip per 16 x NL block)
+template <int NL>
+__device__ __forceinline__ void drain16(uint32_t taddr, long long (&acc)[16])
+{
+    static_assert(NL == 3 || NL == 4, "levels per exact 64-bit group");
+    uint32_t v[NL][16];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) tmem_ld16_nowait(taddr + (uint32_t)(k * BN), v[k]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        long long a = (long long)(int)v[0][c];
+#pragma unroll
+        for (int k = 1; k < NL; ++k) a = a * 256 + (long long)(int)v[k][c];
+        acc[c] = a;
+    }
+}
 constexpr double W_LEVELS_HI = 1.4551915228366852e-11;                           // 2^-36: levels 0..3 as one integer
 constexpr double W_LEVELS_LO = NS == 8 ? 3.3881317890172014e-21 : 8.673617379884035e-19;   // 2^-68 / 2^-60: levels 4..NS-1
 constexpr double FIX_INV = 1.0 / FIX_SCALE;                                      // 2^-54 / 2^-62
@@ -169,20 +200,6 @@ __device__ __forceinline__ void join_quad(const uint4 (&w)[NS], int wi, long lon
     }
 }
 
-// The top four digits of the same 4 entries as one exact integer: q = qt 256^(NS-4) + (the lower digits, |.| < 256^(NS-4) / 2),
-// i.e. v = qt 2^-30 to 2^-31 absolute.  w[0..3]: slices 0..3 (slice 0 = most significant digit).
-constexpr double KF_SCALE = 9.313225746154785e-10;       // 2^-30 = 2^(-FIX_BITS + 8 (NS - 4)) for either NS
-constexpr int KF_ONE = 1 << 30;                          // top digits of q = 2^FIX_BITS
-__device__ __forceinline__ void join_quad_top(const uint4 (&w)[4], int wi, int (&qt)[4])
-{
-    uint32_t in[4], y[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) in[s] = wi == 0 ? w[s].x : wi == 1 ? w[s].y : wi == 2 ? w[s].z : w[s].w;
-    transpose4x4(in[3], in[2], in[1], in[0], y);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) qt[k] = (int)((y[k] ^ 0x80808080u) - 0x80808080u);
-}
-
 // Balanced base-256 digits of q = rint(v 2^FIX_BITS), |v| <= 1, for 4 consecutive entries (word `wi` of a 16-byte k-chunk).
 // q = sum_t d_t 256^t with d_t in [-128, 127]  <=>  q + B = sum_t (d_t + 128) 256^t with B = 0x80...80 (NS bytes), i.e. the
 // plain bytes of q + B (< 2^(8 NS), the bytes above stay 0); and d_t as a two's-complement INT8 is (d_t + 128) ^ 0x80.  So all NS digits of an entry are
@@ -205,9 +222,67 @@ __device__ __forceinline__ void split_quad(double v0, double v1, double v2, doub
     }
 }
 
+// shared-memory carve-up of the two INT8 kernels
+struct Bars {
+    uint64_t full[STAGES], empty[STAGES], tmem_full;
+    uint32_t tmem_slot, pad;
+};
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (int)sizeof(Bars);
+
+// The issue sequence of one stage (one 32-byte k-step): NPAIRS slice pairs; level L = sa + sb -> TMEM columns [64 L, 64 L + 64).
+// `fresh` = this is the first stage of the accumulation (the first MMA of every level overwrites).
+// One thread issues all NPAIRS MMAs, so the sequence is fully unrolled and every descriptor is the stage's base
+// descriptor plus a compile-time constant (the start-address field is the low 14 bits, in 16-byte units; the sums
+// stay below 2^14): 2 integer adds per MMA.  With descriptors rebuilt per MMA the issuing thread, not the tensor
+// pipe, was the limit (85 instead of ~45 cycles per MMA, profiles/r01_ozaki_proto.json).
+__device__ __forceinline__ void issue_stage(uint32_t sbase, uint32_t tmem_base, bool fresh)
+{
+    const uint64_t da0 = make_desc(sbase, 2048, 128);
+    const uint64_t db0 = make_desc(sbase + NS * A_TILE, 1024, 128);
+    const uint32_t keep = fresh ? 0u : 1u;
+#pragma unroll
+    for (int sb = 0; sb < NS; ++sb) {
+#pragma unroll
+        for (int sa = 0; sa < NS; ++sa) {
+            if (sa + sb < NS) {
+                const uint64_t da = da0 + (uint64_t)((sa * A_TILE) >> 4);
+                const uint64_t db = db0 + (uint64_t)((sb * B_TILE) >> 4);
+                // level L is first touched by the pair (sa = L, sb = 0)
+                mma_i8(tmem_base + (uint32_t)(sa + sb) * BN, da, db, sb == 0 ? keep : 1u);
+            }
+        }
+    }
+}
+
+// Producer side of one stage (k-step ks of the operand images, 32 bytes): 8 A slice tiles (128 rows: the two 16-byte
+// k-chunks of a 128-row block image are 4 KB contiguous) and 8 B slice tiles (64 rows = one half of a 128-row block:
+// 1 KB per k-chunk).  a_blk / b_blk: byte offsets of the operands' (block, k-block 0) images inside a slice.
+__device__ __forceinline__ void load_stage(uint32_t sbase, uint64_t *full, const int8_t *a_slices, size_t a_stride, size_t a_blk,
+                                           const int8_t *b_slices, size_t b_stride, size_t b_blk, int b_half, int ks)
+{
+    mbar_expect_tx(full, STAGE_BYTES);
+    const size_t a_off = a_blk + (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * A_TILE;
+    const size_t b_off = b_blk + (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * 4096 + (size_t)b_half * 1024;
+    for (int s = 0; s < NS; ++s) {
+        bulk_g2s(sbase + s * A_TILE, a_slices + s * a_stride + a_off, A_TILE, full);
+        bulk_g2s(sbase + NS * A_TILE + s * B_TILE, b_slices + s * b_stride + b_off, 1024, full);
+        bulk_g2s(sbase + NS * A_TILE + s * B_TILE + 1024, b_slices + s * b_stride + b_off + 2048, 1024, full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 128 x 128 output tiles in TWO SWEEPS over k.  An MMA reads its A tile (128 rows x 32 B) from shared memory whatever N
+// is, so at N = 64 the shared-memory port (128 B/clk: 4 KB + 2 KB per 32-clk MMA) and not the tensor pipe bounds the
+// kernels (tools/ozaki/mma_rate.cu: 48 clk per MMA resident, 58 with the TMA writes; N = 128: 64 clk = the pipe).  N = 128
+// leaves room for 4 accumulators in the 512 TMEM columns, so a tile is computed as two "virtual tiles" over the same k
+// range: sweep 0 = levels 0..3 (10 slice pairs, needs slices 0..3 of both operands only), sweep 1 = levels 4..NS-1 (18
+// pairs, all slices).  Both level groups are contiguous, so each drains as one exact 64-bit integer per entry, and every
+// quantity downstream is linear in the product, so the two sweeps are simply two contributions.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BN2 = 128;
+constexpr int STAGE2_BYTES = NS * 2 * A_TILE;          // 56 KB (NS = 7): NS A tiles + NS B tiles of 4 KB
 __host__ __device__ constexpr int sweep_slices(int sw) { return sw == 0 ? 4 : NS; }       // operand slices a sweep reads
 __host__ __device__ constexpr int sweep_levels(int sw) { return sw == 0 ? 4 : NS - 4; }   // accumulators it fills
-// instruction descriptor: D = S32, A = B = signed INT8, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void mma_i8_n128(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
@@ -240,7 +315,22 @@ __device__ __forceinline__ void issue_stage2(uint32_t a_base, uint32_t b_base, u
     }
 }
 
-// ---- thread-block clusters ----
+// producer side of one stage of sweep sw: slices 0 .. sweep_slices(sw) - 1 of the A block (and of the B block unless it is
+// the same block); a 128-row block's two 16-byte k-chunks of a 32-byte k-step are 4 KB contiguous in the image
+__device__ __forceinline__ void load_stage2(uint32_t sbase, uint64_t *full, const int8_t *a_slices, size_t a_stride, size_t a_blk,
+                                            const int8_t *b_slices, size_t b_stride, size_t b_blk, bool same, int ks, int nsl)
+{
+    mbar_expect_tx(full, (uint32_t)(nsl * A_TILE * (same ? 1 : 2)));
+    const size_t off = (size_t)(ks >> 1) * IMG_BLOCK + (size_t)(ks & 1) * A_TILE;
+    for (int s = 0; s < nsl; ++s) {
+        bulk_g2s(sbase + s * A_TILE, a_slices + s * a_stride + a_blk + off, A_TILE, full);
+        if (!same) bulk_g2s(sbase + (NS + s) * A_TILE, b_slices + s * b_stride + b_blk + off, A_TILE, full);
+    }
+}
+
+// ---- thread-block clusters: operand tiles that several CTAs need at the same time are fetched from L2 once and
+// multicast into the shared memory of all of them (the row passes are bound by the L2 -> SM path, not by the tensor
+// pipe or HBM: profiles/r02_km_bound.txt) ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -251,6 +341,20 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// data lands at the same CTA-relative offset, and complete_tx is signalled on the same-offset mbarrier, in every CTA of
+// `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrives (once the issued MMAs completed) on the same-offset mbarrier of every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask) : "memory");
+}
+
 // ---- CTA pairs (tcgen05 cta_group::2): one MMA spans two SMs -- M = 256 = 128 rows per CTA, each CTA holds its own A
 // tile and HALF of the B tile (the hardware reads the peer's half), each CTA's TMEM receives its 128 rows x N columns.
 // The B operand is therefore fetched from L2 once per pair instead of once per CTA (tools/ozaki/pair_rate.cu checks the
@@ -284,15 +388,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-}
-// The same without the release fence (SASS ERRBAR, ~600 clk): for arrivals that only pass on a completion the arriving
-// thread has observed -- a TMA transfer that has already signalled its own mbarrier, TMEM reads already waited for --
-// and publish no writes of the thread itself.
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32_t rank)
-{
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 // wait on a local mbarrier whose arrivals come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
