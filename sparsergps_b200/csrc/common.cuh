@@ -97,6 +97,7 @@ struct srgp_ctx {
     int64_t n = 0;
     int d = 0;
     bool have_data = false;
+    uint64_t data_version = 0;   // bumped whenever the rows behind Xp may have changed (keys the resident K image, gauss_i8.cu)
 
     // workspace of the fused pipeline (owned by gauss.cu / laplace.cu)
     void *ws = nullptr;

@@ -805,7 +805,7 @@ GaussWS *gauss_ws(srgp_ctx *ctx)
 
 void GaussWS::release()
 {
-    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &coinrow, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal};
+    DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &coinrow, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal, &k2};
     for (auto *b : bufs) b->release();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
@@ -866,6 +866,13 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     SRGP_TRY(w->nspart.reserve((size_t)NS_BLOCKS * PART_STRIDE * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));
     w->planned = true;
+    return SRGP_OK;
+}
+
+int upload_knots(GaussWS *w, const double *host, size_t bytes, cudaStream_t s)
+{
+    w->u_version++;
+    SRGP_CUDA(cudaMemcpyAsync(w->U.p, host, bytes, cudaMemcpyHostToDevice, s));
     return SRGP_OK;
 }
 
@@ -1585,6 +1592,7 @@ static int set_data_common(srgp_ctx *ctx, int64_t n, int d)
     GaussWS *w = gauss_ws(ctx);
     ctx->n = n;
     ctx->d = d;
+    ctx->data_version++;
     SRGP_TRY(w->r.reserve(std::max<size_t>(8, (size_t)n * 8)));
     SRGP_TRY(w->rowa.reserve(GaussWS::row_stride(n) * 8 * GaussWS::NROWV));
     SRGP_CUDA(cudaMemsetAsync(w->rowa.p, 0, GaussWS::row_stride(n) * 8 * GaussWS::NROWV, ctx->stream));
@@ -1665,7 +1673,7 @@ int gauss_eval(srgp_ctx *ctx, int model, int kernel, const double *xu, int64_t m
     SRGP_TRY(use_device(ctx));
     GaussWS *w = gauss_ws(ctx);
     SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
-    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, ctx->stream));
     w->want_knots = knots;
     w->knot_transform = knots && knot_lb && knot_ub;
     if (w->knot_transform)
@@ -1742,7 +1750,7 @@ extern "C" int srgp_test_gen(srgp_ctx *ctx, const double *xu, int64_t m, double 
     GaussWS *w = gauss_ws(ctx);
     SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
     cudaStream_t s = ctx->stream;
-    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, s));
+    SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, s));
     GenParams gp;
     fill_gen(gp, SRGP_ARD, ctx->d, sigma, l);
     const int quantum = BK * w->splits, mp = w->mp, d = w->d;

@@ -45,6 +45,20 @@ struct GaussWS {
     double knot_lb[SRGP_MAX_D], knot_ub[SRGP_MAX_D];
     DevBuf i8scal;   // INT8 weighted Gram: max |w| over the shard (device scalar)
     DevBuf i8buf;    // INT8 tensor-core passes: digit slices of Mop (8 x mp x mp bytes) + per-column scales
+    // The pass-2 operand image of the WHOLE shard (digit slices of exp(-d^2/2), blocks = 128-row blocks, k = knots: NS
+    // bytes per entry, 7.2 GB at n = 1e6, m = 1024), written by the first K*M / row-form pass of an evaluation that
+    // announces several of them (k_reuse) and read by the later ones.  Absent when it does not fit (the passes then
+    // regenerate their chunks).  Keyed on everything K depends on, see K2Key.
+    DevBuf k2;
+    bool k2_valid = false, k_reuse = false;
+    struct K2Key {
+        const double *Xp;
+        int64_t n;
+        int mp, m, d;
+        uint64_t uver, xver;
+        double invl[SRGP_MAX_D];
+    } k2_key = {};
+    uint64_t u_version = 0;    // bumped by upload_knots
     DevBuf Kmat;     // Laplace: the shard's K, row-major [rows][mp], kept for the whole Newton loop (theta fixed)
     double *h_scal = nullptr;   // pinned mirror of scal
 
@@ -83,6 +97,8 @@ struct GaussWS {
 GaussWS *gauss_ws(srgp_ctx *ctx);
 int plan(srgp_ctx *ctx, GaussWS *w, int m, int d);
 void fill_gen(GenParams &p, int kernel, int d, double sigma, const double *l);
+// host knots -> w->U (every change of the knots goes through here: it invalidates the resident K image)
+int upload_knots(GaussWS *w, const double *host, size_t bytes, cudaStream_t s);
 
 // pass 1 over the resident shard: G (mp x mp, both triangles) = K^T diag(rowweight) K, b1 = K^T (rvec)
 // (rowweight may be null = 1; when given, rvec must already contain the weight).

@@ -134,6 +134,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     const size_t mm = (size_t)mp * mp;
     GenParams gp;
     fill_gen(gp, kernel, d, sigma, l);
+    w->k_reuse = true;     // two K*M passes (1a, 2a) over this K: the second reads the image of the first (gauss_i8.cu)
     const double zconst = sigma * sigma + tau * tau + delta;
 
     double *GB = w->red1.d(), *b = GB + mm, *tail = b + mp;   // allreduce buffer of pass 1
@@ -304,6 +305,7 @@ int gauss_posterior(srgp_ctx *ctx, GaussWS *w, int model, int kernel, double sig
     const size_t mm = (size_t)mp * mp;
     GenParams gp;
     fill_gen(gp, kernel, d, sigma, l);
+    w->k_reuse = false;
     double *G = w->red1.d(), *b = G + mm;
     SRGP_CUDA(cudaMemsetAsync(w->scal.d() + W::S_INFO, 0, 16, s));
     double *S = w->mat(W::M_S), *Sinv = w->mat(W::M_SINV), *A = w->mat(W::M_A), *C = w->mat(W::M_C);
@@ -381,7 +383,7 @@ extern "C" int srgp_gauss_posterior_u(srgp_ctx *ctx, int model, int kernel, cons
     GaussWS *w = gauss_ws(ctx);
     SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
     cudaStream_t s = ctx->stream;
-    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, s));
+    SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, s));
     double *uplus = w->vec(GaussWS::V_T3), *uvar = w->mat(GaussWS::M_N);
     SRGP_TRY(gauss_posterior(ctx, w, model, kernel, sigma, l, tau, delta, uplus, uvar));
     std::vector<double> up((size_t)w->mp);
@@ -416,6 +418,7 @@ extern "C" int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int
     SRGP_TRY(ctx->in_x.reserve((size_t)n_pred * d * 8));
     SRGP_CUDA(cudaMemcpyAsync(ctx->in_x.p, x_pred, (size_t)n_pred * d * 8, cudaMemcpyHostToDevice, s));
     ctx->Xp = ctx->in_x.d();
+    ctx->data_version++;
     ctx->n = n_pred;
     ctx->d = d;
     int st = plan(ctx, w, (int)m, d);
@@ -423,6 +426,7 @@ extern "C" int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int
     const size_t mm = (size_t)mp * mp;
     GenParams gp;
     fill_gen(gp, kernel, d, sigma, l);
+    w->k_reuse = false;
     double *S = w->mat(GaussWS::M_S), *Sinv = w->mat(GaussWS::M_SINV), *UV = w->mat(GaussWS::M_A);
     double *T1 = w->mat(GaussWS::M_T1), *T2 = w->mat(GaussWS::M_T2), *Tm = w->mat(GaussWS::M_MOP);
     double *dv = w->vec(GaussWS::V_B), *wv = w->vec(GaussWS::V_V), *gsc = w->gemv_scratch();
@@ -431,7 +435,7 @@ extern "C" int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int
     if (st == SRGP_OK) st = ctx->tmp0.reserve((size_t)n_pred * 8 * 4 + 64) ;
     auto run = [&]() -> int {
         SRGP_CUDA(cudaMemsetAsync(w->scal.d() + GaussWS::S_INFO, 0, 16, s));
-        SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * d * 8, cudaMemcpyHostToDevice, s));
+        SRGP_TRY(upload_knots(w, xu, (size_t)m * d * 8, s));
         SRGP_CUDA(cudaMemcpyAsync(dv, diff.data(), (size_t)mp * 8, cudaMemcpyHostToDevice, s));
         SRGP_CUDA(cudaMemsetAsync(UV, 0, mm * 8, s));
         SRGP_CUDA(cudaMemcpy2DAsync(UV, (size_t)mp * 8, u_var, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice, s));
@@ -468,6 +472,7 @@ extern "C" int srgp_predict(srgp_ctx *ctx, int kernel, const double *x_pred, int
     if (st == SRGP_OK) st = run();
     if (st != SRGP_OK) cudaStreamSynchronize(s);
     ctx->Xp = Xsave;
+    ctx->data_version++;
     ctx->n = nsave;
     ctx->d = dsave;
     return st;

@@ -15,6 +15,7 @@
 // gradient sums (gauss_pass2), the per-row / per-dimension sums (gauss_rowd) or the row quadratic forms (gauss_rowform).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -209,17 +210,24 @@ __device__ __forceinline__ void issue_sweep1(uint32_t a_lo, uint32_t b_lo, uint3
         }
 }
 
-// The MMA stream of one virtual tile (sweep sw over ksteps k-steps whose first ring unit is gbase), as seen by issuer X
-// (0 or 1).  The tensor pipe takes the next MMA only when the previous one has started, so every cycle the issuing
-// thread spends elsewhere is a bubble: a SATISFIED mbarrier wait per k-step costs ~130 clk = 20 % of a 10-MMA k-step
-// (tools/probes/acc_rotation.cu).  Two threads in different warps therefore take the k-steps in turns -- one waits for its
-// next unit while the MMAs of the other run (64.0 clk per MMA in the probe).  The sums are exact integers, so the order in
-// which the two streams interleave does not matter, except that the overwriting MMAs of k-step 0 must come first:
-// issuer 1 starts a virtual tile only after issuer 0 has issued k-step 0 (tcgen05 fences + `go`).  Each issuer commits the
-// units it consumed and, after its last k-step, the tile (tmem_full counts 2).
+// The MMA stream of one virtual tile (sweep sw over ksteps k-steps), as seen by issuer X (0 or 1).  The tensor pipe takes
+// the next MMA only when the previous one has started, so every cycle the issuing thread spends elsewhere is a bubble: a
+// SATISFIED mbarrier wait per k-step costs ~130 clk = 20 % of a 10-MMA k-step (tools/probes/acc_rotation.cu).  Two threads
+// in different warps therefore take the k-steps in turns -- one waits for its next unit while the MMAs of the other run
+// (64.0 clk per MMA in the probe).  The sums are exact integers, so the order in which the two streams interleave does
+// not matter, except that the overwriting MMAs of k-step 0 must come first: issuer 1 starts a virtual tile only after
+// issuer 0 has issued k-step 0 (tcgen05 fences + `go`).  Each issuer commits the units it consumed and, after its last
+// k-step, the tile (tmem_full counts 2).
+// Each issuer has its OWN ring of NR units (k-step ks lives in ring ks & 1): an mbarrier distinguishes only two
+// consecutive phases, so a barrier whose successive phases were waited on by different threads could be passed one lap
+// early by a thread that ran ahead.  With one consumer (and one relay, in a CTA pair) per barrier every wait is for the
+// phase right after the one that thread saw last.  The unit index within ring X counts the units of X over the whole
+// kernel: xbase = units of ring X before this virtual tile.
+__host__ __device__ constexpr int ring_units_before(int vt, int ksteps) { return (vt >> 1) * 3 * (ksteps / 2) + (vt & 1) * (ksteps / 2); }
+
 template <bool PAIR>
-__device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tmem_base, int X, int vt, int sw, int gbase,
-                                         int ksteps, int NU, bool same, bool skip_mma)
+__device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tmem_base, int X, int vt, int sw, int xbase,
+                                         int ksteps, int NR, bool same, bool skip_mma)
 {
     constexpr int UB = RingCfg<PAIR>::UNIT_BYTES;
     if (X == 0) {
@@ -232,9 +240,9 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
         tc_fence_after();
     }
     for (int ks = X; ks < ksteps; ks += 2) {
-        const int g = gbase + (sw ? 2 * ks : ks);
-        const int u0 = g % NU;
-        mbar_wait(&bars.full[u0], (g / NU) & 1);
+        const int g = xbase + (sw ? 2 : 1) * (ks >> 1);
+        const int u0 = X * NR + g % NR;
+        mbar_wait(&bars.full[u0], (g / NR) & 1);
         const uint32_t a0 = smem_u32(smem + u0 * UB), b0 = same ? a0 : a0 + 4 * A_TILE;
         const uint32_t keep = ks == 0 ? 0u : 1u;
         if (sw == 0) {
@@ -243,8 +251,8 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
             if (PAIR) mma_commit_pair(&bars.empty[u0]);
             else mma_commit(&bars.empty[u0]);
         } else {
-            const int u1 = (g + 1) % NU;
-            mbar_wait(&bars.full[u1], ((g + 1) / NU) & 1);
+            const int u1 = X * NR + (g + 1) % NR;
+            mbar_wait(&bars.full[u1], ((g + 1) / NR) & 1);
             tc_fence_after();
             const uint32_t a1 = smem_u32(smem + u1 * UB), b1 = same ? a1 : a1 + 4 * A_TILE;
             if (!skip_mma) issue_sweep1<PAIR>(a0, b0, a1, b1, tmem_base, keep);
@@ -265,7 +273,25 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
     else mma_commit(&bars.tmem_full);
 }
 
+// Producer side of the two rings: k-step ks of a virtual tile goes to ring ks & 1 (one unit in sweep 0, two in sweep 1).
+// gx[X] counts the units of ring X since the start of the kernel.
+template <bool PAIR>
+__device__ __forceinline__ void produce_kstep(uint8_t *smem, Bars2 &bars, int (&gx)[2], int NR, int ks, int sw, const int8_t *a_img,
+                                              const int8_t *b_img, bool same, uint32_t crank, bool skip_load)
+{
+    constexpr int UB = RingCfg<PAIR>::UNIT_BYTES;
+    const int X = ks & 1;
+    for (int part = 0; part <= sw; ++part) {
+        const int g = gx[X]++;
+        const int u = X * NR + g % NR;
+        if (g >= NR) mbar_wait(&bars.empty[u], ((g / NR) - 1) & 1);
+        if (skip_load) mbar_arrive(&bars.full[u]);
+        else load_unit<PAIR>(smem_u32(smem + u * UB), &bars.full[u], a_img, b_img, same, part, crank);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
+// Gram kernel on 128 x 128 tiles, two sweeps (tc_i8.cuh)// ------------------------------------------------------------------------------------------------
 // Gram kernel on 128 x 128 tiles, two sweeps (tc_i8.cuh): slot[tile][split] (+)= scale * sum_L 2^(-12-8L) level_L.
 // tile t -> (I, J), J <= I, 128-row / 128-column knot blocks; on the diagonal tiles of an unweighted Gram the A and B
 // operands are the same block and are loaded once.
@@ -278,14 +304,14 @@ __device__ __forceinline__ void tile2_to_ij(int t, int &I, int &J)
     J = t - I * (I + 1) / 2;
 }
 
-constexpr int GRAM2_UNITS = 7;
-constexpr int GRAM2_SMEM = GRAM2_UNITS * RingCfg<false>::UNIT_BYTES + (int)sizeof(Bars2);
+constexpr int GRAM2_NR = 3;                                    // units per issuer ring: 2 x 3 x 32 KB
+constexpr int GRAM2_SMEM = 2 * GRAM2_NR * RingCfg<false>::UNIT_BYTES + (int)sizeof(Bars2);
 
 __global__ void __launch_bounds__(THREADS, 1)
 i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ slices, int KST, int nsplit, double scale,
                 const double *__restrict__ wmax, double *__restrict__ Gpart, int first)
 {   // slices_a: A operand (rows 128 I ..): the weighted slice set, or `slices` itself; slices: B operand (columns 128 J ..)
-    constexpr int NU = GRAM2_UNITS, UB = RingCfg<false>::UNIT_BYTES;
+    constexpr int NR = GRAM2_NR, NU = 2 * NR, UB = RingCfg<false>::UNIT_BYTES;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars2 &bars = *reinterpret_cast<Bars2 *>(smem + NU * UB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,20 +339,16 @@ i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ 
 
     if (warp == 0) {
         if (lane == 0) {
-            int g = 0;
+            int gx[2] = {0, 0};
             for (int sw = 0; sw < 2; ++sw)
-                for (int it = 0; it < ksteps; ++it) {
-                    const int8_t *a_img = slices_a + img_off(I, KST, ks0 + it), *b_img = slices + img_off(J, KST, ks0 + it);
-                    for (int part = 0; part <= sw; ++part, ++g) {
-                        const int u = g % NU;
-                        if (g >= NU) mbar_wait(&bars.empty[u], ((g / NU) - 1) & 1);
-                        load_unit<false>(smem_u32(smem + u * UB), &bars.full[u], a_img, b_img, same, part, 0u);
-                    }
-                }
+                for (int it = 0; it < ksteps; ++it)
+                    produce_kstep<false>(smem, bars, gx, NR, it, sw, slices_a + img_off(I, KST, ks0 + it),
+                                         slices + img_off(J, KST, ks0 + it), same, 0u, false);
         }
     } else if (warp == 1 || warp == 2) {
         if (lane == 0)
-            for (int sw = 0; sw < 2; ++sw) issue_vt<false>(smem, bars, tmem_base, warp - 1, sw, sw, sw * ksteps, ksteps, NU, same, false);
+            for (int sw = 0; sw < 2; ++sw)
+                issue_vt<false>(smem, bars, tmem_base, warp - 1, sw, sw, ring_units_before(sw, ksteps), ksteps, NR, same, false);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -544,7 +566,8 @@ struct KmI8Args {
 constexpr int KM2_THREADS = 384;
 constexpr int KM2_EPI_REGS = 232, KM2_AUX_REGS = 40;
 template <bool PAIR> struct Km2Cfg : RingCfg<PAIR> {
-    static constexpr int UNITS = PAIR ? 8 : 6;
+    static constexpr int NR = PAIR ? 4 : 3;                     // units per issuer ring
+    static constexpr int UNITS = 2 * NR;
     static constexpr int RING_BYTES = UNITS * RingCfg<PAIR>::UNIT_BYTES;
 };
 
@@ -566,12 +589,17 @@ __device__ __noinline__ void record_if_coincident_i8_part(const double *X, int64
     }
 }
 
+// A column block is two virtual tiles: sweep 0 (levels 0..3), then sweep 1 (levels 4..NS-1).
+__host__ __device__ constexpr int km_sweep(int vt) { return vt & 1; }
+// units of one issuer ring before virtual tile vt
+__host__ __device__ constexpr int km_units_before(int vt, int ksteps) { return ring_units_before(vt, ksteps); }
+
 // PAIR: the two CTAs of a cluster (adjacent row blocks, same column group) form one tcgen05 CTA pair.
 template <int DT, bool ROWD, bool PAIR>
 __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
 {
     using Cfg = Km2Cfg<PAIR>;
-    constexpr int NU = Cfg::UNITS, UB = Cfg::UNIT_BYTES;
+    constexpr int NR = Cfg::NR, NU = Cfg::UNITS;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars2 &bars = *reinterpret_cast<Bars2 *>(smem + Cfg::RING_BYTES);
     double *us = reinterpret_cast<double *>(smem + Cfg::RING_BYTES + sizeof(Bars2));   // [128][DT] scaled knots
@@ -615,34 +643,27 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(KM2_AUX_REGS));
         if (warp == 0 && lane == 0) {
             // ===== TMA producer (every CTA: its own K rows, its share of the Mop columns) =====
-            int g = 0;                                          // unit counter
-            for (int vt = 0; vt < nvt; ++vt) {
-                const int sw = vt & 1;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const int8_t *a_img = a.kslices + img_off(rb, ksteps, ks), *b_img = a.mslices + img_off(jb0 + (vt >> 1), ksteps, ks);
-                    for (int part = 0; part <= sw; ++part, ++g) {
-                        const int u = g % NU;
-                        if (g >= NU) mbar_wait(&bars.empty[u], ((g / NU) - 1) & 1);
-                        if (a.debug & 4) mbar_arrive(&bars.full[u]);
-                        else load_unit<PAIR>(smem_u32(smem + u * UB), &bars.full[u], a_img, b_img, false, part, crank);
-                    }
-                }
-            }
+            int gx[2] = {0, 0};
+            for (int vt = 0; vt < nvt; ++vt)
+                for (int ks = 0; ks < ksteps; ++ks)
+                    produce_kstep<PAIR>(smem, bars, gx, NR, ks, km_sweep(vt), a.kslices + img_off(rb, ksteps, ks),
+                                        a.mslices + img_off(jb0 + (vt >> 1), ksteps, ks), false, crank, (a.debug & 4) != 0);
         } else if (PAIR && !leader) {
-            // ===== peer of a pair: tell the leader when this CTA's half of a unit has landed (warps 1..3 take turns, so
-            // the latency of one relay does not bound the unit rate) =====
-            if (lane == 0) {
-                const int total = (nvt / 2) * ksteps * 3;       // units: 1 per k-step of sweep 0, 2 per k-step of sweep 1
-                for (int g = warp - 1; g < total; g += 3) {
-                    mbar_wait(&bars.full[g % NU], (g / NU) & 1);
-                    if (a.debug & 16) mbar_arrive_remote(&bars.full[g % NU], 0);
-                    else mbar_arrive_remote_relaxed(&bars.full[g % NU], 0);
+            // ===== peer of a pair: tell the leader when this CTA's half of a unit has landed (one relay per issuer ring, so
+            // that each barrier has a single waiter) =====
+            if (lane == 0 && warp <= 2) {
+                const int X = warp - 1, total = km_units_before(nvt, ksteps);
+                for (int g = 0; g < total; ++g) {
+                    const int u = X * NR + g % NR;
+                    mbar_wait(&bars.full[u], (g / NR) & 1);
+                    if (a.debug & 16) mbar_arrive_remote(&bars.full[u], 0);
+                    else mbar_arrive_remote_relaxed(&bars.full[u], 0);
                 }
             }
         } else if ((warp == 1 || warp == 2) && lane == 0) {
             // ===== two MMA issuers (in the leader of a pair: for both CTAs), see issue_vt =====
             for (int vt = 0; vt < nvt; ++vt)
-                issue_vt<PAIR>(smem, bars, tmem_base, warp - 1, vt, vt & 1, ((vt >> 1) * 3 + (vt & 1)) * ksteps, ksteps, NU, false,
+                issue_vt<PAIR>(smem, bars, tmem_base, warp - 1, vt, km_sweep(vt), km_units_before(vt, ksteps), ksteps, NR, false,
                                (a.debug & 2) != 0);
         }
     } else {
@@ -669,9 +690,9 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
         for (int c = 0; c < DT; c++) xif[c] = (float)xi[c];
         const float rsf = (float)rsi, kscale = (float)(a.sigma2 * KF_SCALE);
         for (int vt = 0; vt < nvt; ++vt) {
-            const int sw = vt & 1;
+            const int sw = km_sweep(vt);
             const int j0 = (jb0 + (vt >> 1)) * BN2;
-            if (sw == 0) {
+            if ((vt & 1) == 0) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the previous block's us / bt / cs
                 for (int e = et; e < BN2 * DT; e += 256) {
                     const int jj = e / DT, c = e - jj * DT;
@@ -691,10 +712,13 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
             const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
             const int8_t *kimg = a.kslices + img_off(rb, ksteps, 0) + (size_t)row * 16;
             if (sw == 1) {
-                // ===== sweep 1: levels 4..NS-1, i.e. the part of T below 2^-32 of its scale.  Single precision carries it
-                // with a relative error of 2^-24 -- 2^-56 of the product, below the dropped slice pairs (2^-49) -- and FP32
-                // instructions do not share the datapath of FP64 and the tensor pipe, whereas every FP64 instruction of this
-                // epilogue is a bubble in the MMA stream (profiles/r02_km2_bound.txt).  K_ij comes from its top 4 slices.
+                // ===== sweep 1: levels 4..NS-1, i.e. the part of T below 2^-32 of the operand scales (typically 2^-25 of
+                // them).  Single precision carries it to 2^-24 of ITS size per operation, ~2^-49.7 of the operand scales
+                // over the ~8 roundings below -- the size of the slice pairs NS = 7 drops anyway (2^-49.3); measured: the
+                // ill-conditioned config-4 gradient moves from 0.9e-8 to 1.1e-8 of the long-double value, the float64
+                // transcription of the reference sits at 1.7e-8 (tests/test_stated_sizes_gpu.py).  FP32 instructions do not
+                // share the datapath of FP64 and the tensor pipe, whereas every FP64 instruction of this epilogue is a
+                // bubble in the MMA stream (profiles/r02_km2_bound.txt: 28.3 -> 22.8 ms).  K_ij comes from its top 4 slices.
                 float Tl[64];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -880,6 +904,69 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
         tc_fence_after();
         tmem_free_all(tmem_base);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The resident pass-2 image (GaussWS::k2): when the caller announces several K*M / row-form passes over the same K
+// (GaussWS::k_reuse: FIC has two, the Laplace gradient four), the first of them generates its chunks straight into an
+// image of the whole shard and the later ones read it -- exp and the digit split run once.  (Leaving the image behind from
+// pass 1 by transposing its chunks was measured too: 14 GB of extra traffic through the L2 -> SM path that bounds the
+// tensor kernels cost the Gram pass what the K*M pass gained, so a single-pass evaluation -- VI -- keeps its chunks in L2.)
+// ------------------------------------------------------------------------------------------------
+static bool k2_enabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("SRGP_K2");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
+static size_t k2_chunk_bytes(const GaussWS *w) { return (size_t)w->rblocks * (w->mp / KS) * KSTEP_BYTES; }
+
+static void k2_make_key(const srgp_ctx *ctx, const GaussWS *w, const GenParams &gp, GaussWS::K2Key &k)
+{
+    memset(&k, 0, sizeof(k));
+    k.Xp = ctx->Xp;
+    k.n = ctx->n;
+    k.mp = w->mp, k.m = w->m, k.d = w->d;
+    k.uver = w->u_version, k.xver = ctx->data_version;
+    for (int c = 0; c < w->d && c < SRGP_MAX_D; c++) k.invl[c] = gp.invl[c];   // sigma^2 is not part of the image
+}
+
+// the image holds this shard's K for these parameters
+static bool k2_have(const srgp_ctx *ctx, const GaussWS *w, const GenParams &gp)
+{
+    if (!w->k2_valid) return false;
+    GaussWS::K2Key k;
+    k2_make_key(ctx, w, gp, k);
+    return memcmp(&k, &w->k2_key, sizeof(k)) == 0;
+}
+
+// Make room for the image of the current shard; false when it is switched off or does not fit (the caller then works
+// from its double-buffered chunks as before).  Invalidates the previous contents.
+static bool k2_reserve(srgp_ctx *ctx, GaussWS *w)
+{
+    w->k2_valid = false;
+    if (!k2_enabled() || !w->k_reuse || ctx->n <= 0 || !i8_pass2_supported(w)) return false;
+    const size_t chunks = (size_t)((ctx->n + w->rows2 - 1) / w->rows2);
+    const size_t bytes = chunks * k2_chunk_bytes(w);
+    if (bytes > w->k2.cap) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+        if (bytes > free_b + w->k2.cap || free_b + w->k2.cap - bytes < ((size_t)4 << 30)) return false;   // keep 4 GB of headroom
+        if (w->k2.reserve(bytes) != SRGP_OK) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    return true;
+}
+
+static void k2_commit(const srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
+{
+    k2_make_key(ctx, w, gp, w->k2_key);
+    w->k2_valid = true;
 }
 
 // A/B switch of the measurements in profiles/: SRGP_PAIR=0 runs the K*M pass on single CTAs
@@ -1112,15 +1199,20 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
     const int nslots = nodims ? (vvec ? 2 : 1) : (d + 1) * (beta ? 2 : 1) + (vvec ? 1 : 0), groups = w->cgroups * 2;
     if (rowd) SRGP_TRY(w->rowdpart.reserve((size_t)groups * nslots * w->rows2 * 8));
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
+    // K comes from the resident image when an earlier pass of this evaluation left it; otherwise this pass generates its
+    // chunks -- straight into the image when there is room for it (fill2), else into the two chunk buffers
+    const bool have2 = k2_have(ctx, w, gp);
+    const bool fill2 = !have2 && k2_reserve(ctx, w);
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
     SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
     int cidx = 0;
     for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2, cidx++) {
         const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
         const int b = cidx & 1;
-        int8_t *kslices = reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
-        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
-        {
+        int8_t *kslices = (have2 || fill2) ? reinterpret_cast<int8_t *>(w->k2.p) + (size_t)cidx * k2_chunk_bytes(w)
+                                           : reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
+        if (!have2) {
+            if (cidx >= 2 && !fill2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
             KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(w->rblocks, std::min(KBm, 16));
 #define CALL(D) launch_gen_datarows<D>(sg, grid, ctx->Xp, ctx->n, r0, rows_valid, w->U.d(), m, mp, gp, kslices)
@@ -1136,9 +1228,9 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             }
 #undef CALL
             SRGP_LAUNCH_CHECK();
+            SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
+            SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         }
-        SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
-        SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_KM, s);
             KmI8Args a;
@@ -1198,6 +1290,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
         }
         first = 0;
     }
+    if (fill2) k2_commit(ctx, w, gp);
     if (out) {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
         gram_sum_part(s, w->part2.d(), slots, PART_STRIDE_I8, d + 1, out);

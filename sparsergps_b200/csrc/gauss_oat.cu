@@ -101,6 +101,7 @@ static int gauss_oat_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, con
     const size_t mm = (size_t)mp * mp;
     GenParams gp;
     fill_gen(gp, kernel, d, sigma, l);
+    w->k_reuse = false;
     const double Z = tau * tau + delta, B = 1.0 / Z, itau2 = 1.0 / (tau * tau);
 
     double *G_all = w->red1.d(), *b_all = G_all + mm, *tail = b_all + mp;
@@ -240,7 +241,7 @@ extern "C" int srgp_oat_scores(srgp_ctx *ctx, int model, int kernel, const doubl
                 for (int t = 0; t < T; t++) ua[m + t + (size_t)ma * c] = cand[c0 + t + n_cand * c];
             }
             SRGP_TRY(plan(ctx, w, ma, d));
-            SRGP_CUDA(cudaMemcpyAsync(w->U.p, ua.data(), ua.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            SRGP_TRY(upload_knots(w, ua.data(), ua.size() * 8, ctx->stream));
             SRGP_CUDA(cudaStreamSynchronize(ctx->stream));   // ua is pageable and dies with this iteration
             SRGP_TRY(gauss_oat_vi(ctx, w, kernel, sigma, l, tau, delta, (int)m, T, &o0, scores + c0));
         }
@@ -250,7 +251,7 @@ extern "C" int srgp_oat_scores(srgp_ctx *ctx, int model, int kernel, const doubl
     // FIC: objective-only evaluations with [U; c] on the resident shard
     if (obj0) {
         SRGP_TRY(plan(ctx, w, (int)m, d));
-        SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SRGP_TRY(upload_knots(w, xu, (size_t)m * d * 8, ctx->stream));
         SRGP_TRY(gauss_fic(ctx, w, kernel, sigma, l, tau, delta, obj0, nullptr));
     }
     const int ma = (int)m + 1;
@@ -261,7 +262,7 @@ extern "C" int srgp_oat_scores(srgp_ctx *ctx, int model, int kernel, const doubl
             ua[m + (size_t)ma * c] = cand[t + n_cand * c];
         }
         SRGP_TRY(plan(ctx, w, ma, d));
-        SRGP_CUDA(cudaMemcpyAsync(w->U.p, ua.data(), ua.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SRGP_TRY(upload_knots(w, ua.data(), ua.size() * 8, ctx->stream));
         SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
         const int rc = gauss_fic(ctx, w, kernel, sigma, l, tau, delta, scores + t, nullptr);
         if (rc == SRGP_ERR_NOT_PD) scores[t] = NAN;      // R: try-error -> the caller resamples this candidate

@@ -74,6 +74,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     const size_t mm = (size_t)mp * mp;
     GenParams gp;
     fill_gen(gp, kernel, d, sigma, l);
+    w->k_reuse = false;   // one K*M pass: its chunks stay in L2 (gauss_i8.cu)
     const double Z = tau * tau + delta, B = 1.0 / Z, itau2 = 1.0 / (tau * tau);
 
     double *G1 = w->red1.d(), *b1 = G1 + mm, *tail = b1 + mp;

@@ -311,8 +311,9 @@ static int lap_setup(Lap &L, srgp_ctx *ctx, int family, int kernel, const double
     L.family = family;
     L.pois_m = pois_m;
     cudaStream_t s = L.s;
-    SRGP_CUDA(cudaMemcpyAsync(w->U.p, xu, (size_t)m * ctx->d * 8, cudaMemcpyHostToDevice, s));
+    SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, s));
     fill_gen(L.gp, kernel, L.d, sigma, l);
+    w->k_reuse = true;    // up to four row-form / K*M passes over this K (gauss_i8.cu)
     const int64_t n = L.n;
     double **rv[] = {&L.ff, &L.Z, &L.invZ, &L.d1, &L.Wv, &L.W3, &L.e, &L.om, &L.rz, &L.Kh, &L.Kg, &L.gpsi, &L.egp,
                      &L.t0, &L.t1, &L.t2, &L.t3, &L.t4};
