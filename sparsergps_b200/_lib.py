@@ -106,7 +106,6 @@ SIGNATURES = {
 INTERNAL_SIGNATURES = {
     "srgp_test_gemm": (ci, [vp, ci, ci, ci, ci, ci, cd, dp, ci, dp, ci, cd, dp, ci, ci, ci, dp]),
     "srgp_test_chol_inverse": (ci, [vp, ci, dp, dp, dp, dp, C.POINTER(ci), ci, dp]),
-    "srgp_test_gen": (ci, [vp, dp, i64, cd, dp, ci, dp]),
 }
 
 

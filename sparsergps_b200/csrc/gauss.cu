@@ -14,11 +14,11 @@
 // K is generated in row chunks that stay L2-resident between the generator and the tensor-core kernel (each K entry
 // is generated exactly once per pass instead of once per output tile); K never exists as an n x m matrix.
 //
-// Two tensor-core engines serve the passes.  The default is the INT8 engine of gauss_i8.cu / tc_i8.cuh
-// (tcgen05.mma.kind::i8 with TMEM accumulators, error-free digit splitting: DESIGN.md section 3a); gauss_pass1,
-// gauss_pass2, gauss_rowd and gauss_rowform below route to it whenever it supports the request.  The FP64 DMMA engine
-// of this file (gemm.cuh) remains for the knot-gradient epilogue, d > 8, the Gram over the materialised K of the
-// Laplace Newton loop, and as the SRGP_TENSOR=dmma diagnostic.
+// The row passes run on the INT8 engine of gauss_i8.cu / tc_i8.cuh (tcgen05.mma.kind::i8 with TMEM accumulators,
+// error-free digit splitting: DESIGN.md section 3a): pass 1 always, pass 2 / the row forms (gauss_pass2, gauss_rowd,
+// gauss_rowform below) whenever it supports the request (d <= 8, no knot gradient, m <= 8192).  The FP64 DMMA engine of
+// this file (gemm.cuh) serves what is left -- the knot-gradient epilogue, d > 8 -- and the Gram over the materialised K of
+// the Laplace Newton loop.  There is no run-time switch between the two.
 #include <math.h>
 #include <stdlib.h>
 
@@ -921,68 +921,7 @@ int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *ro
 {
     // the Grams over generated K (VI / FIC pass 1, FIC's K^T diag(rho) K, OAT border Gram) run on the INT8 tensor
     // cores: gauss_i8.cu.  (The Laplace Newton loop keeps K materialised in FP64: gram_materialised below.)
-    if (i8_enabled()) return gauss_pass1_i8(ctx, w, gp, rowweight, rvec, G, b1);
-    cudaStream_t s = ctx->stream;
-    static DeviceOnce once;
-    if (once.need(ctx->device)) {
-        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem)));
-        SRGP_CUDA(cudaFuncSetAttribute(syrk_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(Smem)));
-    }
-    const int mp = w->mp, m = w->m, d = w->d;
-    const int quantum = BK * w->splits;
-    int first = 1;
-    if (ctx->n == 0) {
-        SRGP_CUDA(cudaMemsetAsync(w->Gpart.p, 0, (size_t)w->pairs * w->splits * BM * BN * 8, s));
-        SRGP_CUDA(cudaMemsetAsync(w->b1part.p, 0, (size_t)w->gen_groups * mp * 8, s));
-    }
-    // Generator on its own stream, two chunk buffers: chunk c+1 is generated while the SYRK kernel consumes
-    // chunk c (the generator CTAs are small enough to be co-resident with the DMMA CTAs and fill its FP64 bubbles).
-    cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;   // diagnostic: serialise generator and DMMA kernels
-    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
-    SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
-    int cidx = 0;
-    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1, cidx++) {
-        const int rows_valid = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
-        const int rows_padded = (int)round_up(rows_valid, quantum);
-        const int b = cidx & 1;
-        double *chunk = w->chunk.d() + (size_t)b * w->chunk_elems;
-        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
-        {
-            KernelScope ks(ctx, SRGP_PROF_GEN, sg);
-            dim3 grid(mp / 128, w->gen_groups);
-            const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
-#define CALL(D) launch_gen_rm<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, chunk, w->b1part.d(), first)
-            SRGP_D_SWITCH(d, CALL)
-#undef CALL
-            SRGP_LAUNCH_CHECK();
-        }
-        SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
-        SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
-        {
-            KernelScope ks(ctx, SRGP_PROF_GRAM, s);
-            dim3 grid(w->pairs, w->splits);
-            const int ktiles = rows_padded / quantum;
-            if (rowweight)
-                syrk_chunk_kernel<true><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, rowweight + r0, ktiles,
-                                                                            w->Gpart.d(), first);
-            else
-                syrk_chunk_kernel<false><<<grid, THREADS, sizeof(Smem), s>>>(chunk, mp, nullptr, ktiles,
-                                                                             w->Gpart.d(), first);
-            SRGP_LAUNCH_CHECK();
-        }
-        SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));
-        first = 0;
-    }
-    {
-        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-        syrk_finalize_kernel<<<w->pairs, CONSUMER_THREADS, 0, s>>>(w->Gpart.d(), w->splits, mp, G);
-        SRGP_LAUNCH_CHECK();
-        sum_rows_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->b1part.d(), w->gen_groups, mp, b1);
-        SRGP_LAUNCH_CHECK();
-    }
-    return SRGP_OK;
+    return gauss_pass1_i8(ctx, w, gp, rowweight, rvec, G, b1);
 }
 
 // ---- Laplace helpers: K materialised once per theta (it is reused by every Newton iteration) ----------------
@@ -1742,47 +1681,3 @@ extern "C" int srgp_gauss_obj_grad_host(srgp_ctx *ctx, int model, int kernel, co
     return srgp_gauss_obj_grad(ctx, model, kernel, xu, m, sigma, l, tau, delta, obj, grad);
 }
 
-#include "srgp_internal.h"
-extern "C" int srgp_test_gen(srgp_ctx *ctx, const double *xu, int64_t m, double sigma, const double *l, int reps,
-                             double *ms_out)
-{
-    SRGP_TRY(use_device(ctx));
-    GaussWS *w = gauss_ws(ctx);
-    SRGP_TRY(plan(ctx, w, (int)m, ctx->d));
-    cudaStream_t s = ctx->stream;
-    SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, s));
-    GenParams gp;
-    fill_gen(gp, SRGP_ARD, ctx->d, sigma, l);
-    const int quantum = BK * w->splits, mp = w->mp, d = w->d;
-    for (int which = 0; which < 2; which++) {
-        for (int r = 0; r <= reps; r++) {
-            if (r == 1) SRGP_CUDA(cudaEventRecord(ctx->tim0, s));
-            if (which == 0) {
-                for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows1) {
-                    const int rv = (int)std::min<int64_t>(w->rows1, ctx->n - r0);
-                    dim3 grid(mp / 128, w->gen_groups);
-                    const size_t smem = sizeof(double) * GEN_ROWS_TILE * (d + 1);
-#define CALL(D) launch_gen_rm<D>(s, grid, smem, ctx->Xp, ctx->n, w->r.d(), r0, rv, (int)round_up(rv, quantum), w->U.d(), w->m, mp, d, gp, w->chunk.d(), w->b1part.d(), 1)
-                    SRGP_D_SWITCH(d, CALL)
-#undef CALL
-                }
-            } else {
-                for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2) {
-                    const int rv = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
-                    dim3 grid(ceil_div(w->rows2, GENC_ROWS), std::min(mp / GENC_COLS, 64));
-                    const size_t gs = sizeof(double) * GENC_COLS * d;
-#define CALL(D) launch_gen_cm<D>(s, grid, gs, ctx->Xp, ctx->n, r0, rv, w->rows2, w->U.d(), w->m, mp, d, gp, w->chunk.d(), (int64_t)w->rows2)
-                    SRGP_D_SWITCH(d, CALL)
-#undef CALL
-                }
-            }
-            SRGP_LAUNCH_CHECK();
-        }
-        SRGP_CUDA(cudaEventRecord(ctx->tim1, s));
-        SRGP_CUDA(cudaEventSynchronize(ctx->tim1));
-        float f = 0.f;
-        SRGP_CUDA(cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1));
-        ms_out[which] = f / std::max(1, reps);
-    }
-    return SRGP_OK;
-}

@@ -227,7 +227,7 @@ __host__ __device__ constexpr int ring_units_before(int vt, int ksteps) { return
 
 template <bool PAIR>
 __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tmem_base, int X, int vt, int sw, int xbase,
-                                         int ksteps, int NR, bool same, bool skip_mma)
+                                         int ksteps, int NR, bool same)
 {
     constexpr int UB = RingCfg<PAIR>::UNIT_BYTES;
     if (X == 0) {
@@ -247,7 +247,7 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
         const uint32_t keep = ks == 0 ? 0u : 1u;
         if (sw == 0) {
             tc_fence_after();
-            if (!skip_mma) issue_sweep0<PAIR>(a0, b0, tmem_base, keep);
+            issue_sweep0<PAIR>(a0, b0, tmem_base, keep);
             if (PAIR) mma_commit_pair(&bars.empty[u0]);
             else mma_commit(&bars.empty[u0]);
         } else {
@@ -255,7 +255,7 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
             mbar_wait(&bars.full[u1], ((g + 1) / NR) & 1);
             tc_fence_after();
             const uint32_t a1 = smem_u32(smem + u1 * UB), b1 = same ? a1 : a1 + 4 * A_TILE;
-            if (!skip_mma) issue_sweep1<PAIR>(a0, b0, a1, b1, tmem_base, keep);
+            issue_sweep1<PAIR>(a0, b0, a1, b1, tmem_base, keep);
             if (PAIR) {
                 mma_commit_pair(&bars.empty[u0]);
                 mma_commit_pair(&bars.empty[u1]);
@@ -277,7 +277,7 @@ __device__ __forceinline__ void issue_vt(uint8_t *smem, Bars2 &bars, uint32_t tm
 // gx[X] counts the units of ring X since the start of the kernel.
 template <bool PAIR>
 __device__ __forceinline__ void produce_kstep(uint8_t *smem, Bars2 &bars, int (&gx)[2], int NR, int ks, int sw, const int8_t *a_img,
-                                              const int8_t *b_img, bool same, uint32_t crank, bool skip_load)
+                                              const int8_t *b_img, bool same, uint32_t crank)
 {
     constexpr int UB = RingCfg<PAIR>::UNIT_BYTES;
     const int X = ks & 1;
@@ -285,8 +285,7 @@ __device__ __forceinline__ void produce_kstep(uint8_t *smem, Bars2 &bars, int (&
         const int g = gx[X]++;
         const int u = X * NR + g % NR;
         if (g >= NR) mbar_wait(&bars.empty[u], ((g / NR) - 1) & 1);
-        if (skip_load) mbar_arrive(&bars.full[u]);
-        else load_unit<PAIR>(smem_u32(smem + u * UB), &bars.full[u], a_img, b_img, same, part, crank);
+        load_unit<PAIR>(smem_u32(smem + u * UB), &bars.full[u], a_img, b_img, same, part, crank);
     }
 }
 
@@ -343,12 +342,12 @@ i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ 
             for (int sw = 0; sw < 2; ++sw)
                 for (int it = 0; it < ksteps; ++it)
                     produce_kstep<false>(smem, bars, gx, NR, it, sw, slices_a + img_off(I, KST, ks0 + it),
-                                         slices + img_off(J, KST, ks0 + it), same, 0u, false);
+                                         slices + img_off(J, KST, ks0 + it), same, 0u);
         }
     } else if (warp == 1 || warp == 2) {
         if (lane == 0)
             for (int sw = 0; sw < 2; ++sw)
-                issue_vt<false>(smem, bars, tmem_base, warp - 1, sw, sw, ring_units_before(sw, ksteps), ksteps, NR, same, false);
+                issue_vt<false>(smem, bars, tmem_base, warp - 1, sw, sw, ring_units_before(sw, ksteps), ksteps, NR, same);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -551,7 +550,6 @@ struct KmI8Args {
     int64_t ld;
     int nodims;              // ROWD without the per-dimension slots (gauss_rowform): slot 0 = sum_j T_ij K_ij, slot 1 = K v
     int cluster;             // 2 = adjacent row blocks run as tcgen05 CTA pairs (cta_group::2), 1 = single CTAs
-    int debug;               // measurement only (SRGP_KM_DEBUG): 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no loads
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -561,7 +559,7 @@ struct KmI8Args {
 // CTA = 384 threads = 3 warpgroups: warp 0 TMA producer, warp 1 MMA issuer (warps 2, 3 idle), warps 4..11 epilogue.  The
 // epilogue holds the 64 drained columns of its row in registers (so TMEM is released before the FP64 work starts):
 // setmaxnreg moves registers from the first warpgroup to the two epilogue warpgroups.
-// Operand ring: RingCfg units (above), 5 of 32 KB for a single CTA, 7 of 24 KB for a CTA pair.
+// Operand rings: RingCfg units (above), 2 x 3 of 32 KB for a single CTA, 2 x 4 of 24 KB for a CTA pair.
 // ------------------------------------------------------------------------------------------------
 constexpr int KM2_THREADS = 384;
 constexpr int KM2_EPI_REGS = 232, KM2_AUX_REGS = 40;
@@ -647,7 +645,7 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
             for (int vt = 0; vt < nvt; ++vt)
                 for (int ks = 0; ks < ksteps; ++ks)
                     produce_kstep<PAIR>(smem, bars, gx, NR, ks, km_sweep(vt), a.kslices + img_off(rb, ksteps, ks),
-                                        a.mslices + img_off(jb0 + (vt >> 1), ksteps, ks), false, crank, (a.debug & 4) != 0);
+                                        a.mslices + img_off(jb0 + (vt >> 1), ksteps, ks), false, crank);
         } else if (PAIR && !leader) {
             // ===== peer of a pair: tell the leader when this CTA's half of a unit has landed (one relay per issuer ring, so
             // that each barrier has a single waiter) =====
@@ -656,15 +654,13 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                 for (int g = 0; g < total; ++g) {
                     const int u = X * NR + g % NR;
                     mbar_wait(&bars.full[u], (g / NR) & 1);
-                    if (a.debug & 16) mbar_arrive_remote(&bars.full[u], 0);
-                    else mbar_arrive_remote_relaxed(&bars.full[u], 0);
+                    mbar_arrive_remote_relaxed(&bars.full[u], 0);
                 }
             }
         } else if ((warp == 1 || warp == 2) && lane == 0) {
             // ===== two MMA issuers (in the leader of a pair: for both CTAs), see issue_vt =====
             for (int vt = 0; vt < nvt; ++vt)
-                issue_vt<PAIR>(smem, bars, tmem_base, warp - 1, vt, km_sweep(vt), km_units_before(vt, ksteps), ksteps, NR, false,
-                               (a.debug & 2) != 0);
+                issue_vt<PAIR>(smem, bars, tmem_base, warp - 1, vt, km_sweep(vt), km_units_before(vt, ksteps), ksteps, NR, false);
         }
     } else {
         // ===== epilogue: thread = one data row of the block x 64 columns of the 128-column block =====
@@ -740,7 +736,7 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                     if (PAIR && !leader) mbar_arrive_remote_relaxed(&bars.tmem_empty, 0);
                     else mbar_arrive(&bars.tmem_empty);
                 }
-                if (iv && !(a.debug & 1)) {
+                if (iv) {
                     float s0f = 0.0f, scf[DT], rtf[ROWD ? DT + 1 : 1];
 #pragma unroll
                     for (int c = 0; c < DT; c++) scf[c] = 0.0f;
@@ -809,9 +805,7 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                 if (PAIR && !leader) mbar_arrive_remote_relaxed(&bars.tmem_empty, 0);
                 else mbar_arrive(&bars.tmem_empty);
             }
-            if (a.debug & 1) {
-                s0 += T[0] + T[17] + T[34] + T[51];
-            } else if (iv) {
+            if (iv) {
 #pragma unroll 1                                                // 4 rounds of 16 columns through one copy of the code, as above
                 for (int g = 0; g < 4; ++g) {
                     const int jg = j0 + half * 64 + g * 16;     // first column of this 16-column group
@@ -969,21 +963,15 @@ static void k2_commit(const srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
     w->k2_valid = true;
 }
 
-// A/B switch of the measurements in profiles/: SRGP_PAIR=0 runs the K*M pass on single CTAs
+// Experiment switch (profiles/r02_km2_bound.txt): SRGP_PAIR=1 runs adjacent row blocks of the K*M pass as tcgen05 CTA pairs
+// (cta_group::2, the Mop tiles fetched once per pair).  Measured equal to single CTAs (22.9 ms per evaluation either way:
+// with the operand ring deep enough the pass is bound by its drains and its FP64 epilogue, not by operand traffic), so the
+// simpler single-CTA protocol is the default.
 static bool km_pairs()
 {
     static const bool on = [] {
         const char *e = getenv("SRGP_PAIR");
-        return !(e && atoi(e) == 0);
-    }();
-    return on;
-}
-
-bool i8_enabled()
-{
-    static const bool on = [] {
-        const char *e = getenv("SRGP_TENSOR");
-        return !(e && (e[0] == 'd' || e[0] == 'D'));    // SRGP_TENSOR=dmma: diagnostic, keeps the DMMA kernels
+        return e && atoi(e) == 1;
     }();
     return on;
 }
@@ -1142,7 +1130,7 @@ static cudaError_t launch_km2_i8(cudaStream_t s, dim3 grid, int device, const Km
 // mp <= 8192: one INT32 level accumulator sums up to NS pairs x 2^14 x mp over the knots (tc_i8.cuh)
 bool i8_pass2_supported(const GaussWS *w)
 {
-    return i8_enabled() && !w->want_knots && w->d >= 1 && w->d <= 8 && w->mp <= MAX_ROWS_PER_SPLIT;
+    return !w->want_knots && w->d >= 1 && w->d <= 8 && w->mp <= MAX_ROWS_PER_SPLIT;
 }
 
 static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
@@ -1251,7 +1239,6 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.sigma2 = gp.sigma2;
             a.tiles_per_cta = (mp / BN2) / w->cgroups;
             a.cluster = pair ? 2 : 1;
-            a.debug = getenv("SRGP_KM_DEBUG") ? atoi(getenv("SRGP_KM_DEBUG")) : 0;
             a.part = w->part2.d();
             a.first = first;
             a.coin_count = w->coin_count();

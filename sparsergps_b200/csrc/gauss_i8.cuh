@@ -4,8 +4,6 @@
 
 namespace srgp {
 
-// true unless SRGP_TENSOR=dmma (diagnostic switch that keeps the FP64 DMMA kernels for the unweighted Gram)
-bool i8_enabled();
 // pass 1: G = K^T diag(rowweight) K (mp x mp, both triangles; rowweight null = 1), b1 = K^T rvec over the resident shard
 int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec, double *G,
                    double *b1);

@@ -13,9 +13,6 @@ int srgp_test_gemm(srgp_ctx *ctx, int transA, int transB, int M, int N, int K, d
 /* Cholesky + inverse + logdet of an m x m SPD matrix (host, column-major, ld = m). */
 int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, double *L_out, double *Ainv_out,
                            double *logdet_out, int *info_out, int reps, double *ms_out);
-/* Times the two K-chunk generators alone over the whole resident shard (knots xu, m x d): ms_out[0] row-major
-   (pass 1), ms_out[1] column-major (pass 2), averaged over reps. */
-int srgp_test_gen(srgp_ctx *ctx, const double *xu, int64_t m, double sigma, const double *l, int reps, double *ms_out);
 #ifdef __cplusplus
 }
 #endif

@@ -79,8 +79,8 @@ def test_library_sass_is_blackwell_native():
             for k in per[cur]:
                 if k in line:
                     per[cur][k] += 1
-    gram = [v for f, v in per.items() if "i8_gram_kernel" in f]
-    km = [v for f, v in per.items() if "i8_km_kernel" in f]
+    gram = [v for f, v in per.items() if "i8_gram2_kernel" in f]
+    km = [v for f, v in per.items() if "i8_km2_kernel" in f]
     assert gram and km, "INT8 tensor-core kernels missing from libsrgp.so"
     for v in gram + km:
         assert v["UTCIMMA"] == 28 and v["LDTM"] >= 1 and v["UBLKCP"] >= 1, v      # 28 slice pairs per k-step (7 slices)
