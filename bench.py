@@ -317,6 +317,56 @@ def parity_checks(ctx, world, rank, golden):
     return out
 
 
+def secondary_timings(ctx, hbm_gbs):
+    """The other kernels of SURVEY.md section 8 at the stated size, on one GPU, outside the headline timed region (CUDA events
+    on the library's stream, median of 5 after 2 warm-ups): FIC objective + gradient (a18 / a20), and the materialising
+    HBM-class kernels K1 make_cov_mat_ardC, K2 dsig_dtheta_ardC (one length-scale, tau) and K5 sum Omega o dK over 8.2 GB."""
+    from sparsergps_b200 import _lib as L
+    n, m, d = 1_000_000, 1024, 8
+    x, y, xu, th = workload(n, m, d)
+    out = {}
+    ctx.set_data(x, y, None)
+    ts = []
+    for r in range(5):
+        ctx.timer_start()
+        ctx.gauss_obj_grad("fic", "ard", xu, th["sigma"], th["l"], th["tau"], th["delta"])
+        ts.append(ctx.timer_stop_ms())
+    out["fic_obj_grad_n1M_m1024"] = {"ms": float(np.median(ts[2:]))}
+    xd, ud, big = ctx.dev_alloc(8 * n * d), ctx.dev_alloc(8 * m * d), ctx.dev_alloc(8 * n * m)
+    ctx.fill_normal(xd, n * d, 1312)
+    ctx.fill_normal(ud, m * d, 1313)
+    l = np.ascontiguousarray(th["l"], dtype=np.float64)
+    lib, h = ctx._lib, ctx.handle
+    gb = 8.0 * n * m / 1e9
+    res = np.zeros(d + 2)
+    kernels = (
+        ("K1_make_cov_mat_ardC", lambda: lib.srgp_make_cov_mat_dev(h, L.ARD, xd, n, ud, m, d, 1.0, L.ptr(l), 0.5, 1e-6, big), "write"),
+        ("K2_dsig_dtheta_ardC_l3", lambda: lib.srgp_dsig_dtheta_dev(h, L.ARD, L.PAR_LC, 2, xd, n, ud, m, d, 1.0, L.ptr(l), 0.5, big), "write"),
+        ("K2_dsig_dtheta_ardC_tau", lambda: lib.srgp_dsig_dtheta_dev(h, L.ARD, L.PAR_TAU, 0, xd, n, ud, m, d, 1.0, L.ptr(l), 0.5, big), "write"),
+        ("K5_omega_dk_reduce", lambda: lib.srgp_omega_dk_reduce_dev(h, L.ARD, xd, n, ud, m, d, 1.0, L.ptr(l), 0.5, big, L.ptr(res)), "read"))
+    for name, fn, rw in kernels:
+        ts = []
+        for r in range(7):
+            ctx.timer_start()
+            L.check(fn())
+            ts.append(ctx.timer_stop_ms())
+        ms = float(np.median(ts[2:]))
+        out[name] = {"ms": ms, "GBps": gb / (ms * 1e-3), "frac_of_measured_hbm": gb / (ms * 1e-3) / hbm_gbs,
+                     "algorithmic_bytes": "8 n m (%s once), n = 1e6, m = 1024" % rw}
+    for p_ in (xd, ud, big):
+        ctx.dev_free(p_)
+    out["note"] = ("FP64-pipe bound, not HBM bound: 36 - 54 FP64 instructions per 8-byte entry against a ridge of 20; ncu counters in "
+                   "profiles/r02_hbm_kernels_ncu.txt")
+    return out
+
+
+def measured_hbm_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,6 +380,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-one-thread", action="store_true", help="reference arm: skip the 1-BLAS-thread figure")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded parity checks before the timed region")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the FIC / K1 / K2 / K5 timings after the timed regions (1 GPU only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -473,23 +524,23 @@ def main():
         sms = torch.cuda.get_device_properties(0).multi_processor_count
         rows2 = (sms // 2) * 128                                 # pass-2 chunk: (SMs / 2 column groups) row blocks x 128, rows are padded to it
         km_rows = -(-nloc // rows2) * rows2
-        km_ops8 = pairs * 2.0 * km_rows * mp * mp * steps        # slice pairs x every 64-column tile of every row block
+        km_ops8 = pairs * 2.0 * km_rows * mp * mp * steps        # slice pairs x every 128-column block of every row block
         gram_quant = 128
         gram_rows = -(-nloc // gram_quant) * gram_quant
-        gram_ops8 = pairs * 2.0 * gram_rows * (mp * (mp + 128) / 2.0) * steps   # 128 x 64 tiles of the lower block triangle
-        ncu = ncu_traffic("i8_km_kernel") or {}
-        roof = {"bound": "tensor", "kernel": "i8_km_kernel (K*Mop^T on tcgen05 kind::i8, %d x %d digit slices = %d exact INT8 "
-                "products per FP64 product, fused dK reductions)" % (slices, slices, pairs),
+        gram_ops8 = pairs * 2.0 * gram_rows * (mp * (mp + 128) / 2.0) * steps   # 128 x 128 tiles of the lower block triangle
+        ncu = ncu_traffic("i8_km2_kernel") or {}
+        roof = {"bound": "tensor", "kernel": "i8_km2_kernel (K*Mop^T on tcgen05 kind::i8, 128 x 128 tiles in two sweeps, %d x %d digit "
+                "slices = %d exact INT8 products per FP64 product, fused dK reductions)" % (slices, slices, pairs),
                 "achieved": rate(km_ops8, km_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)", "frac": frac(km_ops8, km_ms, peak8),
                 "peak_source": peak8_src,
                 "fp64_equivalent": {"achieved": rate(km_flops, km_ms), "unit": "TFLOP/s", "algorithmic_flops": "2 n m^2",
                                     "vs_cublas_dgemm": frac(km_flops, km_ms, peak64), "cublas_dgemm_tflops": peak64},
                 "tensor_pipe_active_ncu": ncu.get("tensor_pipe_active"),
                 "traffic": ncu.get("bytes_per_launch"), "traffic_detail": ncu or None}
-        roof_gram = {"kernel": "i8_gram_kernel (K^T K on tcgen05 kind::i8, lower block triangle)",
+        roof_gram = {"kernel": "i8_gram2_kernel (K^T K on tcgen05 kind::i8, 128 x 128 tiles of the lower block triangle)",
                      "achieved": rate(gram_ops8, gram_ms), "peak": peak8, "unit": "TOP/s (INT8, executed)",
                      "frac": frac(gram_ops8, gram_ms, peak8),
-                     "tensor_pipe_active_ncu": (ncu_traffic("i8_gram_kernel") or {}).get("tensor_pipe_active"),
+                     "tensor_pipe_active_ncu": (ncu_traffic("i8_gram2_kernel") or {}).get("tensor_pipe_active"),
                      "fp64_equivalent": {"achieved": rate(gram_flops, gram_ms), "unit": "TFLOP/s",
                                          "algorithmic_flops": "n m (m+1)", "vs_cublas_dgemm": frac(gram_flops, gram_ms, peak64)}}
         roof.update({"launches_per_step": km_launches / steps, "avg_launch_ms": km_ms / max(1, km_launches),
@@ -502,6 +553,12 @@ def main():
             cpu = {"value": 1.0 / tsec, "unit": UNIT, "cores": threads or host_cores(), "kind": "port", "extrapolated": True,
                    "sample": "oracle (NumPy literal transcription on %s, %s threads [threadpoolctl] + single-threaded C assembly): %s"
                              % (blas, threads, note)}
+        secondary = None
+        if world == 1 and not args.no_secondary and (n, m, d) == (1_000_000, 1024, 8):
+            hbm, hbm_src = measured_hbm_gbs()
+            secondary = secondary_timings(ctx, hbm)
+            secondary["hbm_peak_gbs"] = hbm
+            secondary["hbm_peak_source"] = hbm_src
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -514,7 +571,7 @@ def main():
             "roofline": roof, "roofline_gram": roof_gram, "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v[1] / steps for k, v in prof.items()},
             "objective": obj, "grad_norm": float(np.linalg.norm(grad)),
-            "parity": parity, "parity_checks": checks,
+            "parity": parity, "parity_checks": checks, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -917,11 +917,11 @@ static void launch_gen_cm(cudaStream_t s, dim3 grid, size_t smem, const double *
 // G (mp x mp, both triangles), b1 (mp) <- sums over this shard's rows.  w: optional per-row weight
 // (G = K^T diag(w) K, b1 = K^T (w .* rvec)); rvec: per-row vector multiplied into b1.
 int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
-                double *G, double *b1)
+                double *G, double *b1, bool weight_nonneg)
 {
     // the Grams over generated K (VI / FIC pass 1, FIC's K^T diag(rho) K, OAT border Gram) run on the INT8 tensor
     // cores: gauss_i8.cu.  (The Laplace Newton loop keeps K materialised in FP64: gram_materialised below.)
-    return gauss_pass1_i8(ctx, w, gp, rowweight, rvec, G, b1);
+    return gauss_pass1_i8(ctx, w, gp, rowweight, rvec, G, b1, weight_nonneg);
 }
 
 // ---- Laplace helpers: K materialised once per theta (it is reused by every Newton iteration) ----------------

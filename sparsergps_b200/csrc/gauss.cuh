@@ -102,8 +102,9 @@ int upload_knots(GaussWS *w, const double *host, size_t bytes, cudaStream_t s);
 
 // pass 1 over the resident shard: G (mp x mp, both triangles) = K^T diag(rowweight) K, b1 = K^T (rvec)
 // (rowweight may be null = 1; when given, rvec must already contain the weight).
+// weight_nonneg: rowweight >= 0 everywhere (FIC's B = 1 / Z): lets the INT8 pass slice sqrt(w) K once.
 int gauss_pass1(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec,
-                double *G, double *b1);
+                double *G, double *b1, bool weight_nonneg = false);
 // pass 2: out[0] = sum_ij P_ij, out[1 + c] = sum_ij P_ij ((x_ic - u_jc) / l_c)^2 with
 // P = (rs_i (K Mop^T)_ij + ra_i beta_j) K_ij; bit-identical (row, knot) pairs are appended to w->coin.
 // accumulate_slots: add to the per-CTA slots of a previous gauss_pass2 call instead of restarting them.

@@ -189,7 +189,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     }
     SRGP_TRY(set_scalar(ctx, tail + 2, (double)n));
     // ---- pass 1b: G_B, b ---------------------------------------------------------------------------------
-    SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, GB, b));
+    SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, GB, b, true));        // B = 1 / Z > 0
     SRGP_TRY(comm_allreduce(ctx, GB, mm + mp + 3, s));
     SRGP_TRY(copy_scalar(ctx, w->sc(W::S_X), tail, 3));   // s0, s1, n (global)
 
@@ -331,7 +331,7 @@ int gauss_posterior(srgp_ctx *ctx, GaussWS *w, int model, int kernel, double sig
                                                         w->part2.d());
             SRGP_LAUNCH_CHECK();
         }
-        SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, G, b));
+        SRGP_TRY(gauss_pass1(ctx, w, gp, Bv, Br, G, b, true));
         SRGP_TRY(comm_allreduce(ctx, G, mm + mp, s));
     }
     SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, S, 1.0, G, 0.0, A));

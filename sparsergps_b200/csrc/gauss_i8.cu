@@ -38,9 +38,12 @@ __device__ __forceinline__ double pow2_ceil(double x)
     return (x > 0.0 && x < INFINITY) ? scalbn(1.0, ilogb(x) + 1) : 1.0;
 }
 
-// WEIGHTED: a second slice set holds w_i e_ij / 2^ew (2^ew >= max_i |w_i|, *wmax on the device) for the weighted Grams
+// WMODE 1: a second slice set holds w_i e_ij / 2^ew (2^ew >= max_i |w_i|, *wmax on the device) for the weighted Grams
 // K^T diag(w) K = (diag(w) K)^T K of the FIC model; w may have either sign.
-template <int DT, bool WEIGHTED>
+// WMODE 2 (w >= 0, e.g. FIC's B = 1 / Z): ONE slice set sqrt(w_i) e_ij / s with s = the power of two >= sqrt(max w):
+// K^T diag(w) K = s^2 (that set)^T (that set) is then an unweighted Gram -- half the generator output, twice the rows per
+// chunk, and the diagonal tiles load their operand once.
+template <int DT, int WMODE>
 __global__ void __launch_bounds__(128)
 gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const double *__restrict__ r, int64_t r0,
                            int rows_valid, int rows_padded, const double *__restrict__ U, int m, int mp, int d_rt,
@@ -54,7 +57,8 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
     const int d = DT > 0 ? DT : d_rt;
     double *sr = sx + 64 * d;
     double *sw = sr + 64;
-    const double winv = WEIGHTED ? 1.0 / pow2_ceil(*wmax) : 0.0;
+    constexpr bool WEIGHTED = WMODE == 1;
+    const double winv = WMODE == 1 ? 1.0 / pow2_ceil(*wmax) : WMODE == 2 ? 1.0 / pow2_ceil(sqrt(*wmax)) : 0.0;
     const int j = blockIdx.x * 128 + threadIdx.x;
     const bool jvalid = j < m;
     double uj[DT > 0 ? DT : 1];
@@ -77,7 +81,8 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
         if (threadIdx.x < BK) {
             const int i = it0 + threadIdx.x;
             sr[threadIdx.x] = (i < rows_valid) ? r[r0 + i] : 0.0;
-            if (WEIGHTED) sw[threadIdx.x] = (i < rows_valid) ? rw[r0 + i] * winv : 0.0;
+            if (WMODE == 1) sw[threadIdx.x] = (i < rows_valid) ? rw[r0 + i] * winv : 0.0;
+            if (WMODE == 2) sw[threadIdx.x] = (i < rows_valid) ? sqrt(fmax(rw[r0 + i], 0.0)) * winv : 0.0;
         }
         __syncthreads();
 #pragma unroll 1
@@ -116,7 +121,8 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                         bacc = fma(p.sigma2 * ev[q], sr[ii + q], bacc);
                     }
                 }
-                split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
+                if (WMODE == 2) split_quad(ev[0] * sw[ii], ev[1] * sw[ii + 1], ev[2] * sw[ii + 2], ev[3] * sw[ii + 3], e0 >> 2, w);
+                else split_quad(ev[0], ev[1], ev[2], ev[3], e0 >> 2, w);
                 if (WEIGHTED)
                     split_quad(ev[0] * sw[ii], ev[1] * sw[ii + 1], ev[2] * sw[ii + 2], ev[3] * sw[ii + 3], e0 >> 2,
                                reinterpret_cast<uint32_t (&)[NS][4]>(ww));
@@ -308,7 +314,7 @@ constexpr int GRAM2_SMEM = 2 * GRAM2_NR * RingCfg<false>::UNIT_BYTES + (int)size
 
 __global__ void __launch_bounds__(THREADS, 1)
 i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ slices, int KST, int nsplit, double scale,
-                const double *__restrict__ wmax, double *__restrict__ Gpart, int first)
+                const double *__restrict__ wmax, int wsqrt, double *__restrict__ Gpart, int first)
 {   // slices_a: A operand (rows 128 I ..): the weighted slice set, or `slices` itself; slices: B operand (columns 128 J ..)
     constexpr int NR = GRAM2_NR, NU = 2 * NR, UB = RingCfg<false>::UNIT_BYTES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -351,7 +357,10 @@ i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ 
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        if (wmax) scale *= pow2_ceil(*wmax);
+        if (wmax) {                                             // the power-of-two scale(s) of the weighted operand(s)
+            const double sc1 = pow2_ceil(wsqrt ? sqrt(*wmax) : *wmax);
+            scale *= wsqrt ? sc1 * sc1 : sc1;
+        }
         double *out = Gpart + ((size_t)blockIdx.x * BM + row) * BN2;
 #pragma unroll 1
         for (int sw = 0; sw < 2; ++sw) {
@@ -980,14 +989,17 @@ template <int DT>
 static void launch_gen_knotrows(cudaStream_t s, dim3 grid, size_t smem, const double *X, int64_t ldx, const double *r,
                                 int64_t r0, int rows_valid, int rows_padded, const double *U, int m, int mp, int d,
                                 const GenParams &p, int8_t *slices, double *b1part, int first,
-                                const double *rw, const double *wmax, int8_t *slices_w)
+                                const double *rw, const double *wmax, int8_t *slices_w, bool wsqrt)
 {
-    if (rw)
-        gen_slices_knotrows_kernel<DT, true><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
-                                                                   slices, b1part, first, rw, wmax, slices_w);
+    if (rw && wsqrt)
+        gen_slices_knotrows_kernel<DT, 2><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                                slices, b1part, first, rw, wmax, nullptr);
+    else if (rw)
+        gen_slices_knotrows_kernel<DT, 1><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                                slices, b1part, first, rw, wmax, slices_w);
     else
-        gen_slices_knotrows_kernel<DT, false><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
-                                                                    slices, b1part, first, nullptr, nullptr, nullptr);
+        gen_slices_knotrows_kernel<DT, 0><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                                slices, b1part, first, nullptr, nullptr, nullptr);
 }
 
 // *out = max_i |w_i| over the shard (one block; n is at most a few million)
@@ -1024,7 +1036,7 @@ __global__ void __launch_bounds__(1024) absmax_kernel(const double *__restrict__
 // Pass 1 on the INT8 tensor cores: G = K^T diag(rowweight) K (mp x mp, both triangles; rowweight may be null = 1),
 // b1 = K^T rvec.  With weights the chunk holds two slice sets (e and w e / 2^ew), so it covers half the rows.
 int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec, double *G,
-                   double *b1)
+                   double *b1, bool weight_nonneg)
 {
     cudaStream_t s = ctx->stream;
     static DeviceOnce once;
@@ -1034,7 +1046,8 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     const int tiles = w->nt * (w->nt + 1) / 2;
     const int nsplit = std::max(1, std::min(16, ctx->sm_count / tiles));
     const int quantum = BK * nsplit;
-    const int sets = rowweight ? 2 : 1;
+    const bool wsqrt = rowweight && weight_nonneg;                  // one slice set sqrt(w) e instead of two (e, w e)
+    const int sets = (rowweight && !wsqrt) ? 2 : 1;
     // rows per launch: the chunk buffer holds sets x 8 slices x rows x mp bytes, and one INT32 accumulator may sum at
     // most MAX_ROWS_PER_SPLIT rows
     int64_t rows1 = std::min<int64_t>((int64_t)w->chunk_elems / mp / sets, (int64_t)MAX_ROWS_PER_SPLIT * nsplit);
@@ -1063,13 +1076,13 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         const int rows_padded = (int)round_up(rows_valid, quantum);
         const int b = cidx & 1;
         int8_t *slices = reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
-        int8_t *slices_w = rowweight ? slices + (size_t)rows_padded * mp * NS : slices;
+        int8_t *slices_w = sets == 2 ? slices + (size_t)rows_padded * mp * NS : slices;
         if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(mp / 128, w->gen_groups);
             const size_t smem = sizeof(double) * BK * (d + 2);
-#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, w->b1part.d(), first, rowweight, wmax, slices_w)
+#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, w->b1part.d(), first, rowweight, wmax, slices_w, wsqrt)
             SRGP_D_SWITCH_I8(d, CALL)
 #undef CALL
             SRGP_LAUNCH_CHECK();
@@ -1079,7 +1092,7 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
         {
             KernelScope ks(ctx, SRGP_PROF_GRAM, s);
             i8_gram2_kernel<<<tiles * nsplit, THREADS, GRAM2_SMEM, s>>>(slices_w, slices, rows_padded / KS, nsplit,
-                                                                        gp.sigma2 * gp.sigma2, wmax, w->Gpart.d(), first);
+                                                                        gp.sigma2 * gp.sigma2, wmax, wsqrt ? 1 : 0, w->Gpart.d(), first);
             SRGP_LAUNCH_CHECK();
         }
         SRGP_CUDA(cudaEventRecord(ctx->ev_used[b], s));

@@ -5,8 +5,9 @@
 namespace srgp {
 
 // pass 1: G = K^T diag(rowweight) K (mp x mp, both triangles; rowweight null = 1), b1 = K^T rvec over the resident shard
+// weight_nonneg: the caller guarantees rowweight >= 0 (one slice set sqrt(w) e serves both operands)
 int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *rowweight, const double *rvec, double *G,
-                   double *b1);
+                   double *b1, bool weight_nonneg = false);
 // pass 2 (MODE_GRAD of gauss.cu: sum P, sum P o D_c, coincident pairs) on the INT8 tensor cores; same per-CTA slots
 constexpr int PART_STRIDE_I8 = SRGP_MAX_D + 8;
 bool i8_pass2_supported(const GaussWS *w);

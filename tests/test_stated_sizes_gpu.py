@@ -83,13 +83,13 @@ def test_config4_newton_and_gradient_full_size(ctx):
     fit = Lp.newtrap_sparseGP(np.zeros(g["n"]), "bernoulli", cp, "ard", c["x"], c["xu"], c["y"], c["mu"], np.zeros(g["m"]),
                               maxit=g["maxit"], tol=g["tol"], delta=c["delta"], ctx=ctx)
     h = fit["objective_function_values"]
-    # The search ends when an objective step falls below tol = 1e-5; the golden's last four steps are 1.14e-5, 1.04e-5,
-    # 1.14e-5, 9.0e-6 on a value of 7e4, i.e. the stopping iteration is decided by rounding at 1e-11 relative.  The
-    # count is therefore held to +-2 and the history to 1e-8 on the common prefix (the small cases of
-    # test_laplace_gpu.py / test_golden_r_gpu.py, which stop on a clear step, keep the exact-count assertion).
-    assert abs(len(h) - g["iterations"]) <= 2
+    # The search ends when an objective step falls below tol = 1e-5, and over its last ~15 iterations the steps hover at
+    # 1.0e-5 .. 1.3e-5 on a value of 7e4 (golden tail: 1.14e-5, 1.04e-5, 1.14e-5, 9.0e-6): the stopping iteration is decided
+    # by rounding at 1e-11 relative -- 422, 425 and 426 iterations have all been observed for bit-different but equally
+    # accurate evaluations.  The count is therefore held to +-8 and the history to 1e-8 on the common prefix (the small
+    # cases of test_laplace_gpu.py / test_golden_r_gpu.py, which stop on a clear step, keep the exact-count assertion).
+    assert abs(len(h) - g["iterations"]) <= 8
     k = min(len(h), g["iterations"])
-    assert k >= g["iterations"] - 2
     np.testing.assert_allclose(h[:k], g["hist"][:k], rtol=RTOL)
     # one Newton step near the stopping point moves the mode by ~1e-8 (absolute, entries of order 1)
     np.testing.assert_allclose(fit["gp"][:64], g["gp_head"], rtol=1e-7, atol=1e-7)
