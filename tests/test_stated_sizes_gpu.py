@@ -91,19 +91,22 @@ def test_config4_newton_and_gradient_full_size(ctx):
     assert abs(len(h) - g["iterations"]) <= 8
     k = min(len(h), g["iterations"])
     np.testing.assert_allclose(h[:k], g["hist"][:k], rtol=RTOL)
-    # one Newton step near the stopping point moves the mode by ~1e-8 (absolute, entries of order 1)
-    np.testing.assert_allclose(fit["gp"][:64], g["gp_head"], rtol=1e-7, atol=1e-7)
-    assert float(np.linalg.norm(fit["gp"])) == pytest.approx(g["gp_norm"], rel=1e-8)
+    # one Newton step near the stopping point moves the mode by ~1e-8 (absolute, entries of order 1), the posterior mean
+    # and variance at the knots by ~1e-5 of their largest entry: the absolute tolerances below grow with the number of
+    # steps the two searches differ by
+    dsteps = 1 + abs(len(h) - g["iterations"])
+    np.testing.assert_allclose(fit["gp"][:64], g["gp_head"], rtol=1e-7, atol=1e-7 * dsteps)
+    assert float(np.linalg.norm(fit["gp"])) == pytest.approx(g["gp_norm"], rel=1e-8 * dsteps)
     # u_mean = muu + a - G_Z C_Z a cancels ~6 digits at this size (|a| ~ n / Z): the reference's own float64 formula is
     # 9e-7 (relative to max |u_mean|) from a long-double evaluation of the same expression, a Cholesky-solve form
     # 3e-10 (tests/tools/make_golden_sizes.py header; measured at the closed-form ff).  The golden holds the reference's
     # formula, so the comparison is stated at 1e-5, not at the 1e-7 of the small cases.
     um_ref = np.asarray(g["u_mean"])
-    np.testing.assert_allclose(fit["u_posterior_mean"], um_ref, rtol=0, atol=1e-5 * np.abs(um_ref).max())
+    np.testing.assert_allclose(fit["u_posterior_mean"], um_ref, rtol=0, atol=1e-5 * dsteps * np.abs(um_ref).max())
     # the posterior variance moves by ~1e-5 (absolute) per Newton step near the stopping point, and the stopping
     # iteration itself is decided by rounding (above): held to 2e-5 of its largest entry
     uv_ref = np.asarray(g["u_var_diag"])
-    np.testing.assert_allclose(np.diag(fit["u_posterior_variance"]), uv_ref, rtol=1e-5, atol=2e-5 * np.abs(uv_ref).max())
+    np.testing.assert_allclose(np.diag(fit["u_posterior_variance"]), uv_ref, rtol=1e-5, atol=2e-5 * dsteps * np.abs(uv_ref).max())
     ff = cfg4_ff_closed_form(c["x"])
     got = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], c["y"], ff, "bernoulli", c["mu"], c["delta"], ctx=ctx)["gradient"]
     # n / Z ~ 1e7 in the row sums: at this size the float64 transcription of the reference is itself 1.7e-8 away from a
