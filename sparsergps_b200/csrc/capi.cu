@@ -62,6 +62,8 @@ using namespace srgp;
 extern "C" int srgp_version(void) { return SRGP_VERSION; }
 extern "C" const char *srgp_last_error(void) { return g_err; }
 
+extern "C" void srgp_ctx_destroy(srgp_ctx *ctx);
+
 extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
 {
     if (!out) {
@@ -90,17 +92,26 @@ extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
     srgp_ctx *ctx = new srgp_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
-        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
-        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
+    // a failed step must not leak the context and what it already owns (srgp_ctx_destroy skips null handles)
+    auto build = [&]() -> int {
+        SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
+            SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
+        }
+        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        SRGP_CUDA(cudaEventCreate(&ctx->tim0));
+        SRGP_CUDA(cudaEventCreate(&ctx->tim1));
+        return SRGP_OK;
+    };
+    const int st = build();
+    if (st != SRGP_OK) {
+        srgp_ctx_destroy(ctx);
+        return st;
     }
-    SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    SRGP_CUDA(cudaEventCreate(&ctx->tim0));
-    SRGP_CUDA(cudaEventCreate(&ctx->tim1));
     *out = ctx;
     return SRGP_OK;
 }

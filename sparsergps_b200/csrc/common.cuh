@@ -69,6 +69,17 @@ struct DevBuf {
     double *d() const { return static_cast<double *>(p); }
 };
 
+// releases a set of local DevBufs on every exit path of a function
+struct DevBufScope {
+    DevBuf *bufs[8];
+    int n = 0;
+    void own(DevBuf &b) { bufs[n++] = &b; }
+    ~DevBufScope()
+    {
+        for (int i = 0; i < n; i++) bufs[i]->release();
+    }
+};
+
 struct ProfSlot {
     int64_t launches = 0;
     double ms = 0.0;

@@ -579,6 +579,8 @@ extern "C" int srgp_test_gemm(srgp_ctx *ctx, int transA, int transB, int M, int 
     const size_t a_elems = (size_t)lda * (transA ? M : K), b_elems = (size_t)ldb * (transB ? K : N);
     const size_t c_elems = (size_t)ldc * N;
     DevBuf dA, dB, dC;
+    DevBufScope scope;
+    scope.own(dA), scope.own(dB), scope.own(dC);
     SRGP_TRY(dA.reserve(a_elems * 8));
     SRGP_TRY(dB.reserve(b_elems * 8));
     SRGP_TRY(dC.reserve(c_elems * 8));
@@ -611,9 +613,6 @@ extern "C" int srgp_test_gemm(srgp_ctx *ctx, int transA, int transB, int M, int 
         SRGP_CUDA(cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1));
         *ms_out = f / reps;
     }
-    dA.release();
-    dB.release();
-    dC.release();
     return st;
 }
 
@@ -624,6 +623,8 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
     const int mp = (int)round_up(m, dense::NB);
     const size_t mm = (size_t)mp * mp;
     DevBuf dA, dA0, dDinv, dLinv, dLinvT, dTmp, dAinv, dMisc;
+    DevBufScope scope;
+    for (DevBuf *b : {&dA, &dA0, &dDinv, &dLinv, &dLinvT, &dTmp, &dAinv, &dMisc}) scope.own(*b);
     SRGP_TRY(dA.reserve(mm * 8));
     SRGP_TRY(dA0.reserve(mm * 8));
     SRGP_TRY(dDinv.reserve(((size_t)2 * mp * dense::NB + mp / dense::NB) * 8));
@@ -640,19 +641,19 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
     int st = SRGP_OK;
     const int total = 1 + (reps > 0 ? reps : 0);
     for (int r = 0; r < total && st == SRGP_OK; r++) {
-        if (r == 1) cudaEventRecord(ctx->tim0, ctx->stream);
-        cudaMemcpyAsync(dA.p, dA0.p, mm * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-        cudaMemsetAsync(dMisc.p, 0, 64, ctx->stream);
+        if (r == 1) SRGP_CUDA(cudaEventRecord(ctx->tim0, ctx->stream));
+        SRGP_CUDA(cudaMemcpyAsync(dA.p, dA0.p, mm * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        SRGP_CUDA(cudaMemsetAsync(dMisc.p, 0, 64, ctx->stream));
         st = dense::pad_identity(ctx, ctx->stream, dA.d(), mp, m, 1.0);
         if (st == SRGP_OK)
             st = dense::chol_inverse(ctx, ctx->stream, dA.d(), mp, m, dDinv.d(), dLinv.d(), dLinvT.d(), dTmp.d(),
                                      dAinv.d(), info, logdet);
     }
     if (st == SRGP_OK && reps > 0) {
-        cudaEventRecord(ctx->tim1, ctx->stream);
-        cudaEventSynchronize(ctx->tim1);
+        SRGP_CUDA(cudaEventRecord(ctx->tim1, ctx->stream));
+        SRGP_CUDA(cudaEventSynchronize(ctx->tim1));
         float f = 0.f;
-        cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1);
+        SRGP_CUDA(cudaEventElapsedTime(&f, ctx->tim0, ctx->tim1));
         if (ms_out) *ms_out = f / reps;
     }
     if (st == SRGP_OK) {
@@ -675,7 +676,5 @@ extern "C" int srgp_test_chol_inverse(srgp_ctx *ctx, int m, const double *A, dou
         if (logdet_out) *logdet_out = misc[0];
         if (info_out) *info_out = *reinterpret_cast<int *>(&misc[1]);
     }
-    DevBuf *bufs[] = {&dA, &dA0, &dDinv, &dLinv, &dLinvT, &dTmp, &dAinv, &dMisc};
-    for (auto *b : bufs) b->release();
     return st;
 }
