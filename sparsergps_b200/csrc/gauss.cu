@@ -1049,6 +1049,7 @@ static int km_pass(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, int mode, con
     if (grad_like && ctx->n == 0 && first)
         SRGP_CUDA(cudaMemsetAsync(w->part2.p, 0, (size_t)slots * PART_STRIDE * 8, s));
     if (mode == MODE_GRAD_KNOT) {
+        w->knot_slots = w->rblocks;
         SRGP_TRY(w->knotpart.reserve((size_t)w->rblocks * d * mp * 8));
         if (ctx->n == 0 && first) SRGP_CUDA(cudaMemsetAsync(w->knotpart.p, 0, (size_t)w->rblocks * d * mp * 8, s));
     }
@@ -1303,7 +1304,7 @@ int knot_finish(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *N,
     double *sums = w->knotsum.d(), *out = sums + dm;
     {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
-        knot_colsum_kernel<<<(unsigned)ceil_div(dm, (int64_t)256), 256, 0, s>>>(w->knotpart.d(), w->rblocks, dm, sums);
+        knot_colsum_kernel<<<(unsigned)ceil_div(dm, (int64_t)256), 256, 0, s>>>(w->knotpart.d(), w->knot_slots, dm, sums);
         SRGP_LAUNCH_CHECK();
     }
     SRGP_TRY(comm_allreduce(ctx, sums, dm, s));

@@ -38,7 +38,8 @@ struct GaussWS {
     DevBuf nspart;   // scratch of ns_reduce (runs on the side stream)
     DevBuf rowdpart; // per-(column group, warp column) partials of one chunk in the per-row / per-dimension mode
     DevBuf rowd;     // FIC: per-row, per-dimension sums of passes 1a and 2a
-    DevBuf knotpart; // pass 2 with knot gradients: [rblocks][d][mp] column sums of P o (x - u) / l
+    DevBuf knotpart; // pass 2 with knot gradients: [knot_slots][d][mp] column sums of P o (x - u) / l
+    int knot_slots = 0;   // rblocks x 4 (INT8 epilogue: one slot per row block and lane quadrant), rblocks (DMMA epilogue)
     DevBuf knotsum;  // [d][mp] sums over the shard (allreduced), then the m x d knot gradient (knot-major)
     // knot-gradient request of the current call (set by the entry point, read by gauss_pass2 / knot_finish)
     bool want_knots = false, knot_transform = false;

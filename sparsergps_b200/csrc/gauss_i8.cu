@@ -559,6 +559,7 @@ struct KmI8Args {
     int64_t ld;
     int nodims;              // ROWD without the per-dimension slots (gauss_rowform): slot 0 = sum_j T_ij K_ij, slot 1 = K v
     int cluster;             // 2 = adjacent row blocks run as tcgen05 CTA pairs (cta_group::2), 1 = single CTAs
+    double *knot_part;       // KNOT: [row block x 4 lane quadrants][d][mp] column sums of P_ij (x_ic - u_jc) / l_c
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -596,15 +597,58 @@ __device__ __noinline__ void record_if_coincident_i8_part(const double *X, int64
     }
 }
 
+// Knot-location gradient: per-knot COLUMN sums over the rows of P_ij (x_ic - u_jc) / l_c.  The
+// epilogue owns one row per thread, so a column sum is a sum over the 32 lanes of a warp: 16 values per thread (2 columns x 8
+// dimensions) go through four halving exchanges and one full exchange -- 16 shuffles per thread instead of 80 -- after which
+// lane L holds the sum of value index L >> 1, i.e. column (L >> 4) of the pair, dimension (L >> 1) & 7, in both lanes of a pair.
+template <typename T>
+__device__ __forceinline__ T warp_colsum16(T (&v)[16], int lane)
+{
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const T send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T send = b3 ? v[i] : v[i + 4], keep = b3 ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = b2 ? v[i] : v[i + 2], keep = b2 ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const T send = b1 ? v[0] : v[1], keep = b1 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// the 8 column-pair sums of one 16-column round -> this warp's slot of knot_part ([slot][d][mp]); even lanes write
+template <int DT, typename T>
+__device__ __forceinline__ void knot_round_out(const T (&kn)[8], int lane, double *slot, int mp, int col0, bool overwrite)
+{
+    const int k = (lane >> 1) & 7;
+    if ((lane & 1) == 0 && k < DT) {
+        double *p = slot + (int64_t)k * mp + col0 + (lane >> 4);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) p[2 * b] = overwrite ? (double)kn[b] : p[2 * b] + (double)kn[b];
+    }
+}
+
 // A column block is two virtual tiles: sweep 0 (levels 0..3), then sweep 1 (levels 4..NS-1).
 __host__ __device__ constexpr int km_sweep(int vt) { return vt & 1; }
 // units of one issuer ring before virtual tile vt
 __host__ __device__ constexpr int km_units_before(int vt, int ksteps) { return ring_units_before(vt, ksteps); }
 
 // PAIR: the two CTAs of a cluster (adjacent row blocks, same column group) form one tcgen05 CTA pair.
-template <int DT, bool ROWD, bool PAIR>
+template <int DT, bool ROWD, bool PAIR, bool KNOT = false>
 __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
 {
+    static_assert(!KNOT || (!ROWD && !PAIR), "the knot-gradient epilogue exists for the gradient mode on single CTAs");
     using Cfg = Km2Cfg<PAIR>;
     constexpr int NR = Cfg::NR, NU = Cfg::UNITS;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -745,7 +789,8 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                     if (PAIR && !leader) mbar_arrive_remote_relaxed(&bars.tmem_empty, 0);
                     else mbar_arrive(&bars.tmem_empty);
                 }
-                if (iv) {
+                double *kslot = KNOT ? a.knot_part + ((int64_t)(rb * 4 + q) * DT) * a.mp : nullptr;
+                if (KNOT || iv) {                               // KNOT: every lane takes part in the column sums (shuffles)
                     float s0f = 0.0f, scf[DT], rtf[ROWD ? DT + 1 : 1];
 #pragma unroll
                     for (int c = 0; c < DT; c++) scf[c] = 0.0f;
@@ -762,15 +807,17 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                         for (int s = 0; s < 4; ++s)
                             w[s] = __ldg(reinterpret_cast<const uint4 *>(kimg + (size_t)(jg / KS) * KSTEP_BYTES + s * A_TILE +
                                                                          (size_t)((jg % KS) / 16) * 2048));
+                        float vb[KNOT ? 16 : 1], kn[KNOT ? 8 : 1];
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
                             const int jj = half * 64 + g * 16 + e;
                             int qt[4];
                             if ((e & 3) == 0) join_quad_top(w, e >> 2, qt);
-                            if (j0 + jj < a.m) {
+                            const bool ok = iv && j0 + jj < a.m;
+                            if (KNOT || ok) {
                                 const float kf = kscale * (float)qt[e & 3];
                                 const float tf = csf[jj] * Tl[e];                // T_ij (low part), scaled
-                                const float pf = (ROWD ? tf : rsf * tf) * kf;
+                                const float pf = ok ? (ROWD ? tf : rsf * tf) * kf : 0.0f;
                                 if (ROWD) rtf[0] += pf;
                                 else s0f += pf;
                                 if (!ROWD || !a.nodims) {
@@ -779,13 +826,20 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                                         const float tt = xif[k] - usf[jj * DT + k];
                                         if (ROWD) rtf[ROWD ? 1 + k : 0] = fmaf(pf, tt * tt, rtf[ROWD ? 1 + k : 0]);
                                         else scf[k] = fmaf(pf, tt * tt, scf[k]);
+                                        if (KNOT) vb[KNOT ? (e & 1) * 8 + k : 0] = pf * tt;
                                     }
-                                    if (qt[e & 3] == KF_ONE)    // top digits of exp(0) = 1: candidate for the bit-identical test
+                                    if (ok && qt[e & 3] == KF_ONE)   // top digits of exp(0) = 1: candidate for the bit-identical test
                                         record_if_coincident_i8_part(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
                                                                      a.coin_omega, a.coin_cap, (double)(ROWD ? tf : rsf * tf), 1);
                                 }
                             }
+                            if (KNOT) {
+#pragma unroll
+                                for (int k = DT; k < 8; k++) vb[KNOT ? (e & 1) * 8 + k : 0] = 0.0f;
+                                if (e & 1) kn[KNOT ? e >> 1 : 0] = warp_colsum16(reinterpret_cast<float (&)[16]>(vb), lane);
+                            }
                         }
+                        if (KNOT) knot_round_out<DT>(reinterpret_cast<const float (&)[8]>(kn), lane, kslot, a.mp, jg, false);
 #pragma unroll
                         for (int c = 0; c < 48; ++c) Tl[c] = Tl[c + 16];
                     }
@@ -814,7 +868,8 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                 if (PAIR && !leader) mbar_arrive_remote_relaxed(&bars.tmem_empty, 0);
                 else mbar_arrive(&bars.tmem_empty);
             }
-            if (iv) {
+            double *kslot = KNOT ? a.knot_part + ((int64_t)(rb * 4 + q) * DT) * a.mp : nullptr;
+            if (KNOT || iv) {
 #pragma unroll 1                                                // 4 rounds of 16 columns through one copy of the code, as above
                 for (int g = 0; g < 4; ++g) {
                     const int jg = j0 + half * 64 + g * 16;     // first column of this 16-column group
@@ -823,12 +878,14 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                     for (int s = 0; s < NS; ++s)
                         w[s] = __ldg(reinterpret_cast<const uint4 *>(kimg + (size_t)(jg / KS) * KSTEP_BYTES + s * A_TILE +
                                                                      (size_t)((jg % KS) / 16) * 2048));
+                    double vb[KNOT ? 16 : 1], kn[KNOT ? 8 : 1];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int jj = half * 64 + g * 16 + e;
                         long long q4[4];
                         if ((e & 3) == 0) join_quad(w, e >> 2, q4);
-                        if (j0 + jj < a.m) {
+                        const bool ok = iv && j0 + jj < a.m;
+                        if (KNOT || ok) {
                             const long long qd = q4[e & 3];
                             const double kij = a.sigma2 * FIX_INV * (double)qd;
                             if (ROWD) {
@@ -851,19 +908,26 @@ __global__ void __launch_bounds__(KM2_THREADS, 1) i8_km2_kernel(KmI8Args a)
                                                                  a.coin_omega, a.coin_cap, tij, 0);
                             } else {
                                 const double om = fma(rsi, cs[jj] * T[e], rai * bt[jj]);
-                                const double pk = om * kij;
+                                const double pk = ok ? om * kij : 0.0;
                                 s0 += pk;
 #pragma unroll
                                 for (int k = 0; k < DT; k++) {
                                     const double tt = xi[k] - us[jj * DT + k];
                                     sc[k] = fma(pk, tt * tt, sc[k]);
+                                    if (KNOT) vb[KNOT ? (e & 1) * 8 + k : 0] = pk * tt;
                                 }
-                                if (qd == FIX_ONE)
+                                if (ok && qd == FIX_ONE)
                                     record_if_coincident_i8_part(a.X, a.ldx, ig, a.U, a.m, j0 + jj, DT, a.coin_count, a.coin_list,
                                                                  a.coin_omega, a.coin_cap, om, 0);
                             }
                         }
+                        if (KNOT) {
+#pragma unroll
+                            for (int k = DT; k < 8; k++) vb[KNOT ? (e & 1) * 8 + k : 0] = 0.0;
+                            if (e & 1) kn[KNOT ? e >> 1 : 0] = warp_colsum16(reinterpret_cast<double (&)[16]>(vb), lane);
+                        }
                     }
+                    if (KNOT) knot_round_out<DT>(reinterpret_cast<const double (&)[8]>(kn), lane, kslot, a.mp, jg, a.first != 0);
 #pragma unroll
                     for (int c = 0; c < 48; ++c) T[c] = T[c + 16];
                 }
@@ -1115,14 +1179,14 @@ static void launch_gen_datarows(cudaStream_t s, dim3 grid, const double *X, int6
     gen_slices_datarows_kernel<DT><<<grid, 128, sizeof(double) * BK * DT, s>>>(X, ldx, r0, rows_valid, U, m, mp, p, slices);
 }
 
-template <int DT, bool ROWD, bool PAIR>
+template <int DT, bool ROWD, bool PAIR, bool KNOT = false>
 static cudaError_t launch_km2_i8(cudaStream_t s, dim3 grid, int device, const KmI8Args &a)
 {
     const size_t smem = Km2Cfg<PAIR>::RING_BYTES + sizeof(Bars2) + sizeof(double) * (BN2 * DT + 3 * BN2 + 8 * PART_STRIDE_I8) +
                         sizeof(float) * (BN2 * DT + BN2);
     static DeviceOnce once;
     if (once.need(device)) {
-        cudaError_t e = cudaFuncSetAttribute(i8_km2_kernel<DT, ROWD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(i8_km2_kernel<DT, ROWD, PAIR, KNOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1137,13 +1201,13 @@ static cudaError_t launch_km2_i8(cudaStream_t s, dim3 grid, int device, const Km
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, i8_km2_kernel<DT, ROWD, PAIR>, a);
+    return cudaLaunchKernelEx(&cfg, i8_km2_kernel<DT, ROWD, PAIR, KNOT>, a);
 }
 
 // mp <= 8192: one INT32 level accumulator sums up to NS pairs x 2^14 x mp over the knots (tc_i8.cuh)
 bool i8_pass2_supported(const GaussWS *w)
 {
-    return !w->want_knots && w->d >= 1 && w->d <= 8 && w->mp <= MAX_ROWS_PER_SPLIT;
+    return w->d >= 1 && w->d <= 8 && w->mp <= MAX_ROWS_PER_SPLIT;
 }
 
 static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
@@ -1185,7 +1249,14 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
     int8_t *mslices = reinterpret_cast<int8_t *>(w->i8buf.p);
     double *colscale = reinterpret_cast<double *>(mslices + mbytes);
     // adjacent row blocks as tcgen05 CTA pairs (cta_group::2: the Mop tiles are fetched once per pair)
-    const bool pair = km_pairs() && w->rblocks % 2 == 0;
+    const bool knot = w->want_knots && !rowd;                      // the knot-location gradient rides on the gradient sums
+    const bool pair = km_pairs() && w->rblocks % 2 == 0 && !knot;
+    if (knot) {
+        w->knot_slots = w->rblocks * 4;                           // one slot per (row block, lane quadrant of the epilogue)
+        const size_t kbytes = (size_t)w->knot_slots * d * mp * 8;
+        SRGP_TRY(w->knotpart.reserve(kbytes));
+        if (ctx->n == 0 && !accumulate_slots) SRGP_CUDA(cudaMemsetAsync(w->knotpart.p, 0, kbytes, s));
+    }
     unsigned long long *colbits = reinterpret_cast<unsigned long long *>(colscale + mp);
     {
         SRGP_CUDA(cudaMemsetAsync(colbits, 0, (size_t)mp * 8, s));
@@ -1252,6 +1323,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.sigma2 = gp.sigma2;
             a.tiles_per_cta = (mp / BN2) / w->cgroups;
             a.cluster = pair ? 2 : 1;
+            a.knot_part = knot ? w->knotpart.d() : nullptr;
             a.part = w->part2.d();
             a.first = first;
             a.coin_count = w->coin_count();
@@ -1266,7 +1338,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             dim3 grid(w->rblocks, w->cgroups);
             cudaError_t e = cudaSuccess;
 #define CALL2(D, R) (pair ? launch_km2_i8<D, R, true>(s, grid, ctx->device, a) : launch_km2_i8<D, R, false>(s, grid, ctx->device, a))
-#define CALL(D) e = rowd ? CALL2(D, true) : CALL2(D, false)
+#define CALL(D) e = knot ? launch_km2_i8<D, false, false, true>(s, grid, ctx->device, a) : rowd ? CALL2(D, true) : CALL2(D, false)
             switch (d) {
             case 1: CALL(1); break;
             case 2: CALL(2); break;

@@ -1,7 +1,8 @@
-"""The two tensor-core engines of pass 2 must tell the same story: the INT8 engine (tcgen05.mma.kind::i8 with
-error-free digit splitting) serves srgp_gauss_obj_grad, the FP64 DMMA engine serves the same sums when the
-knot-location gradient is requested (its epilogue lives there) -- one process, no switch.  Pass 1 always runs on the INT8
-engine; its yardsticks are the CPU oracle (test_vi_gpu.py, test_fic_gpu.py) and oracle/ozaki_model.py.  Also shapes
+"""Two routes through pass 2 must tell the same story: srgp_gauss_obj_grad (INT8 engine, tcgen05.mma.kind::i8 with error-free
+digit splitting, plain gradient epilogue; FIC: the per-row sum passes) and srgp_gauss_obj_grad_knots (the same engine with the
+knot-gradient epilogue -- warp column sums -- and, for FIC, the two explicit K*M passes).  The yardsticks of both are the CPU
+oracle (test_vi_gpu.py, test_fic_gpu.py, test_knots_gpu.py) and oracle/ozaki_model.py; d > 8 still runs pass 2 on the FP64
+DMMA engine and is compared with the oracle in test_vi_gpu.py.  Also shapes
 that stress the INT8 path's padding: m below one tile, m not a multiple of 64, n below one chunk, a knot that is a data
 row (the q == 2^FIX_BITS marker of quirk Q4)."""
 import numpy as np
@@ -12,7 +13,7 @@ from tests import cases
 pytestmark = pytest.mark.gpu
 
 
-def test_int8_and_dmma_pass2_agree(ctx):
+def test_gradient_and_knot_gradient_routes_agree(ctx):
     for name, c in (("config5", cases.config5(n=30011, m=300, seed=5)), ("config2", cases.config2()),
                     ("config3_coincident", cases.config3(n=3000, m=70)), ("tiny", cases.config5(n=97, m=5, seed=6)),
                     ("config1", cases.config1())):
