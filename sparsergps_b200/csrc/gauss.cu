@@ -17,8 +17,8 @@
 // The row passes run on the INT8 engine of gauss_i8.cu / tc_i8.cuh (tcgen05.mma.kind::i8 with TMEM accumulators,
 // error-free digit splitting: DESIGN.md section 3a): pass 1 always, pass 2 / the row forms (gauss_pass2, gauss_rowd,
 // gauss_rowform below) whenever it supports the request (d <= 8, no knot gradient, m <= 8192).  The FP64 DMMA engine of
-// this file (gemm.cuh) serves what is left -- the knot-gradient epilogue, d > 8 -- and the Gram over the materialised K of
-// the Laplace Newton loop.  There is no run-time switch between the two.
+// this file (gemm.cuh) serves what is left -- d > 8 in pass 2 / the row forms -- and the Gram over a K the caller
+// materialised (srgp_gauss_obj_mats).  There is no run-time switch between the two.
 #include <math.h>
 #include <stdlib.h>
 

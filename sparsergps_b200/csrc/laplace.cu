@@ -352,7 +352,9 @@ static int lap_setup(Lap &L, srgp_ctx *ctx, int family, int kernel, const double
     }
     // G_Z = K^T diag(1/Z) K ; C_Z = (S + G_Z)^-1 (the R of grad_loglik_fn / update / objective)
     double *buf = w->red1.d();
-    SRGP_TRY(gram_materialised(ctx, w, L.invZ, buf));
+    // (INT8 tensor-core Gram over regenerated K, as every Gram of the Gaussian models: 1 / Z > 0, so one slice set
+    // sqrt(1 / Z) K serves both operands; its K^T r by-product is not needed here)
+    SRGP_TRY(gauss_pass1(ctx, w, L.gp, L.invZ, L.invZ, buf, w->vec(W_::V_T1), true));
     SRGP_TRY(comm_allreduce(ctx, buf, mm, s));
     SRGP_CUDA(cudaMemcpyAsync(L.GZ, buf, mm * 8, cudaMemcpyDeviceToDevice, s));
     SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, L.S, 1.0, L.GZ, 0.0, L.A));
@@ -373,8 +375,8 @@ static int lap_objective_stage(Lap &L, double *W3out)
     double *buf = w->red1.d(), *a = buf + mm, *tail = a + mp;
     SRGP_TRY(L.rows(W3out, tail));
     SRGP_TRY(set_scalar(L.ctx, tail + 3, (double)L.n));
-    SRGP_TRY(L.ktv(L.rz, a));
-    SRGP_TRY(gram_materialised(L.ctx, w, L.om, buf));
+    // G_omega = K^T diag(omega) K and a = K^T rz in one INT8 pass (omega may have either sign with quirk Q1: two slice sets)
+    SRGP_TRY(gauss_pass1(L.ctx, w, L.gp, L.om, L.rz, buf, a));
     SRGP_TRY(comm_allreduce(L.ctx, buf, mm + mp + 4, s));
     SRGP_TRY(copy_scalar(L.ctx, w->sc(W_::S_X), tail, 4));
     SRGP_CUDA(cudaMemcpyAsync(L.av, a, (size_t)mp * 8, cudaMemcpyDeviceToDevice, s));
@@ -532,9 +534,8 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     // B = 1/(Z - 1/W) = omega ; G_B, a = K^T rz, K^T g in one allreduce (R/laplace_approx_gradient.R:127-155)
     double *GB = w->red1.d(), *a = GB + mm, *ktg = a + mp, *tail = ktg + mp;
     SRGP_TRY(L.rows(L.W3, tail));
-    SRGP_TRY(L.ktv(L.rz, a));
     SRGP_TRY(L.ktv(L.d1, ktg));
-    SRGP_TRY(gram_materialised(ctx, w, L.om, GB));
+    SRGP_TRY(gauss_pass1(ctx, w, L.gp, L.om, L.rz, GB, a));
     SRGP_TRY(comm_allreduce(ctx, GB, mm + 2 * mp, s));
     double *C = w->mat(W_::M_C), *M2 = w->mat(W_::M_CGS), *SG = w->mat(W_::M_SG);
     double *SGS = w->mat(W_::M_SGS), *N = w->mat(W_::M_N), *Grho = w->mat(W_::M_X2);
@@ -589,8 +590,7 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     // G_rho, K^T t -> one allreduce with the gradient partials
     double *red2 = w->mat(W_::M_T2);   // [G_rho (mm)] then M_X1.. is LinvT: use a separate tail buffer
     double *tail2 = w->vec(W_::V_T2);  // [K^T t (mp) | p2 (d + 4)]  (V_T2, V_T3 adjacent: 2 mp >= mp + d + 4)
-    SRGP_TRY(gram_materialised(ctx, w, rho, red2));
-    SRGP_TRY(L.ktv(tt, tail2));
+    SRGP_TRY(gauss_pass1(ctx, w, L.gp, rho, tt, red2, tail2));     // G_rho and K^T t
     SRGP_TRY(copy_scalar(ctx, tail2 + mp, p2, W_::p2_len(d)));
     SRGP_TRY(comm_allreduce(ctx, red2, mm, s));
     SRGP_TRY(comm_allreduce(ctx, tail2, mp + W_::p2_len(d), s));
