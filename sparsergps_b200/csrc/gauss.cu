@@ -807,6 +807,8 @@ void GaussWS::release()
 {
     DevBuf *bufs[] = {&U, &chunk, &Gpart, &b1part, &red1, &r, &rowa, &mats, &vecs, &scal, &part2, &coin, &coinrow, &rowpart, &Kmat, &nspart, &knotpart, &knotsum, &rowdpart, &rowd, &i8buf, &i8scal, &k2};
     for (auto *b : bufs) b->release();
+    for (auto e : k2_ev) cudaEventDestroy(e);
+    k2_ev.clear();
     if (h_scal) cudaFreeHost(h_scal);
     h_scal = nullptr;
 }

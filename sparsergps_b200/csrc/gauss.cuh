@@ -1,6 +1,7 @@
 // gauss.cuh -- workspace of the fused Gaussian (VI / FIC) and Laplace pipelines.
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -52,6 +53,10 @@ struct GaussWS {
     // regenerate their chunks).  Keyed on everything K depends on, see K2Key.
     DevBuf k2;
     bool k2_valid = false, k_reuse = false;
+    // VI: the image is generated AHEAD of pass 2, on the generator stream, while the m x m stage keeps the tensor pipe idle
+    // (gauss_pregen_k2); k2_ev[c] fires when chunk c is complete, k2_pending until pass 2 has waited for them
+    std::vector<cudaEvent_t> k2_ev;
+    bool k2_pending = false;
     struct K2Key {
         const double *Xp;
         int64_t n;

@@ -1012,10 +1012,11 @@ static bool k2_have(const srgp_ctx *ctx, const GaussWS *w, const GenParams &gp)
 
 // Make room for the image of the current shard; false when it is switched off or does not fit (the caller then works
 // from its double-buffered chunks as before).  Invalidates the previous contents.
-static bool k2_reserve(srgp_ctx *ctx, GaussWS *w)
+static bool k2_reserve(srgp_ctx *ctx, GaussWS *w, bool ahead = false)
 {
     w->k2_valid = false;
-    if (!k2_enabled() || !w->k_reuse || ctx->n <= 0 || !i8_pass2_supported(w)) return false;
+    w->k2_pending = false;
+    if (!k2_enabled() || !(w->k_reuse || ahead) || ctx->n <= 0 || !i8_pass2_supported(w)) return false;
     const size_t chunks = (size_t)((ctx->n + w->rows2 - 1) / w->rows2);
     const size_t bytes = chunks * k2_chunk_bytes(w);
     if (bytes > w->k2.cap) {
@@ -1214,6 +1215,52 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
                       const double *beta, double *out, bool accumulate_slots, bool rowd, const double *vvec, double *rowd_out,
                       int64_t rowd_stride, bool nodims = false);
 
+// one pass-2 chunk (rows r0 .. of the shard) of digit slices into `kslices`, on stream sg
+static int gen_datarows_chunk(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, cudaStream_t sg, int64_t r0, int rows_valid,
+                              int8_t *kslices)
+{
+    const int mp = w->mp, m = w->m, d = w->d;
+    KernelScope ks(ctx, SRGP_PROF_GEN, sg);
+    dim3 grid(w->rblocks, std::min(mp / BK, 16));
+#define CALL(D) launch_gen_datarows<D>(sg, grid, ctx->Xp, ctx->n, r0, rows_valid, w->U.d(), m, mp, gp, kslices)
+    switch (d) {
+    case 1: CALL(1); break;
+    case 2: CALL(2); break;
+    case 3: CALL(3); break;
+    case 4: CALL(4); break;
+    case 5: CALL(5); break;
+    case 6: CALL(6); break;
+    case 7: CALL(7); break;
+    default: CALL(8); break;
+    }
+#undef CALL
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+int gauss_pregen_k2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
+{
+    if (getenv("SRGP_NO_OVERLAP") || k2_have(ctx, w, gp) || !k2_reserve(ctx, w, true)) return SRGP_OK;
+    cudaStream_t s = ctx->stream, sg = ctx->stream3;
+    const size_t chunks = (size_t)((ctx->n + w->rows2 - 1) / w->rows2);
+    while (w->k2_ev.size() < chunks) {
+        cudaEvent_t e;
+        SRGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        w->k2_ev.push_back(e);
+    }
+    SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    size_t c = 0;
+    for (int64_t r0 = 0; r0 < ctx->n; r0 += w->rows2, c++) {
+        const int rows_valid = (int)std::min<int64_t>(w->rows2, ctx->n - r0);
+        SRGP_TRY(gen_datarows_chunk(ctx, w, gp, sg, r0, rows_valid, reinterpret_cast<int8_t *>(w->k2.p) + c * k2_chunk_bytes(w)));
+        SRGP_CUDA(cudaEventRecord(w->k2_ev[c], sg));
+    }
+    k2_commit(ctx, w, gp);
+    w->k2_pending = true;
+    return SRGP_OK;
+}
+
 // Pass 2 (gradient sums) on the INT8 tensor cores; same contract and the same per-CTA slots as gauss_pass2.
 int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                    const double *beta, double *out, bool accumulate_slots)
@@ -1285,23 +1332,11 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
                                            : reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
         if (!have2) {
             if (cidx >= 2 && !fill2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
-            KernelScope ks(ctx, SRGP_PROF_GEN, sg);
-            dim3 grid(w->rblocks, std::min(KBm, 16));
-#define CALL(D) launch_gen_datarows<D>(sg, grid, ctx->Xp, ctx->n, r0, rows_valid, w->U.d(), m, mp, gp, kslices)
-            switch (d) {
-            case 1: CALL(1); break;
-            case 2: CALL(2); break;
-            case 3: CALL(3); break;
-            case 4: CALL(4); break;
-            case 5: CALL(5); break;
-            case 6: CALL(6); break;
-            case 7: CALL(7); break;
-            default: CALL(8); break;
-            }
-#undef CALL
-            SRGP_LAUNCH_CHECK();
+            SRGP_TRY(gen_datarows_chunk(ctx, w, gp, sg, r0, rows_valid, kslices));
             SRGP_CUDA(cudaEventRecord(ctx->ev_gen[b], sg));
             SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_gen[b], 0));
+        } else if (w->k2_pending) {
+            SRGP_CUDA(cudaStreamWaitEvent(s, w->k2_ev[cidx], 0));   // generated ahead (gauss_pregen_k2)
         }
         {
             KernelScope ks(ctx, SRGP_PROF_KM, s);
@@ -1363,6 +1398,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
         first = 0;
     }
     if (fill2) k2_commit(ctx, w, gp);
+    w->k2_pending = false;
     if (out) {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s);
         gram_sum_part(s, w->part2.d(), slots, PART_STRIDE_I8, d + 1, out);

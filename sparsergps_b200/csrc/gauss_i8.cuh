@@ -11,6 +11,9 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
 // pass 2 (MODE_GRAD of gauss.cu: sum P, sum P o D_c, coincident pairs) on the INT8 tensor cores; same per-CTA slots
 constexpr int PART_STRIDE_I8 = SRGP_MAX_D + 8;
 bool i8_pass2_supported(const GaussWS *w);
+// Start generating the pass-2 operand image of the whole shard on the generator stream (after everything issued so far on
+// ctx->stream); the next K*M pass with the same parameters waits chunk by chunk.  A no-op when the image does not fit.
+int gauss_pregen_k2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp);
 int gauss_pass2_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *rs, const double *ra,
                    const double *beta, double *out, bool accumulate_slots);
 int gauss_rowd_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double *Mop, const double *beta, const double *vvec,

@@ -17,6 +17,7 @@
 
 #include "dense.cuh"
 #include "gauss.cuh"
+#include "gauss_i8.cuh"
 
 namespace srgp {
 
@@ -100,6 +101,9 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
 
     // ---- pass 1 (main stream) --------------------------------------------------------------------------------
     SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G1, b1));
+    // pass 2's K does not depend on the m x m stage: its generators start now, on their own stream, and work while that
+    // stage (latency-bound, tensor pipe idle) runs; pass 2 then finds most of its chunks waiting
+    if (grad) SRGP_TRY(gauss_pregen_k2(ctx, w, gp));
     SRGP_TRY(copy_scalar(ctx, tail, w->sc(W::S_S0), 1));
     SRGP_TRY(set_scalar(ctx, tail + 1, (double)ctx->n));
     SRGP_TRY(comm_allreduce(ctx, G1, mm + mp + 2, s));
