@@ -119,7 +119,128 @@ int gemm(srgp_ctx *ctx, cudaStream_t s, char transA, char transB, int M, int N, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cholesky: diagonal block factor + inverse in shared memory (one CTA), panel / trailing updates by DMMA GEMM
+// The m x m products of the Cholesky / inverse on MANY SMs.  On sm_100 a DMMA CTA and a DFMA CTA run at the same FP64 rate
+// (profiles/r01_microbench.json), so what a 128 x 128 x 128 tile costs is the 17 us ONE SM needs for its 4.2 MFLOP.  The
+// trailing update of a factorisation step, the recursive-doubling products of the triangular inverse and W W^T therefore go
+// in 64 x 64 tiles, 256 threads x (4 x 4) outputs, plain DFMA from shared memory: four times the CTAs of the 128 x 128 DMMA
+// tiles, i.e. all 148 SMs instead of 16 .. 64 at m = 1024.
+//   C (+)= alpha A B^T with A (M x K), B (N x K) column-major (MN-contiguous); beta in {0, 1}; lower_only skips the tiles
+//   strictly above the diagonal; kmode skips the k range where a triangular operand is zero.  C must not alias A or B (the
+//   in-place panel has its own kernel below).
+// ------------------------------------------------------------------------------------------------
+constexpr int ST = 64, SK = 16;      // tile, k-chunk
+
+struct SmallNT {
+    const double *A, *B;
+    double *C, *Ct;              // Ct: optional second, transposed store (Ct[c + r ldct])
+    int64_t lda, ldb, ldc, ldct, sA, sB, sC, sCt;   // leading dimensions, batch strides (blockIdx.z)
+    int K;
+    double alpha;
+    int beta_one, lower_only, kmode;
+};
+
+__global__ void __launch_bounds__(256) small_nt_kernel(SmallNT g)
+{
+    const int tm = blockIdx.x, tn = blockIdx.y;
+    if (g.lower_only && tn > tm) return;
+    __shared__ double As[SK][ST + 4], Bs[SK][ST + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double *Ab = g.A + blockIdx.z * g.sA + (int64_t)tm * ST, *Bb = g.B + blockIdx.z * g.sB + (int64_t)tn * ST;
+    // k range: skip where a triangular operand is known to be zero (dense.cuh)
+    int k_lo = 0, k_hi = g.K;
+    if (g.kmode == KMODE_A_UPPER) k_lo = tm * ST;
+    else if (g.kmode == KMODE_B_LOWER) k_hi = min(g.K, (tn + 1) * ST);
+    else if (g.kmode == KMODE_AB_UPPER) k_lo = max(tm, tn) * ST;
+    double acc[4][4] = {};
+    for (int k0 = k_lo; k0 < k_hi; k0 += SK) {
+        // 64 rows x 16 k of each operand: thread -> (row = threadIdx.x % 64, four k's)
+        const int r = threadIdx.x & 63, kq = threadIdx.x >> 6;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = kq * 4 + q;
+            As[k][r] = Ab[r + (int64_t)(k0 + k) * g.lda];
+            Bs[k][r] = Bb[r + (int64_t)(k0 + k) * g.ldb];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SK; k++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) av[i] = As[k][tx + 16 * i], bv[i] = Bs[k][ty + 16 * i];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    double *Cb = g.C + blockIdx.z * g.sC + (int64_t)tm * ST + (int64_t)tn * ST * g.ldc;
+    double *Ctb = g.Ct ? g.Ct + blockIdx.z * g.sCt + (int64_t)tn * ST + (int64_t)tm * ST * g.ldct : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * j;
+            double *p = Cb + r + (int64_t)c * g.ldc;
+            const double v = g.beta_one ? fma(g.alpha, acc[i][j], *p) : g.alpha * acc[i][j];
+            *p = v;
+            if (Ctb) Ctb[c + (int64_t)r * g.ldct] = v;
+        }
+}
+
+// C (+)= alpha A B^T in 64 x 64 DFMA tiles (M, N multiples of 64, K of 16)
+int gemm_nt_small(srgp_ctx *ctx, cudaStream_t s, int M, int N, int K, double alpha, const double *A, int64_t lda,
+                  const double *B, int64_t ldb, bool beta_one, double *C, int64_t ldc, BatchDesc bd, bool lower_only, int kmode,
+                  double *Ct, int64_t ldct)
+{
+    SmallNT g{A, B, C, Ct, lda, ldb, ldc, ldct, bd.strideA, bd.strideB, bd.strideC, bd.strideCt, K, alpha,
+              beta_one ? 1 : 0, lower_only ? 1 : 0, kmode};
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    small_nt_kernel<<<dim3(M / ST, N / ST, bd.batch), 256, 0, s>>>(g);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
+// The panel L21 = A21 X^T (X = L11^-1, 128 x 128, ld = 128) IN PLACE: a CTA owns 32 rows of A21 with all 128 columns, reads
+// them completely, then stores -- no other CTA touches those rows.
+__global__ void __launch_bounds__(256)
+panel_kernel(double *A, int64_t lda, const double *__restrict__ X)
+{
+    __shared__ double As[SK][32 + 4], Xs[SK][NB + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double *Ab = A + (int64_t)blockIdx.x * 32;
+    double acc[2][8] = {};
+    for (int k0 = 0; k0 < NB; k0 += SK) {
+        {
+            const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;          // 32 rows x 16 k: two k's per thread
+            As[kq * 2][r] = Ab[r + (int64_t)(k0 + kq * 2) * lda];
+            As[kq * 2 + 1][r] = Ab[r + (int64_t)(k0 + kq * 2 + 1) * lda];
+            const int j = threadIdx.x & 127, kh = threadIdx.x >> 7;         // 128 columns x 16 k: eight k's per thread
+#pragma unroll
+            for (int q = 0; q < 8; q++) Xs[kh * 8 + q][j] = X[j + (k0 + kh * 8 + q) * NB];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SK; k++) {
+            const double a0 = As[k][tx], a1 = As[k][tx + 16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double b = Xs[k][ty + 16 * j];
+                acc[0][j] = fma(a0, b, acc[0][j]);
+                acc[1][j] = fma(a1, b, acc[1][j]);
+            }
+        }
+        __syncthreads();                                                    // also: every read of A precedes the stores below
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        Ab[tx + (int64_t)(ty + 16 * j) * lda] = acc[0][j];
+        Ab[tx + 16 + (int64_t)(ty + 16 * j) * lda] = acc[1][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky: diagonal block factor + inverse in shared memory (one CTA), panel / trailing updates in 64 x 64 DFMA tiles
 // ------------------------------------------------------------------------------------------------
 constexpr int DLD = NB + 1;   // 129: odd stride, column-major block in shared memory
 
@@ -301,10 +422,14 @@ int potrf(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv,
         if (Mr > 0) {
             double *A21 = Akk + NB;
             double *A22 = Akk + NB * ((size_t)mp + 1);
-            // L21 = A21 * L11^-T  (in place: a CTA reads its 128 rows completely before writing them)
-            SRGP_TRY(gemm(ctx, s, 'N', 'T', Mr, NB, NB, 1.0, A21, mp, Dk, NB, 0.0, A21, mp));
+            // L21 = A21 * L11^-T  (in place: a CTA reads its rows completely before writing them)
+            {
+                KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+                panel_kernel<<<Mr / 32, 256, 0, s>>>(A21, mp, Dk);
+                SRGP_LAUNCH_CHECK();
+            }
             // A22 -= L21 L21^T on the lower block triangle
-            SRGP_TRY(gemm(ctx, s, 'N', 'T', Mr, Mr, NB, -1.0, A21, mp, A21, mp, 1.0, A22, mp, BatchDesc(), true));
+            SRGP_TRY(gemm_nt_small(ctx, s, Mr, Mr, NB, -1.0, A21, mp, A21, mp, true, A22, mp, BatchDesc(), true, KMODE_FULL, nullptr, 0));
         }
     }
     {
@@ -357,11 +482,11 @@ int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *
         bd.strideA = bd.strideB = bd.strideC = bd.strideCt = (int64_t)2 * sl * NB * (ld + 1);
         const int S = sl * NB, Mr = sr * NB;
         // T' = W11 * L21^T   (S x Mr, at tmp[b0, b0+sl])
-        SRGP_TRY(gemm(ctx, s, 'N', 'T', S, Mr, S, 1.0, at(LinvT, b0, b0), ld, at(L, b0 + sl, b0), ld, 0.0,
-                      at(tmp, b0, b0 + sl), ld, bd, false, KMODE_A_UPPER));
+        SRGP_TRY(gemm_nt_small(ctx, s, S, Mr, S, 1.0, at(LinvT, b0, b0), ld, at(L, b0 + sl, b0), ld, false,
+                               at(tmp, b0, b0 + sl), ld, bd, false, KMODE_A_UPPER, nullptr, 0));
         // W12 = -T' * X22^T  (S x Mr, at LinvT[b0, b0+sl]);  X21 = W12^T at Linv[b0+sl, b0]
-        SRGP_TRY(gemm(ctx, s, 'N', 'T', S, Mr, Mr, -1.0, at(tmp, b0, b0 + sl), ld, at(Linv, b0 + sl, b0 + sl), ld,
-                      0.0, at(LinvT, b0, b0 + sl), ld, bd, false, KMODE_B_LOWER, at(Linv, b0 + sl, b0), ld));
+        SRGP_TRY(gemm_nt_small(ctx, s, S, Mr, Mr, -1.0, at(tmp, b0, b0 + sl), ld, at(Linv, b0 + sl, b0 + sl), ld, false,
+                               at(LinvT, b0, b0 + sl), ld, bd, false, KMODE_B_LOWER, at(Linv, b0 + sl, b0), ld));
         return SRGP_OK;
     };
     for (int sblk = 1; sblk < nb; sblk *= 2) {
@@ -376,8 +501,8 @@ int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *
 // Ainv = X^T X = W W^T (full symmetric); k >= max(i, j) because W is upper triangular.
 int lauum(srgp_ctx *ctx, cudaStream_t s, const double *LinvT, int mp, double *Ainv)
 {
-    return gemm(ctx, s, 'N', 'T', mp, mp, mp, 1.0, LinvT, mp, LinvT, mp, 0.0, Ainv, mp, BatchDesc(), false,
-                KMODE_AB_UPPER);
+    return gemm_nt_small(ctx, s, mp, mp, mp, 1.0, LinvT, mp, LinvT, mp, false, Ainv, mp, BatchDesc(), false, KMODE_AB_UPPER,
+                         nullptr, 0);
 }
 
 int chol_inverse(srgp_ctx *ctx, cudaStream_t s, double *A, int mp, int m, double *dinv, double *Linv, double *LinvT,
