@@ -41,9 +41,9 @@ for name, fn in (("make_cov_mat_ard", lambda: lib.srgp_make_cov_mat_dev(ctx.hand
         ts.append(ctx.timer_stop_ms())
     ms = float(np.median(ts))
     gb = 8.0 * n * m / 1e9
-    # FP64-pipe roofline: 3d (difference, scale, square-accumulate) + 17 (libdevice exp) + 2..4 instructions per entry
+    # FP64-pipe roofline: 3d (difference, scale, square-accumulate) + 10 (table exp, fastexp.cuh) + 2..4 instructions per entry
     dfma = 33.38e12 / 2      # profiles/r01_microbench.json: 16.7e12 DFMA lane-instructions/s
-    instr = 0 if "tau" in name else (3 * d + 19 + (2 if "l3" in name else 0))
+    instr = 0 if "tau" in name else (3 * d + 12 + (2 if "l3" in name else 0))
     print(json.dumps({"kernel": name, "n": n, "m": m, "d": d, "ms": round(ms, 4), "GBps": round(gb / (ms * 1e-3), 1),
                       "frac_of_measured_hbm": round(gb / (ms * 1e-3) / hbm, 3), "fp64_pipe_instr_per_entry": instr,
                       "frac_of_fp64_pipe": round(instr * n * m / (ms * 1e-3) / dfma, 3),

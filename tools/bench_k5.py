@@ -36,9 +36,9 @@ for _ in range(10):
     ts.append(ctx.timer_stop_ms())
 ms = float(np.median(ts))
 gb = 8.0 * n * m / 1e9
-# FP64-pipe roofline: 2d + 17 (libdevice exp) + 2d + 5 instructions per entry against the measured DFMA issue rate
+# FP64-pipe roofline: 2d + 10 (table exp) + 2d + 5 instructions per entry against the measured DFMA issue rate
 dfma = 33.38e12 / 2          # profiles/r01_microbench.json: 33.38 TFLOP/s of DFMA = 16.7e12 lane-instructions/s
-instr = 4 * d + 22
+instr = 4 * d + 15
 print(json.dumps({"kernel": "omega_dk_kernel (sum Omega o dK, all theta)", "n": n, "m": m, "d": d, "ms": round(ms, 4),
                   "GBps": round(gb / (ms * 1e-3), 1), "frac_of_%s_hbm" % src: round(gb / (ms * 1e-3) / hbm, 3),
                   "fp64_pipe_instr_per_entry": instr,
