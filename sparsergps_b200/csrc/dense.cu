@@ -1,7 +1,5 @@
 // dense.cu -- replicated m x m stage (K6): what R's chol / solve / det / %*% do on m x m matrices in
 // R/vi_functions.R:96-118,227-246, R/laplace_approx_obj_funs.R:30-48, R/newtrap_sparseGP.R:244-289.
-#include <type_traits>
-
 #include "dense.cuh"
 #include "gemm.cuh"
 
@@ -273,45 +271,34 @@ potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *_
             const int i = ti + 16 * ii, k = tk + 16 * kk;
             a[ii][kk] = (i >= k) ? A[i + (int64_t)k * ld] : 0.0;
         }
-    // ---- Cholesky (right-looking, looking one column ahead) ----
-    // Step j applies column j (already scaled, in vec[j & 1]) to the rest of the block.  The chain that bounds a step is
-    // shuffle (pivot) -> rsqrt -> scale -> shared store -> barrier -> shared load -> FMA -> next pivot; so a step first updates
-    // the 16-column sub-block that holds column j + 1, lets that column's owners compute its pivot and scaling at once
-    // (into the other half of vec), and only then updates the remaining sub-blocks -- the long part of the chain runs
-    // beside the bulk of the FMAs instead of after it.
-    auto scale_column = [&](auto JBc, int jt1, double *cvn) {
-        constexpr int JB = decltype(JBc)::value;
-        const int j1 = JB * 16 + jt1;
-        // the 16 owners of the column sit in one half-warp (tk == jt1); the pivot owner is its lane ti == jt1
-        const double piv = __shfl_sync(0xffffffffu, a[JB][JB], (lane & 16) + jt1);
-        if (tk == jt1) {
-            // 1/sqrt and one multiply instead of sqrt followed by a division: the pivot computation is the
-            // serial part of every column step (rsqrt is within 1 ulp; L_jj = piv / sqrt(piv) within 2)
-            const double rj = rsqrt(piv);
-            const double dj = piv * rj;
-            if (ti == jt1) {
-                if (!(piv > 0.0) && *info == 0) *info = col0 + j1 + 1;
-                diag[j1] = dj;
-                rdiag[j1] = rj;
-            }
-#pragma unroll
-            for (int ii = 0; ii < 8; ii++) {
-                const int i = ti + 16 * ii;
-                double v = 0.0;
-                if (ii > JB || (ii == JB && ti > jt1)) v = a[ii][JB] * rj;
-                else if (ii == JB && ti == jt1) v = dj;
-                if (ii >= JB) a[ii][JB] = v;
-                cvn[i] = (i > j1) ? v : 0.0;
-            }
-        }
-    };
-    scale_column(std::integral_constant<int, 0>(), 0, vec);
+    // ---- Cholesky (right-looking) ----
 #pragma unroll
     for (int jb = 0; jb < 8; jb++) {
         for (int jt = 0; jt < 16; jt++) {
             const int j = jb * 16 + jt;
-            const double *cv = vec + (j & 1) * NB;
-            double *cvn = vec + ((j + 1) & 1) * NB;
+            double *cv = vec + (j & 1) * NB;
+            // the 16 owners of column j sit in one half-warp (tk == jt); the pivot owner is its lane ti == jt
+            const double piv = __shfl_sync(0xffffffffu, a[jb][jb], (lane & 16) + jt);
+            if (tk == jt) {
+                // 1/sqrt and one multiply instead of sqrt followed by a division: the pivot computation is the
+                // serial part of every column step (rsqrt is within 1 ulp; L_jj = piv / sqrt(piv) within 2)
+                const double rj = rsqrt(piv);
+                const double dj = piv * rj;
+                if (ti == jt) {
+                    if (!(piv > 0.0) && *info == 0) *info = col0 + j + 1;
+                    diag[j] = dj;
+                    rdiag[j] = rj;
+                }
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    const int i = ti + 16 * ii;
+                    double v = 0.0;
+                    if (ii > jb || (ii == jb && ti > jt)) v = a[ii][jb] * rj;
+                    else if (ii == jb && ti == jt) v = dj;
+                    if (ii >= jb) a[ii][jb] = v;
+                    cv[i] = (i > j) ? v : 0.0;
+                }
+            }
             __syncthreads();
             double li[8], lk[8];
 #pragma unroll
@@ -319,41 +306,15 @@ potrf_diag_kernel(double *__restrict__ A, int64_t ld, int col0, int m, double *_
                 li[q] = cv[ti + 16 * q];
                 lk[q] = cv[tk + 16 * q];
             }
-            // sub-block kk of this thread's 8 x 8 tile: columns tk + 16 kk (strictly upper sub-blocks are never read)
-            auto update = [&](int kk, bool kact) {
 #pragma unroll
-                for (int ii = 0; ii < 8; ii++)
-                    if (ii >= kk && kact) a[ii][kk] = fma(-li[ii], lk[kk], a[ii][kk]);
-            };
-            if (jt < 15) {
-                update(jb, tk > jt);                             // holds column j + 1
-                switch (jb) {                                    // (jb is a constant after unrolling; the lambda wants a type)
-                case 0: scale_column(std::integral_constant<int, 0>(), jt + 1, cvn); break;
-                case 1: scale_column(std::integral_constant<int, 1>(), jt + 1, cvn); break;
-                case 2: scale_column(std::integral_constant<int, 2>(), jt + 1, cvn); break;
-                case 3: scale_column(std::integral_constant<int, 3>(), jt + 1, cvn); break;
-                case 4: scale_column(std::integral_constant<int, 4>(), jt + 1, cvn); break;
-                case 5: scale_column(std::integral_constant<int, 5>(), jt + 1, cvn); break;
-                case 6: scale_column(std::integral_constant<int, 6>(), jt + 1, cvn); break;
-                default: scale_column(std::integral_constant<int, 7>(), jt + 1, cvn); break;
+            for (int kk = 0; kk < 8; kk++) {
+                if (kk < jb) continue;                           // columns of finished blocks
+                const bool kact = (kk > jb) || (tk > jt);        // k > j
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    if (ii < kk) continue;                       // strictly upper sub-blocks are never read
+                    if (kact) a[ii][kk] = fma(-li[ii], lk[kk], a[ii][kk]);
                 }
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-                    if (kk > jb) update(kk, true);
-            } else if (jb < 7) {
-                update(jb + 1, true);                            // column j + 1 opens the next sub-block
-                switch (jb) {
-                case 0: scale_column(std::integral_constant<int, 1>(), 0, cvn); break;
-                case 1: scale_column(std::integral_constant<int, 2>(), 0, cvn); break;
-                case 2: scale_column(std::integral_constant<int, 3>(), 0, cvn); break;
-                case 3: scale_column(std::integral_constant<int, 4>(), 0, cvn); break;
-                case 4: scale_column(std::integral_constant<int, 5>(), 0, cvn); break;
-                case 5: scale_column(std::integral_constant<int, 6>(), 0, cvn); break;
-                default: scale_column(std::integral_constant<int, 7>(), 0, cvn); break;
-                }
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-                    if (kk > jb + 1) update(kk, true);
             }
         }
     }
