@@ -27,3 +27,44 @@ def test_gradient_and_knot_gradient_routes_agree(ctx):
             tol = 1e-8 if name.startswith("config3") else 1e-10
             assert obj == pytest.approx(obj2, rel=tol), (name, model)
             np.testing.assert_allclose(grad, grad2, rtol=tol, atol=tol * np.max(np.abs(grad2)), err_msg=name + "/" + model)
+
+
+PAIR_SCRIPT = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from tests import cases
+from sparsergps_b200.context import Context
+out = {}
+with Context(0) as ctx:
+    for name, c in (("config5", cases.config5(n=30011, m=300, seed=5)), ("config3_coincident", cases.config3(n=3000, m=70))):
+        cp = c["cov_par"]
+        ctx.set_data(c["x"], c["y"], c["mu"])
+        for model in ("vi", "fic"):
+            obj, grad = ctx.gauss_obj_grad(model, c["cov_fun"], c["xu"], cp["sigma"], cases.lvec(cp), cp["tau"], c["delta"])
+            out[name + "/" + model] = [obj] + [float(g) for g in grad]
+print("RESULT " + json.dumps(out))
+'''
+
+
+def test_cta_pair_experiment_agrees():
+    """SRGP_PAIR=1 (read once per process, hence the subprocesses) runs the K*M pass on tcgen05 CTA pairs (cta_group::2): the
+    same exact integer sums and the same epilogue arithmetic per row.  VI comes out bit-identical; FIC's per-row sum mode
+    differs in the last bits (1.7e-14: the two template instantiations contract their multiply-adds differently), so the
+    assertion is 1e-12."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for pair in ("0", "1"):
+        env = dict(os.environ, SRGP_PAIR=pair)
+        r = subprocess.run([sys.executable, "-c", PAIR_SCRIPT % root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):]))
+    for k in res[0]:
+        a, b = np.array(res[0][k]), np.array(res[1][k])
+        np.testing.assert_allclose(a, b, rtol=1e-12, err_msg=k)
+        if k.endswith("/vi"):
+            assert np.array_equal(a, b), k
