@@ -97,6 +97,14 @@ extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
         SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         SRGP_CUDA(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+        // VI generates pass 2's K while the m x m stage runs (gauss_pregen_k2): that work goes to the lowest-priority
+        // stream so the short, dependent kernels of the stage do not queue behind waves of generator CTAs (measured gain
+        // <= 1 %, at the run-to-run noise: 45.0 -> 44.5 ms at 1e6 rows).  The chunk generators of the passes themselves
+        // stay on stream3 at the default priority: starving them delays the pass that waits for them (FIC 98.7 -> 102.4 ms
+        // with every generator on the low priority).
+        int prio_least = 0, prio_greatest = 0;
+        SRGP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        SRGP_CUDA(cudaStreamCreateWithPriority(&ctx->stream4, cudaStreamNonBlocking, prio_least));
         for (int k = 0; k < 2; k++) {
             SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
             SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
@@ -141,6 +149,7 @@ extern "C" void srgp_ctx_destroy(srgp_ctx *ctx)
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->stream4) cudaStreamDestroy(ctx->stream4);
     delete ctx;
 }
 
@@ -150,6 +159,7 @@ extern "C" int srgp_ctx_sync(srgp_ctx *ctx)
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream));
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream2));
     SRGP_CUDA(cudaStreamSynchronize(ctx->stream3));
+    SRGP_CUDA(cudaStreamSynchronize(ctx->stream4));
     return SRGP_OK;
 }
 

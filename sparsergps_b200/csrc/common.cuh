@@ -94,6 +94,7 @@ struct srgp_ctx {
     cudaStream_t stream = nullptr;   // main stream: passes, dense chain
     cudaStream_t stream2 = nullptr;  // side stream: work independent of the main chain
     cudaStream_t stream3 = nullptr;  // generator stream: K chunk c+1 is generated while the DMMA kernel eats chunk c
+    cudaStream_t stream4 = nullptr;  // lowest priority: pass 2's K generated ahead, under the m x m stage (gauss_pregen_k2)
     cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t tim0 = nullptr, tim1 = nullptr;

@@ -152,16 +152,31 @@ __global__ void __launch_bounds__(256) small_nt_kernel(SmallNT g)
     else if (g.kmode == KMODE_B_LOWER) k_hi = min(g.K, (tn + 1) * ST);
     else if (g.kmode == KMODE_AB_UPPER) k_lo = max(tm, tn) * ST;
     double acc[4][4] = {};
-    for (int k0 = k_lo; k0 < k_hi; k0 += SK) {
-        // 64 rows x 16 k of each operand: thread -> (row = threadIdx.x % 64, four k's)
-        const int r = threadIdx.x & 63, kq = threadIdx.x >> 6;
+    // 64 rows x 16 k of each operand: thread -> (row = threadIdx.x % 64, four k's).  The next k-chunk is fetched into
+    // registers while the current one is multiplied (these kernels are short dependent launches: latency, not rate).
+    const int r = threadIdx.x & 63, kq = threadIdx.x >> 6;
+    double pa[4], pb[4];
+    if (k_lo < k_hi) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int k = kq * 4 + q;
-            As[k][r] = Ab[r + (int64_t)(k0 + k) * g.lda];
-            Bs[k][r] = Bb[r + (int64_t)(k0 + k) * g.ldb];
+            pa[q] = Ab[r + (int64_t)(k_lo + kq * 4 + q) * g.lda];
+            pb[q] = Bb[r + (int64_t)(k_lo + kq * 4 + q) * g.ldb];
+        }
+    }
+    for (int k0 = k_lo; k0 < k_hi; k0 += SK) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            As[kq * 4 + q][r] = pa[q];
+            Bs[kq * 4 + q][r] = pb[q];
         }
         __syncthreads();
+        if (k0 + SK < k_hi) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                pa[q] = Ab[r + (int64_t)(k0 + SK + kq * 4 + q) * g.lda];
+                pb[q] = Bb[r + (int64_t)(k0 + SK + kq * 4 + q) * g.ldb];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < SK; k++) {
             double av[4], bv[4];
@@ -210,24 +225,33 @@ panel_kernel(double *A, int64_t lda, const double *__restrict__ X)
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double *Ab = A + (int64_t)blockIdx.x * 32;
     double acc[2][8] = {};
-    for (int k0 = 0; k0 < NB; k0 += SK) {
-        {
-            const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;          // 32 rows x 16 k: two k's per thread
-            As[kq * 2][r] = Ab[r + (int64_t)(k0 + kq * 2) * lda];
-            As[kq * 2 + 1][r] = Ab[r + (int64_t)(k0 + kq * 2 + 1) * lda];
-            const int j = threadIdx.x & 127, kh = threadIdx.x >> 7;         // 128 columns x 16 k: eight k's per thread
+    const int r = threadIdx.x & 31, kq = threadIdx.x >> 5;          // A: 32 rows x 16 k, two k's per thread
+    const int j = threadIdx.x & 127, kh = threadIdx.x >> 7;         // X: 128 columns x 16 k, eight k's per thread
+    double pa[2], px[8];                                            // the next k-chunk, fetched while the current one is used
+    pa[0] = Ab[r + (int64_t)(kq * 2) * lda];
+    pa[1] = Ab[r + (int64_t)(kq * 2 + 1) * lda];
 #pragma unroll
-            for (int q = 0; q < 8; q++) Xs[kh * 8 + q][j] = X[j + (k0 + kh * 8 + q) * NB];
-        }
+    for (int q = 0; q < 8; q++) px[q] = X[j + (kh * 8 + q) * NB];
+    for (int k0 = 0; k0 < NB; k0 += SK) {
+        As[kq * 2][r] = pa[0];
+        As[kq * 2 + 1][r] = pa[1];
+#pragma unroll
+        for (int q = 0; q < 8; q++) Xs[kh * 8 + q][j] = px[q];
         __syncthreads();
+        if (k0 + SK < NB) {
+            pa[0] = Ab[r + (int64_t)(k0 + SK + kq * 2) * lda];
+            pa[1] = Ab[r + (int64_t)(k0 + SK + kq * 2 + 1) * lda];
+#pragma unroll
+            for (int q = 0; q < 8; q++) px[q] = X[j + (k0 + SK + kh * 8 + q) * NB];
+        }
 #pragma unroll
         for (int k = 0; k < SK; k++) {
             const double a0 = As[k][tx], a1 = As[k][tx + 16];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const double b = Xs[k][ty + 16 * j];
-                acc[0][j] = fma(a0, b, acc[0][j]);
-                acc[1][j] = fma(a1, b, acc[1][j]);
+            for (int jj = 0; jj < 8; jj++) {
+                const double b = Xs[k][ty + 16 * jj];
+                acc[0][jj] = fma(a0, b, acc[0][jj]);
+                acc[1][jj] = fma(a1, b, acc[1][jj]);
             }
         }
         __syncthreads();                                                    // also: every read of A precedes the stores below

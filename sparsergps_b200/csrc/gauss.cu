@@ -863,7 +863,7 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     SRGP_TRY(w->mats.reserve((size_t)GaussWS::NMATS * mp * mp * 8 + ((size_t)4 * mp * dense::NB + 512) * 8));
     SRGP_TRY(w->vecs.reserve((size_t)GaussWS::NVECS * mp * 8 + (size_t)dense::GEMV_SCRATCH * mp * 8));
     SRGP_TRY(w->scal.reserve(GaussWS::NSCAL * 8));
-    SRGP_TRY(w->part2.reserve(std::max((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE, (size_t)128 * mp) * 8));
+    SRGP_TRY(w->part2.reserve(std::max((size_t)std::max(w->rblocks * w->cgroups, 256) * PART_STRIDE, (size_t)PART2_VEC_GROUPS * mp) * 8));
     SRGP_TRY(w->rowpart.reserve((size_t)2 * w->cgroups * w->rows2 * 8));
     SRGP_TRY(w->nspart.reserve((size_t)NS_BLOCKS * PART_STRIDE * 8));
     if (!w->h_scal) SRGP_CUDA(cudaMallocHost(&w->h_scal, GaussWS::NSCAL * 8));

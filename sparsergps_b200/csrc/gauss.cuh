@@ -12,6 +12,8 @@ struct GenParams {
     double invl[SRGP_MAX_D];       // 1 / l_c (sqexp: the same 1 / l in every dimension)
 };
 
+constexpr int PART2_VEC_GROUPS = 320;   // part2 holds at least this many mp-vectors (laplace.cu: the K^T v partials)
+
 struct GaussWS {
     // plan (depends on m, d and the SM count)
     bool planned = false;
@@ -22,6 +24,8 @@ struct GaussWS {
 
     DevBuf U;        // knots, m x d column-major
     DevBuf chunk;    // L2-resident K chunk (row-major in pass 1, column-major in pass 2)
+    const double *pass1_kmat = nullptr;   // set around a gauss_pass1 call: the shard's K as a row-major matrix (ld = mp) the
+                                          // sqrt-weight generator may read instead of recomputing exp (laplace.cu)
     DevBuf Gpart;    // pass-1 Gram slots [pairs][splits][128*128] in fragment order
     DevBuf b1part;   // pass-1 K^T r slots [gen_groups][mp]
     DevBuf red1;     // pass-1 allreduce buffer: [G1 mp*mp | b1 mp | 16 scalars]

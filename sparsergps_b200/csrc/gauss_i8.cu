@@ -43,13 +43,16 @@ __device__ __forceinline__ double pow2_ceil(double x)
 // WMODE 2 (w >= 0, e.g. FIC's B = 1 / Z): ONE slice set sqrt(w_i) e_ij / s with s = the power of two >= sqrt(max w):
 // K^T diag(w) K = s^2 (that set)^T (that set) is then an unweighted Gram -- half the generator output, twice the rows per
 // chunk, and the diagonal tiles load their operand once.
+// WMODE 3 = WMODE 2 with K read from the shard's materialised row-major matrix Kr (ld = mp; the Laplace Newton loop keeps it
+// for its matrix-vector products and K does not change between its iterations): no distance, no exp -- one coalesced 8-byte
+// load per entry, and 1 / sigma^2 folded into the row scale.
 template <int DT, int WMODE>
 __global__ void __launch_bounds__(128)
 gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const double *__restrict__ r, int64_t r0,
                            int rows_valid, int rows_padded, const double *__restrict__ U, int m, int mp, int d_rt,
                            GenParams p, int8_t *__restrict__ slices, double *__restrict__ b1part,
                            int first, const double *__restrict__ rw, const double *__restrict__ wmax,
-                           int8_t *__restrict__ slices_w)
+                           int8_t *__restrict__ slices_w, const double *__restrict__ Kr)
 {
     extern __shared__ double sx[];   // [64][d] scaled rows, then [64] residuals, then [64] scaled row weights
     __shared__ double etab[EXP_TAB_DOUBLES];
@@ -57,8 +60,10 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
     const int d = DT > 0 ? DT : d_rt;
     double *sr = sx + 64 * d;
     double *sw = sr + 64;
-    constexpr bool WEIGHTED = WMODE == 1;
-    const double winv = WMODE == 1 ? 1.0 / pow2_ceil(*wmax) : WMODE == 2 ? 1.0 / pow2_ceil(sqrt(*wmax)) : 0.0;
+    constexpr bool WEIGHTED = WMODE == 1, FROMK = WMODE == 3;
+    const double winv = WMODE == 1 ? 1.0 / pow2_ceil(*wmax)
+                      : WMODE == 2 ? 1.0 / pow2_ceil(sqrt(*wmax))
+                      : WMODE == 3 ? 1.0 / (pow2_ceil(sqrt(*wmax)) * p.sigma2) : 0.0;
     const int j = blockIdx.x * 128 + threadIdx.x;
     const bool jvalid = j < m;
     double uj[DT > 0 ? DT : 1];
@@ -73,16 +78,17 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
     for (int kb = kb_begin; kb < kb_end; kb++) {
         const int it0 = kb * BK;
         __syncthreads();
-        for (int t = threadIdx.x; t < BK * d; t += 128) {
-            const int ii = t / d, c = t - ii * d;
-            const int i = it0 + ii;
-            sx[t] = (i < rows_valid) ? X[r0 + i + ldx * c] * p.invl[c] : 0.0;
-        }
+        if (!FROMK)
+            for (int t = threadIdx.x; t < BK * d; t += 128) {
+                const int ii = t / d, c = t - ii * d;
+                const int i = it0 + ii;
+                sx[t] = (i < rows_valid) ? X[r0 + i + ldx * c] * p.invl[c] : 0.0;
+            }
         if (threadIdx.x < BK) {
             const int i = it0 + threadIdx.x;
             sr[threadIdx.x] = (i < rows_valid) ? r[r0 + i] : 0.0;
             if (WMODE == 1) sw[threadIdx.x] = (i < rows_valid) ? rw[r0 + i] * winv : 0.0;
-            if (WMODE == 2) sw[threadIdx.x] = (i < rows_valid) ? sqrt(fmax(rw[r0 + i], 0.0)) * winv : 0.0;
+            if (WMODE == 2 || WMODE == 3) sw[threadIdx.x] = (i < rows_valid) ? sqrt(fmax(rw[r0 + i], 0.0)) * winv : 0.0;
         }
         __syncthreads();
 #pragma unroll 1
@@ -93,6 +99,16 @@ gen_slices_knotrows_kernel(const double *__restrict__ X, int64_t ldx, const doub
                 // 4 rows in flight per thread: independent distance / exp chains hide the FP64 latency
                 double sq[4] = {0.0, 0.0, 0.0, 0.0};
                 const int ii = c16 * 16 + e0;
+                if (FROMK) {
+                    double kv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        kv[q] = (jvalid && it0 + ii + q < rows_valid) ? __ldcs(Kr + (size_t)(r0 + it0 + ii + q) * mp + j) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) bacc = fma(kv[q], sr[ii + q], bacc);
+                    split_quad(kv[0] * sw[ii], kv[1] * sw[ii + 1], kv[2] * sw[ii + 2], kv[3] * sw[ii + 3], e0 >> 2, w);
+                    continue;
+                }
                 if (DT > 0) {
 #pragma unroll
                     for (int c = 0; c < DT; c++) {
@@ -401,19 +417,42 @@ i8_gram2_kernel(const int8_t *__restrict__ slices_a, const int8_t *__restrict__ 
 }
 
 // Sum the split slots of the 128 x 128 tiles and scatter to the full symmetric matrix (column-major, ld = mp).
-__global__ void __launch_bounds__(128)
+// One CTA per 32 x 32 piece of a tile (grid: tiles x 16): the slots are row-major per tile, so a warp reads 32 consecutive
+// columns of one row (256 B) and the piece goes through shared memory for the column-major stores.  Splits are summed in
+// slot order (deterministic).
+__global__ void __launch_bounds__(256)
 i8_gram2_finalize_kernel(const double *__restrict__ Gpart, int nsplit, int mp, double *__restrict__ G)
 {
+    __shared__ double sm[32][33];
     int I, J;
     tile2_to_ij(blockIdx.x, I, J);
-    const int r = I * BM + threadIdx.x;
-    const double *base = Gpart + ((size_t)blockIdx.x * nsplit * BM + threadIdx.x) * BN2;
-    for (int c = 0; c < BN2; ++c) {
+    const int r0 = (blockIdx.y >> 2) * 32, c0 = (blockIdx.y & 3) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const double *base = Gpart + (size_t)blockIdx.x * nsplit * BM * BN2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k;
+        const double *p = base + (size_t)r * BN2 + c0 + tx;
         double v = 0.0;
-        for (int s = 0; s < nsplit; ++s) v += base[(size_t)s * BM * BN2 + c];
-        const int col = J * BN2 + c;
-        G[r + (int64_t)col * mp] = v;
-        if (J < I) G[col + (int64_t)r * mp] = v;          // strictly below the diagonal block: mirror
+        for (int s = 0; s < nsplit; ++s) v += p[(size_t)s * BM * BN2];
+        sm[ty + 8 * k][tx] = v;                            // [row][column]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = ty + 8 * k;                          // column of the piece; tx = row
+        const double v = sm[tx][c];
+        const int row = I * BM + r0 + tx, col = J * BN2 + c0 + c;
+        G[row + (int64_t)col * mp] = v;
+    }
+    if (J < I) {                                           // strictly below the diagonal block: mirror (coalesced along columns)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = ty + 8 * k;
+            const double v = sm[r][tx];
+            const int row = I * BM + r0 + r, col = J * BN2 + c0 + tx;
+            G[col + (int64_t)row * mp] = v;
+        }
     }
 }
 
@@ -1054,17 +1093,20 @@ template <int DT>
 static void launch_gen_knotrows(cudaStream_t s, dim3 grid, size_t smem, const double *X, int64_t ldx, const double *r,
                                 int64_t r0, int rows_valid, int rows_padded, const double *U, int m, int mp, int d,
                                 const GenParams &p, int8_t *slices, double *b1part, int first,
-                                const double *rw, const double *wmax, int8_t *slices_w, bool wsqrt)
+                                const double *rw, const double *wmax, int8_t *slices_w, bool wsqrt, const double *Kr)
 {
-    if (rw && wsqrt)
+    if (rw && wsqrt && Kr)
+        gen_slices_knotrows_kernel<0, 3><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
+                                                               slices, b1part, first, rw, wmax, nullptr, Kr);
+    else if (rw && wsqrt)
         gen_slices_knotrows_kernel<DT, 2><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
-                                                                slices, b1part, first, rw, wmax, nullptr);
+                                                                slices, b1part, first, rw, wmax, nullptr, nullptr);
     else if (rw)
         gen_slices_knotrows_kernel<DT, 1><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
-                                                                slices, b1part, first, rw, wmax, slices_w);
+                                                                slices, b1part, first, rw, wmax, slices_w, nullptr);
     else
         gen_slices_knotrows_kernel<DT, 0><<<grid, 128, smem, s>>>(X, ldx, r, r0, rows_valid, rows_padded, U, m, mp, d, p,
-                                                                slices, b1part, first, nullptr, nullptr, nullptr);
+                                                                slices, b1part, first, nullptr, nullptr, nullptr, nullptr);
 }
 
 // *out = max_i |w_i| over the shard (one block; n is at most a few million)
@@ -1147,7 +1189,7 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
             KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(mp / 128, w->gen_groups);
             const size_t smem = sizeof(double) * BK * (d + 2);
-#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, w->b1part.d(), first, rowweight, wmax, slices_w, wsqrt)
+#define CALL(D) launch_gen_knotrows<D>(sg, grid, smem, ctx->Xp, ctx->n, rvec, r0, rows_valid, rows_padded, w->U.d(), m, mp, d, gp, slices, w->b1part.d(), first, rowweight, wmax, slices_w, wsqrt, w->pass1_kmat)
             SRGP_D_SWITCH_I8(d, CALL)
 #undef CALL
             SRGP_LAUNCH_CHECK();
@@ -1165,7 +1207,7 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     }
     {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-        i8_gram2_finalize_kernel<<<tiles, 128, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
+        i8_gram2_finalize_kernel<<<dim3(tiles, 16), 256, 0, s>>>(w->Gpart.d(), nsplit, mp, G);
         SRGP_LAUNCH_CHECK();
         gram_sum_rows(s, w->b1part.d(), w->gen_groups, mp, b1);
         SRGP_LAUNCH_CHECK();
@@ -1241,7 +1283,7 @@ static int gen_datarows_chunk(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, cu
 int gauss_pregen_k2(srgp_ctx *ctx, GaussWS *w, const GenParams &gp)
 {
     if (getenv("SRGP_NO_OVERLAP") || k2_have(ctx, w, gp) || !k2_reserve(ctx, w, true)) return SRGP_OK;
-    cudaStream_t s = ctx->stream, sg = ctx->stream3;
+    cudaStream_t s = ctx->stream, sg = ctx->stream4;
     const size_t chunks = (size_t)((ctx->n + w->rows2 - 1) / w->rows2);
     while (w->k2_ev.size() < chunks) {
         cudaEvent_t e;

@@ -55,7 +55,7 @@ lap_rows_kernel(const double *__restrict__ ff, const double *__restrict__ y, con
                 double *__restrict__ omo, double *__restrict__ rzo, double *__restrict__ part)
 {
     __shared__ double red[8];
-    double s_quad = 0.0, s_lpy = 0.0, s_lz2 = 0.0;
+    double s_quad = 0.0, s_lpy = 0.0, s_lz2 = 0.0, s_neg = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double f = ff[i], yi = y[i], z = Z[i], fm = f - (mu ? mu[i] : 0.0);
         double d1, w, w3, lpy;
@@ -84,43 +84,63 @@ lap_rows_kernel(const double *__restrict__ ff, const double *__restrict__ y, con
         s_quad = fma(fm, fm / z, s_quad);
         s_lpy += lpy;
         s_lz2 += log(z2);
+        if (!(-w / z2 >= 0.0)) s_neg += 1.0;      // omega < 0 or NaN: the one-slice-set Gram (sqrt(omega) K) does not apply
     }
     s_quad = block_sum_256(s_quad, red);
     s_lpy = block_sum_256(s_lpy, red);
     s_lz2 = block_sum_256(s_lz2, red);
+    s_neg = block_sum_256(s_neg, red);
     if (threadIdx.x == 0) {
-        part[3 * blockIdx.x] = s_quad;
-        part[3 * blockIdx.x + 1] = s_lpy;
-        part[3 * blockIdx.x + 2] = s_lz2;
+        part[4 * blockIdx.x] = s_quad;
+        part[4 * blockIdx.x + 1] = s_lpy;
+        part[4 * blockIdx.x + 2] = s_lz2;
+        part[4 * blockIdx.x + 3] = s_neg;
     }
 }
 
-// part[g][j] = sum over the rows of group g of K[i][j] v_i   (K row-major, ld = mp; one thread per knot)
+// part[g][j] = sum over the rows of group g of K[i][j] v_i   (K row-major, ld = mp; one thread per knot, eight rows in
+// flight per thread: with 8 CTAs of 128 threads per SM that is 64 KB of loads in flight per SM, what the HBM latency needs)
 __global__ void __launch_bounds__(128)
 kt_v_kernel(const double *__restrict__ K, int mp, int64_t n, const double *__restrict__ v, double *__restrict__ part)
 {
     const int j = blockIdx.x * 128 + threadIdx.x;
     const int64_t per = (n + gridDim.y - 1) / gridDim.y;
     const int64_t i0 = (int64_t)blockIdx.y * per, i1 = min(n, i0 + per);
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double a[8] = {};
     int64_t i = i0;
-    for (; i + 3 < i1; i += 4) {
-        a0 = fma(K[i * mp + j], v[i], a0);
-        a1 = fma(K[(i + 1) * mp + j], v[i + 1], a1);
-        a2 = fma(K[(i + 2) * mp + j], v[i + 2], a2);
-        a3 = fma(K[(i + 3) * mp + j], v[i + 3], a3);
+    for (; i + 7 < i1; i += 8) {
+        double k[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) k[q] = __ldcs(K + (i + q) * mp + j);
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = fma(k[q], v[i + q], a[q]);
     }
-    for (; i < i1; i++) a0 = fma(K[i * mp + j], v[i], a0);
-    part[(int64_t)blockIdx.y * mp + j] = (a0 + a1) + (a2 + a3);
+    for (; i < i1; i++) a[0] = fma(K[i * mp + j], v[i], a[0]);
+    part[(int64_t)blockIdx.y * mp + j] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
-__global__ void sum_groups_kernel(const double *__restrict__ part, int groups, int mp, double *__restrict__ out)
+// out[j] = sum_g part[g][j]: 32 columns x 8 group lanes per CTA (launch with 256 threads, mp / 32 CTAs), fixed order
+__global__ void __launch_bounds__(256)
+sum_groups_kernel(const double *__restrict__ part, int groups, int mp, double *__restrict__ out)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= mp) return;
-    double s = 0.0;
-    for (int g = 0; g < groups; g++) s += part[(int64_t)g * mp + j];
-    out[j] = s;
+    __shared__ double sm[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double s0 = 0.0, s1 = 0.0;
+    int g = ty;
+    for (; g + 8 < groups; g += 16) {
+        s0 += part[(int64_t)g * mp + j];
+        s1 += part[(int64_t)(g + 8) * mp + j];
+    }
+    if (g < groups) s0 += part[(int64_t)g * mp + j];
+    sm[ty][tx] = s0 + s1;
+    __syncthreads();
+    if (ty == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += sm[k][tx];
+        out[j] = s;
+    }
 }
 
 // out1[i] = K[i,:] h1, out2[i] = K[i,:] h2 (h2 / out2 may be null): one warp per row, coalesced over knots
@@ -242,8 +262,19 @@ __global__ void sum_strided2_kernel(const double *__restrict__ part, int count, 
     if (threadIdx.x == 0) *out = s;
 }
 
+// out[k] = sum_i part[i * stride + k], k = blockIdx.x (one launch for all the partial sums of a row kernel)
+__global__ void sum_strided_multi_kernel(const double *__restrict__ part, int count, int stride, double *__restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += part[i * stride + blockIdx.x];
+    s = block_sum_256(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 constexpr int LROW_BLOCKS = 128;
-constexpr int KTV_GROUPS = 96;
+constexpr int KTV_GROUPS = 296;   // x mp / 128 column blocks: 8 CTAs per SM at m = 512
+static_assert(KTV_GROUPS <= PART2_VEC_GROUPS, "part2 is sized by plan() in gauss.cu");
 
 struct Lap {
     srgp_ctx *ctx;
@@ -259,13 +290,14 @@ struct Lap {
     // matrices / vectors
     double *S, *Sinv, *GZ, *CZ, *A, *Linv, *LinvT, *tmp;
     double *av, *hv, *cv, *g2v, *tv, *gsc;
+    bool om_nonneg = true;   // Newton loop: omega >= 0 so far (checked on the device every stage): one slice set sqrt(omega) K
 
     int ktv(const double *v, double *out)
     {
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
         kt_v_kernel<<<dim3(mp / 128, KTV_GROUPS), 128, 0, s>>>(w->Kmat.d(), mp, n, v, w->part2.d());
         SRGP_LAUNCH_CHECK();
-        sum_groups_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->part2.d(), KTV_GROUPS, mp, out);
+        sum_groups_kernel<<<mp / 32, 256, 0, s>>>(w->part2.d(), KTV_GROUPS, mp, out);
         SRGP_LAUNCH_CHECK();
         return SRGP_OK;
     }
@@ -277,9 +309,10 @@ struct Lap {
         SRGP_LAUNCH_CHECK();
         return SRGP_OK;
     }
-    int rows(double *W3out, double *scal3)
+    // scal4 = [s_quad, log p, sum log Z2, #rows with omega < 0 or NaN]
+    int rows(double *W3out, double *scal4)
     {
-        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 4);
+        KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
         if (family == SRGP_BERNOULLI)
             lap_rows_kernel<SRGP_BERNOULLI><<<LROW_BLOCKS, 256, 0, s>>>(ff, ctx->yp, ctx->mup, Z, n, pois_m, d1, Wv, W3out,
                                                                          e, om, rz, w->part2.d());
@@ -287,10 +320,8 @@ struct Lap {
             lap_rows_kernel<SRGP_POISSON><<<LROW_BLOCKS, 256, 0, s>>>(ff, ctx->yp, ctx->mup, Z, n, pois_m, d1, Wv, W3out, e,
                                                                        om, rz, w->part2.d());
         SRGP_LAUNCH_CHECK();
-        for (int k = 0; k < 3; k++) {
-            sum_strided2_kernel<<<1, 256, 0, s>>>(w->part2.d(), LROW_BLOCKS, 3, k, scal3 + k);
-            SRGP_LAUNCH_CHECK();
-        }
+        sum_strided_multi_kernel<<<4, 256, 0, s>>>(w->part2.d(), LROW_BLOCKS, 4, scal4);
+        SRGP_LAUNCH_CHECK();
         return SRGP_OK;
     }
 };
@@ -314,6 +345,7 @@ static int lap_setup(Lap &L, srgp_ctx *ctx, int family, int kernel, const double
     SRGP_TRY(upload_knots(w, xu, (size_t)m * ctx->d * 8, s));
     fill_gen(L.gp, kernel, L.d, sigma, l);
     w->k_reuse = true;    // up to four row-form / K*M passes over this K (gauss_i8.cu)
+    L.om_nonneg = getenv("SRGP_LAP_TWO_SETS") == nullptr;   // test switch: start with the two-slice-set Gram (lap_stage_checked)
     const int64_t n = L.n;
     double **rv[] = {&L.ff, &L.Z, &L.invZ, &L.d1, &L.Wv, &L.W3, &L.e, &L.om, &L.rz, &L.Kh, &L.Kg, &L.gpsi, &L.egp,
                      &L.t0, &L.t1, &L.t2, &L.t3, &L.t4};
@@ -364,7 +396,7 @@ static int lap_setup(Lap &L, srgp_ctx *ctx, int family, int kernel, const double
 }
 
 // objective pieces at the current ff: rows, a = K^T rz, G_omega; allreduce; factor S + G_omega.
-// On return: red1 = [G_omega | a | s_quad, log p, sum log Z2, n], Linv / LinvT of S + G_omega, S_X+0..3 scalars,
+// On return: red1 = [G_omega | a | s_quad, log p, sum log Z2, #omega<0, n], Linv / LinvT of S + G_omega, S_X+0..4 scalars,
 // S_LOGDET_A = log|S + G_omega|, S_BV = a^T C_Z a.
 static int lap_objective_stage(Lap &L, double *W3out)
 {
@@ -374,11 +406,18 @@ static int lap_objective_stage(Lap &L, double *W3out)
     const size_t mm = (size_t)mp * mp;
     double *buf = w->red1.d(), *a = buf + mm, *tail = a + mp;
     SRGP_TRY(L.rows(W3out, tail));
-    SRGP_TRY(set_scalar(L.ctx, tail + 3, (double)L.n));
-    // G_omega = K^T diag(omega) K and a = K^T rz in one INT8 pass (omega may have either sign with quirk Q1: two slice sets)
-    SRGP_TRY(gauss_pass1(L.ctx, w, L.gp, L.om, L.rz, buf, a));
-    SRGP_TRY(comm_allreduce(L.ctx, buf, mm + mp + 4, s));
-    SRGP_TRY(copy_scalar(L.ctx, w->sc(W_::S_X), tail, 4));
+    SRGP_TRY(set_scalar(L.ctx, tail + 4, (double)L.n));
+    // G_omega = K^T diag(omega) K and a = K^T rz in one INT8 pass.  omega = -W / (1 - Z W) >= 0 for the reference's
+    // likelihoods (W < 0 also with quirk Q1, Z > 0), so one slice set sqrt(omega) K serves both operands -- half the
+    // generator output and half the launches of the two-set form (omega K, K).  Nothing guarantees the sign for arbitrary
+    // y, so the row kernel counts the rows with omega < 0 (or NaN), the count travels with the allreduce, and
+    // lap_stage_checked() repeats the stage with two slice sets if it is not zero.
+    w->pass1_kmat = w->Kmat.d();     // K is materialised for the matrix-vector products: the generator reads it (WMODE 3)
+    const int rc1 = gauss_pass1(L.ctx, w, L.gp, L.om, L.rz, buf, a, L.om_nonneg);
+    w->pass1_kmat = nullptr;
+    SRGP_TRY(rc1);
+    SRGP_TRY(comm_allreduce(L.ctx, buf, mm + mp + 5, s));
+    SRGP_TRY(copy_scalar(L.ctx, w->sc(W_::S_X), tail, 5));
     SRGP_CUDA(cudaMemcpyAsync(L.av, a, (size_t)mp * 8, cudaMemcpyDeviceToDevice, s));
     // h = C_Z a ; a^T h
     SRGP_TRY(dense::gemv(L.ctx, s, mp, 1.0, L.CZ, L.av, 0.0, nullptr, L.hv, L.gsc));
@@ -395,6 +434,22 @@ static double lap_objective_value(const double *h)
     // -quad/2 + a^T C_Z a/2 + log p(y|ff) - (-log|S| + log|S + G_omega|)/2 - sum log(1 - W Z)/2
     return -0.5 * h[W_::S_X] + 0.5 * h[W_::S_BV] + h[W_::S_X + 1] - 0.5 * (-h[W_::S_LOGDET_S] + h[W_::S_LOGDET_A]) -
            0.5 * h[W_::S_X + 2];
+}
+
+// One objective stage + the scalars on the host.  A negative (or NaN) omega found while the one-slice-set Gram was
+// in use invalidates that Gram (and possibly its Cholesky flag): every rank sees the same summed count and repeats the
+// stage with two slice sets, which it keeps for the rest of the call.
+static int lap_stage_checked(Lap &L)
+{
+    SRGP_TRY(lap_objective_stage(L, nullptr));
+    int rc = fetch_scalars(L.ctx, L.w);
+    if (L.om_nonneg && (rc == SRGP_OK || rc == SRGP_ERR_NOT_PD) && !(L.w->h_scal[W_::S_X + 3] == 0.0)) {
+        L.om_nonneg = false;
+        SRGP_CUDA(cudaMemsetAsync(L.w->info(1), 0, sizeof(int), L.s));
+        SRGP_TRY(lap_objective_stage(L, nullptr));
+        rc = fetch_scalars(L.ctx, L.w);
+    }
+    return rc;
 }
 
 }  // namespace srgp
@@ -443,8 +498,7 @@ extern "C" int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const 
     double *Gw = w->red1.d(), *GwPrev = w->mat(W_::M_GWP);
     SRGP_CUDA(cudaMemcpyAsync(L.ff, ff, (size_t)n * 8, cudaMemcpyHostToDevice, s));
 
-    SRGP_TRY(lap_objective_stage(L, nullptr));
-    SRGP_TRY(fetch_scalars(ctx, w));
+    SRGP_TRY(lap_stage_checked(L));
     obj_hist[0] = lap_objective_value(w->h_scal);
     int it = 1;
     while (true) {
@@ -476,8 +530,7 @@ extern "C" int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const 
             SRGP_LAUNCH_CHECK();
         }
         // ---- objective at the new ff (its Gram and factor serve the next update) ----
-        SRGP_TRY(lap_objective_stage(L, nullptr));
-        SRGP_TRY(fetch_scalars(ctx, w));
+        SRGP_TRY(lap_stage_checked(L));
         obj_hist[it - 1] = lap_objective_value(w->h_scal);
         const bool grad_big = w->h_scal[W_::S_X + 8] > 0.0;
         const double dobj = fabs(obj_hist[it - 1] - obj_hist[it - 2]);
@@ -793,7 +846,7 @@ extern "C" int srgp_gauss_obj_mats(srgp_ctx *ctx, const double *Sigma12, int64_t
         KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
         kt_v_kernel<<<dim3(mp / 128, KTV_GROUPS), 128, 0, s>>>(w->Kmat.d(), mp, n, rz, w->part2.d());
         SRGP_LAUNCH_CHECK();
-        sum_groups_kernel<<<ceil_div(mp, 256), 256, 0, s>>>(w->part2.d(), KTV_GROUPS, mp, bv);
+        sum_groups_kernel<<<mp / 32, 256, 0, s>>>(w->part2.d(), KTV_GROUPS, mp, bv);
         SRGP_LAUNCH_CHECK();
     }
     SRGP_TRY(dense::axpby(ctx, s, mp, (int)m, 1.0, S, 1.0, buf, 0.0, A));
