@@ -64,11 +64,12 @@ fic_rows1_kernel(const double *__restrict__ q, const double *__restrict__ r, int
     }
 }
 
-// alpha, rho, rs1 = -B - 2 rho from c, K v; per-block partial sums of rho
+// alpha, rho, rs1 = -B - 2 rho from c, K v; per-block partial sums of rho; rhos = rho + B / 2 = (alpha^2 + B^2 c) / 2 >= 0,
+// the weights of the shifted Gram that gives G_rho from ONE slice set (see pass 2c)
 __global__ void __launch_bounds__(256)
 fic_rows2_kernel(const double *__restrict__ c, const double *__restrict__ kv, const double *__restrict__ r,
                  const double *__restrict__ B, int64_t n, double *__restrict__ alpha, double *__restrict__ rho,
-                 double *__restrict__ rs1, double *__restrict__ part)
+                 double *__restrict__ rs1, double *__restrict__ rhos, double *__restrict__ part)
 {
     __shared__ double red[8];
     double sr = 0.0;
@@ -80,6 +81,7 @@ fic_rows2_kernel(const double *__restrict__ c, const double *__restrict__ kv, co
         alpha[i] = a;
         rho[i] = rh;
         rs1[i] = -b - 2.0 * rh;
+        rhos[i] = 0.5 * (a * a + b * b * c[i]);
         sr += rh;
     }
     sr = block_reduce_256(sr, red);
@@ -148,7 +150,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
     double *v = w->vec(W::V_V), *gv = w->vec(W::V_GV), *tv = w->vec(W::V_TMP), *beta = w->vec(W::V_BETA);
     double *gsc = w->gemv_scratch();
     double *q = w->rowv(0, n), *Bv = w->rowv(1, n), *Br = w->rowv(2, n), *kv = w->rowv(3, n);
-    double *alpha = w->rowv(4, n), *rho = w->rowv(5, n);
+    double *alpha = w->rowv(4, n), *rho = w->rowv(5, n), *rhos = w->rowv(6, n);
     double *cq = q, *rs1 = Br;   // reuse: q is dead once B exists, B r once b is reduced
 
     // ---- S, S^-1 ----------------------------------------------------------------------------------------
@@ -223,7 +225,7 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
         }
         {
             KernelScope ks(ctx, SRGP_PROF_REDUCE, s, 2);
-            fic_rows2_kernel<<<ROW_BLOCKS, 256, 0, s>>>(cq, kv, w->r.d(), Bv, n, alpha, rho, rs1, w->part2.d());
+            fic_rows2_kernel<<<ROW_BLOCKS, 256, 0, s>>>(cq, kv, w->r.d(), Bv, n, alpha, rho, rs1, rhos, w->part2.d());
             SRGP_LAUNCH_CHECK();
             sum_strided_kernel<<<1, 256, 0, s>>>(w->part2.d(), ROW_BLOCKS, 1, 0, p2 + d + 2);
             SRGP_LAUNCH_CHECK();
@@ -246,13 +248,17 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
             // quirk Q4: sum of Omega_ij over bit-identical (row, knot) pairs (both terms were recorded)
             SRGP_TRY(coin_fix(ctx, w, gp, Sinv, 0.0, p2 + 1 + d));
         }
-        // ---- G_rho ----------------------------------------------------------------------------------------------
-        double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho | p2 (d + 4)]
-        SRGP_TRY(gauss_pass1(ctx, w, gp, rho, rho, red2, tv));
+        // ---- pass 2c: G_rho = K^T diag(rho) K.  rho has either sign, but rho_i = alpha_i^2/2 - B_i (1 - B_i c_i)/2 with
+        //      c_i = K_i C K_i^T >= 0, so rho_i + B_i/2 = (alpha_i^2 + B_i^2 c_i)/2 >= 0:  G_rho = K^T diag(rho + B/2) K - G_B/2
+        //      is ONE slice set sqrt(rho + B/2) K (half the generator output and launches of the two-set weighted Gram)
+        //      minus the Gram pass 1b left behind (already summed over the ranks; the shift is linear, so the allreduce
+        //      of the shifted partial Grams commutes with it) ----------------------------------------------------------
+        double *red2 = w->mat(W::M_T2);   // allreduce buffer of pass 2: [G_rho + G_B/2 | p2 (d + 4)]
+        SRGP_TRY(gauss_pass1(ctx, w, gp, rhos, rhos, red2, tv, true));
         SRGP_TRY(copy_scalar(ctx, red2 + mm, p2, W::p2_len(d)));
         SRGP_TRY(comm_allreduce(ctx, red2, mm + W::p2_len(d), s));
         SRGP_TRY(copy_scalar(ctx, p2, red2 + mm, W::p2_len(d)));
-        SRGP_CUDA(cudaMemcpyAsync(Grho, red2, mm * 8, cudaMemcpyDeviceToDevice, s));
+        SRGP_TRY(dense::axpby(ctx, s, mp, m, 1.0, red2, -0.5, GB, 0.0, Grho));
 
         // ---- N = S^-1 G_B S^-1/2 - S^-1 G_B M2/2 - beta beta^T/2 + S^-1 G_rho S^-1; with M2 = S^-1 - C and
         //      S^-1 G_B C = S^-1 (A - S) C = S^-1 - C the first two terms collapse to M2/2 --------------------------

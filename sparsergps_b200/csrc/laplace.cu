@@ -565,9 +565,11 @@ extern "C" int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const 
 
 // dlogq_dcov_par on the resident shard; knot_grad (host, m * d, knot-major; null = none) adds the knot-location
 // gradient, which reuses Omega (the two pass-2 launches collect its per-knot column sums) and N.
-static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+// om_nonneg: G_B = K^T diag(omega) K from one slice set sqrt(omega) K (as in the Newton loop, lap_objective_stage); the
+// rows with omega < 0 are counted on the device and *retry is set when there were any (the caller repeats with two sets).
+static int laplace_grad_body(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
                              const double *l, double tau, double delta, double pois_m, const double *ff, double *grad,
-                             const double *knot_lb, const double *knot_ub, double *knot_grad)
+                             const double *knot_lb, const double *knot_ub, double *knot_grad, bool om_nonneg, bool *retry)
 {
     SRGP_TRY(lap_check(ctx, family, kernel, xu, m, l));
     if (!ff || !grad) {
@@ -588,8 +590,12 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     double *GB = w->red1.d(), *a = GB + mm, *ktg = a + mp, *tail = ktg + mp;
     SRGP_TRY(L.rows(L.W3, tail));
     SRGP_TRY(L.ktv(L.d1, ktg));
-    SRGP_TRY(gauss_pass1(ctx, w, L.gp, L.om, L.rz, GB, a));
-    SRGP_TRY(comm_allreduce(ctx, GB, mm + 2 * mp, s));
+    w->pass1_kmat = w->Kmat.d();
+    const int rc1 = gauss_pass1(ctx, w, L.gp, L.om, L.rz, GB, a, om_nonneg);
+    w->pass1_kmat = nullptr;
+    SRGP_TRY(rc1);
+    SRGP_TRY(comm_allreduce(ctx, GB, mm + 2 * mp + 4, s));
+    SRGP_TRY(copy_scalar(ctx, w->sc(W_::S_X + 3), tail + 3, 1));      // rows with omega < 0 or NaN, over all ranks
     double *C = w->mat(W_::M_C), *M2 = w->mat(W_::M_CGS), *SG = w->mat(W_::M_SG);
     double *SGS = w->mat(W_::M_SGS), *N = w->mat(W_::M_N), *Grho = w->mat(W_::M_X2);
     double *beta = w->vec(W_::V_BETA), *GG = w->vec(W_::V_T4), *c2 = w->vec(W_::V_T5), *Cc2 = w->vec(W_::V_T6);
@@ -659,7 +665,15 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     SRGP_TRY(dense::ger(ctx, s, mp, 0.5, skt, GG, N));
     SRGP_TRY(ns_reduce(ctx, w, L.gp, N, L.S, tau * tau + delta, w->sc(W_::S_NS), s));
     if (knot_grad) SRGP_TRY(knot_finish(ctx, w, L.gp, N, L.S));
-    SRGP_TRY(fetch_scalars(ctx, w));
+    {
+        const int rcf = fetch_scalars(ctx, w);
+        if (rcf == SRGP_ERR_CUDA) return rcf;
+        if (om_nonneg && !(w->h_scal[W_::S_X + 3] == 0.0)) {
+            *retry = true;
+            return SRGP_OK;
+        }
+        SRGP_TRY(rcf);
+    }
     SRGP_TRY(coin_check(w));
     if (knot_grad) {
         SRGP_CUDA(cudaMemcpyAsync(knot_grad, w->knotsum.d() + (int64_t)d * mp, (size_t)m * d * 8, cudaMemcpyDeviceToHost, s));
@@ -680,6 +694,19 @@ static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double
     // dS(tau) = 2 tau^2 on identical knot pairs is NOT zeroed in the Laplace gradient (R/laplace_approx_gradient.R:214-237)
     grad[ti] = 2.0 * tau * tau * (sum_rho + ns[1 + d] + hp2[1 + d]);
     return SRGP_OK;
+}
+
+static int laplace_grad_impl(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,
+                             const double *l, double tau, double delta, double pois_m, const double *ff, double *grad,
+                             const double *knot_lb, const double *knot_ub, double *knot_grad)
+{
+    bool retry = false;
+    int rc = laplace_grad_body(ctx, family, kernel, xu, m, sigma, l, tau, delta, pois_m, ff, grad, knot_lb, knot_ub, knot_grad,
+                               getenv("SRGP_LAP_TWO_SETS") == nullptr, &retry);
+    if (rc == SRGP_OK && retry)
+        rc = laplace_grad_body(ctx, family, kernel, xu, m, sigma, l, tau, delta, pois_m, ff, grad, knot_lb, knot_ub, knot_grad,
+                               false, &retry);
+    return rc;
 }
 
 extern "C" int srgp_laplace_grad(srgp_ctx *ctx, int family, int kernel, const double *xu, int64_t m, double sigma,

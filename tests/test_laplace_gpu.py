@@ -132,3 +132,25 @@ def test_newton_one_and_two_slice_set_grams_agree(ctx, monkeypatch):
     else:
         np.testing.assert_array_equal(a[0], b[0])
         np.testing.assert_array_equal(a[1], b[1])
+
+    # the gradient's first Gram (G_B, weights omega) takes the same two routes
+    from sparsergps_b200 import laplace as Lp
+    cp = c["cov_par"]
+
+    def grad(yy, ff):
+        try:
+            g = Lp.dlogq_dcov_par(cp, "ard", c["xu"], c["x"], yy, ff, "bernoulli", c["mu"], c["delta"], ctx=ctx)["gradient"]
+            return np.array([g[k] for k in cp])
+        except Exception as e:          # noqa: BLE001
+            return type(e).__name__
+    g1 = grad(c["y"], f1)
+    gneg1 = grad(y, 0.3 * f1)
+    monkeypatch.setenv("SRGP_LAP_TWO_SETS", "1")
+    g2 = grad(c["y"], f1)
+    gneg2 = grad(y, 0.3 * f1)
+    monkeypatch.delenv("SRGP_LAP_TWO_SETS")
+    np.testing.assert_allclose(g1, g2, rtol=1e-9, atol=1e-9 * np.max(np.abs(g2)))
+    if isinstance(gneg1, str) or isinstance(gneg2, str):
+        assert gneg1 == gneg2
+    else:
+        np.testing.assert_array_equal(gneg1, gneg2)
