@@ -1398,7 +1398,17 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.beta = beta;
             for (int c = 0; c < 8; c++) a.invl[c] = gp.invl[c];
             a.sigma2 = gp.sigma2;
-            a.tiles_per_cta = (mp / BN2) / w->cgroups;
+            // A short last chunk (row shards of multi-GPU runs: 125 000 rows = 13.2 chunks) would cost a full launch: its few
+            // row blocks each walk all their column tiles.  Spread it over more column groups instead -- the slots are
+            // addressed by the linear CTA index and all of them are summed at the end, so any grid within `slots` will do
+            // once the first launch has initialised them.
+            int cg = w->cgroups, rb = w->rblocks;
+            if (!first && !rowd && !knot && !pair) {
+                const int rb_valid = (rows_valid + BM - 1) / BM;
+                while (cg * 2 <= mp / BN2 && (mp / BN2) % (cg * 2) == 0 && rb_valid * cg * 2 <= slots) cg *= 2;
+                if (cg != w->cgroups) rb = rb_valid;
+            }
+            a.tiles_per_cta = (mp / BN2) / cg;
             a.cluster = pair ? 2 : 1;
             a.knot_part = knot ? w->knotpart.d() : nullptr;
             a.part = w->part2.d();
@@ -1412,7 +1422,7 @@ static int km_pass_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const doub
             a.nslots = nslots;
             a.ld = w->rows2;
             a.nodims = nodims ? 1 : 0;
-            dim3 grid(w->rblocks, w->cgroups);
+            dim3 grid(rb, cg);
             cudaError_t e = cudaSuccess;
 #define CALL2(D, R) (pair ? launch_km2_i8<D, R, true>(s, grid, ctx->device, a) : launch_km2_i8<D, R, false>(s, grid, ctx->device, a))
 #define CALL(D) e = knot ? launch_km2_i8<D, false, false, true>(s, grid, ctx->device, a) : rowd ? CALL2(D, true) : CALL2(D, false)
