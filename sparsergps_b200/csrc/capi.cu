@@ -105,12 +105,13 @@ extern "C" int srgp_ctx_create(int device, srgp_ctx **out)
         int prio_least = 0, prio_greatest = 0;
         SRGP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         SRGP_CUDA(cudaStreamCreateWithPriority(&ctx->stream4, cudaStreamNonBlocking, prio_least));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < 4; k++) {
             SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_gen[k], cudaEventDisableTiming));
             SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_used[k], cudaEventDisableTiming));
         }
         SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        SRGP_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
         SRGP_CUDA(cudaEventCreate(&ctx->tim0));
         SRGP_CUDA(cudaEventCreate(&ctx->tim1));
         return SRGP_OK;
@@ -142,8 +143,9 @@ extern "C" void srgp_ctx_destroy(srgp_ctx *ctx)
             cudaEventDestroy(pr.second);
         }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    cudaEvent_t evs[] = {ctx->ev_fork, ctx->ev_join, ctx->tim0, ctx->tim1,
-                         ctx->ev_gen[0], ctx->ev_gen[1], ctx->ev_used[0], ctx->ev_used[1]};
+    cudaEvent_t evs[] = {ctx->ev_fork, ctx->ev_join, ctx->ev_aux, ctx->tim0, ctx->tim1, ctx->tl_ref,
+                         ctx->ev_gen[0], ctx->ev_gen[1], ctx->ev_gen[2], ctx->ev_gen[3],
+                         ctx->ev_used[0], ctx->ev_used[1], ctx->ev_used[2], ctx->ev_used[3]};
     for (auto e : evs)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -232,18 +234,33 @@ extern "C" int srgp_prof_enable(srgp_ctx *ctx, int on)
     return SRGP_OK;
 }
 
+// SRGP_TIMELINE=<file> (diagnostic): every accounted kernel bracket is appended as "class start_ms end_ms" relative to the
+// last srgp_prof_reset -- where the time of an evaluation goes between the passes (tools/timeline.py).
 static int prof_drain(srgp_ctx *ctx, int id)
 {
     auto &slot = ctx->prof[id];
+    static const char *tl_path = getenv("SRGP_TIMELINE");
+    FILE *tl = (tl_path && ctx->tl_ref && !slot.pending.empty()) ? fopen(tl_path, "a") : nullptr;
+    size_t k = 0;
     for (auto &pr : slot.pending) {
         SRGP_CUDA(cudaEventSynchronize(pr.second));
         float f = 0.f;
         SRGP_CUDA(cudaEventElapsedTime(&f, pr.first, pr.second));
+        if (tl) {
+            float t0 = 0.f;
+            const int tag = k < slot.tags.size() ? slot.tags[k] : 0;
+            if (cudaEventElapsedTime(&t0, ctx->tl_ref, pr.first) == cudaSuccess)
+                fprintf(tl, "%d %.4f %.4f %d\n", id, t0, t0 + f, tag);
+            else cudaGetLastError();
+        }
+        k++;
         slot.ms += (double)f;
         ctx->ev_pool.push_back(pr.first);
         ctx->ev_pool.push_back(pr.second);
     }
     slot.pending.clear();
+    slot.tags.clear();
+    if (tl) fclose(tl);
     return SRGP_OK;
 }
 
@@ -254,6 +271,14 @@ extern "C" int srgp_prof_reset(srgp_ctx *ctx)
         SRGP_TRY(prof_drain(ctx, id));
         ctx->prof[id].launches = 0;
         ctx->prof[id].ms = 0.0;
+    }
+    if (getenv("SRGP_TIMELINE")) {
+        if (!ctx->tl_ref) SRGP_CUDA(cudaEventCreate(&ctx->tl_ref));
+        SRGP_CUDA(cudaEventRecord(ctx->tl_ref, ctx->stream));
+        if (FILE *tl = fopen(getenv("SRGP_TIMELINE"), "a")) {
+            fprintf(tl, "# reset\n");
+            fclose(tl);
+        }
     }
     return SRGP_OK;
 }

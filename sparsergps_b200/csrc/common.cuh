@@ -84,6 +84,7 @@ struct ProfSlot {
     int64_t launches = 0;
     double ms = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<int> tags;           // stream of each pending bracket (1 = main, 2, 3, 4), for SRGP_TIMELINE
 };
 
 }  // namespace srgp
@@ -95,9 +96,11 @@ struct srgp_ctx {
     cudaStream_t stream2 = nullptr;  // side stream: work independent of the main chain
     cudaStream_t stream3 = nullptr;  // generator stream: K chunk c+1 is generated while the DMMA kernel eats chunk c
     cudaStream_t stream4 = nullptr;  // lowest priority: pass 2's K generated ahead, under the m x m stage (gauss_pregen_k2)
-    cudaEvent_t ev_gen[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    cudaEvent_t ev_gen[4] = {}, ev_used[4] = {};   // per chunk buffer: generated / consumed (pass 1 of the INT8 engine uses 4)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_aux = nullptr;    // side stream -> main: an intermediate result is ready (gauss_vi.cu: S before its inverse)
     cudaEvent_t tim0 = nullptr, tim1 = nullptr;
+    cudaEvent_t tl_ref = nullptr;    // SRGP_TIMELINE: reference event of the last srgp_prof_reset
 
     // API-parity scratch (K1/K2/K5 with host pointers)
     srgp::DevBuf in_x, in_xp, out_mat, tmp0, tmp1;
@@ -149,6 +152,7 @@ struct KernelScope {
         if (e0) {
             cudaEventRecord(e1, s);
             ctx->prof[id].pending.emplace_back(e0, e1);
+            ctx->prof[id].tags.push_back(s == ctx->stream ? 1 : s == ctx->stream2 ? 2 : s == ctx->stream3 ? 3 : 4);
         }
     }
     cudaEvent_t take()

@@ -854,7 +854,7 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->rows2 = w->rblocks * BM;
     const size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
     w->chunk_elems = chunk_elems;
-    SRGP_TRY(w->chunk.reserve(2 * chunk_elems * 8));   // double buffered: generation overlaps consumption
+    SRGP_TRY(w->chunk.reserve(PASS1_BUFS * chunk_elems * 8));   // generation overlaps consumption (pass 1: 4 buffers, the others 2)
     SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));
     w->gen_groups = std::max(1, std::min(192, (ctx->sm_count * 8) / w->nt));
     SRGP_TRY(w->b1part.reserve((size_t)w->gen_groups * mp * 8));

@@ -12,6 +12,9 @@ struct GenParams {
     double invl[SRGP_MAX_D];       // 1 / l_c (sqexp: the same 1 / l in every dimension)
 };
 
+// Chunk buffers of the INT8 pass 1.  With two, generator c + 2 cannot start before Gram c has finished and the two kernels
+// alternate instead of overlapping (timeline of pass 1: 207 us per chunk = 64 us generator + 144 us Gram, the serial sum).
+constexpr int PASS1_BUFS = 4;
 constexpr int PART2_VEC_GROUPS = 320;   // part2 holds at least this many mp-vectors (laplace.cu: the K^T v partials)
 
 struct GaussWS {

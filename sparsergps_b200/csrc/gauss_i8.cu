@@ -1177,14 +1177,15 @@ int gauss_pass1_i8(srgp_ctx *ctx, GaussWS *w, const GenParams &gp, const double 
     cudaStream_t sg = getenv("SRGP_NO_OVERLAP") ? s : ctx->stream3;
     SRGP_CUDA(cudaEventRecord(ctx->ev_fork, s));
     SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_fork, 0));
+    static const int nb1 = getenv("SRGP_PASS1_BUFS") ? std::min(PASS1_BUFS, std::max(2, atoi(getenv("SRGP_PASS1_BUFS")))) : PASS1_BUFS;
     int cidx = 0;
     for (int64_t r0 = 0; r0 < ctx->n; r0 += rows1, cidx++) {
         const int rows_valid = (int)std::min<int64_t>(rows1, ctx->n - r0);
         const int rows_padded = (int)round_up(rows_valid, quantum);
-        const int b = cidx & 1;
+        const int b = cidx % nb1;
         int8_t *slices = reinterpret_cast<int8_t *>(w->chunk.d() + (size_t)b * w->chunk_elems);
         int8_t *slices_w = sets == 2 ? slices + (size_t)rows_padded * mp * NS : slices;
-        if (cidx >= 2) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
+        if (cidx >= nb1) SRGP_CUDA(cudaStreamWaitEvent(sg, ctx->ev_used[b], 0));
         {
             KernelScope ks(ctx, SRGP_PROF_GEN, sg);
             dim3 grid(mp / 128, w->gen_groups);

@@ -91,16 +91,19 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     cudaStream_t s2 = ctx->stream2;
 
     // ---- side stream: S = K_uu + delta I (self-covariance minus tau^2 I: R/vi_functions.R:736-741), identity on
-    //      the padding; Cholesky, S^-1, log|S|.  Independent of the data rows, so it overlaps pass 1. ----
+    //      the padding; Cholesky, S^-1, log|S|.  Independent of the data rows, so it overlaps pass 1.  The fork is taken
+    //      here, but the ~45 launches of that chain are enqueued AFTER pass 1's: the host needs ~0.2 ms for them, and the
+    //      first generator of pass 1 would otherwise start that much later (timeline of a 125 000-row shard). ----
     SRGP_TRY(stream_fork(ctx));
-    SRGP_TRY(assemble_dev_ld(ctx, s2, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
-    SRGP_TRY(dense::pad_identity(ctx, s2, S, mp, m, 1.0));
-    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s2));
-    SRGP_TRY(dense::chol_inverse(ctx, s2, T1, mp, m, w->dinv(0), w->mat(W::M_L1), w->mat(W::M_L2), w->mat(W::M_L3), Sinv,
-                                 w->info(0), w->sc(W::S_LOGDET_S)));
 
     // ---- pass 1 (main stream) --------------------------------------------------------------------------------
     SRGP_TRY(gauss_pass1(ctx, w, gp, nullptr, w->r.d(), G1, b1));
+    SRGP_TRY(assemble_dev_ld(ctx, s2, kernel, w->U.d(), m, d, sigma, l, delta, S, mp));
+    SRGP_TRY(dense::pad_identity(ctx, s2, S, mp, m, 1.0));
+    SRGP_CUDA(cudaEventRecord(ctx->ev_aux, s2));                    // S itself is ready long before its inverse
+    SRGP_CUDA(cudaMemcpyAsync(T1, S, mm * 8, cudaMemcpyDeviceToDevice, s2));
+    SRGP_TRY(dense::chol_inverse(ctx, s2, T1, mp, m, w->dinv(0), w->mat(W::M_L1), w->mat(W::M_L2), w->mat(W::M_L3), Sinv,
+                                 w->info(0), w->sc(W::S_LOGDET_S)));
     // pass 2's K does not depend on the m x m stage: its generators start now, on their own stream, and work while that
     // stage (latency-bound, tensor pipe idle) runs; pass 2 then finds most of its chunks waiting
     if (grad) SRGP_TRY(gauss_pregen_k2(ctx, w, gp));
@@ -109,7 +112,7 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(comm_allreduce(ctx, G1, mm + mp + 2, s));
     SRGP_TRY(copy_scalar(ctx, w->sc(W::S_S0TOT), tail, 1));
     SRGP_TRY(copy_scalar(ctx, w->sc(W::S_NTOT), tail + 1, 1));
-    SRGP_TRY(stream_join(ctx));
+    SRGP_CUDA(cudaStreamWaitEvent(s, ctx->ev_aux, 0));
 
     // ---- replicated m x m stage: the chain pass 2 waits for ------------------------------------------------------
     // A = S + B G1 ; C = A^-1
@@ -125,6 +128,9 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv, gsc));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, bv, -B, gv, tv));
+    // the factorisation of A above needed S only; the factors and the inverse of S (side stream) are needed from here on.
+    // On a short shard (8-GPU runs) that chain, slowed by the co-running pass 1, ends after pass 1 does.
+    SRGP_TRY(stream_join(ctx));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L1), tv, 0.0, nullptr, t2, gsc));
     SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L2), t2, 0.0, nullptr, beta, gsc));
     if (grad) {
