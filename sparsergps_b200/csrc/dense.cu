@@ -645,6 +645,39 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// y = alpha AT^T x + beta y0 from the TRANSPOSE of the matrix (column-major, ld = mp): output row i is the dot product of
+// column i of AT with x, one warp per row, coalesced -- one launch instead of the split-k pair of gemv().  The chains use it
+// wherever the transpose is at hand (L^-1 and its transposed copy from trtri, symmetric Grams and inverses).
+__global__ void __launch_bounds__(256) gemv_t_kernel(int mp, double alpha, const double *__restrict__ AT,
+                                                     const double *__restrict__ x, double beta,
+                                                     const double *__restrict__ y0, double *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const double *col = AT + (int64_t)row * mp;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int k = lane; k < mp; k += 128) {          // mp is a multiple of 128
+        a0 = fma(col[k], x[k], a0);
+        a1 = fma(col[k + 32], x[k + 32], a1);
+        a2 = fma(col[k + 64], x[k + 64], a2);
+        a3 = fma(col[k + 96], x[k + 96], a3);
+    }
+    const double acc = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) {
+        double v = alpha * acc;
+        if (beta != 0.0) v += beta * y0[row];
+        y[row] = v;
+    }
+}
+
+int gemv_t(srgp_ctx *ctx, cudaStream_t s, int mp, double alpha, const double *AT, const double *x, double beta,
+           const double *y0, double *y)
+{
+    KernelScope ks(ctx, SRGP_PROF_DENSE, s);
+    gemv_t_kernel<<<mp / 8, 256, 0, s>>>(mp, alpha, AT, x, beta, y0, y);
+    SRGP_LAUNCH_CHECK();
+    return SRGP_OK;
+}
+
 // block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
 __device__ __forceinline__ double block_sum(double v)
 {

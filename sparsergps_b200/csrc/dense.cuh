@@ -40,6 +40,9 @@ int trtri(srgp_ctx *ctx, cudaStream_t s, const double *L, int mp, const double *
           double *tmp);
 
 // Ainv = L^-T L^-1 (full symmetric) from LinvT.
+// y = alpha AT^T x + beta y0 given the transpose AT of the matrix (one launch; see dense.cu)
+int gemv_t(srgp_ctx *ctx, cudaStream_t s, int mp, double alpha, const double *AT, const double *x, double beta,
+           const double *y0, double *y);
 int lauum(srgp_ctx *ctx, cudaStream_t s, const double *LinvT, int mp, double *Ainv);
 
 // Convenience: A (mp x mp, destroyed -> L) ; Ainv, logdet as above.  Linv / LinvT / tmp are mp x mp scratch.

@@ -201,12 +201,12 @@ int gauss_fic(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double 
                                  w->sc(W::S_LOGDET_A)));
     // vector solves through the triangular factors (forward error ~ sqrt(cond) instead of cond)
     double *t1 = w->vec(W::V_T1), *t2 = w->vec(W::V_T2);
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Linv, b, 0.0, nullptr, t1, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, GB, v, 0.0, nullptr, gv, gsc));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, LinvT, b, 0.0, nullptr, t1));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, Linv, t1, 0.0, nullptr, v));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, GB, v, 0.0, nullptr, gv));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, b, -1.0, gv, tv));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvS, tv, 0.0, nullptr, t2, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvTS, t2, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, LinvTS, tv, 0.0, nullptr, t2));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, LinvS, t2, 0.0, nullptr, beta));
     SRGP_TRY(dense::dot_v(ctx, s, m, t1, t1, w->sc(W::S_BV)));   // b^T (S+G_B)^-1 b = |L^-1 b|^2
     if (grad) {
         // M2 = C G_B S^-1 = S^-1 - C   (G_B = A - S, C A = I): no product needed

@@ -124,15 +124,16 @@ int gauss_vi(srgp_ctx *ctx, GaussWS *w, int kernel, double sigma, const double *
     //  sqrt(cond) instead of cond for the explicit inverse -- matters for the OAT-shaped configs, cond(S) ~ 1e4+)
     double *t1 = w->vec(W::V_T1), *t2 = w->vec(W::V_T2);
     SRGP_TRY(axpby_vec(ctx, mp, B, b1, 0.0, nullptr, bv));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, Linv, bv, 0.0, nullptr, t1, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, LinvT, t1, 0.0, nullptr, v, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv, gsc));
+    // (gemv_t: one launch per product, from the transposed copy trtri leaves behind; G1 is symmetric)
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, LinvT, bv, 0.0, nullptr, t1));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, Linv, t1, 0.0, nullptr, v));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, G1, v, 0.0, nullptr, gv));
     SRGP_TRY(axpby_vec(ctx, mp, 1.0, bv, -B, gv, tv));
     // the factorisation of A above needed S only; the factors and the inverse of S (side stream) are needed from here on.
     // On a short shard (8-GPU runs) that chain, slowed by the co-running pass 1, ends after pass 1 does.
     SRGP_TRY(stream_join(ctx));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L1), tv, 0.0, nullptr, t2, gsc));
-    SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, w->mat(W::M_L2), t2, 0.0, nullptr, beta, gsc));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, w->mat(W::M_L2), tv, 0.0, nullptr, t2));
+    SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, w->mat(W::M_L1), t2, 0.0, nullptr, beta));
     if (grad) {
         // Mop = (1/tau^2 - B) S^-1 + B^2 C G1 S^-1 - B beta v^T.  With C (S + B G1) = I,  B C G1 S^-1 = S^-1 - C, so
         // Mop = S^-1 / tau^2 - B C - B beta v^T: no product on the chain pass 2 waits for

@@ -420,7 +420,7 @@ static int lap_objective_stage(Lap &L, double *W3out)
     SRGP_TRY(copy_scalar(L.ctx, w->sc(W_::S_X), tail, 5));
     SRGP_CUDA(cudaMemcpyAsync(L.av, a, (size_t)mp * 8, cudaMemcpyDeviceToDevice, s));
     // h = C_Z a ; a^T h
-    SRGP_TRY(dense::gemv(L.ctx, s, mp, 1.0, L.CZ, L.av, 0.0, nullptr, L.hv, L.gsc));
+    SRGP_TRY(dense::gemv_t(L.ctx, s, mp, 1.0, L.CZ, L.av, 0.0, nullptr, L.hv));      // C_Z is symmetric
     SRGP_TRY(dense::dot_v(L.ctx, s, m, L.av, L.hv, w->sc(W_::S_BV)));
     // factor S + G_omega
     SRGP_TRY(dense::axpby(L.ctx, s, mp, m, 1.0, L.S, 1.0, buf, 0.0, L.A));
@@ -520,8 +520,8 @@ extern "C" int srgp_laplace_newton(srgp_ctx *ctx, int family, int kernel, const 
         SRGP_TRY(comm_allreduce(ctx, cbuf, mp + 1, s));
         SRGP_TRY(copy_scalar(ctx, w->sc(W_::S_X + 8), cbuf + mp, 1));
         // g2 = (S + G_omega)^-1 c = L^-T (L^-1 c)
-        SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, L.Linv, cbuf, 0.0, nullptr, L.tv, L.gsc));
-        SRGP_TRY(dense::gemv(ctx, s, mp, 1.0, L.LinvT, L.tv, 0.0, nullptr, L.g2v, L.gsc));
+        SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, L.LinvT, cbuf, 0.0, nullptr, L.tv));
+        SRGP_TRY(dense::gemv_t(ctx, s, mp, 1.0, L.Linv, L.tv, 0.0, nullptr, L.g2v));
         SRGP_TRY(L.kv(L.g2v, nullptr, L.Kg, nullptr));
         SRGP_CUDA(cudaMemcpyAsync(GwPrev, Gw, mm * 8, cudaMemcpyDeviceToDevice, s));
         if (n > 0) {
