@@ -816,7 +816,13 @@ void GaussWS::release()
 int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
 {
     const int mp = (int)round_up(m, BM);
-    if (w->mp == mp && w->m == m && w->d == d && w->planned) return SRGP_OK;
+    // shards of 2 GiB of K or more (n mp doubles) give the INT8 pass 1 chunk buffers of 256 MB: 32 768 rows per launch at
+    // m = 1024, the most one INT32 accumulator may sum (tc_i8.cuh MAX_ROWS_PER_SPLIT x 4 splits), 31 launches instead of
+    // 82 at n = 1e6 and Gram 14.9 -> 13.3 ms per evaluation (profiles/r02_chunk_sweep_final.txt).  Smaller shards keep
+    // 96 MB: their pass 1 is a handful of chunks and lives on the generator / Gram overlap between them.
+    const bool big = (int64_t)ctx->n * mp * 8 >= (int64_t(2) << 30);
+    if (w->mp == mp && w->m == m && w->d == d && w->big_chunks == big && w->planned) return SRGP_OK;
+    w->big_chunks = big;
     w->m = m;
     w->mp = mp;
     w->d = d;
@@ -852,7 +858,8 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->cgroups = cg;
     w->rblocks = std::max(1, ctx->sm_count / cg);
     w->rows2 = w->rblocks * BM;
-    const size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
+    size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
+    if (big && !getenv("SRGP_CHUNK_MB")) chunk_elems = std::max(chunk_elems, (size_t(256) << 20) / 8);   // w->rows1 (DMMA pass 1) stays at 96 MB
     w->chunk_elems = chunk_elems;
     SRGP_TRY(w->chunk.reserve(PASS1_BUFS * chunk_elems * 8));   // generation overlaps consumption (pass 1: 4 buffers, the others 2)
     SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));

@@ -23,7 +23,8 @@ struct GaussWS {
     int m = 0, mp = 0, d = 0, nt = 0, pairs = 0;
     int splits = 1, rows1 = 0, gen_groups = 1;    // pass 1: SYRK split-K over the chunk rows
     int cgroups = 1, rblocks = 1, rows2 = 0;      // pass 2: row blocks x column groups
-    size_t chunk_elems = 0;                       // doubles per chunk buffer (two buffers)
+    size_t chunk_elems = 0;                       // doubles per chunk buffer (PASS1_BUFS buffers)
+    bool big_chunks = false;                      // shard of >= 2 GiB of K: 256 MB chunk buffers for the INT8 pass 1 (plan)
 
     DevBuf U;        // knots, m x d column-major
     DevBuf chunk;    // L2-resident K chunk (row-major in pass 1, column-major in pass 2)
