@@ -859,7 +859,9 @@ int plan(srgp_ctx *ctx, GaussWS *w, int m, int d)
     w->rblocks = std::max(1, ctx->sm_count / cg);
     w->rows2 = w->rblocks * BM;
     size_t chunk_elems = std::max((size_t)w->rows1 * mp, (size_t)w->rows2 * mp);
-    if (big && !getenv("SRGP_CHUNK_MB")) chunk_elems = std::max(chunk_elems, (size_t(256) << 20) / 8);   // w->rows1 (DMMA pass 1) stays at 96 MB
+    // w->rows1 (DMMA pass 1) stays at 96 MB; the large buffers hold at most 32 768 rows, the launch size that was measured
+    if (big && !getenv("SRGP_CHUNK_MB"))
+        chunk_elems = std::max(chunk_elems, std::min((size_t(256) << 20) / 8, (size_t)32768 * mp));
     w->chunk_elems = chunk_elems;
     SRGP_TRY(w->chunk.reserve(PASS1_BUFS * chunk_elems * 8));   // generation overlaps consumption (pass 1: 4 buffers, the others 2)
     SRGP_TRY(w->Gpart.reserve((size_t)w->pairs * w->splits * BM * BN * 8));
